@@ -1,0 +1,86 @@
+// TEST INFRASTRUCTURE ONLY. Compiles the lane-level codec functions of
+// vector_db_id_compression_b200/csrc (idc_core.cuh, roc_lane.cuh, ef_core.cuh)
+// with g++ so their logic can be checked against the oracle in the CPU test
+// suite (no GPU in the build container). Not part of libidcodec.so; nothing in
+// the product loads it.
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../../vector_db_id_compression_b200/csrc/roc_lane.cuh"
+#include "../../vector_db_id_compression_b200/csrc/ef_core.cuh"
+
+using namespace idc;
+
+static void tables(uint32_t* mt) {
+    std::mt19937 g(1234);
+    for (int i = 0; i < kMtWords; i++) mt[i] = (uint32_t)g();
+}
+
+extern "C" {
+
+// ids ascending. Returns words used (or -1), fills head/words/order/status.
+int64_t sim_roc_encode(uint32_t n, const uint64_t* ids, int prec, uint64_t* head_out, uint32_t* words_out,
+                       uint32_t cap, uint32_t* order_out, uint32_t* status_out) {
+    uint32_t mt[kMtWords];
+    tables(mt);
+    std::vector<uint8_t> ws(enc_tree_bytes(n) + 64, 0);
+    EncLane<int64_t> L;
+    L.tree = enc_tree_at(ws.data(), n);
+    EncTreeLayout lay = enc_tree_layout(n);
+    for (uint32_t e = 0; e < lay.leaf_sectors * 16u; e++) L.tree.leaf[e] = enc_tree_init_leaf(n, e);
+    for (uint32_t e = 0; e < lay.l1_sectors * 16u; e++) L.tree.l1[e] = enc_tree_init_count(n, e, 256u);
+    for (uint32_t e = 0; e < 16u; e++) L.tree.l2[e] = enc_tree_init_count(n, e, 4096u);
+    L.st = EncState{kRansL, words_out, 0, cap, 0, 0};
+    L.src = reinterpret_cast<const int64_t*>(ids);
+    L.sort_idx = nullptr;
+    L.order = order_out;
+    L.pos_base = 0;
+    L.n = n;
+    L.prec = prec;
+    for (uint32_t t = n; t >= 1; --t)
+        enc_lane_step(L, t, ~0ull / t, (uint32_t)((1ull << 31) / t), mt);
+    *head_out = L.st.head;
+    *status_out = L.st.status;
+    return L.st.status & kStScratch ? -1 : (int64_t)L.st.sp;
+}
+
+void sim_roc_decode(uint64_t head, const uint32_t* words, uint32_t nwords, uint32_t n, int prec, uint32_t lo,
+                    uint32_t hi, int64_t* out, uint32_t* status_out, uint32_t force_degenerate) {
+    uint32_t mt[kMtWords];
+    tables(mt);
+    std::vector<uint8_t> ws(dec_tree_bytes(n) + 64, 0);
+    DecLane<int64_t> L;
+    L.tree = dec_tree_at(ws.data(), n, lo, hi);
+    if (force_degenerate) L.tree.ovf_cap = force_degenerate - 1;  // shrink the overflow list to exercise the fallback
+    L.st = DecState{head, words, nwords, 0, 0, 0, 0};
+    L.out = out;
+    L.n = n;
+    L.prec = prec;
+    for (uint32_t i = 0; i < n; i++)
+        dec_lane_step(L, i, (uint32_t)((1ull << 31) / (i + 1)), mt);
+    *status_out = L.st.status;
+}
+
+uint64_t sim_dec_tree_bytes(uint32_t n) { return dec_tree_bytes(n); }
+uint64_t sim_enc_tree_bytes(uint32_t n) { return enc_tree_bytes(n); }
+
+
+// Elias-Fano: every output word through the gather functions of ef_core.cuh
+void sim_ef_shape(uint64_t universe, uint64_t m, uint64_t* out6) {
+    EfShape s = ef_shape(universe, m);
+    out6[0] = s.l, out6[1] = s.low_bits, out6[2] = s.high_bits, out6[3] = s.low_words, out6[4] = s.high_words,
+    out6[5] = s.samples;
+}
+void sim_ef_encode(const int64_t* ids, uint64_t m, uint64_t universe, uint64_t* low, uint64_t* high, uint32_t* samples) {
+    EfShape s = ef_shape(universe, m);
+    for (uint64_t w = 0; w < s.low_words; w++) low[w] = ef_low_word(ids, m, s.l, w);
+    for (uint64_t w = 0; w < s.high_words; w++) high[w] = ef_high_word(ids, m, s.l, universe, w);
+    for (uint64_t i = 0; i < m; i += kEfSample) samples[i >> kEfSampleLog] = (uint32_t)ef_high_pos(ids, i, s.l);
+}
+uint64_t sim_ef_select(const uint64_t* low, const uint64_t* high, const uint32_t* samples, uint32_t l, uint64_t k) {
+    return ef_select(low, high, samples, l, k);
+}
+
+}  // extern "C"

@@ -1,0 +1,601 @@
+// idc_core.cuh -- lane-level building blocks of the ROC codec.
+//
+// Everything here is written once as IDC_HD (host + device) code: the CUDA
+// kernels in roc_kernels.cu run one rANS stream per lane ("32-way interleaved
+// across lists": 32 independent heads per warp, one per unit), and
+// tests/hostsim compiles the very same functions with g++ to check them
+// against the oracle before any GPU time is spent. The host build is test
+// infrastructure only -- the shipped library contains no CPU code path.
+//
+// Reference semantics restated here (paths relative to the reference tree):
+//   ANSState                         custom_invlist_cpp/codec.h:13-45
+//   pop/push_with_finer_precision    custom_invlist_cpp/codec.cpp:21-63
+//   vrans_push / vrans_pop           custom_invlist_cpp/codec.cpp:65-90
+//   codec_push / codec_pop           custom_invlist_cpp/codec.cpp:92-121
+//   order statistics                 fenwick_tree_cpp/src/fenwick_tree.h:42-140
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define IDC_HD __host__ __device__ __forceinline__
+#else
+#define IDC_HD inline
+#endif
+
+namespace idc {
+
+constexpr uint64_t kRansL = 1ull << 31;  // codec.cpp:19
+constexpr int kMtWords = 8;              // words of std::mt19937(1234) kept on the device
+constexpr uint32_t kMaxUnit = 65536;     // reference round-trip domain
+
+// status bits reported per unit
+constexpr uint32_t kStOverlay = 1u;      // decoder stack rose 2 words above its low-water mark
+constexpr uint32_t kStMtDraws = 2u;      // more than kMtWords draws from the mt19937 fallback
+constexpr uint32_t kStUnsorted = 4u;     // ids not ascending although IDC_F_SORTED was given
+constexpr uint32_t kStWide = 8u;         // id does not fit 32 bits
+constexpr uint32_t kStScratch = 16u;     // encoder ran out of scratch words (cannot happen within the bound)
+constexpr uint32_t kStDegenerate = 32u;  // decoder fell back to brute-force ranks (informational)
+
+struct uint4x {  // 16 bytes; uint4 on device
+    uint32_t x, y, z, w;
+};
+
+// ------------------------------------------------------------- primitives --
+
+IDC_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+IDC_HD int popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// sum of the two 16-bit halves of a, each multiplied by byte 0 / byte 1 of sel
+IDC_HD uint32_t dp2a(uint32_t a, uint32_t sel, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+    return __dp2a_lo(a, sel, acc);
+#else
+    return acc + (a & 0xffffu) * (sel & 0xffu) + (a >> 16) * ((sel >> 8) & 0xffu);
+#endif
+}
+
+// Workspace accesses. Device: L2-only loads (.cg) so that fire-and-forget
+// reductions (RED at L2) and later loads of the same word stay coherent
+// without relying on L1 invalidation; host: plain memory.
+IDC_HD uint4x ld_ws16(const void* p) {
+#if defined(__CUDA_ARCH__)
+    uint4 v = __ldcg(reinterpret_cast<const uint4*>(p));
+    return uint4x{v.x, v.y, v.z, v.w};
+#else
+    return *reinterpret_cast<const uint4x*>(p);
+#endif
+}
+// read-only inputs (id arrays, compressed streams): normal cached loads
+IDC_HD uint32_t ld_ro32(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+IDC_HD uint32_t ld_ws32(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+IDC_HD uint64_t ld_ws64(const uint64_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(reinterpret_cast<const unsigned long long*>(p));
+#else
+    return *p;
+#endif
+}
+IDC_HD void st_ws32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
+IDC_HD void st_ws64(uint64_t* p, uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    __stcg(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+#else
+    *p = v;
+#endif
+}
+IDC_HD void red_add32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);  // result unused -> RED.ADD
+#else
+    *p += v;
+#endif
+}
+IDC_HD void red_and32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicAnd(p, v);  // result unused -> RED.AND
+#else
+    *p &= v;
+#endif
+}
+
+// ------------------------------------------------ sector-of-16-counts math --
+// A "sector" is 32 bytes = 16 unsigned 16-bit counts = two 16-byte loads.
+
+struct Sector {
+    uint32_t w[8];
+};
+
+IDC_HD Sector ld_sector(const uint16_t* base, uint32_t sector_idx) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(base) + (size_t)sector_idx * 32;
+    uint4x a = ld_ws16(p), b = ld_ws16(p + 16);
+    Sector s;
+    s.w[0] = a.x, s.w[1] = a.y, s.w[2] = a.z, s.w[3] = a.w;
+    s.w[4] = b.x, s.w[5] = b.y, s.w[6] = b.z, s.w[7] = b.w;
+    return s;
+}
+
+// sum of entries [0, slot), slot in 0..16
+IDC_HD uint32_t sector_sum_below(const Sector& s, uint32_t slot) {
+    uint32_t incl = (1u << slot) - 1u;  // bit t set <=> entry t counted
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        uint32_t two = (incl >> (2 * j)) & 3u;
+        uint32_t sel = (two & 1u) | ((two & 2u) << 7);
+        acc = dp2a(s.w[j], sel, acc);
+    }
+    return acc;
+}
+
+// entry at dynamic position slot (0..15)
+IDC_HD uint32_t sector_get(const Sector& s, uint32_t slot) {
+    uint32_t j = slot >> 1, w = s.w[0];
+#pragma unroll
+    for (int t = 1; t < 8; t++)
+        w = (j == (uint32_t)t) ? s.w[t] : w;
+    return (slot & 1u) ? (w >> 16) : (w & 0xffffu);
+}
+
+// Given counts c[0..15] and k < sum(c): the first entry j whose inclusive
+// prefix exceeds k; k is reduced by the exclusive prefix of j.
+IDC_HD uint32_t sector_select(const Sector& s, uint32_t& k) {
+    uint32_t run = 0, j = 0, sub = 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint32_t c = (t & 1) ? (s.w[t >> 1] >> 16) : (s.w[t >> 1] & 0xffffu);
+        run += c;
+        bool le = run <= k;
+        j += le ? 1u : 0u;
+        sub = le ? run : sub;
+    }
+    k -= sub;
+    return j < 15u ? j : 15u;
+}
+
+// same, where each 16-bit entry is a presence mask and its count is popc
+IDC_HD uint32_t sector_select_masks(const Sector& s, uint32_t& k) {
+    uint32_t run = 0, j = 0, sub = 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint32_t m = (t & 1) ? (s.w[t >> 1] >> 16) : (s.w[t >> 1] & 0xffffu);
+        run += (uint32_t)popc32(m);
+        bool le = run <= k;
+        j += le ? 1u : 0u;
+        sub = le ? run : sub;
+    }
+    k -= sub;
+    return j < 15u ? j : 15u;
+}
+
+// position of the r-th (0-based) set bit of a 16-bit mask
+IDC_HD uint32_t select16(uint32_t m, uint32_t r) {
+    uint32_t pos = 0, c;
+    c = (uint32_t)popc32(m & 0xffu);
+    if (r >= c) { r -= c; pos += 8; m >>= 8; }
+    c = (uint32_t)popc32(m & 0xfu);
+    if (r >= c) { r -= c; pos += 4; m >>= 4; }
+    c = (uint32_t)popc32(m & 0x3u);
+    if (r >= c) { r -= c; pos += 2; m >>= 2; }
+    if (r >= (m & 1u)) pos += 1;
+    return pos;
+}
+
+// ------------------------------------------------------ encoder rANS state --
+// The encoder's stack is append-only in the codec's valid domain; the rare
+// pop-from-stack cases are still implemented exactly (read back the word just
+// written, or draw from the mt19937(1234) table when the stack is empty).
+
+struct EncState {
+    uint64_t head;
+    uint32_t* words;   // this unit's scratch slot
+    uint32_t sp;       // words on the stack
+    uint32_t cap;
+    uint32_t draws;
+    uint32_t status;
+};
+
+IDC_HD void enc_spill(EncState& st, uint32_t w) {
+    if (st.sp < st.cap)
+        st_ws32(st.words + st.sp, w);
+    else
+        st.status |= kStScratch;
+    st.sp++;
+}
+
+IDC_HD uint32_t enc_refill(EncState& st, const uint32_t* mt) {
+    if (st.sp) {
+        st.sp--;
+        return st.sp < st.cap ? ld_ws32(st.words + st.sp) : 0u;
+    }
+    uint32_t d = st.draws++;
+    if (d >= (uint32_t)kMtWords) {
+        st.status |= kStMtDraws;
+        return 0;
+    }
+    return mt[d];
+}
+
+// codec.cpp:21-42. rcp = floor((2^64-1)/nmax), q31 = 2^31/nmax.
+// The spill test `head >= nmax*((2^31/nmax) << 32)` only looks at the upper
+// word because the threshold's lower word is zero.
+IDC_HD uint32_t enc_pop_uniform(EncState& st, uint32_t nmax, uint64_t rcp, uint32_t q31, const uint32_t* mt) {
+    uint64_t h = st.head;
+    bool spill = (uint32_t)(h >> 32) >= nmax * q31;  // nmax*q31 <= 2^31: no overflow
+    uint32_t low = (uint32_t)h;
+    if (spill)
+        h >>= 32;
+    uint64_t q = mulhi64(h, rcp);
+    uint64_t r = h - q * nmax;
+    if (r >= nmax) { q++; r -= nmax; }
+    bool refill = h < kRansL;
+    if (spill && refill) {
+        // the word just spilled is popped straight back: the stack is unchanged
+        q = (uint64_t)low | (q << 32);
+    } else {
+        if (spill)
+            enc_spill(st, low);
+        if (refill)
+            q = (uint64_t)enc_refill(st, mt) | (q << 32);
+    }
+    st.head = q;
+    return (uint32_t)r;
+}
+
+// codec.cpp:65-76, start added unmasked; p in 0..16
+IDC_HD void enc_push_bits(EncState& st, uint32_t start, uint32_t p) {
+    uint64_t h = st.head;
+    if ((uint32_t)(h >> 32) >= (uint32_t)(kRansL >> p)) {
+        enc_spill(st, (uint32_t)h);
+        h >>= 32;
+    }
+    st.head = (h << p) + start;
+}
+
+// codec.cpp:92-105
+IDC_HD void enc_push_id(EncState& st, uint64_t id, int precision) {
+#pragma unroll
+    for (int lower = 0; lower < 64; lower += 16) {
+        int p = precision - lower;
+        p = p < 0 ? 0 : (p > 16 ? 16 : p);
+        enc_push_bits(st, (uint32_t)(id >> lower) & 0xffffu, (uint32_t)p);
+    }
+}
+
+// ------------------------------------------------------ decoder rANS state --
+// Reads the blob's words top-down; pushes go to a one-word overlay register
+// (the decoder never holds more than one word above its low-water mark inside
+// the codec's valid domain -- violations are flagged, not assumed away).
+
+struct DecState {
+    uint64_t head;
+    const uint32_t* words;
+    uint32_t sp;
+    uint32_t ov;
+    uint32_t has_ov;
+    uint32_t draws;
+    uint32_t status;
+};
+
+IDC_HD uint32_t dec_refill(DecState& st, const uint32_t* mt) {
+    if (st.has_ov) {
+        st.has_ov = 0;
+        return st.ov;
+    }
+    if (st.sp) {
+        st.sp--;
+        return ld_ro32(st.words + st.sp);
+    }
+    uint32_t d = st.draws++;
+    if (d >= (uint32_t)kMtWords) {
+        st.status |= kStMtDraws;
+        return 0;
+    }
+    return mt[d];
+}
+
+IDC_HD void dec_spill(DecState& st, uint32_t w) {
+    if (st.has_ov)
+        st.status |= kStOverlay;
+    st.ov = w;
+    st.has_ov = 1;
+}
+
+// codec.cpp:78-90; p in 0..16
+IDC_HD uint32_t dec_pop_bits(DecState& st, uint32_t p, const uint32_t* mt) {
+    uint64_t h = st.head;
+    uint32_t sym = (uint32_t)h & ((1u << p) - 1u);
+    h >>= p;
+    if (h < kRansL)
+        h = (h << 32) | (uint64_t)dec_refill(st, mt);
+    st.head = h;
+    return sym;
+}
+
+// codec.cpp:107-121
+IDC_HD uint64_t dec_pop_id(DecState& st, int precision, const uint32_t* mt) {
+    uint64_t id = 0;
+#pragma unroll
+    for (int lower = 48; lower >= 0; lower -= 16) {
+        int p = precision - lower;
+        p = p < 0 ? 0 : (p > 16 ? 16 : p);
+        id = (id << 16) | dec_pop_bits(st, (uint32_t)p, mt);
+    }
+    return id;
+}
+
+// codec.cpp:44-63; q31 = 2^31/nmax
+IDC_HD void dec_push_uniform(DecState& st, uint32_t sym, uint32_t nmax, uint32_t q31, const uint32_t* mt) {
+    uint64_t h = st.head;
+    if ((uint32_t)(h >> 32) >= q31) {
+        dec_spill(st, (uint32_t)h);
+        h >>= 32;
+    }
+    h = h * nmax + sym;
+    if (h < kRansL)
+        h = (uint64_t)dec_refill(st, mt) | (h << 32);
+    st.head = h;
+}
+
+// ------------------------------------------------- encoder: select-remove --
+// Order statistics over the unit's id-sorted array, replacing
+// FenwickTree::reverse_lookup_then_remove (fenwick_tree.h:96-140): a 16-ary
+// tree of 16-bit counts over a presence bitmap. One 32-byte sector per level:
+//   leaf sector s : 16 masks of 16 bits  -> positions [256 s, 256 s + 256)
+//   L1 sector  t  : 16 counts, entry e = ids left in leaf sector 16 t + e
+//   L2 sector     : 16 counts, entry e = ids left in L1 sector e (n <= 65536)
+
+struct EncTreeLayout {
+    uint32_t leaf_sectors;  // ceil(n / 256)
+    uint32_t l1_sectors;    // ceil(leaf_sectors / 16)
+};
+
+IDC_HD EncTreeLayout enc_tree_layout(uint32_t n) {
+    EncTreeLayout L;
+    L.leaf_sectors = (n + 255u) / 256u;
+    if (L.leaf_sectors == 0) L.leaf_sectors = 1;
+    L.l1_sectors = (L.leaf_sectors + 15u) / 16u;
+    return L;
+}
+IDC_HD uint64_t enc_tree_bytes(uint32_t n) {
+    EncTreeLayout L = enc_tree_layout(n);
+    return 32ull * (L.leaf_sectors + L.l1_sectors + 1u);
+}
+
+struct EncTree {
+    uint16_t* leaf;
+    uint16_t* l1;
+    uint16_t* l2;
+};
+
+IDC_HD EncTree enc_tree_at(uint8_t* ws, uint32_t n) {
+    EncTreeLayout L = enc_tree_layout(n);
+    EncTree t;
+    t.leaf = reinterpret_cast<uint16_t*>(ws);
+    t.l1 = t.leaf + 16u * L.leaf_sectors;
+    t.l2 = t.l1 + 16u * L.l1_sectors;
+    return t;
+}
+
+// value of 16-bit entry `e` (global entry index) of each level for a full tree
+// over n present ids -- used by the init kernel, one entry per thread.
+IDC_HD uint16_t enc_tree_init_leaf(uint32_t n, uint32_t e) {
+    uint32_t lo = e * 16u;
+    if (lo >= n) return 0;
+    uint32_t c = n - lo;
+    return c >= 16u ? 0xffffu : (uint16_t)((1u << c) - 1u);
+}
+IDC_HD uint16_t enc_tree_init_count(uint32_t n, uint32_t e, uint32_t span) {
+    uint64_t lo = (uint64_t)e * span;
+    if (lo >= n) return 0;
+    uint64_t c = n - lo;
+    return (uint16_t)(c >= span ? span : c);
+}
+
+// returns the position (in the id-sorted unit) of the k-th remaining id and removes it
+IDC_HD uint32_t enc_tree_select_remove(const EncTree& t, uint32_t k) {
+    Sector s2 = ld_sector(t.l2, 0);
+    uint32_t j2 = sector_select(s2, k);
+    Sector s1 = ld_sector(t.l1, j2);
+    uint32_t j1 = sector_select(s1, k);
+    uint32_t leaf_sector = j2 * 16u + j1;
+    Sector s0 = ld_sector(t.leaf, leaf_sector);
+    uint32_t j0 = sector_select_masks(s0, k);
+    uint32_t b = select16(sector_get(s0, j0), k);
+    // removal: clear the bit, decrement the two counts on the path
+    uint32_t* leaf_word = reinterpret_cast<uint32_t*>(t.leaf) + leaf_sector * 8u + (j0 >> 1);
+    red_and32(leaf_word, ~(1u << (b + 16u * (j0 & 1u))));
+    uint32_t* l1_word = reinterpret_cast<uint32_t*>(t.l1) + j2 * 8u + (j1 >> 1);
+    red_add32(l1_word, 0u - (1u << (16u * (j1 & 1u))));
+    uint32_t* l2_word = reinterpret_cast<uint32_t*>(t.l2) + (j2 >> 1);
+    red_add32(l2_word, 0u - (1u << (16u * (j2 & 1u))));
+    return (leaf_sector * 16u + j0) * 16u + b;
+}
+
+// ---------------------------------------------------- decoder: insert-rank --
+// Replaces FenwickTree::insert_then_forward_lookup (fenwick_tree.h:42-94):
+// number of already decoded ids strictly smaller than v, then insert v.
+// Ids are not known in advance, so the structure is indexed by VALUE: a
+// monotone map id -> bucket, a 16-ary tree of 16-bit counts over the buckets
+// (all node addresses follow from v alone: the loads are independent), and one
+// 32-byte record of up to 8 ids per bucket for the exact tie-break. Buckets
+// that overflow spill (bucket, id) pairs to a small per-unit list; if that
+// fills up too (adversarial input) the unit switches to brute-force counting
+// over its already written output. Exact in every case.
+
+constexpr uint32_t kBucketCap = 8;
+
+struct DecTreeLayout {
+    uint32_t nb;          // buckets, multiple of 16
+    uint32_t sectors[4];  // sectors per level (level 0 = per-bucket counts)
+    uint32_t nlev;        // levels in use: level k has ceil(nb / 16^(k+1)) sectors
+    uint32_t ovf_cap;     // (bucket,id) pairs
+};
+
+IDC_HD DecTreeLayout dec_tree_layout(uint32_t n) {
+    DecTreeLayout L;
+    uint32_t want = n - (n >> 2);  // ~0.75 n buckets: mean load 1.33, P(load > 8) ~ 1.5e-5
+    L.nb = ((want + 15u) / 16u) * 16u;
+    if (L.nb < 16u) L.nb = 16u;
+    uint32_t entries = L.nb;
+    L.nlev = 0;
+    for (int k = 0; k < 4; k++) {
+        L.sectors[k] = (entries + 15u) / 16u;
+        if (k == 0 || entries > 1u) L.nlev = (uint32_t)k + 1u;
+        entries = L.sectors[k];
+        if (entries <= 1u) {
+            for (int q = k + 1; q < 4; q++) L.sectors[q] = 0;
+            break;
+        }
+    }
+    L.ovf_cap = n / 16u + 32u;
+    return L;
+}
+
+IDC_HD uint64_t dec_tree_bytes(uint32_t n) {
+    DecTreeLayout L = dec_tree_layout(n);
+    uint64_t b = 0;
+    for (int k = 0; k < 4; k++) b += 32ull * L.sectors[k];
+    b += 32ull * L.nb;              // bucket records
+    b += 8ull * L.ovf_cap;          // overflow pairs
+    return (b + 31ull) & ~31ull;
+}
+
+struct DecTree {
+    uint16_t* lev[4];
+    uint32_t* rec;      // nb records of 8 ids
+    uint32_t* ovf;      // pairs (bucket, id)
+    uint32_t nb, nlev, ovf_cap, ovf_n;
+    uint32_t lo, hi;    // id range mapped onto the buckets (hint; exactness does not depend on it)
+    uint64_t scale;     // bucket = ((v - lo) * scale) >> 32
+    uint32_t degenerate;
+};
+
+IDC_HD DecTree dec_tree_at(uint8_t* ws, uint32_t n, uint32_t lo, uint32_t hi) {
+    DecTreeLayout L = dec_tree_layout(n);
+    DecTree t;
+    uint8_t* p = ws;
+    for (int k = 0; k < 4; k++) {
+        t.lev[k] = reinterpret_cast<uint16_t*>(p);
+        p += 32ull * L.sectors[k];
+    }
+    t.rec = reinterpret_cast<uint32_t*>(p);
+    p += 32ull * L.nb;
+    t.ovf = reinterpret_cast<uint32_t*>(p);
+    t.nb = L.nb;
+    t.nlev = L.nlev;
+    t.ovf_cap = L.ovf_cap;
+    t.ovf_n = 0;
+    if (hi < lo) hi = lo;
+    t.lo = lo;
+    t.hi = hi;
+    uint64_t range = (uint64_t)hi - lo + 1ull;
+    t.scale = ((uint64_t)L.nb << 32) / range;  // <= nb * 2^32
+    t.degenerate = 0;
+    return t;
+}
+
+IDC_HD uint32_t dec_bucket(const DecTree& t, uint32_t v) {
+    uint32_t c = v < t.lo ? t.lo : (v > t.hi ? t.hi : v);
+    // (c - lo) < range and scale <= nb*2^32/range  =>  product < nb * 2^32: fits 64 bits
+    uint64_t b = ((uint64_t)(c - t.lo) * t.scale) >> 32;
+    return b >= t.nb ? t.nb - 1u : (uint32_t)b;
+}
+
+// out_prev: the ids decoded so far, most recent first is NOT required -- any
+// order; count of them is `decoded`. Only touched on the degenerate path.
+template <typename OutT>
+IDC_HD uint32_t dec_tree_insert_rank(DecTree& t, uint32_t v, const OutT* out_prev, uint32_t decoded) {
+    if (t.degenerate) {
+        uint32_t r = 0;
+        for (uint32_t i = 0; i < decoded; i++)
+            r += ((uint32_t)out_prev[i] < v) ? 1u : 0u;
+        return r;
+    }
+    uint32_t b = dec_bucket(t, v);
+    // issue every load first: all addresses depend on b only
+    Sector s[4];
+    uint32_t idx = b;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if ((uint32_t)k < t.nlev)
+            s[k] = ld_sector(t.lev[k], idx >> 4);
+        idx >>= 4;
+    }
+    const uint8_t* recp = reinterpret_cast<const uint8_t*>(t.rec) + (size_t)b * 32;
+    uint4x ra = ld_ws16(recp), rb = ld_ws16(recp + 16);
+
+    uint32_t rank = 0;
+    idx = b;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if ((uint32_t)k < t.nlev)
+            rank += sector_sum_below(s[k], idx & 15u);
+        idx >>= 4;
+    }
+    uint32_t cnt = sector_get(s[0], b & 15u);
+    uint32_t in_rec = cnt < kBucketCap ? cnt : kBucketCap;
+    uint32_t rv[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        rank += ((uint32_t)q < in_rec && rv[q] < v) ? 1u : 0u;
+    if (cnt > kBucketCap) {
+        for (uint32_t e = 0; e < t.ovf_n; e++) {
+            uint64_t pr = ld_ws64(reinterpret_cast<const uint64_t*>(t.ovf) + e);
+            rank += ((uint32_t)pr == b && (uint32_t)(pr >> 32) < v) ? 1u : 0u;
+        }
+    }
+    // insert
+    if (cnt < kBucketCap) {
+        st_ws32(t.rec + (size_t)b * 8u + cnt, v);
+    } else if (t.ovf_n < t.ovf_cap) {
+        st_ws64(reinterpret_cast<uint64_t*>(t.ovf) + t.ovf_n, (uint64_t)b | ((uint64_t)v << 32));
+        t.ovf_n++;
+    } else {
+        t.degenerate = 1;  // from now on ranks come from the output array
+        return rank;
+    }
+    idx = b;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if ((uint32_t)k < t.nlev) {
+            uint32_t* word = reinterpret_cast<uint32_t*>(t.lev[k]) + (idx >> 1);
+            red_add32(word, 1u << (16u * (idx & 1u)));
+        }
+        idx >>= 4;
+    }
+    return rank;
+}
+
+}  // namespace idc

@@ -1,0 +1,174 @@
+// idc_ctx.cu -- context, error reporting and constant tables of libidcodec.
+#include <cstring>
+#include <random>
+
+#include "idc_core.cuh"
+#include "idc_host.h"
+
+namespace idc {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int check_last_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("kernel launch %s failed: %s", what, cudaGetErrorString(e));
+        return IDC_ERR_CUDA;
+    }
+    return IDC_OK;
+}
+
+}  // namespace idc
+
+void idc_ctx::begin_call() {
+    times.clear();
+    events_used = 0;
+}
+
+void idc_ctx::mark(const char* name) {
+    launches++;
+    if (!timing) return;
+    while (event_pool.size() < events_used + 2) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        event_pool.push_back(e);
+    }
+    idc::KernelTime kt{name, event_pool[events_used], event_pool[events_used + 1]};
+    events_used += 2;
+    cudaEventRecord(kt.a, stream);
+    times.push_back(kt);
+}
+
+void idc_ctx::mark_end() {
+    if (!timing || times.empty()) return;
+    cudaEventRecord(times.back().b, stream);
+}
+
+extern "C" {
+
+const char* idc_last_error(void) { return idc::g_last_error.c_str(); }
+
+int idc_version(void) { return 100; }
+
+int idc_ctx_create_on_stream(int device, void* cuda_stream, idc_ctx** out) {
+    IDC_REQUIRE(out != nullptr, IDC_ERR_ARG, "idc_ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        idc::set_error("no usable CUDA device (%s): this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return IDC_ERR_CUDA;
+    }
+    IDC_REQUIRE(device >= 0 && device < ndev, IDC_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+    IDC_CUDA(cudaSetDevice(device));
+    idc_ctx* c = new idc_ctx();
+    c->device = device;
+    if (cuda_stream == (void*)-1) {
+        IDC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    } else {
+        c->stream = (cudaStream_t)cuda_stream;
+        c->own_stream = false;
+    }
+    cudaDeviceProp prop;
+    IDC_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+
+    // mt19937(1234): the fallback word source of ANSState::stack_slice (codec.h:16-18,32-40)
+    uint32_t mt[idc::kMtWords];
+    {
+        std::mt19937 g(1234);
+        for (int i = 0; i < idc::kMtWords; i++) mt[i] = (uint32_t)g();
+    }
+    IDC_CUDA(cudaMalloc(&c->d_mt, sizeof(mt)));
+    IDC_CUDA(cudaMemcpy(c->d_mt, mt, sizeof(mt), cudaMemcpyHostToDevice));
+
+    // reciprocal tables for the uniform coder (codec.cpp:21-63), indexed by nmax <= 65536
+    const uint32_t N = idc::kMaxUnit + 1;
+    std::vector<uint64_t> rcp(N);
+    std::vector<uint32_t> q31(N);
+    rcp[0] = 0;
+    q31[0] = 0;
+    for (uint32_t d = 1; d < N; d++) {
+        rcp[d] = ~0ull / d;
+        q31[d] = (uint32_t)((1ull << 31) / d);
+    }
+    IDC_CUDA(cudaMalloc(&c->d_rcp64, N * sizeof(uint64_t)));
+    IDC_CUDA(cudaMalloc(&c->d_q31, N * sizeof(uint32_t)));
+    IDC_CUDA(cudaMemcpy(c->d_rcp64, rcp.data(), N * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    IDC_CUDA(cudaMemcpy(c->d_q31, q31.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    *out = c;
+    return IDC_OK;
+}
+
+int idc_ctx_create(int device, idc_ctx** out) { return idc_ctx_create_on_stream(device, (void*)-1, out); }
+
+int idc_ctx_destroy(idc_ctx* c) {
+    if (!c) return IDC_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    cudaFree(c->d_mt);
+    cudaFree(c->d_rcp64);
+    cudaFree(c->d_q31);
+    c->ws.release();
+    c->scratch.release();
+    c->stage.release();
+    c->meta.release();
+    c->status.release();
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return IDC_OK;
+}
+
+int idc_ctx_synchronize(idc_ctx* c) {
+    IDC_REQUIRE(c != nullptr, IDC_ERR_ARG, "ctx is NULL");
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    return IDC_OK;
+}
+
+uint64_t idc_ctx_launch_count(const idc_ctx* c) { return c ? c->launches : 0; }
+
+int idc_ctx_set_timing(idc_ctx* c, int enable) {
+    IDC_REQUIRE(c != nullptr, IDC_ERR_ARG, "ctx is NULL");
+    c->timing = enable != 0;
+    return IDC_OK;
+}
+
+float idc_ctx_last_kernel_ms(const idc_ctx* c) {
+    if (!c) return 0.f;
+    float total = 0.f;
+    for (auto& kt : c->times) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(kt.b) == cudaSuccess && cudaEventElapsedTime(&ms, kt.a, kt.b) == cudaSuccess)
+            total += ms;
+    }
+    return total;
+}
+
+int idc_ctx_last_kernel_breakdown(const idc_ctx* c, const char** names, float* ms, int cap) {
+    if (!c) return 0;
+    int n = 0;
+    for (auto& kt : c->times) {
+        if (n >= cap) break;
+        float t = 0.f;
+        cudaEventSynchronize(kt.b);
+        cudaEventElapsedTime(&t, kt.a, kt.b);
+        names[n] = kt.name;
+        ms[n] = t;
+        n++;
+    }
+    return n;
+}
+
+}  // extern "C"

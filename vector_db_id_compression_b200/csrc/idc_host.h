@@ -1,0 +1,117 @@
+// idc_host.h -- host-side plumbing shared by the C-ABI translation units:
+// error reporting, the context object, device buffers, launch accounting.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/idcodec.h"
+
+namespace idc {
+
+void set_error(const char* fmt, ...);
+
+#define IDC_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            idc::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return IDC_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define IDC_TRY(call)        \
+    do {                     \
+        int r_ = (call);     \
+        if (r_ != IDC_OK)    \
+            return r_;       \
+    } while (0)
+
+#define IDC_REQUIRE(cond, code, ...)     \
+    do {                                 \
+        if (!(cond)) {                   \
+            idc::set_error(__VA_ARGS__); \
+            return (code);               \
+        }                                \
+    } while (0)
+
+// grow-only device allocation
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return IDC_OK;
+        release();
+        if (bytes == 0) return IDC_OK;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            return IDC_ERR_NOMEM;
+        }
+        cap = bytes;
+        return IDC_OK;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct KernelTime {
+    const char* name;
+    cudaEvent_t a, b;
+};
+
+}  // namespace idc
+
+struct idc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    bool timing = false;
+    std::vector<idc::KernelTime> times;      // events of the current/last call
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+    // constant tables (device)
+    uint32_t* d_mt = nullptr;     // first kMtWords outputs of std::mt19937(1234)
+    uint64_t* d_rcp64 = nullptr;  // floor((2^64-1)/d), d = 0..65536
+    uint32_t* d_q31 = nullptr;    // 2^31 / d
+    // grow-only scratch reused across calls
+    idc::DevBuf ws;       // order-statistic workspaces
+    idc::DevBuf scratch;  // encoder word scratch / staging
+    idc::DevBuf stage;    // host<->device staging of ids
+    idc::DevBuf meta;     // per-call unit tables
+    idc::DevBuf status;   // per-call status words
+
+    void begin_call();
+    void mark(const char* name);   // call right before a kernel launch
+    void mark_end();               // call right after it
+};
+
+namespace idc {
+
+// RAII helper: times one kernel launch when ctx->timing is on, counts it always
+struct LaunchScope {
+    idc_ctx* c;
+    LaunchScope(idc_ctx* ctx, const char* name) : c(ctx) { c->mark(name); }
+    ~LaunchScope() { c->mark_end(); }
+};
+
+int check_last_launch(const char* what);
+
+}  // namespace idc

@@ -1,0 +1,192 @@
+// idc_prep.cuh -- preparation kernels shared by the ROC and Elias-Fano paths:
+// per-unit metadata (min / max id, precision rule, input checks), NSG row
+// lengths, and the per-unit sort used when the caller's ids are not ascending.
+#pragma once
+
+#include <algorithm>
+#include <vector>
+
+#include "idc_core.cuh"
+#include "idc_host.h"
+#include "roc_lane.cuh"
+
+namespace {
+
+using namespace idc;
+
+constexpr int kThreads = 128;  // 4 warps per CTA
+
+template <typename T>
+int dev_alloc(T** p, size_t count, uint64_t* acct = nullptr) {
+    *p = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return IDC_ERR_NOMEM;
+    }
+    if (acct) *acct += bytes;
+    return IDC_OK;
+}
+
+template <typename T>
+int upload(idc_ctx* c, T* dst, const std::vector<T>& src) {
+    if (src.empty()) return IDC_OK;
+    IDC_CUDA(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return IDC_OK;
+}
+
+// ------------------------------------------------------------------ kernels
+
+struct MetaArgs {
+    const void* ids;
+    const uint64_t* unit_src;
+    const uint32_t* unit_n;
+    uint32_t nunits;
+    uint32_t expect_sorted;
+    uint32_t precision_safe;
+    uint8_t* unit_prec;
+    uint32_t* unit_lo;
+    uint32_t* unit_hi;
+    uint32_t* status;  // single word, OR of per-unit flags
+};
+
+__device__ __forceinline__ uint32_t bit_length64(uint64_t x) { return x ? 64u - (uint32_t)__clzll((long long)x) : 0u; }
+
+// One warp per unit: min / max id, ascending check, 32-bit width check and the
+// reference precision rule (uint64_t)ceil(log2((int)max_id))
+// (custom_invlists_impl.cpp:163-164, altid_impl.cpp:124-125) restated in
+// integers: ceil(log2(m)) = bit_length(m - 1) for m >= 1.
+template <typename IdT>
+__global__ void __launch_bounds__(kThreads) k_unit_meta(MetaArgs a) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.nunits) return;
+    const IdT* src = reinterpret_cast<const IdT*>(a.ids) + a.unit_src[warp];
+    uint32_t n = a.unit_n[warp];
+    uint64_t mx = 0, mn = ~0ull;
+    uint32_t bad = 0;
+    for (uint32_t i = lane; i < n; i += 32) {
+        uint64_t v = load_id(src + i);
+        if (sizeof(IdT) == 8 && (v >> 32)) bad |= kStWide;
+        if (a.expect_sorted && i + 1 < n && load_id(src + i + 1) < v) bad |= kStUnsorted;
+        mx = v > mx ? v : mx;
+        mn = v < mn ? v : mn;
+    }
+    for (int o = 16; o; o >>= 1) {
+        uint64_t omx = __shfl_xor_sync(0xffffffffu, mx, o), omn = __shfl_xor_sync(0xffffffffu, mn, o);
+        mx = omx > mx ? omx : mx;
+        mn = omn < mn ? omn : mn;
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane == 0) {
+        uint32_t p;
+        if (n == 0)
+            p = 0;
+        else if (a.precision_safe)
+            p = bit_length64(mx);
+        else
+            p = mx ? bit_length64(mx - 1) : 0;  // max_id == 0 is undefined in the reference; 0 here
+        a.unit_prec[warp] = (uint8_t)p;
+        a.unit_lo[warp] = n ? (uint32_t)mn : 0u;
+        a.unit_hi[warp] = n ? (uint32_t)mx : 0u;
+        if (bad) atomicOr(a.status, bad);
+    }
+}
+
+// NSG rows: number of entries before the first -1 (altid_impl.cpp:110-117)
+__global__ void __launch_bounds__(kThreads) k_row_counts(const int32_t* data, uint64_t nrows, uint32_t K, uint32_t* counts) {
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (warp >= nrows) return;
+    const int32_t* row = data + warp * K;
+    uint32_t cnt = K;
+    for (uint32_t base = 0; base < K; base += 32) {
+        uint32_t j = base + lane;
+        bool stop = j < K && __ldg(row + j) == -1;
+        uint32_t m = __ballot_sync(0xffffffffu, stop);
+        if (m) {
+            cnt = base + (uint32_t)__ffs((int)m) - 1u;
+            break;
+        }
+    }
+    if (lane == 0) counts[warp] = cnt;
+}
+
+// Per-unit bitonic sort of (id << 32 | position) keys. One CTA per unit; the
+// keys live in shared memory when the padded unit fits (<= 4096), otherwise in
+// a global scratch slot. Only used when the caller did not pass IDC_F_SORTED.
+struct SortArgs {
+    const void* ids;
+    const uint64_t* unit_src;
+    const uint32_t* unit_n;
+    const uint32_t* unit_posbase;
+    uint32_t nunits;
+    uint32_t* sorted_ids;   // same element layout as ids
+    uint32_t* sort_idx;
+    uint64_t* big_scratch;  // 65536 keys per CTA slot (gridDim.x slots)
+};
+
+constexpr uint32_t kSortSmem = 4096;
+
+template <typename IdT>
+__global__ void __launch_bounds__(256) k_sort_units(SortArgs a) {
+    __shared__ uint64_t skeys[kSortSmem];
+    for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+        uint32_t n = a.unit_n[u];
+        if (n == 0) continue;
+        uint64_t src_off = a.unit_src[u];
+        const IdT* src = reinterpret_cast<const IdT*>(a.ids) + src_off;
+        uint32_t npad = 1;
+        while (npad < n) npad <<= 1;
+        uint64_t* keys = npad <= kSortSmem ? skeys : a.big_scratch + (size_t)blockIdx.x * kMaxUnit;
+        uint32_t base = a.unit_posbase[u];
+        for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x)
+            keys[i] = i < n ? ((load_id(src + i) << 32) | (uint64_t)(base + i)) : ~0ull;
+        __syncthreads();
+        for (uint32_t k = 2; k <= npad; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+                    uint32_t p = i ^ j;
+                    if (p > i) {
+                        uint64_t x = keys[i], y = keys[p];
+                        bool up = (i & k) == 0;
+                        if ((x > y) == up) {
+                            keys[i] = y;
+                            keys[p] = x;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            uint64_t kv = keys[i];
+            a.sorted_ids[src_off + i] = (uint32_t)(kv >> 32);
+            a.sort_idx[src_off + i] = (uint32_t)kv;
+        }
+        __syncthreads();
+    }
+}
+
+
+inline uint32_t grid_for(uint64_t threads) { return (uint32_t)((threads + kThreads - 1) / kThreads); }
+
+
+int status_to_error(uint32_t st, const char* what) {
+    if (st & kStWide) {
+        set_error("%s: an id does not fit 32 bits (the sm_100a path codes ids < 2^32)", what);
+        return IDC_ERR_DOMAIN;
+    }
+    if (st & kStUnsorted) {
+        set_error("%s: IDC_F_SORTED was given but a list is not ascending", what);
+        return IDC_ERR_DOMAIN;
+    }
+    if (st & (kStOverlay | kStMtDraws | kStScratch)) {
+        set_error("%s: stream invariant violated (status 0x%x)", what, st);
+        return IDC_ERR_STREAM;
+    }
+    return IDC_OK;
+}
+
+
+}  // namespace

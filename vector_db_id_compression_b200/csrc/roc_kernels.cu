@@ -1,0 +1,831 @@
+// roc_kernels.cu -- ROC (bits-back rANS over sets) encode / decode on sm_100a.
+//
+// Execution model: ONE UNIT PER LANE. The reference stream is a single serial
+// rANS head per list (codec.cpp:131-137,144-151), so the only bit-exact way to
+// interleave 32 coders per warp is across lists: every lane owns one unit's
+// head, stream pointer and order-statistic workspace. Units are sorted by
+// length so the 32 lanes of a warp run in lock step, and the encoder walks
+// them END-ALIGNED so that `nmax` (ids left in the set) is the same in every
+// lane -- the reciprocal used by the uniform pop is then one broadcast load.
+//
+// Kernels (all integer, HBM/L2-latency bound; no tensor cores):
+//   k_unit_meta     per unit min/max id, precision rule, sortedness / width checks
+//   k_row_counts    NSG rows: length = entries before the first -1
+//   k_sort_units    per unit bitonic sort (only when the input is not sorted)
+//   k_enc_tree_init order-statistic tree of the encoder, all ids present
+//   k_roc_encode    the coder
+//   k_roc_compact   gather the per-unit scratch streams into the packed blob
+//   k_roc_decode    the decoder
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include <memory>
+
+#include "idc_host.h"
+#include "idc_prep.cuh"
+#include "roc_lane.cuh"
+
+using namespace idc;
+
+// --------------------------------------------------------------------------
+// blob
+// --------------------------------------------------------------------------
+struct idc_roc_blob {
+    idc_ctx* ctx = nullptr;
+    uint64_t nlist = 0, nunits = 0, total_ids = 0, total_words = 0, ans_bytes = 0;
+    uint32_t max_unit = IDC_MAX_UNIT_DEFAULT, row_stride = 0;
+    // host metadata
+    std::vector<uint64_t> list_offsets;  // nlist+1 (CSR of ids; rows: l*K)
+    std::vector<uint64_t> unit_offsets;  // nlist+1
+    std::vector<uint32_t> unit_n;        // nunits
+    std::vector<uint64_t> unit_src;      // nunits: element offset of the unit in the id array
+    // device arrays
+    uint32_t* d_unit_n = nullptr;
+    uint8_t* d_unit_prec = nullptr;
+    uint64_t* d_unit_head = nullptr;
+    uint64_t* d_word_off = nullptr;  // nunits+1
+    uint32_t* d_words = nullptr;
+    uint32_t* d_unit_lo = nullptr;   // id range hints for the decoder's bucket map
+    uint32_t* d_unit_hi = nullptr;
+    uint32_t* d_order = nullptr;     // total_ids (rows: nlist*K), optional
+    uint64_t device_bytes = 0;
+    // cached decode-everything plan
+    bool plan_ready = false;
+    uint32_t* d_plan_unit = nullptr;
+    uint64_t* d_plan_out = nullptr;
+    uint64_t* d_plan_ws = nullptr;
+    uint64_t plan_ws_bytes = 0;
+
+    ~idc_roc_blob() {
+        cudaFree(d_unit_n);
+        cudaFree(d_unit_prec);
+        cudaFree(d_unit_head);
+        cudaFree(d_word_off);
+        cudaFree(d_words);
+        cudaFree(d_unit_lo);
+        cudaFree(d_unit_hi);
+        cudaFree(d_order);
+        cudaFree(d_plan_unit);
+        cudaFree(d_plan_out);
+        cudaFree(d_plan_ws);
+    }
+};
+
+namespace {
+
+struct EncArgs {
+    const void* ids;             // ascending inside each unit
+    const uint32_t* sort_idx;    // null when the caller's order was already ascending
+    const uint64_t* unit_src;
+    const uint32_t* unit_n;
+    const uint32_t* unit_posbase;
+    const uint8_t* unit_prec;
+    const uint32_t* perm;        // launch slot -> unit, by descending n
+    const uint64_t* ws_off;      // per unit byte offset into ws
+    const uint64_t* scratch_off; // per unit word offset into scratch
+    uint8_t* ws;
+    uint32_t* scratch;
+    uint64_t* unit_head;
+    uint32_t* unit_nwords;
+    uint32_t* order;             // null: not recorded
+    uint32_t* status;
+    const uint32_t* mt;
+    const uint64_t* rcp64;
+    const uint32_t* q31;
+    uint32_t nunits;
+};
+
+// one warp per unit, lanes stride over the tree's 16-bit entries
+__global__ void __launch_bounds__(kThreads) k_enc_tree_init(EncArgs a) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.nunits) return;
+    uint32_t n = a.unit_n[warp];
+    if (n == 0) return;
+    EncTree t = enc_tree_at(a.ws + a.ws_off[warp], n);
+    EncTreeLayout L = enc_tree_layout(n);
+    for (uint32_t e = lane; e < L.leaf_sectors * 16u; e += 32) t.leaf[e] = enc_tree_init_leaf(n, e);
+    for (uint32_t e = lane; e < L.l1_sectors * 16u; e += 32) t.l1[e] = enc_tree_init_count(n, e, 256u);
+    if (lane < 16) t.l2[lane] = enc_tree_init_count(n, lane, 4096u);
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(kThreads) k_roc_encode(EncArgs a) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = slot < a.nunits;
+    uint32_t u = valid ? a.perm[slot] : 0u;
+    uint32_t n = valid ? a.unit_n[u] : 0u;
+    EncLane<IdT> L;
+    L.n = n;
+    L.prec = valid ? (int)a.unit_prec[u] : 0;
+    uint64_t src_off = valid ? a.unit_src[u] : 0ull;
+    L.src = reinterpret_cast<const IdT*>(a.ids) + src_off;
+    L.sort_idx = a.sort_idx ? a.sort_idx + src_off : nullptr;
+    L.order = a.order ? a.order + src_off : nullptr;
+    L.pos_base = valid ? a.unit_posbase[u] : 0u;
+    L.tree = enc_tree_at(a.ws + (valid ? a.ws_off[u] : 0ull), n ? n : 1u);
+    L.st.head = kRansL;
+    L.st.words = a.scratch + (valid ? a.scratch_off[u] : 0ull);
+    L.st.sp = 0;
+    L.st.cap = n + 4u;
+    L.st.draws = 0;
+    L.st.status = 0;
+    // end-aligned lock step: at warp step t every active lane has nmax == t
+    uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
+    for (uint32_t t = tmax; t >= 1u; --t) {
+        uint64_t rcp = __ldg(a.rcp64 + t);
+        uint32_t q31 = __ldg(a.q31 + t);
+        if (t <= n) enc_lane_step(L, t, rcp, q31, a.mt);
+    }
+    if (valid) {
+        a.unit_head[u] = L.st.head;
+        a.unit_nwords[u] = L.st.sp;
+        if (L.st.status) atomicOr(a.status, L.st.status);
+    }
+}
+
+// one warp per unit: scratch slot -> packed stream
+__global__ void __launch_bounds__(kThreads) k_roc_compact(const uint32_t* scratch, const uint64_t* scratch_off,
+                                                          const uint64_t* word_off, uint32_t* words, uint32_t nunits) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nunits) return;
+    uint64_t d0 = word_off[warp], d1 = word_off[warp + 1];
+    const uint32_t* src = scratch + scratch_off[warp];
+    uint32_t cnt = (uint32_t)(d1 - d0);
+    for (uint32_t i = lane; i < cnt; i += 32) words[d0 + i] = __ldcs(src + i);
+}
+
+struct DecArgs {
+    const uint32_t* sel_unit;   // launch slot -> blob unit, by descending n
+    const uint64_t* sel_out;    // launch slot -> element offset in out
+    const uint64_t* sel_ws;     // launch slot -> byte offset in ws
+    const uint32_t* unit_n;
+    const uint8_t* unit_prec;
+    const uint64_t* unit_head;
+    const uint64_t* word_off;
+    const uint32_t* words;
+    const uint32_t* unit_lo;
+    const uint32_t* unit_hi;
+    uint8_t* ws;
+    void* out;
+    uint32_t* counts;           // rows: true neighbour count per slot (may be null)
+    uint32_t* status;
+    const uint32_t* mt;
+    const uint32_t* q31;
+    uint32_t nsel;
+    uint32_t row_stride;        // rows: pad the slot's output to this many entries with -1
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = slot < a.nsel;
+    uint32_t u = valid ? a.sel_unit[slot] : 0u;
+    uint32_t n = valid ? a.unit_n[u] : 0u;
+    DecLane<OutT> L;
+    L.n = n;
+    L.prec = valid ? (int)a.unit_prec[u] : 0;
+    L.out = reinterpret_cast<OutT*>(a.out) + (valid ? a.sel_out[slot] : 0ull);
+    uint64_t w0 = valid ? a.word_off[u] : 0ull, w1 = valid ? a.word_off[u + 1] : 0ull;
+    L.st.head = valid ? a.unit_head[u] : kRansL;
+    L.st.words = a.words + w0;
+    L.st.sp = (uint32_t)(w1 - w0);
+    L.st.ov = 0;
+    L.st.has_ov = 0;
+    L.st.draws = 0;
+    L.st.status = 0;
+    L.tree = dec_tree_at(a.ws + (valid ? a.sel_ws[slot] : 0ull), n ? n : 1u, valid ? a.unit_lo[u] : 0u,
+                         valid ? a.unit_hi[u] : 0u);
+    uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
+    for (uint32_t i = 0; i < tmax; ++i) {
+        uint32_t q31 = __ldg(a.q31 + i + 1u);
+        if (i < n) dec_lane_step(L, i, q31, a.mt);
+    }
+    if (valid) {
+        if (a.row_stride)
+            for (uint32_t t = n; t < a.row_stride; ++t) L.out[t] = (OutT)-1;
+        if (a.counts) a.counts[slot] = n;
+        uint32_t st = L.st.status & ~kStDegenerate;
+        if (st) atomicOr(a.status, st);
+    }
+}
+
+// --------------------------------------------------------------- host side
+
+// launch order: units by descending n (counting sort; n <= 65536)
+void length_sorted_order(const uint32_t* n, uint64_t count, std::vector<uint32_t>& perm) {
+    std::vector<uint64_t> hist(kMaxUnit + 2, 0);
+    for (uint64_t i = 0; i < count; i++) hist[kMaxUnit - n[i] + 1]++;
+    for (size_t i = 1; i < hist.size(); i++) hist[i] += hist[i - 1];
+    perm.resize(count);
+    for (uint64_t i = 0; i < count; i++) perm[hist[kMaxUnit - n[i]]++] = (uint32_t)i;
+}
+
+// Shared encode driver. ids_dev: device pointer to the caller's ids (CSR or
+// row-strided); blob has list_offsets / unit tables filled in already.
+int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_bytes, uint32_t flags,
+                     const std::vector<uint32_t>& unit_posbase, uint64_t id_elems) {
+    const uint64_t nu = b->nunits;
+    uint64_t acct = 0;
+    IDC_TRY(dev_alloc(&b->d_unit_n, nu, &acct));
+    IDC_TRY(dev_alloc(&b->d_unit_prec, nu, &acct));
+    IDC_TRY(dev_alloc(&b->d_unit_head, nu, &acct));
+    IDC_TRY(dev_alloc(&b->d_word_off, nu + 1, &acct));
+    IDC_TRY(dev_alloc(&b->d_unit_lo, nu, &acct));
+    IDC_TRY(dev_alloc(&b->d_unit_hi, nu, &acct));
+    if (flags & IDC_F_WANT_ORDER) IDC_TRY(dev_alloc(&b->d_order, id_elems, &acct));
+    IDC_TRY(upload(c, b->d_unit_n, b->unit_n));
+
+    // per-call tables: unit_src, posbase, perm, ws_off, scratch_off, nwords
+    std::vector<uint32_t> perm;
+    length_sorted_order(b->unit_n.data(), nu, perm);
+    std::vector<uint64_t> ws_off(nu), scratch_off(nu);
+    uint64_t ws_bytes = 0, scratch_words = 0;
+    for (uint64_t u = 0; u < nu; u++) {
+        ws_off[u] = ws_bytes;
+        ws_bytes += b->unit_n[u] ? enc_tree_bytes(b->unit_n[u]) : 0;
+        scratch_off[u] = scratch_words;
+        scratch_words += b->unit_n[u] ? (uint64_t)b->unit_n[u] + 4u : 0;
+    }
+    size_t meta_bytes = nu * (8 + 4 + 4 + 8 + 8 + 4) + 64;
+    IDC_TRY(c->meta.reserve(meta_bytes + 256));
+    uint8_t* mp = c->meta.as<uint8_t>();
+    auto carve = [&](size_t bytes) {
+        uint8_t* r = mp;
+        mp += (bytes + 15) & ~size_t(15);
+        return r;
+    };
+    uint64_t* d_unit_src = (uint64_t*)carve(nu * 8);
+    uint64_t* d_ws_off = (uint64_t*)carve(nu * 8);
+    uint64_t* d_scratch_off = (uint64_t*)carve(nu * 8);
+    uint32_t* d_posbase = (uint32_t*)carve(nu * 4);
+    uint32_t* d_perm = (uint32_t*)carve(nu * 4);
+    uint32_t* d_nwords = (uint32_t*)carve(nu * 4);
+    IDC_TRY(c->status.reserve(64));
+    uint32_t* d_status = c->status.as<uint32_t>();
+    IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    IDC_TRY(upload(c, d_unit_src, b->unit_src));
+    IDC_TRY(upload(c, d_ws_off, ws_off));
+    IDC_TRY(upload(c, d_scratch_off, scratch_off));
+    IDC_TRY(upload(c, d_posbase, unit_posbase));
+    IDC_TRY(upload(c, d_perm, perm));
+
+    const bool sorted_in = (flags & IDC_F_SORTED) != 0;
+    // 1. unit metadata
+    {
+        MetaArgs m{ids_dev, d_unit_src, b->d_unit_n, (uint32_t)nu, sorted_in ? 1u : 0u,
+                   (flags & IDC_F_PRECISION_SAFE) ? 1u : 0u, b->d_unit_prec, b->d_unit_lo, b->d_unit_hi, d_status};
+        LaunchScope ls(c, "k_unit_meta");
+        if (id_bytes == 8)
+            k_unit_meta<int64_t><<<grid_for(nu * 32), kThreads, 0, c->stream>>>(m);
+        else
+            k_unit_meta<uint32_t><<<grid_for(nu * 32), kThreads, 0, c->stream>>>(m);
+    }
+    IDC_TRY(check_last_launch("k_unit_meta"));
+    {
+        uint32_t st = 0;
+        IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+        IDC_CUDA(cudaStreamSynchronize(c->stream));
+        IDC_TRY(status_to_error(st, "roc_encode"));
+    }
+
+    // 2. sort when needed
+    const void* enc_ids = ids_dev;
+    int enc_id_bytes = id_bytes;
+    uint32_t* d_sort_idx = nullptr;
+    size_t ws_need = ws_bytes;
+    size_t sorted_off = 0, sortidx_off = 0, big_off = 0;
+    uint32_t sort_grid = 0;
+    if (!sorted_in) {
+        sort_grid = (uint32_t)std::min<uint64_t>(nu, (uint64_t)c->sm_count * 8);
+        bool need_big = false;
+        for (uint64_t u = 0; u < nu && !need_big; u++) need_big = b->unit_n[u] > kSortSmem;
+        sorted_off = (ws_need + 255) & ~size_t(255);
+        sortidx_off = sorted_off + ((id_elems * 4 + 255) & ~size_t(255));
+        big_off = sortidx_off + ((id_elems * 4 + 255) & ~size_t(255));
+        ws_need = big_off + (need_big ? (size_t)sort_grid * kMaxUnit * 8 : 0);
+    }
+    IDC_TRY(c->ws.reserve(ws_need + 256));
+    IDC_TRY(c->scratch.reserve(scratch_words * 4 + 256));
+    if (!sorted_in) {
+        uint32_t* d_sorted = (uint32_t*)(c->ws.as<uint8_t>() + sorted_off);
+        d_sort_idx = (uint32_t*)(c->ws.as<uint8_t>() + sortidx_off);
+        SortArgs s{ids_dev, d_unit_src, b->d_unit_n, d_posbase, (uint32_t)nu, d_sorted, d_sort_idx,
+                   (uint64_t*)(c->ws.as<uint8_t>() + big_off)};
+        LaunchScope ls(c, "k_sort_units");
+        if (id_bytes == 8)
+            k_sort_units<int64_t><<<sort_grid, 256, 0, c->stream>>>(s);
+        else
+            k_sort_units<uint32_t><<<sort_grid, 256, 0, c->stream>>>(s);
+        enc_ids = d_sorted;
+        enc_id_bytes = 4;
+    }
+    IDC_TRY(check_last_launch("k_sort_units"));
+
+    // 3. encode
+    EncArgs e{};
+    e.ids = enc_ids;
+    e.sort_idx = d_sort_idx;
+    e.unit_src = d_unit_src;
+    e.unit_n = b->d_unit_n;
+    e.unit_posbase = d_posbase;
+    e.unit_prec = b->d_unit_prec;
+    e.perm = d_perm;
+    e.ws_off = d_ws_off;
+    e.scratch_off = d_scratch_off;
+    e.ws = c->ws.as<uint8_t>();
+    e.scratch = c->scratch.as<uint32_t>();
+    e.unit_head = b->d_unit_head;
+    e.unit_nwords = d_nwords;
+    e.order = b->d_order;
+    e.status = d_status;
+    e.mt = c->d_mt;
+    e.rcp64 = c->d_rcp64;
+    e.q31 = c->d_q31;
+    e.nunits = (uint32_t)nu;
+    {
+        LaunchScope ls(c, "k_enc_tree_init");
+        k_enc_tree_init<<<grid_for(nu * 32), kThreads, 0, c->stream>>>(e);
+    }
+    IDC_TRY(check_last_launch("k_enc_tree_init"));
+    {
+        LaunchScope ls(c, "k_roc_encode");
+        if (enc_id_bytes == 8)
+            k_roc_encode<int64_t><<<grid_for(nu), kThreads, 0, c->stream>>>(e);
+        else
+            k_roc_encode<uint32_t><<<grid_for(nu), kThreads, 0, c->stream>>>(e);
+    }
+    IDC_TRY(check_last_launch("k_roc_encode"));
+
+    // 4. sizes -> packed offsets -> compaction
+    std::vector<uint32_t> nwords(nu);
+    uint32_t st = 0;
+    IDC_CUDA(cudaMemcpyAsync(nwords.data(), d_nwords, nu * 4, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    IDC_TRY(status_to_error(st, "roc_encode"));
+    std::vector<uint64_t> word_off(nu + 1);
+    word_off[0] = 0;
+    uint64_t ans_bytes = 0;
+    for (uint64_t u = 0; u < nu; u++) {
+        if (b->unit_n[u] == 0) nwords[u] = 0;
+        word_off[u + 1] = word_off[u] + nwords[u];
+        if (b->unit_n[u]) ans_bytes += 8 + 4ull * nwords[u];  // ANSState::size(), codec.h:42-44
+    }
+    b->total_words = word_off[nu];
+    b->ans_bytes = ans_bytes;
+    IDC_TRY(dev_alloc(&b->d_words, b->total_words, &acct));
+    IDC_TRY(upload(c, b->d_word_off, word_off));
+    {
+        LaunchScope ls(c, "k_roc_compact");
+        k_roc_compact<<<grid_for(nu * 32), kThreads, 0, c->stream>>>(c->scratch.as<uint32_t>(), d_scratch_off,
+                                                                       b->d_word_off, b->d_words, (uint32_t)nu);
+    }
+    IDC_TRY(check_last_launch("k_roc_compact"));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    b->device_bytes = acct;
+    return IDC_OK;
+}
+
+// list -> unit tables for CSR input
+int plan_units_csr(idc_roc_blob* b, uint64_t nlist, const uint64_t* offsets, uint32_t max_unit,
+                   std::vector<uint32_t>& posbase) {
+    b->nlist = nlist;
+    b->max_unit = max_unit;
+    b->list_offsets.assign(offsets, offsets + nlist + 1);
+    b->unit_offsets.resize(nlist + 1);
+    b->unit_n.clear();
+    b->unit_src.clear();
+    posbase.clear();
+    for (uint64_t l = 0; l < nlist; l++) {
+        IDC_REQUIRE(offsets[l + 1] >= offsets[l], IDC_ERR_ARG, "offsets must be non-decreasing (list %llu)",
+                    (unsigned long long)l);
+        b->unit_offsets[l] = b->unit_n.size();
+        uint64_t n = offsets[l + 1] - offsets[l];
+        if (n == 0) {  // an empty list still owns one (empty) unit so that list <-> unit stays total
+            b->unit_n.push_back(0);
+            b->unit_src.push_back(offsets[l]);
+            posbase.push_back(0);
+            continue;
+        }
+        for (uint64_t s = 0; s < n; s += max_unit) {
+            b->unit_n.push_back((uint32_t)std::min<uint64_t>(max_unit, n - s));
+            b->unit_src.push_back(offsets[l] + s);
+            posbase.push_back((uint32_t)s);
+        }
+    }
+    b->unit_offsets[nlist] = b->unit_n.size();
+    b->nunits = b->unit_n.size();
+    b->total_ids = offsets[nlist] - offsets[0];
+    IDC_REQUIRE(b->nunits < (1ull << 32), IDC_ERR_ARG, "too many units");
+    return IDC_OK;
+}
+
+int build_decode_plan(idc_ctx* c, const idc_roc_blob* b, const std::vector<uint32_t>& units,
+                      const std::vector<uint64_t>& out_off, uint32_t** d_unit, uint64_t** d_out, uint64_t** d_ws,
+                      uint64_t* ws_bytes) {
+    const uint64_t m = units.size();
+    std::vector<uint32_t> ns(m), perm;
+    for (uint64_t i = 0; i < m; i++) ns[i] = b->unit_n[units[i]];
+    length_sorted_order(ns.data(), m, perm);
+    std::vector<uint32_t> su(m);
+    std::vector<uint64_t> so(m), sw(m);
+    uint64_t wsb = 0;
+    for (uint64_t i = 0; i < m; i++) {
+        su[i] = units[perm[i]];
+        so[i] = out_off[perm[i]];
+        sw[i] = wsb;
+        wsb += ns[perm[i]] ? dec_tree_bytes(ns[perm[i]]) : 0;
+    }
+    IDC_TRY(dev_alloc(d_unit, m));
+    IDC_TRY(dev_alloc(d_out, m));
+    IDC_TRY(dev_alloc(d_ws, m));
+    IDC_TRY(upload(c, *d_unit, su));
+    IDC_TRY(upload(c, *d_out, so));
+    IDC_TRY(upload(c, *d_ws, sw));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    *ws_bytes = wsb;
+    return IDC_OK;
+}
+
+int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const uint64_t* d_out, const uint64_t* d_ws,
+               uint64_t ws_bytes, uint64_t nsel, void* out_dev, int id_bytes, uint32_t* counts_dev, uint32_t row_stride) {
+    if (nsel == 0) return IDC_OK;
+    IDC_TRY(c->ws.reserve(ws_bytes + 256));
+    IDC_TRY(c->status.reserve(64));
+    uint32_t* d_status = c->status.as<uint32_t>();
+    IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    {
+        LaunchScope ls(c, "memset_ws");
+        IDC_CUDA(cudaMemsetAsync(c->ws.p, 0, ws_bytes, c->stream));
+    }
+    DecArgs a{};
+    a.sel_unit = d_unit;
+    a.sel_out = d_out;
+    a.sel_ws = d_ws;
+    a.unit_n = b->d_unit_n;
+    a.unit_prec = b->d_unit_prec;
+    a.unit_head = b->d_unit_head;
+    a.word_off = b->d_word_off;
+    a.words = b->d_words;
+    a.unit_lo = b->d_unit_lo;
+    a.unit_hi = b->d_unit_hi;
+    a.ws = c->ws.as<uint8_t>();
+    a.out = out_dev;
+    a.counts = counts_dev;
+    a.status = d_status;
+    a.mt = c->d_mt;
+    a.q31 = c->d_q31;
+    a.nsel = (uint32_t)nsel;
+    a.row_stride = row_stride;
+    {
+        LaunchScope ls(c, "k_roc_decode");
+        if (id_bytes == 8)
+            k_roc_decode<int64_t><<<grid_for(nsel), kThreads, 0, c->stream>>>(a);
+        else
+            k_roc_decode<int32_t><<<grid_for(nsel), kThreads, 0, c->stream>>>(a);
+    }
+    IDC_TRY(check_last_launch("k_roc_decode"));
+    uint32_t st = 0;
+    IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    return status_to_error(st, "roc_decode");
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------
+// C ABI
+// --------------------------------------------------------------------------
+extern "C" {
+
+int idc_roc_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const void* ids, int id_bytes, int ids_mem,
+                   uint32_t flags, uint32_t max_unit, idc_roc_blob** out) {
+    IDC_REQUIRE(c && offsets && out, IDC_ERR_ARG, "idc_roc_encode: null argument");
+    IDC_REQUIRE(id_bytes == 8 || id_bytes == 4, IDC_ERR_ARG, "id_bytes must be 4 or 8");
+    if (max_unit == 0) max_unit = IDC_MAX_UNIT_DEFAULT;
+    IDC_REQUIRE(max_unit <= kMaxUnit, IDC_ERR_ARG,
+                "max_unit %u > 65536: the reference codec does not round-trip larger sets", max_unit);
+    *out = nullptr;
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
+    b->ctx = c;
+    std::vector<uint32_t> posbase;
+    IDC_TRY(plan_units_csr(b.get(), nlist, offsets, max_unit, posbase));
+    uint64_t first = offsets[0], elems = offsets[nlist];
+    IDC_REQUIRE(ids != nullptr || elems == 0, IDC_ERR_ARG, "ids is NULL");
+    const void* ids_dev = ids;
+    if (ids_mem == IDC_MEM_HOST && elems) {
+        IDC_TRY(c->stage.reserve(elems * id_bytes));
+        IDC_CUDA(cudaMemcpyAsync(c->stage.p, ids, elems * id_bytes, cudaMemcpyHostToDevice, c->stream));
+        ids_dev = c->stage.p;
+    }
+    (void)first;
+    IDC_TRY(roc_encode_units(c, b.get(), ids_dev, id_bytes, flags, posbase, elems));
+    *out = b.release();
+    return IDC_OK;
+}
+
+int idc_roc_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* data, int data_mem, uint32_t flags,
+                        idc_roc_blob** out) {
+    IDC_REQUIRE(c && out && (data || nrows == 0), IDC_ERR_ARG, "idc_roc_encode_rows: null argument");
+    IDC_REQUIRE(K >= 1 && K <= kMaxUnit, IDC_ERR_ARG, "K out of range");
+    IDC_REQUIRE(nrows < (1ull << 32), IDC_ERR_ARG, "too many rows");
+    *out = nullptr;
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
+    b->ctx = c;
+    b->row_stride = K;
+    b->nlist = nrows;
+    b->nunits = nrows;
+    b->max_unit = kMaxUnit;
+    const int32_t* d_data = data;
+    uint64_t elems = nrows * K;
+    if (data_mem == IDC_MEM_HOST && elems) {
+        IDC_TRY(c->stage.reserve(elems * 4));
+        IDC_CUDA(cudaMemcpyAsync(c->stage.p, data, elems * 4, cudaMemcpyHostToDevice, c->stream));
+        d_data = c->stage.as<int32_t>();
+    }
+    // row lengths on the device, then back for planning
+    IDC_TRY(c->meta.reserve(nrows * 4 + 256));
+    b->unit_n.resize(nrows);
+    if (nrows) {
+        uint32_t* d_cnt = c->meta.as<uint32_t>();
+        {
+            LaunchScope ls(c, "k_row_counts");
+            k_row_counts<<<grid_for(nrows * 32), kThreads, 0, c->stream>>>(d_data, nrows, K, d_cnt);
+        }
+        IDC_TRY(check_last_launch("k_row_counts"));
+        IDC_CUDA(cudaMemcpyAsync(b->unit_n.data(), d_cnt, nrows * 4, cudaMemcpyDeviceToHost, c->stream));
+        IDC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    b->list_offsets.resize(nrows + 1);
+    b->unit_offsets.resize(nrows + 1);
+    b->unit_src.resize(nrows);
+    std::vector<uint32_t> posbase(nrows, 0);
+    uint64_t total = 0;
+    for (uint64_t r = 0; r < nrows; r++) {
+        b->list_offsets[r] = total;
+        b->unit_offsets[r] = r;
+        b->unit_src[r] = r * K;
+        total += b->unit_n[r];
+    }
+    b->list_offsets[nrows] = total;
+    b->unit_offsets[nrows] = nrows;
+    b->total_ids = total;
+    IDC_TRY(roc_encode_units(c, b.get(), d_data, 4, flags & ~IDC_F_SORTED, posbase, elems));
+    *out = b.release();
+    return IDC_OK;
+}
+
+int idc_roc_blob_info(const idc_roc_blob* b, idc_roc_info* info) {
+    IDC_REQUIRE(b && info, IDC_ERR_ARG, "null argument");
+    info->nlist = b->nlist;
+    info->nunits = b->nunits;
+    info->total_ids = b->total_ids;
+    info->total_words = b->total_words;
+    info->ans_bytes = b->ans_bytes;
+    info->device_bytes = b->device_bytes;
+    info->max_unit = b->max_unit;
+    info->row_stride = b->row_stride;
+    return IDC_OK;
+}
+
+int idc_roc_blob_export(const idc_roc_blob* b, uint64_t* list_offsets, uint64_t* unit_offsets, uint32_t* unit_n,
+                        uint8_t* unit_precision, uint64_t* unit_heads, uint64_t* word_offsets, uint32_t* words) {
+    IDC_REQUIRE(b, IDC_ERR_ARG, "null blob");
+    IDC_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    if (list_offsets) memcpy(list_offsets, b->list_offsets.data(), (b->nlist + 1) * 8);
+    if (unit_offsets) memcpy(unit_offsets, b->unit_offsets.data(), (b->nlist + 1) * 8);
+    if (unit_n && b->nunits) memcpy(unit_n, b->unit_n.data(), b->nunits * 4);
+    if (unit_precision && b->nunits)
+        IDC_CUDA(cudaMemcpyAsync(unit_precision, b->d_unit_prec, b->nunits, cudaMemcpyDeviceToHost, s));
+    if (unit_heads && b->nunits)
+        IDC_CUDA(cudaMemcpyAsync(unit_heads, b->d_unit_head, b->nunits * 8, cudaMemcpyDeviceToHost, s));
+    if (word_offsets)
+        IDC_CUDA(cudaMemcpyAsync(word_offsets, b->d_word_off, (b->nunits + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (words && b->total_words)
+        IDC_CUDA(cudaMemcpyAsync(words, b->d_words, b->total_words * 4, cudaMemcpyDeviceToHost, s));
+    IDC_CUDA(cudaStreamSynchronize(s));
+    return IDC_OK;
+}
+
+int idc_roc_blob_import(idc_ctx* c, uint64_t nlist, const uint32_t* unit_n, const uint8_t* unit_precision,
+                        const uint64_t* unit_heads, const uint64_t* word_offsets, const uint32_t* words,
+                        idc_roc_blob** out) {
+    IDC_REQUIRE(c && out && (nlist == 0 || (unit_n && unit_precision && unit_heads)) && word_offsets, IDC_ERR_ARG,
+                "idc_roc_blob_import: null argument");
+    IDC_CUDA(cudaSetDevice(c->device));
+    *out = nullptr;
+    std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
+    b->ctx = c;
+    b->nlist = b->nunits = nlist;
+    b->unit_n.assign(unit_n, unit_n + nlist);
+    b->list_offsets.resize(nlist + 1);
+    b->unit_offsets.resize(nlist + 1);
+    b->unit_src.resize(nlist);
+    uint64_t total = 0, ans = 0;
+    std::vector<uint32_t> lo(nlist, 0), hi(nlist);
+    for (uint64_t l = 0; l < nlist; l++) {
+        IDC_REQUIRE(unit_n[l] <= kMaxUnit, IDC_ERR_DOMAIN, "unit %llu has %u ids (> 65536)", (unsigned long long)l,
+                    unit_n[l]);
+        IDC_REQUIRE(unit_precision[l] <= 32, IDC_ERR_DOMAIN, "unit %llu: precision %u > 32 not supported on device",
+                    (unsigned long long)l, unit_precision[l]);
+        IDC_REQUIRE(word_offsets[l + 1] >= word_offsets[l], IDC_ERR_ARG, "word_offsets must be non-decreasing");
+        b->list_offsets[l] = total;
+        b->unit_offsets[l] = l;
+        b->unit_src[l] = total;
+        total += unit_n[l];
+        if (unit_n[l]) ans += 8 + 4 * (word_offsets[l + 1] - word_offsets[l]);
+        hi[l] = unit_precision[l] >= 32 ? 0xffffffffu : ((1u << unit_precision[l]) - 1u);
+    }
+    b->list_offsets[nlist] = total;
+    b->unit_offsets[nlist] = nlist;
+    b->total_ids = total;
+    b->total_words = word_offsets[nlist] - word_offsets[0];
+    b->ans_bytes = ans;
+    uint64_t acct = 0;
+    IDC_TRY(dev_alloc(&b->d_unit_n, nlist, &acct));
+    IDC_TRY(dev_alloc(&b->d_unit_prec, nlist, &acct));
+    IDC_TRY(dev_alloc(&b->d_unit_head, nlist, &acct));
+    IDC_TRY(dev_alloc(&b->d_word_off, nlist + 1, &acct));
+    IDC_TRY(dev_alloc(&b->d_unit_lo, nlist, &acct));
+    IDC_TRY(dev_alloc(&b->d_unit_hi, nlist, &acct));
+    IDC_TRY(dev_alloc(&b->d_words, b->total_words, &acct));
+    std::vector<uint64_t> woff(nlist + 1);
+    for (uint64_t l = 0; l <= nlist; l++) woff[l] = word_offsets[l] - word_offsets[0];
+    cudaStream_t s = c->stream;
+    if (nlist) {
+        IDC_CUDA(cudaMemcpyAsync(b->d_unit_n, unit_n, nlist * 4, cudaMemcpyHostToDevice, s));
+        IDC_CUDA(cudaMemcpyAsync(b->d_unit_prec, unit_precision, nlist, cudaMemcpyHostToDevice, s));
+        IDC_CUDA(cudaMemcpyAsync(b->d_unit_head, unit_heads, nlist * 8, cudaMemcpyHostToDevice, s));
+        IDC_CUDA(cudaMemcpyAsync(b->d_unit_lo, lo.data(), nlist * 4, cudaMemcpyHostToDevice, s));
+        IDC_CUDA(cudaMemcpyAsync(b->d_unit_hi, hi.data(), nlist * 4, cudaMemcpyHostToDevice, s));
+    }
+    IDC_CUDA(cudaMemcpyAsync(b->d_word_off, woff.data(), (nlist + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (b->total_words)
+        IDC_CUDA(cudaMemcpyAsync(b->d_words, words + word_offsets[0], b->total_words * 4, cudaMemcpyHostToDevice, s));
+    IDC_CUDA(cudaStreamSynchronize(s));
+    b->device_bytes = acct;
+    *out = b.release();
+    return IDC_OK;
+}
+
+int idc_roc_blob_order(const idc_roc_blob* b, uint32_t* order, int order_mem) {
+    IDC_REQUIRE(b && order, IDC_ERR_ARG, "null argument");
+    IDC_REQUIRE(b->d_order != nullptr, IDC_ERR_ARG, "blob was encoded without IDC_F_WANT_ORDER");
+    IDC_CUDA(cudaSetDevice(b->ctx->device));
+    uint64_t elems = b->row_stride ? b->nlist * b->row_stride : b->total_ids;
+    IDC_CUDA(cudaMemcpyAsync(order, b->d_order, elems * 4,
+                             order_mem == IDC_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                             b->ctx->stream));
+    IDC_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return IDC_OK;
+}
+
+int idc_roc_blob_free(idc_roc_blob* b) {
+    if (b) {
+        cudaSetDevice(b->ctx->device);
+        delete b;
+    }
+    return IDC_OK;
+}
+
+int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, uint64_t nsel, void* ids_out,
+                   int id_bytes, int out_mem, uint64_t* out_offsets) {
+    IDC_REQUIRE(c && b, IDC_ERR_ARG, "idc_roc_decode: null argument");
+    IDC_REQUIRE(id_bytes == 8 || id_bytes == 4, IDC_ERR_ARG, "id_bytes must be 4 or 8");
+    IDC_REQUIRE(b->row_stride == 0, IDC_ERR_ARG, "row blob: use idc_roc_decode_rows");
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    idc_roc_blob* mb = const_cast<idc_roc_blob*>(b);
+    const uint32_t* d_unit;
+    const uint64_t *d_out, *d_ws;
+    uint64_t ws_bytes, nunits_sel, total_out;
+    uint32_t *t_unit = nullptr;
+    uint64_t *t_out = nullptr, *t_ws = nullptr;
+    if (list_nos == nullptr) {
+        if (!mb->plan_ready) {
+            std::vector<uint32_t> units(b->nunits);
+            std::iota(units.begin(), units.end(), 0u);
+            std::vector<uint64_t> out_off(b->nunits);
+            for (uint64_t u = 0; u < b->nunits; u++) out_off[u] = b->unit_src[u] - b->list_offsets[0];
+            IDC_TRY(build_decode_plan(c, b, units, out_off, &mb->d_plan_unit, &mb->d_plan_out, &mb->d_plan_ws,
+                                      &mb->plan_ws_bytes));
+            mb->plan_ready = true;
+        }
+        d_unit = b->d_plan_unit;
+        d_out = b->d_plan_out;
+        d_ws = b->d_plan_ws;
+        ws_bytes = b->plan_ws_bytes;
+        nunits_sel = b->nunits;
+        total_out = b->total_ids;
+        if (out_offsets)
+            for (uint64_t l = 0; l <= b->nlist; l++) out_offsets[l] = b->list_offsets[l] - b->list_offsets[0];
+    } else {
+        std::vector<uint32_t> units;
+        std::vector<uint64_t> out_off;
+        uint64_t pos = 0;
+        for (uint64_t i = 0; i < nsel; i++) {
+            uint64_t l = list_nos[i];
+            IDC_REQUIRE(l < b->nlist, IDC_ERR_ARG, "list_no %llu out of range", (unsigned long long)l);
+            if (out_offsets) out_offsets[i] = pos;
+            for (uint64_t u = b->unit_offsets[l]; u < b->unit_offsets[l + 1]; u++) {
+                units.push_back((uint32_t)u);
+                out_off.push_back(pos);
+                pos += b->unit_n[u];
+            }
+        }
+        if (out_offsets) out_offsets[nsel] = pos;
+        total_out = pos;
+        nunits_sel = units.size();
+        IDC_TRY(build_decode_plan(c, b, units, out_off, &t_unit, &t_out, &t_ws, &ws_bytes));
+        d_unit = t_unit;
+        d_out = t_out;
+        d_ws = t_ws;
+    }
+    int rc = IDC_OK;
+    if (total_out) {
+        IDC_REQUIRE(ids_out != nullptr, IDC_ERR_ARG, "ids_out is NULL");
+        void* out_dev = ids_out;
+        if (out_mem == IDC_MEM_HOST) {
+            rc = c->stage.reserve(total_out * id_bytes);
+            out_dev = c->stage.p;
+        }
+        if (rc == IDC_OK)
+            rc = run_decode(c, b, d_unit, d_out, d_ws, ws_bytes, nunits_sel, out_dev, id_bytes, nullptr, 0);
+        if (rc == IDC_OK && out_mem == IDC_MEM_HOST) {
+            cudaError_t e = cudaMemcpyAsync(ids_out, out_dev, total_out * id_bytes, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            if (e != cudaSuccess) {
+                set_error("D2H copy failed: %s", cudaGetErrorString(e));
+                rc = IDC_ERR_CUDA;
+            }
+        }
+    }
+    cudaFree(t_unit);
+    cudaFree(t_out);
+    cudaFree(t_ws);
+    return rc;
+}
+
+int idc_roc_decode_rows(idc_ctx* c, const idc_roc_blob* b, const int32_t* row_nos, int rows_mem, uint64_t nsel,
+                        int32_t* out, uint32_t* counts, int out_mem) {
+    IDC_REQUIRE(c && b, IDC_ERR_ARG, "idc_roc_decode_rows: null argument");
+    IDC_REQUIRE(b->row_stride != 0, IDC_ERR_ARG, "not a row blob");
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    const uint32_t K = b->row_stride;
+    if (row_nos == nullptr) nsel = b->nlist;
+    if (nsel == 0) return IDC_OK;
+    IDC_REQUIRE(out != nullptr, IDC_ERR_ARG, "out is NULL");
+    // rows are short and near-uniform in length: no length sort, one fixed-size workspace slot per row
+    std::vector<int32_t> rows_h;
+    if (row_nos && rows_mem == IDC_MEM_DEVICE) {
+        rows_h.resize(nsel);
+        IDC_CUDA(cudaMemcpyAsync(rows_h.data(), row_nos, nsel * 4, cudaMemcpyDeviceToHost, c->stream));
+        IDC_CUDA(cudaStreamSynchronize(c->stream));
+        row_nos = rows_h.data();
+    }
+    const uint64_t slot_ws = dec_tree_bytes(K);
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(nsel, (4ull << 30) / slot_ws));
+    int32_t* out_dev = out;
+    uint32_t* cnt_dev = counts;
+    if (out_mem == IDC_MEM_HOST) {
+        IDC_TRY(c->stage.reserve(chunk * K * 4 + chunk * 4 + 256));
+        out_dev = c->stage.as<int32_t>();
+        cnt_dev = reinterpret_cast<uint32_t*>(c->stage.as<uint8_t>() + chunk * K * 4);
+    }
+    for (uint64_t s = 0; s < nsel; s += chunk) {
+        uint64_t m = std::min(chunk, nsel - s);
+        std::vector<uint32_t> su(m);
+        std::vector<uint64_t> so(m), sw(m);
+        for (uint64_t i = 0; i < m; i++) {
+            int64_t r = row_nos ? row_nos[s + i] : (int64_t)(s + i);
+            IDC_REQUIRE(r >= 0 && (uint64_t)r < b->nlist, IDC_ERR_ARG, "row %lld out of range", (long long)r);
+            su[i] = (uint32_t)r;
+            so[i] = (out_mem == IDC_MEM_HOST ? i : s + i) * K;
+            sw[i] = i * slot_ws;
+        }
+        IDC_TRY(c->meta.reserve(m * 20 + 256));
+        uint32_t* d_unit = c->meta.as<uint32_t>();
+        uint64_t* d_out = reinterpret_cast<uint64_t*>(c->meta.as<uint8_t>() + ((m * 4 + 15) & ~15ull));
+        uint64_t* d_ws = d_out + m;
+        IDC_TRY(upload(c, d_unit, su));
+        IDC_TRY(upload(c, d_out, so));
+        IDC_TRY(upload(c, d_ws, sw));
+        uint32_t* cd = cnt_dev ? (out_mem == IDC_MEM_HOST ? cnt_dev : cnt_dev + s) : nullptr;
+        IDC_TRY(run_decode(c, b, d_unit, d_out, d_ws, m * slot_ws, m, out_dev, 4, cd, K));
+        if (out_mem == IDC_MEM_HOST) {
+            IDC_CUDA(cudaMemcpyAsync(out + s * K, out_dev, m * K * 4, cudaMemcpyDeviceToHost, c->stream));
+            if (counts) IDC_CUDA(cudaMemcpyAsync(counts + s, cnt_dev, m * 4, cudaMemcpyDeviceToHost, c->stream));
+            IDC_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    }
+    return IDC_OK;
+}
+
+}  // extern "C"
