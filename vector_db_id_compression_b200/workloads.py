@@ -32,7 +32,7 @@ def random_partition_lists(n_total: int, sizes: np.ndarray, seed: int, device):
     sizes_t = torch.as_tensor(sizes, dtype=torch.int64, device=device)
     perm = torch.randperm(n_total, generator=g, device=device, dtype=torch.int64)
     labels = torch.repeat_interleave(torch.arange(sizes.size, device=device, dtype=torch.int64), sizes_t)
-    perm.add_(labels.shl_(32))  # key = list << 32 | id
+    perm.add_(labels.bitwise_left_shift_(32))  # key = list << 32 | id
     del labels
     key, _ = torch.sort(perm)
     del perm, _
