@@ -1,0 +1,137 @@
+"""CPU: the lane-level device code (csrc/idc_core.cuh, roc_lane.cuh, ef_core.cuh), compiled for the host by
+tests/hostsim, against the oracle. This checks the exact arithmetic and the order-statistic structures the
+CUDA kernels run per lane -- without a GPU. The GPU parity tests proper are tests/test_gpu_parity.py."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+
+HERE = Path(__file__).resolve().parent / "hostsim"
+u64p = np.ctypeslib.ndpointer(np.uint64, flags="C")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
+i64p = np.ctypeslib.ndpointer(np.int64, flags="C")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    so = HERE / "libhostsim.so"
+    cc = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    subprocess.run([cc, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(so),
+                    str(HERE / "hostsim.cpp")], check=True)
+    lib = C.CDLL(str(so))
+    lib.sim_roc_encode.restype = C.c_int64
+    lib.sim_roc_encode.argtypes = [C.c_uint32, u64p, C.c_int, C.POINTER(C.c_uint64), u32p, C.c_uint32, u32p,
+                                   C.POINTER(C.c_uint32)]
+    lib.sim_roc_decode.restype = None
+    lib.sim_roc_decode.argtypes = [C.c_uint64, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, i64p,
+                                   C.POINTER(C.c_uint32), C.c_uint32]
+    lib.sim_ef_shape.argtypes = [C.c_uint64, C.c_uint64, u64p]
+    lib.sim_ef_encode.argtypes = [i64p, C.c_uint64, C.c_uint64, u64p, u64p, u32p]
+    lib.sim_ef_select.restype = C.c_uint64
+    lib.sim_ef_select.argtypes = [u64p, u64p, u32p, C.c_uint32, C.c_uint64]
+    return lib
+
+
+def sim_enc(lib, ids, p):
+    ids = np.sort(np.asarray(ids, dtype=np.uint64))
+    n = ids.size
+    w = np.zeros(n + 4, np.uint32)
+    o = np.zeros(max(n, 1), np.uint32)
+    h, st = C.c_uint64(), C.c_uint32()
+    r = lib.sim_roc_encode(n, ids, p, C.byref(h), w, n + 4, o, C.byref(st))
+    assert r >= 0, st.value
+    return h.value, w[:r].copy(), o[:n], st.value
+
+
+def sim_dec(lib, h, w, n, p, lo=0, hi=None, force=0):
+    if hi is None:
+        hi = (1 << p) - 1 if p < 32 else 0xFFFFFFFF
+    out = np.zeros(max(n, 1), np.int64)
+    st = C.c_uint32()
+    lib.sim_roc_decode(h, w if w.size else np.zeros(1, np.uint32), w.size, n, p, lo, hi, out, C.byref(st), force)
+    return out[:n], st.value
+
+
+def rand_set(rng, n, p):
+    if (1 << p) <= 1 << 16:
+        return rng.choice(1 << p, size=min(n, 1 << p), replace=False)
+    return np.unique(rng.integers(0, 1 << p, size=n, dtype=np.uint64))
+
+
+def test_lane_codec_random_sets(sim):
+    rng = np.random.default_rng(0)
+    for trial in range(1200):
+        p = int(rng.integers(1, 33))
+        n = min(int(rng.integers(1, 700)), 1 << p)
+        if rng.random() < 0.3:
+            p = max(1, int(np.ceil(np.log2(n + 1))))
+        ids = rand_set(rng, n, p)
+        n = ids.size
+        h, w, o = oracle.port.encode(ids, p, want_order=True)
+        d = oracle.port.decode(h, w, n, p)
+        h2, w2, o2, st = sim_enc(sim, ids, p)
+        assert (h, w.tolist()) == (h2, w2.tolist()) and st == 0
+        srt = np.sort(ids.astype(np.uint64))
+        assert np.array_equal(srt[o2], d)
+        mode = trial % 3
+        if mode == 0:
+            d2, st = sim_dec(sim, h, w, n, p)
+        elif mode == 1:
+            d2, st = sim_dec(sim, h, w, n, p, lo=int(srt[0]), hi=int(srt[-1]))
+        else:  # tiny overflow list: exercises the brute-force fallback
+            d2, st = sim_dec(sim, h, w, n, p, lo=int(srt[0]), hi=int(srt[-1]), force=1 + int(rng.integers(0, 3)))
+        assert np.array_equal(d2.astype(np.uint64), d)
+        assert st & ~32 == 0
+
+
+@pytest.mark.parametrize("n,p", [(15259, 30), (65536, 17), (65536, 31), (65000, 20), (4097, 13), (4096, 12), (257, 9)])
+def test_lane_codec_large_units(sim, n, p):
+    rng = np.random.default_rng(n + p)
+    ids = rng.choice(1 << p, size=n, replace=False) if p <= 24 else rand_set(rng, n, p)
+    n = ids.size
+    h, w = oracle.port.encode(ids, p)
+    h2, w2, _, st = sim_enc(sim, ids, p)
+    assert (h, st) == (h2, 0) and np.array_equal(w, w2)
+    d2, st = sim_dec(sim, h, w, n, p)
+    assert np.array_equal(d2.astype(np.uint64), oracle.port.decode(h, w, n, p)) and st == 0
+
+
+def test_lane_codec_golden_and_adversarial(sim, roc_golden):
+    for c in roc_golden:
+        if c["p"] > 32:
+            continue
+        h2, w2, _, _ = sim_enc(sim, c["ids"], c["p"])
+        assert h2 == c["head"] and np.array_equal(w2, c["words"]), c["tag"]
+        d2, _ = sim_dec(sim, c["head"], c["words"], c["ids"].size, c["p"])
+        assert np.array_equal(d2.astype(np.uint64), c["dec"]), c["tag"]
+    ids = np.arange(5000, dtype=np.uint64) + (1 << 29)  # one narrow cluster, no range hint: degenerate path
+    h, w = oracle.port.encode(ids, 30)
+    d = oracle.port.decode(h, w, 5000, 30)
+    d2, st = sim_dec(sim, h, w, 5000, 30)
+    assert np.array_equal(d2.astype(np.uint64), d) and st == 32
+    d2, st = sim_dec(sim, h, w, 5000, 30, lo=1 << 29, hi=(1 << 29) + 4999)
+    assert np.array_equal(d2.astype(np.uint64), d) and st == 0
+
+
+def test_ef_gather_words(sim):
+    rng = np.random.default_rng(1)
+    for trial in range(250):
+        m = int(rng.integers(1, 3000))
+        top = max(m + 1, int(rng.integers(1, 1 << int(rng.integers(8, 33)))))
+        ids = np.sort(rng.choice(top, size=m, replace=False)) if top < 1 << 22 else np.unique(rng.integers(0, top, size=m))
+        m, uni = ids.size, int(ids.max())
+        enc = oracle.ef.encode(ids, uni)
+        sh = np.zeros(6, np.uint64)
+        sim.sim_ef_shape(uni, m, sh)
+        assert (int(sh[0]), int(sh[1]), int(sh[2])) == (enc["l"], enc["low_bits"], enc["high_bits"])
+        low = np.zeros(max(int(sh[3]), 1), np.uint64)
+        high = np.zeros(max(int(sh[4]), 1), np.uint64)
+        smp = np.zeros(max(int(sh[5]), 1), np.uint32)
+        sim.sim_ef_encode(ids.astype(np.int64), m, uni, low, high, smp)
+        assert np.array_equal(low[: int(sh[3])], enc["low"]) and np.array_equal(high[: int(sh[4])], enc["high"])
+        for k in rng.integers(0, m, size=8):
+            assert sim.sim_ef_select(low, high, smp, enc["l"], int(k)) == int(ids[k])

@@ -1,0 +1,139 @@
+"""Sharding of lists / adjacency rows across the GPUs of one box.
+
+Lists are independent coding units (custom_invlists_impl.h:59,76; altid_impl.h:43,58), so the codec needs
+no collective: one process per GPU, each encodes / decodes its own lists. NCCL (over NVLink 5 / NVSwitch) is
+used only to move data when a single rank owns the index: scatter-v of raw id blocks, gather-v of the
+compressed blobs. All functions work on any torch.distributed backend (tests run them on gloo / CPU with an
+injected codec; production passes a capi.Context-based codec on nccl / CUDA).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+
+
+def roc_cost(n: np.ndarray) -> np.ndarray:
+    """Serial steps dominate ROC: cost ~ n (each step is a fixed-latency chain); EF cost ~ n as well."""
+    return np.asarray(n, dtype=np.float64)
+
+
+def lpt_partition(costs: np.ndarray, nparts: int) -> list[np.ndarray]:
+    """Longest-processing-time-first greedy partition. Returns, per part, the item indices (ascending)."""
+    costs = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-costs, kind="stable")
+    loads = np.zeros(nparts)
+    parts: list[list[int]] = [[] for _ in range(nparts)]
+    # large items individually, the long tail in round-robin blocks (keeps this O(n log n) in numpy terms)
+    head = min(order.size, 64 * nparts)
+    for i in order[:head]:
+        p = int(np.argmin(loads))
+        parts[p].append(int(i))
+        loads[p] += costs[i]
+    tail = order[head:]
+    if tail.size:
+        # water-filling: every part is topped up to the common target with a run of consecutive tail items
+        tc = costs[tail]
+        need = np.maximum(costs.sum() / nparts - loads, 0.0)
+        need = need / need.sum() * tc.sum() if need.sum() > 0 else np.full(nparts, tc.sum() / nparts)
+        cuts = np.searchsorted(np.cumsum(tc), np.cumsum(need)[:-1], side="left")
+        for p, seg in enumerate(np.split(tail, cuts)):
+            parts[p].extend(int(x) for x in seg)
+            loads[p] += costs[seg].sum()
+    return [np.sort(np.asarray(p, dtype=np.int64)) for p in parts]
+
+
+def shard_csr(offsets: np.ndarray, lists: np.ndarray):
+    """Sub-CSR of the given lists: (local offsets, gather index ranges)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    sizes = offsets[lists + 1] - offsets[lists]
+    loc = np.zeros(lists.size + 1, dtype=np.uint64)
+    loc[1:] = np.cumsum(sizes)
+    return loc, sizes
+
+
+def scatter_lists(offsets, ids, device, src: int = 0, group=None):
+    """Rank `src` owns (offsets, ids); every rank gets (its list numbers, local offsets, its ids on `device`).
+
+    Plan = LPT over list lengths, broadcast as an object; raw id blocks move with batched send/recv
+    (ncclSend/ncclRecv under nccl) -- one message per destination rank."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    plan = [None]
+    if rank == src:
+        offsets = np.asarray(offsets, dtype=np.int64)
+        sizes = np.diff(offsets)
+        plan = [(lpt_partition(roc_cost(sizes), world), offsets)]
+    dist.broadcast_object_list(plan, src=src, group=group)
+    parts, goff = plan[0]
+    mine = parts[rank]
+    loc, sizes = shard_csr(goff, mine)
+    n_mine = int(loc[-1])
+    recv = torch.empty(n_mine, dtype=torch.int64, device=device)
+    ops = []
+    if rank == src:
+        ids_t = torch.as_tensor(ids, dtype=torch.int64, device=device)
+        blocks = []
+        for r in range(world):
+            lists = parts[r]
+            idx = (np.concatenate([np.arange(goff[l], goff[l + 1]) for l in lists]) if lists.size
+                   else np.zeros(0, np.int64))
+            blk = ids_t[torch.as_tensor(idx, device=device)] if idx.size else torch.empty(0, dtype=torch.int64, device=device)
+            if r == src:
+                recv.copy_(blk)
+            elif blk.numel():
+                blocks.append(blk)
+                ops.append(dist.P2POp(dist.isend, blk, r, group))
+    elif n_mine:
+        ops.append(dist.P2POp(dist.irecv, recv, src, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return mine, loc, recv
+
+
+def gather_blobs(mine: np.ndarray, local: dict, nlist: int, dst: int = 0, group=None) -> Optional[dict]:
+    """Re-assemble per-rank ROC exports (capi.RocBlob.export() dicts over the rank's lists) in global list
+    order on rank `dst`. Sizes travel with all_gather_object, payload arrays with gather_object (gather-v)."""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    payload = dict(lists=np.asarray(mine), **{k: np.asarray(v) for k, v in local.items()})
+    out = [None] * world if rank == dst else None
+    dist.gather_object(payload, out, dst=dst, group=group)
+    if rank != dst:
+        return None
+    # global tables in list order
+    per_list = [None] * nlist
+    for p in out:
+        uo = p["unit_offsets"]
+        for j, l in enumerate(p["lists"]):
+            u0, u1 = int(uo[j]), int(uo[j + 1])
+            w0, w1 = int(p["word_offsets"][u0]), int(p["word_offsets"][u1])
+            per_list[int(l)] = dict(unit_n=p["unit_n"][u0:u1], precision=p["precision"][u0:u1],
+                                    heads=p["heads"][u0:u1], nwords=np.diff(p["word_offsets"][u0: u1 + 1]),
+                                    words=p["words"][w0:w1])
+    unit_offsets = np.zeros(nlist + 1, np.uint64)
+    unit_offsets[1:] = np.cumsum([x["unit_n"].size for x in per_list])
+    cat = lambda k, dt: (np.concatenate([x[k] for x in per_list]).astype(dt) if nlist else np.zeros(0, dt))
+    nwords = cat("nwords", np.uint64)
+    word_offsets = np.zeros(nwords.size + 1, np.uint64)
+    word_offsets[1:] = np.cumsum(nwords)
+    return dict(unit_offsets=unit_offsets, unit_n=cat("unit_n", np.uint32), precision=cat("precision", np.uint8),
+                heads=cat("heads", np.uint64), word_offsets=word_offsets, words=cat("words", np.uint32))
+
+
+def encode_sharded(offsets, ids, encode_fn: Callable, device, src: int = 0, group=None) -> Optional[dict]:
+    """scatter -> per-rank encode -> gather. encode_fn(local_offsets, local_ids) must return a
+    RocBlob.export()-style dict. Returns the global blob tables on rank `src`, None elsewhere."""
+    import torch.distributed as dist
+
+    nlist = [None]
+    if dist.get_rank(group) == src:
+        nlist = [int(np.asarray(offsets).size - 1)]
+    dist.broadcast_object_list(nlist, src=src, group=group)
+    mine, loc, local_ids = scatter_lists(offsets, ids, device, src=src, group=group)
+    local = encode_fn(loc, local_ids)
+    return gather_blobs(mine, local, nlist[0], dst=src, group=group)
