@@ -26,12 +26,14 @@ int64_t sim_roc_encode(uint32_t n, const uint64_t* ids, int prec, uint64_t* head
     uint32_t mt[kMtWords];
     tables(mt);
     std::vector<uint8_t> ws(enc_tree_bytes(n) + 64, 0);
+    std::vector<uint32_t> sm(enc_tree_sm_words(n) + 8, 0);
     EncLane<int64_t> L;
-    L.tree = enc_tree_at(ws.data(), n);
+    L.tree.leaf = reinterpret_cast<uint16_t*>(ws.data());
+    L.tree.sm = sm.data();
+    L.tree.stride = 1;
     EncTreeLayout lay = enc_tree_layout(n);
     for (uint32_t e = 0; e < lay.leaf_sectors * 16u; e++) L.tree.leaf[e] = enc_tree_init_leaf(n, e);
-    for (uint32_t e = 0; e < lay.l1_sectors * 16u; e++) L.tree.l1[e] = enc_tree_init_count(n, e, 256u);
-    for (uint32_t e = 0; e < 16u; e++) L.tree.l2[e] = enc_tree_init_count(n, e, 4096u);
+    enc_tree_init_sm(L.tree, n);
     L.st = EncState{kRansL, words_out, 0, cap, 0, 0};
     L.src = reinterpret_cast<const int64_t*>(ids);
     L.sort_idx = nullptr;
@@ -51,8 +53,9 @@ void sim_roc_decode(uint64_t head, const uint32_t* words, uint32_t nwords, uint3
     uint32_t mt[kMtWords];
     tables(mt);
     std::vector<uint8_t> ws(dec_tree_bytes(n) + 64, 0);
+    std::vector<uint32_t> sm(dec_tree_sm_words(n) + 8, 0);
     DecLane<int64_t> L;
-    L.tree = dec_tree_at(ws.data(), n, lo, hi);
+    L.tree = dec_tree_at(ws.data(), sm.data(), 1, n, lo, hi);
     if (force_degenerate) L.tree.ovf_cap = force_degenerate - 1;  // shrink the overflow list to exercise the fallback
     L.st = DecState{head, words, nwords, 0, 0, 0, 0};
     L.out = out;

@@ -1,4 +1,5 @@
 // idc_ctx.cu -- context, error reporting and constant tables of libidcodec.
+#include <cstdlib>
 #include <cstring>
 #include <random>
 
@@ -53,6 +54,29 @@ void idc_ctx::mark_end() {
     cudaEventRecord(times.back().b, stream);
 }
 
+int idc_ctx::fork(int n) {
+    if (!fork_ev) IDC_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+    while ((int)aux.size() < n) {
+        cudaStream_t s;
+        cudaEvent_t e;
+        IDC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        IDC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        aux.push_back(s);
+        aux_done.push_back(e);
+    }
+    IDC_CUDA(cudaEventRecord(fork_ev, stream));
+    for (int i = 0; i < n; i++) IDC_CUDA(cudaStreamWaitEvent(aux[i], fork_ev, 0));
+    return IDC_OK;
+}
+
+int idc_ctx::join(int n) {
+    for (int i = 0; i < n; i++) {
+        IDC_CUDA(cudaEventRecord(aux_done[i], aux[i]));
+        IDC_CUDA(cudaStreamWaitEvent(stream, aux_done[i], 0));
+    }
+    return IDC_OK;
+}
+
 extern "C" {
 
 const char* idc_last_error(void) { return idc::g_last_error.c_str(); }
@@ -83,6 +107,15 @@ int idc_ctx_create_on_stream(int device, void* cuda_stream, idc_ctx** out) {
     cudaDeviceProp prop;
     IDC_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    // The ROC kernels read isolated 32-byte sectors (tree nodes, bucket records) scattered over GBs: ask L2 not
+    // to promote such misses to 64/128-byte DRAM fetches (measured 3 sectors fetched per sector used otherwise).
+    // A hint only; IDC_L2_FETCH=32|64|128 overrides it for experiments.
+    {
+        size_t gran = 32;
+        if (const char* e = getenv("IDC_L2_FETCH")) gran = (size_t)atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
 
     // mt19937(1234): the fallback word source of ANSState::stack_slice (codec.h:16-18,32-40)
     uint32_t mt[idc::kMtWords];
@@ -118,6 +151,9 @@ int idc_ctx_destroy(idc_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto e : c->event_pool) cudaEventDestroy(e);
+    for (auto s : c->aux) cudaStreamDestroy(s);
+    for (auto e : c->aux_done) cudaEventDestroy(e);
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     cudaFree(c->d_mt);
     cudaFree(c->d_rcp64);
     cudaFree(c->d_q31);

@@ -97,6 +97,12 @@ struct idc_ctx {
     idc::DevBuf stage;    // host<->device staging of ids
     idc::DevBuf meta;     // per-call unit tables
     idc::DevBuf status;   // per-call status words
+    // auxiliary streams: size classes of one logical kernel run concurrently (fork/join around c->stream)
+    std::vector<cudaStream_t> aux;
+    std::vector<cudaEvent_t> aux_done;
+    cudaEvent_t fork_ev = nullptr;
+    int fork(int n);              // make aux[0..n) wait for everything queued on `stream`
+    int join(int n);              // make `stream` wait for aux[0..n)
 
     void begin_call();
     void mark(const char* name);   // call right before a kernel launch

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <numeric>
 
+#include <functional>
 #include <memory>
 
 #include "idc_host.h"
@@ -35,6 +36,7 @@ struct idc_roc_blob {
     idc_ctx* ctx = nullptr;
     uint64_t nlist = 0, nunits = 0, total_ids = 0, total_words = 0, ans_bytes = 0;
     uint32_t max_unit = IDC_MAX_UNIT_DEFAULT, row_stride = 0;
+    uint32_t max_n = 0;  // largest unit
     // host metadata
     std::vector<uint64_t> list_offsets;  // nlist+1 (CSR of ids; rows: l*K)
     std::vector<uint64_t> unit_offsets;  // nlist+1
@@ -56,6 +58,7 @@ struct idc_roc_blob {
     uint64_t* d_plan_out = nullptr;
     uint64_t* d_plan_ws = nullptr;
     uint64_t plan_ws_bytes = 0;
+    std::vector<uint32_t> plan_ns;   // unit lengths in launch order
 
     ~idc_roc_blob() {
         cudaFree(d_unit_n);
@@ -94,25 +97,27 @@ struct EncArgs {
     const uint64_t* rcp64;
     const uint32_t* q31;
     uint32_t nunits;
+    uint32_t sm_words;           // shared-memory words per lane (upper tree levels)
+    uint32_t slot_base;          // this launch covers launch slots [slot_base, slot_end)
+    uint32_t slot_end;
 };
 
-// one warp per unit, lanes stride over the tree's 16-bit entries
+// one warp per unit, lanes stride over the leaf bitmap's 16-bit entries
 __global__ void __launch_bounds__(kThreads) k_enc_tree_init(EncArgs a) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.nunits) return;
     uint32_t n = a.unit_n[warp];
     if (n == 0) return;
-    EncTree t = enc_tree_at(a.ws + a.ws_off[warp], n);
+    uint16_t* leaf = reinterpret_cast<uint16_t*>(a.ws + a.ws_off[warp]);
     EncTreeLayout L = enc_tree_layout(n);
-    for (uint32_t e = lane; e < L.leaf_sectors * 16u; e += 32) t.leaf[e] = enc_tree_init_leaf(n, e);
-    for (uint32_t e = lane; e < L.l1_sectors * 16u; e += 32) t.l1[e] = enc_tree_init_count(n, e, 256u);
-    if (lane < 16) t.l2[lane] = enc_tree_init_count(n, lane, 4096u);
+    for (uint32_t e = lane; e < L.leaf_sectors * 16u; e += 32) leaf[e] = enc_tree_init_leaf(n, e);
 }
 
 template <typename IdT>
 __global__ void __launch_bounds__(kThreads) k_roc_encode(EncArgs a) {
-    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = slot < a.nunits;
+    extern __shared__ uint32_t smem[];
+    uint32_t slot = a.slot_base + blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = slot < a.slot_end;
     uint32_t u = valid ? a.perm[slot] : 0u;
     uint32_t n = valid ? a.unit_n[u] : 0u;
     EncLane<IdT> L;
@@ -123,7 +128,10 @@ __global__ void __launch_bounds__(kThreads) k_roc_encode(EncArgs a) {
     L.sort_idx = a.sort_idx ? a.sort_idx + src_off : nullptr;
     L.order = a.order ? a.order + src_off : nullptr;
     L.pos_base = valid ? a.unit_posbase[u] : 0u;
-    L.tree = enc_tree_at(a.ws + (valid ? a.ws_off[u] : 0ull), n ? n : 1u);
+    L.tree.leaf = reinterpret_cast<uint16_t*>(a.ws + (valid ? a.ws_off[u] : 0ull));
+    L.tree.sm = smem + (threadIdx.x >> 5) * (a.sm_words * 32u) + (threadIdx.x & 31);
+    L.tree.stride = 32u;
+    if (n) enc_tree_init_sm(L.tree, n);
     L.st.head = kRansL;
     L.st.words = a.scratch + (valid ? a.scratch_off[u] : 0ull);
     L.st.sp = 0;
@@ -174,12 +182,16 @@ struct DecArgs {
     const uint32_t* q31;
     uint32_t nsel;
     uint32_t row_stride;        // rows: pad the slot's output to this many entries with -1
+    uint32_t sm_words;          // shared-memory words per lane (all count levels)
+    uint32_t slot_base;         // this launch covers launch slots [slot_base, slot_end)
+    uint32_t slot_end;
 };
 
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
-    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = slot < a.nsel;
+    extern __shared__ uint32_t smem[];
+    uint32_t slot = a.slot_base + blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = slot < a.slot_end;
     uint32_t u = valid ? a.sel_unit[slot] : 0u;
     uint32_t n = valid ? a.unit_n[u] : 0u;
     DecLane<OutT> L;
@@ -194,7 +206,9 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
     L.st.has_ov = 0;
     L.st.draws = 0;
     L.st.status = 0;
-    L.tree = dec_tree_at(a.ws + (valid ? a.sel_ws[slot] : 0ull), n ? n : 1u, valid ? a.unit_lo[u] : 0u,
+    uint32_t* sm = smem + (threadIdx.x >> 5) * (a.sm_words * 32u) + (threadIdx.x & 31);
+    for (uint32_t w = 0; w < a.sm_words; w++) sm[w * 32u] = 0u;
+    L.tree = dec_tree_at(a.ws + (valid ? a.sel_ws[slot] : 0ull), sm, 32u, n ? n : 1u, valid ? a.unit_lo[u] : 0u,
                          valid ? a.unit_hi[u] : 0u);
     uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
     for (uint32_t i = 0; i < tmax; ++i) {
@@ -219,6 +233,42 @@ void length_sorted_order(const uint32_t* n, uint64_t count, std::vector<uint32_t
     for (size_t i = 1; i < hist.size(); i++) hist[i] += hist[i - 1];
     perm.resize(count);
     for (uint64_t i = 0; i < count; i++) perm[hist[kMaxUnit - n[i]]++] = (uint32_t)i;
+}
+
+// Size classes. Units are launched in descending length; a class is a contiguous slot range whose shared
+// memory footprint is set by its first (longest) unit. Classes run concurrently on auxiliary streams, so the
+// long units (which bound the kernel's duration) start first and the short ones fill the rest of the chip.
+struct SizeClass {
+    uint32_t slot_base, slot_end, max_n;
+};
+
+template <typename NofSlot>
+std::vector<SizeClass> size_classes(uint64_t nslots, NofSlot n_of_slot) {
+    static const uint32_t bounds[] = {32768, 16384, 8192, 4096, 2048, 1024, 256, 0};
+    std::vector<SizeClass> cls;
+    uint64_t s = 0;
+    for (uint32_t lo : bounds) {
+        if (s >= nslots) break;
+        if (n_of_slot(s) <= lo && lo != 0) continue;
+        // first slot whose n <= lo (slots are sorted by descending n)
+        uint64_t a = s, b = nslots;
+        while (a < b) {
+            uint64_t m = (a + b) / 2;
+            if (n_of_slot(m) > lo) a = m + 1; else b = m;
+        }
+        if (lo == 0) a = nslots;
+        if (a > s) cls.push_back(SizeClass{(uint32_t)s, (uint32_t)a, n_of_slot(s)});
+        s = a;
+    }
+    return cls;
+}
+
+// warps per CTA such that several CTAs fit an SM's 227 KB of shared memory
+inline uint32_t warps_for(uint32_t sm_words) {
+    size_t per_warp = (size_t)sm_words * 128;
+    if (per_warp * 4 <= 56 * 1024) return 4;
+    if (per_warp * 2 <= 56 * 1024) return 2;
+    return 1;
 }
 
 // Shared encode driver. ids_dev: device pointer to the caller's ids (CSR or
@@ -343,17 +393,41 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
     e.rcp64 = c->d_rcp64;
     e.q31 = c->d_q31;
     e.nunits = (uint32_t)nu;
+    uint32_t max_n = 0;
+    for (uint64_t u = 0; u < nu; u++) max_n = std::max(max_n, b->unit_n[u]);
+    b->max_n = max_n;
     {
         LaunchScope ls(c, "k_enc_tree_init");
         k_enc_tree_init<<<grid_for(nu * 32), kThreads, 0, c->stream>>>(e);
     }
     IDC_TRY(check_last_launch("k_enc_tree_init"));
     {
+        auto cls = size_classes(nu, [&](uint64_t slot) { return b->unit_n[perm[slot]]; });
+        size_t max_smem = 0;
+        for (auto& k : cls) {
+            uint32_t w = enc_tree_sm_words(k.max_n ? k.max_n : 1u);
+            max_smem = std::max(max_smem, (size_t)w * 128 * warps_for(w));
+        }
+        IDC_CUDA(cudaFuncSetAttribute(k_roc_encode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        IDC_CUDA(cudaFuncSetAttribute(k_roc_encode<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         LaunchScope ls(c, "k_roc_encode");
-        if (enc_id_bytes == 8)
-            k_roc_encode<int64_t><<<grid_for(nu), kThreads, 0, c->stream>>>(e);
-        else
-            k_roc_encode<uint32_t><<<grid_for(nu), kThreads, 0, c->stream>>>(e);
+        IDC_TRY(c->fork((int)cls.size()));
+        for (size_t k = 0; k < cls.size(); k++) {
+            EncArgs ek = e;
+            ek.slot_base = cls[k].slot_base;
+            ek.slot_end = cls[k].slot_end;
+            ek.sm_words = enc_tree_sm_words(cls[k].max_n ? cls[k].max_n : 1u);
+            uint32_t warps = warps_for(ek.sm_words), threads = warps * 32;
+            uint32_t slots = ek.slot_end - ek.slot_base, grid = (slots + threads - 1) / threads;
+            size_t smem = (size_t)ek.sm_words * 128 * warps;
+            if (enc_id_bytes == 8)
+                k_roc_encode<int64_t><<<grid, threads, smem, c->aux[k]>>>(ek);
+            else
+                k_roc_encode<uint32_t><<<grid, threads, smem, c->aux[k]>>>(ek);
+            c->launches++;
+        }
+        c->launches--;  // LaunchScope counted one already
+        IDC_TRY(c->join((int)cls.size()));
     }
     IDC_TRY(check_last_launch("k_roc_encode"));
 
@@ -423,7 +497,7 @@ int plan_units_csr(idc_roc_blob* b, uint64_t nlist, const uint64_t* offsets, uin
 
 int build_decode_plan(idc_ctx* c, const idc_roc_blob* b, const std::vector<uint32_t>& units,
                       const std::vector<uint64_t>& out_off, uint32_t** d_unit, uint64_t** d_out, uint64_t** d_ws,
-                      uint64_t* ws_bytes) {
+                      uint64_t* ws_bytes, std::vector<uint32_t>* ns_sorted) {
     const uint64_t m = units.size();
     std::vector<uint32_t> ns(m), perm;
     for (uint64_t i = 0; i < m; i++) ns[i] = b->unit_n[units[i]];
@@ -445,20 +519,19 @@ int build_decode_plan(idc_ctx* c, const idc_roc_blob* b, const std::vector<uint3
     IDC_TRY(upload(c, *d_ws, sw));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
     *ws_bytes = wsb;
+    ns_sorted->resize(m);
+    for (uint64_t i = 0; i < m; i++) (*ns_sorted)[i] = ns[perm[i]];
     return IDC_OK;
 }
 
 int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const uint64_t* d_out, const uint64_t* d_ws,
-               uint64_t ws_bytes, uint64_t nsel, void* out_dev, int id_bytes, uint32_t* counts_dev, uint32_t row_stride) {
+               uint64_t ws_bytes, uint64_t nsel, void* out_dev, int id_bytes, uint32_t* counts_dev, uint32_t row_stride,
+               uint32_t max_n, const std::function<uint32_t(uint64_t)>& n_of_slot) {
     if (nsel == 0) return IDC_OK;
     IDC_TRY(c->ws.reserve(ws_bytes + 256));
     IDC_TRY(c->status.reserve(64));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
-    {
-        LaunchScope ls(c, "memset_ws");
-        IDC_CUDA(cudaMemsetAsync(c->ws.p, 0, ws_bytes, c->stream));
-    }
     DecArgs a{};
     a.sel_unit = d_unit;
     a.sel_out = d_out;
@@ -479,11 +552,33 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     a.nsel = (uint32_t)nsel;
     a.row_stride = row_stride;
     {
+        auto cls = size_classes(nsel, n_of_slot);
+        size_t max_smem = 0;
+        for (auto& k : cls) {
+            uint32_t w = dec_tree_sm_words(k.max_n ? k.max_n : 1u);
+            max_smem = std::max(max_smem, (size_t)w * 128 * warps_for(w));
+        }
+        (void)max_n;
+        IDC_CUDA(cudaFuncSetAttribute(k_roc_decode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+        IDC_CUDA(cudaFuncSetAttribute(k_roc_decode<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         LaunchScope ls(c, "k_roc_decode");
-        if (id_bytes == 8)
-            k_roc_decode<int64_t><<<grid_for(nsel), kThreads, 0, c->stream>>>(a);
-        else
-            k_roc_decode<int32_t><<<grid_for(nsel), kThreads, 0, c->stream>>>(a);
+        IDC_TRY(c->fork((int)cls.size()));
+        for (size_t k = 0; k < cls.size(); k++) {
+            DecArgs ak = a;
+            ak.slot_base = cls[k].slot_base;
+            ak.slot_end = cls[k].slot_end;
+            ak.sm_words = dec_tree_sm_words(cls[k].max_n ? cls[k].max_n : 1u);
+            uint32_t warps = warps_for(ak.sm_words), threads = warps * 32;
+            uint32_t slots = ak.slot_end - ak.slot_base, grid = (slots + threads - 1) / threads;
+            size_t smem = (size_t)ak.sm_words * 128 * warps;
+            if (id_bytes == 8)
+                k_roc_decode<int64_t><<<grid, threads, smem, c->aux[k]>>>(ak);
+            else
+                k_roc_decode<int32_t><<<grid, threads, smem, c->aux[k]>>>(ak);
+            c->launches++;
+        }
+        c->launches--;
+        IDC_TRY(c->join((int)cls.size()));
     }
     IDC_TRY(check_last_launch("k_roc_decode"));
     uint32_t st = 0;
@@ -645,6 +740,7 @@ int idc_roc_blob_import(idc_ctx* c, uint64_t nlist, const uint32_t* unit_n, cons
     b->list_offsets[nlist] = total;
     b->unit_offsets[nlist] = nlist;
     b->total_ids = total;
+    for (uint64_t l = 0; l < nlist; l++) b->max_n = std::max(b->max_n, unit_n[l]);
     b->total_words = word_offsets[nlist] - word_offsets[0];
     b->ans_bytes = ans;
     uint64_t acct = 0;
@@ -707,6 +803,7 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
     uint64_t ws_bytes, nunits_sel, total_out;
     uint32_t *t_unit = nullptr;
     uint64_t *t_out = nullptr, *t_ws = nullptr;
+    std::vector<uint32_t> t_ns;
     if (list_nos == nullptr) {
         if (!mb->plan_ready) {
             std::vector<uint32_t> units(b->nunits);
@@ -714,7 +811,7 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
             std::vector<uint64_t> out_off(b->nunits);
             for (uint64_t u = 0; u < b->nunits; u++) out_off[u] = b->unit_src[u] - b->list_offsets[0];
             IDC_TRY(build_decode_plan(c, b, units, out_off, &mb->d_plan_unit, &mb->d_plan_out, &mb->d_plan_ws,
-                                      &mb->plan_ws_bytes));
+                                      &mb->plan_ws_bytes, &mb->plan_ns));
             mb->plan_ready = true;
         }
         d_unit = b->d_plan_unit;
@@ -742,7 +839,7 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
         if (out_offsets) out_offsets[nsel] = pos;
         total_out = pos;
         nunits_sel = units.size();
-        IDC_TRY(build_decode_plan(c, b, units, out_off, &t_unit, &t_out, &t_ws, &ws_bytes));
+        IDC_TRY(build_decode_plan(c, b, units, out_off, &t_unit, &t_out, &t_ws, &ws_bytes, &t_ns));
         d_unit = t_unit;
         d_out = t_out;
         d_ws = t_ws;
@@ -755,8 +852,12 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
             rc = c->stage.reserve(total_out * id_bytes);
             out_dev = c->stage.p;
         }
-        if (rc == IDC_OK)
-            rc = run_decode(c, b, d_unit, d_out, d_ws, ws_bytes, nunits_sel, out_dev, id_bytes, nullptr, 0);
+        {
+            const std::vector<uint32_t>& ns = list_nos == nullptr ? b->plan_ns : t_ns;
+            if (rc == IDC_OK)
+                rc = run_decode(c, b, d_unit, d_out, d_ws, ws_bytes, nunits_sel, out_dev, id_bytes, nullptr, 0,
+                                ns.empty() ? 0u : ns[0], [&](uint64_t slot) { return ns[slot]; });
+        }
         if (rc == IDC_OK && out_mem == IDC_MEM_HOST) {
             cudaError_t e = cudaMemcpyAsync(ids_out, out_dev, total_out * id_bytes, cudaMemcpyDeviceToHost, c->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -818,7 +919,8 @@ int idc_roc_decode_rows(idc_ctx* c, const idc_roc_blob* b, const int32_t* row_no
         IDC_TRY(upload(c, d_out, so));
         IDC_TRY(upload(c, d_ws, sw));
         uint32_t* cd = cnt_dev ? (out_mem == IDC_MEM_HOST ? cnt_dev : cnt_dev + s) : nullptr;
-        IDC_TRY(run_decode(c, b, d_unit, d_out, d_ws, m * slot_ws, m, out_dev, 4, cd, K));
+        IDC_TRY(run_decode(c, b, d_unit, d_out, d_ws, m * slot_ws, m, out_dev, 4, cd, K, K,
+                           [&](uint64_t) { return K; }));
         if (out_mem == IDC_MEM_HOST) {
             IDC_CUDA(cudaMemcpyAsync(out + s * K, out_dev, m * K * 4, cudaMemcpyDeviceToHost, c->stream));
             if (counts) IDC_CUDA(cudaMemcpyAsync(counts + s, cnt_dev, m * 4, cudaMemcpyDeviceToHost, c->stream));
