@@ -52,7 +52,7 @@ void sim_roc_decode(uint64_t head, const uint32_t* words, uint32_t nwords, uint3
                     uint32_t hi, int64_t* out, uint32_t* status_out, uint32_t force_degenerate) {
     uint32_t mt[kMtWords];
     tables(mt);
-    std::vector<uint8_t> ws(dec_tree_bytes(n) + 64, 0);
+    std::vector<uint8_t> ws(dec_tree_bytes(n) + 64, 0xff);  // bucket slots pre-filled, as the device memset does
     std::vector<uint32_t> sm(dec_tree_sm_words(n) + 8, 0);
     DecLane<int64_t> L;
     L.tree = dec_tree_at(ws.data(), sm.data(), 1, n, lo, hi);

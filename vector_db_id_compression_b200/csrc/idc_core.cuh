@@ -608,15 +608,18 @@ IDC_HD uint32_t dec_tree_insert_rank(DecTree& t, uint32_t v, const OutT* out_pre
             rank = dp2a(t.sm[(size_t)j * st], sel, rank);
         }
     }
-    // exact tie-break inside the bucket
+    // exact tie-break inside the bucket. Unused slots hold 0xffffffff (the workspace is pre-filled), which is
+    // never < v, so one compare per slot suffices; one accumulator per sector keeps the adds independent.
+    uint32_t part[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
+        part[j] = 0;
         if (sv > 8u * j) {
 #pragma unroll
-            for (int q = 0; q < 8; q++)
-                rank += ((uint32_t)(8 * j + q) < sv && rs[j].w[q] < v) ? 1u : 0u;
+            for (int q = 0; q < 8; q++) part[j] += rs[j].w[q] < v ? 1u : 0u;
         }
     }
+    rank += ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
     if (cnt > kBkSlots) {
         for (uint32_t e = 0; e < t.ovf_n; e++) {
             uint64_t pr = ld_ws64(reinterpret_cast<const uint64_t*>(t.ovf) + e);

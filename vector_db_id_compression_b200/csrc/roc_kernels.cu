@@ -532,6 +532,10 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     IDC_TRY(c->status.reserve(64));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    {
+        LaunchScope ls(c, "memset_ws");  // empty bucket slots must read as 0xffffffff (dec_tree_insert_rank)
+        IDC_CUDA(cudaMemsetAsync(c->ws.p, 0xff, ws_bytes, c->stream));
+    }
     DecArgs a{};
     a.sel_unit = d_unit;
     a.sel_out = d_out;
