@@ -20,13 +20,33 @@
 
 using namespace idc;
 
+namespace {
+
+constexpr uint32_t kEncTileWords = 1024;  // output words per warp in k_ef_encode
+constexpr uint32_t kDecChunkWords = 16;   // 64-bit high words per warp in k_ef_decode (1024 bits, <= 1024 ids)
+constexpr uint32_t kDecTile = 1024;       // max ids of one chunk
+constexpr int kDecThreads = 256;          // 8 warps per CTA in k_ef_decode
+
+// Chunk descriptor, written by the encoder, 32 bytes: everything k_ef_decode needs for one chunk.
+struct EfChunk {
+    uint64_t a;         // high32:40 | count:11 | l:5 | nwords32:6
+                        //   high32 = offset (32-bit words) of the chunk's first upper-bits word
+    uint64_t low32;     // offset (32-bit words) of the lower-bits word that holds id number (r0 & ~31)
+    uint64_t out_base;  // element offset of the list's first id in a decode-everything output
+    uint64_t b;         // r0:32 | zeros:32   r0 = ids of the list before this chunk,
+                        //                    zeros = chunk's first bit position - r0
+};
+
+}  // namespace
+
 struct idc_ef_blob {
     idc_ctx* ctx = nullptr;
     uint64_t nlist = 0, total_ids = 0, low_words = 0, high_words = 0, bits_total = 0, nsamples = 0;
     uint32_t row_stride = 0;
+    uint32_t max_l = 0;
     std::vector<uint64_t> list_offsets;  // nlist+1, ids per list (CSR)
     std::vector<uint8_t> l;
-    std::vector<uint64_t> universe, low_off, high_off, samp_off;  // nlist(+1)
+    std::vector<uint64_t> universe, low_off, high_off, samp_off, dir_off;  // nlist(+1)
     uint64_t* d_list_off = nullptr;
     uint8_t* d_l = nullptr;
     uint64_t* d_low_off = nullptr;
@@ -35,6 +55,9 @@ struct idc_ef_blob {
     uint64_t* d_low = nullptr;
     uint64_t* d_high = nullptr;
     uint32_t* d_samples = nullptr;
+    uint64_t* d_dir_off = nullptr;
+    EfChunk* d_dir = nullptr;        // one descriptor per chunk of 16 high words (1024 bits)
+    uint64_t ndir = 0;
     uint64_t device_bytes = 0;
     // cached decode-everything tile table
     bool plan_ready = false;
@@ -51,6 +74,8 @@ struct idc_ef_blob {
         cudaFree(d_low);
         cudaFree(d_high);
         cudaFree(d_samples);
+        cudaFree(d_dir_off);
+        cudaFree(d_dir);
         cudaFree(d_tile_list);
         cudaFree(d_tile_idx);
         cudaFree(d_tile_out);
@@ -58,9 +83,6 @@ struct idc_ef_blob {
 };
 
 namespace {
-
-constexpr uint32_t kEncTileWords = 1024;  // output words per warp in k_ef_encode
-constexpr uint32_t kDecTile = 1024;       // ids per warp in k_ef_decode (4 select samples)
 
 struct EfEncArgs {
     const void* ids;
@@ -74,6 +96,8 @@ struct EfEncArgs {
     uint64_t* low;
     uint64_t* high;
     uint32_t* samples;
+    const uint64_t* dir_off;
+    EfChunk* dir;
     const uint32_t* tile_list;
     const uint32_t* tile_idx;
     uint32_t ntiles;
@@ -111,6 +135,21 @@ __global__ void __launch_bounds__(kThreads) k_ef_encode(EfEncArgs a) {
                 else
                     hi = mid;
             }
+            // `lo` = ids before this word. At a chunk boundary, write the chunk's descriptor for the decoder.
+            if ((hwi & (kDecChunkWords - 1)) == 0) {
+                // ids in the chunk: known here for a list's last chunk, otherwise next chunk's r0 - r0,
+                // filled in by k_ef_finish_chunks (0x7ff marks "take it from the next descriptor")
+                const bool last = hwi + kDecChunkWords >= hw;
+                const uint64_t cnt = last ? m - lo : 0x7ffull;
+                uint64_t rest = hw - hwi;
+                uint64_t nw32 = 2 * (rest < kDecChunkWords ? rest : kDecChunkWords);
+                EfChunk d;
+                d.a = (2 * (a.high_off[L] + hwi)) | (cnt << 40) | ((uint64_t)l << 51) | (nw32 << 56);
+                d.low32 = 2 * a.low_off[L] + (lo >> 5) * l;
+                d.out_base = a.list_off[L];
+                d.b = lo | ((p0 - lo) << 32);
+                a.dir[a.dir_off[L] + hwi / kDecChunkWords] = d;
+            }
             uint64_t out = 0;
             for (uint64_t i = lo; i < m; i++) {
                 uint64_t hp = ef_high_pos(ids, i, l);
@@ -123,79 +162,133 @@ __global__ void __launch_bounds__(kThreads) k_ef_encode(EfEncArgs a) {
     }
 }
 
+__global__ void __launch_bounds__(kThreads) k_ef_finish_chunks(EfChunk* dir, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t a = dir[i].a;
+    if (((a >> 40) & 0x7ffull) == 0x7ffull) {
+        uint64_t cnt = (dir[i + 1].b & 0xffffffffull) - (dir[i].b & 0xffffffffull);
+        dir[i].a = (a & ~(0x7ffull << 40)) | (cnt << 40);
+    }
+}
+
 struct EfDecArgs {
-    const uint64_t* list_off;
-    const uint8_t* l;
-    const uint64_t* low_off;
-    const uint64_t* high_off;
-    const uint64_t* samp_off;
+    const EfChunk* dir;
     const uint64_t* low;
     const uint64_t* high;
-    const uint32_t* samples;
-    const uint32_t* tile_list;
-    const uint32_t* tile_idx;
-    const uint64_t* tile_out;   // element offset in out of the tile's first id
+    const uint32_t* sel_desc;   // subset decode: descriptor index per tile (null: tile i = descriptor i)
+    const uint64_t* sel_out;    // subset decode: element offset in out of the LIST's first id
+    const int32_t* row_nos;     // row mode: descriptor = row_nos[slot] (null: slot), out = slot * row_stride
     void* out;
-    uint32_t* counts;           // rows: ids in the row (indexed by tile = slot)
-    uint32_t ntiles;
-    uint32_t row_stride;
+    uint32_t* counts;           // row mode: ids in the row
+    uint64_t ntiles;
+    uint32_t row_stride;        // != 0: row mode
+    uint32_t low_stage_words;   // shared-memory words per warp for staging lower-bits words
 };
 
+// One warp per chunk of 16 64-bit words (= 32 32-bit words, one per lane) of the upper-bits vector:
+//   1. one 32-byte descriptor (written by the encoder) tells the warp everything: where the chunk's words
+//      are, the id number it starts at, how many ids it holds, l, where they go;
+//   2. popcount + warp scan -> where each word's ids land;
+//   3. every lane peels the set bits of its word (highest first: FLO, clear, store) into shared memory as
+//      upper parts (position - id number);
+//   4. a coalesced pass over the chunk's ids: the l-bit lower fields of 32 consecutive ids are exactly l
+//      consecutive 32-bit words; the chunk's words were fetched into shared memory by cp.async while steps
+//      2-3 ran (LDGSTS), a field is two LDS + a funnel shift; ids leave as full 256-byte warp stores.
 template <typename OutT>
-__global__ void __launch_bounds__(kThreads) k_ef_decode(EfDecArgs a) {
-    __shared__ uint32_t s_hi[kThreads / 32][kDecTile];
-    uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t warp = blockIdx.x * (kThreads / 32) + wib;
+__global__ void __launch_bounds__(kDecThreads, 6) k_ef_decode(EfDecArgs a) {
+    // per warp: 1024 upper parts as u16 (position - id number inside the chunk <= 1023) + the chunk's lower-bits
+    // words, staged by cp.async while the upper bits are being scanned
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t warp = (uint64_t)blockIdx.x * (kDecThreads / 32) + wib;
     if (warp >= a.ntiles) return;
-    uint32_t L = a.tile_list[warp];
-    uint64_t m = a.list_off[L + 1] - a.list_off[L];
-    uint64_t e0 = (uint64_t)a.tile_idx[warp] * kDecTile;
-    uint32_t tn = (uint32_t)(m - e0 < kDecTile ? m - e0 : kDecTile);
-    if (m <= e0) tn = 0;
-    OutT* out = reinterpret_cast<OutT*>(a.out) + a.tile_out[warp];
-    uint32_t l = a.l[L];
-    const uint64_t* low = a.low + a.low_off[L];
-    const uint64_t* high = a.high + a.high_off[L];
-    uint64_t hw = a.high_off[L + 1] - a.high_off[L];
-    uint32_t* hi_part = s_hi[wib];
-    if (tn) {
-        uint64_t pos = a.samples[a.samp_off[L] + (e0 >> kEfSampleLog)];
-        uint64_t w = pos >> 6;
-        uint32_t cnt = 0;
-        bool first = true;
-        while (cnt < tn) {
-            uint64_t wi = w + lane;
-            uint64_t bits = wi < hw ? __ldg(reinterpret_cast<const unsigned long long*>(high) + wi) : 0ull;
-            if (first && lane == 0) bits &= ~0ull << (pos & 63);
-            uint32_t c = (uint32_t)__popcll(bits);
-            uint32_t incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((int)lane >= o) incl += v;
-            }
-            uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t idx = cnt + incl - c;
-            while (bits && idx < tn) {
-                uint32_t b = (uint32_t)__ffsll((long long)bits) - 1u;
-                bits &= bits - 1;
-                hi_part[idx] = (uint32_t)(wi * 64 + b - (e0 + idx));
-                idx++;
-            }
-            cnt += total;
-            w += 32;
-            first = false;
-            if (total == 0 && w >= hw) break;  // corrupt blob guard
+    uint8_t* s_warp = s_dyn + (size_t)wib * (2u * kDecTile + 4u * a.low_stage_words);
+    uint16_t* hi_part = reinterpret_cast<uint16_t*>(s_warp);
+    uint32_t* s_low = reinterpret_cast<uint32_t*>(s_warp + 2u * kDecTile);
+    uint64_t di = warp;
+    if (a.row_stride) {
+        if (a.row_nos) di = (uint64_t)(uint32_t)a.row_nos[warp];
+    } else if (a.sel_desc) {
+        di = a.sel_desc[warp];
+    }
+    const uint4* dp = reinterpret_cast<const uint4*>(a.dir + di);
+    const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
+    const uint64_t da = (uint64_t)d0.x | ((uint64_t)d0.y << 32);
+    const uint64_t high32 = da & ((1ull << 40) - 1);
+    const uint32_t count = (uint32_t)(da >> 40) & 0x7ffu, l = (uint32_t)(da >> 51) & 31u, nw32 = (uint32_t)(da >> 56) & 63u;
+    const uint64_t low32o = (uint64_t)d0.z | ((uint64_t)d0.w << 32);
+    const uint64_t out_base = (uint64_t)d1.x | ((uint64_t)d1.y << 32);
+    const uint32_t r0 = d1.z, zeros = d1.w;
+    OutT* out;
+    if (a.row_stride)
+        out = reinterpret_cast<OutT*>(a.out) + warp * a.row_stride;
+    else
+        out = reinterpret_cast<OutT*>(a.out) + (a.sel_out ? a.sel_out[warp] : out_base) + r0;
+    if (count) {
+        const uint32_t lead = r0 & 31u;
+        const uint32_t ngroups = (lead + count + 31u) >> 5;   // groups of 32 consecutive id numbers
+        const uint32_t nlow = ngroups * l;                     // 32-bit lower-bits words covering them
+        const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(a.low) + low32o;
+        const bool staged = nlow <= a.low_stage_words;
+        if (staged) {
+            uint32_t sdst = (uint32_t)__cvta_generic_to_shared(s_low);
+            for (uint32_t i = lane; i < nlow; i += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 4u * i), "l"(lsrc + i));
+            asm volatile("cp.async.commit_group;");
         }
+        const uint32_t* h32 = reinterpret_cast<const uint32_t*>(a.high) + high32;
+        uint32_t w = lane < nw32 ? __ldg(h32 + lane) : 0u;
+        uint32_t sc = (uint32_t)__popc(w);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, sc, o);
+            if ((int)lane >= o) sc += v;
+        }
+        // The id with chunk-relative number j whose one sits at chunk bit P has upper part
+        //   (chunk_bit0 + P) - (r0 + j) = zeros + (P - j);  shared memory gets P - j, `zeros` is added on the way out.
+        {
+            uint16_t* p = hi_part + sc;   // one past this word's last id
+            uint32_t v = 32u * lane - sc; // (bit base) - (id number): grows by one for every step back
+            while (w) {
+                uint32_t b = 31u - (uint32_t)__clz((int)w);
+                w ^= 1u << b;
+                --p;
+                ++v;
+                *p = (uint16_t)(v + b);
+            }
+        }
+        if (staged) asm volatile("cp.async.wait_group 0;");
         __syncwarp();
-        for (uint32_t t = lane; t < tn; t += 32) {
-            uint64_t id = ((uint64_t)hi_part[t] << l) | ef_get_low(low, e0 + t, l);
-            out[t] = (OutT)id;
+        const uint32_t fw = (lane * l) >> 5, fs = (lane * l) & 31u, fmask = l ? (0xffffffffu >> (32u - l)) : 0u;
+        const int32_t end = (int32_t)count;
+        int32_t j = (int32_t)lane - (int32_t)lead;
+        if (staged) {
+            const uint32_t* sp = s_low + fw;
+            for (uint32_t g = 0; g < ngroups; g++, j += 32, sp += l) {
+                if (j >= 0 && j < end) {
+                    uint32_t f = l ? (__funnelshift_r(sp[0], sp[1], fs) & fmask) : 0u;
+                    uint64_t id = ((uint64_t)((uint32_t)hi_part[j] + zeros) << l) | f;
+                    out[j] = (OutT)id;
+                }
+            }
+        } else {
+            const uint32_t* lp = lsrc + lane;
+            for (uint32_t g = 0; g < ngroups; g++, j += 32, lp += l) {
+                uint32_t lwv = lane < l ? __ldg(lp) : 0u;
+                uint32_t x0 = __shfl_sync(0xffffffffu, lwv, fw);
+                uint32_t x1 = __shfl_sync(0xffffffffu, lwv, (fw + 1) & 31);
+                uint32_t f = __funnelshift_r(x0, x1, fs) & fmask;
+                if (j >= 0 && j < end) {
+                    uint64_t id = ((uint64_t)((uint32_t)hi_part[j] + zeros) << l) | f;
+                    out[j] = (OutT)id;
+                }
+            }
         }
     }
     if (a.row_stride) {
-        for (uint32_t t = tn + lane; t < a.row_stride; t += 32) out[t] = (OutT)-1;
-        if (a.counts && lane == 0) a.counts[warp] = tn;
+        for (uint32_t t = count + lane; t < a.row_stride; t += 32) out[t] = (OutT)-1;
+        if (a.counts && lane == 0) a.counts[warp] = count;
     }
 }
 
@@ -320,15 +413,18 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     b->low_off.assign(nl + 1, 0);
     b->high_off.assign(nl + 1, 0);
     b->samp_off.assign(nl + 1, 0);
+    b->dir_off.assign(nl + 1, 0);
     std::vector<uint32_t> tile_list, tile_idx;
     uint64_t bits_total = 0;
     for (uint64_t i = 0; i < nl; i++) {
         EfShape s = ef_shape(hi[i], n32[i]);
         b->l[i] = (uint8_t)s.l;
+        b->max_l = std::max<uint32_t>(b->max_l, s.l);
         b->universe[i] = hi[i];
         b->low_off[i + 1] = b->low_off[i] + s.low_words;
         b->high_off[i + 1] = b->high_off[i] + s.high_words;
         b->samp_off[i + 1] = b->samp_off[i] + s.samples;
+        b->dir_off[i + 1] = b->dir_off[i] + std::max<uint64_t>(1, (s.high_words + kDecChunkWords - 1) / kDecChunkWords);
         bits_total += s.low_bits + s.high_bits;
         uint64_t words = s.low_words + s.high_words;
         for (uint64_t t = 0; t * kEncTileWords < words; t++) {
@@ -339,6 +435,7 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     b->low_words = b->low_off[nl];
     b->high_words = b->high_off[nl];
     b->nsamples = b->samp_off[nl];
+    b->ndir = b->dir_off[nl];
     b->bits_total = bits_total;
     uint64_t acct = 0;
     IDC_TRY(dev_alloc(&b->d_list_off, nl + 1, &acct));
@@ -346,7 +443,9 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     IDC_TRY(dev_alloc(&b->d_low_off, nl + 1, &acct));
     IDC_TRY(dev_alloc(&b->d_high_off, nl + 1, &acct));
     IDC_TRY(dev_alloc(&b->d_samp_off, nl + 1, &acct));
-    IDC_TRY(dev_alloc(&b->d_low, b->low_words, &acct));
+    IDC_TRY(dev_alloc(&b->d_dir_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(&b->d_dir, b->ndir, &acct));
+    IDC_TRY(dev_alloc(&b->d_low, b->low_words + 32, &acct));  // +256 B: the decoder's last group may read past the end
     IDC_TRY(dev_alloc(&b->d_high, b->high_words, &acct));
     IDC_TRY(dev_alloc(&b->d_samples, b->nsamples, &acct));
     IDC_TRY(upload(c, b->d_list_off, b->list_offsets));
@@ -354,6 +453,8 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     IDC_TRY(upload(c, b->d_low_off, b->low_off));
     IDC_TRY(upload(c, b->d_high_off, b->high_off));
     IDC_TRY(upload(c, b->d_samp_off, b->samp_off));
+    IDC_TRY(upload(c, b->d_dir_off, b->dir_off));
+    IDC_CUDA(cudaMemsetAsync(b->d_dir, 0, std::max<uint64_t>(b->ndir, 1) * sizeof(EfChunk), c->stream));  // empty lists: count 0
 
     // sort when needed (ids < 2^32 was checked by the metadata kernel)
     const void* enc_ids = ids_dev;
@@ -401,7 +502,7 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     IDC_TRY(check_last_launch("k_sort_units"));
     if (ntiles) {
         EfEncArgs e{enc_ids, d_src, b->d_list_off, b->d_l, d_hi, b->d_low_off, b->d_high_off, b->d_samp_off,
-                    b->d_low, b->d_high, b->d_samples, d_tile_list, d_tile_idx, (uint32_t)ntiles};
+                    b->d_low, b->d_high, b->d_samples, b->d_dir_off, b->d_dir, d_tile_list, d_tile_idx, (uint32_t)ntiles};
         LaunchScope ls(c, "k_ef_encode");
         if (enc_id_bytes == 8)
             k_ef_encode<int64_t><<<grid_for(ntiles * 32), kThreads, 0, c->stream>>>(e);
@@ -409,23 +510,36 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
             k_ef_encode<uint32_t><<<grid_for(ntiles * 32), kThreads, 0, c->stream>>>(e);
     }
     IDC_TRY(check_last_launch("k_ef_encode"));
+    if (b->ndir) {
+        LaunchScope ls(c, "k_ef_finish_chunks");
+        k_ef_finish_chunks<<<grid_for(b->ndir), kThreads, 0, c->stream>>>(b->d_dir, b->ndir);
+    }
+    IDC_TRY(check_last_launch("k_ef_finish_chunks"));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
     b->device_bytes = acct;
     return IDC_OK;
 }
 
-int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_tile_list, const uint32_t* d_tile_idx,
-                  const uint64_t* d_tile_out, uint64_t ntiles, void* out_dev, int id_bytes, uint32_t* counts_dev,
+int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_sel_desc, const uint64_t* d_sel_out,
+                  const int32_t* d_row_nos, uint64_t ntiles, void* out_dev, int id_bytes, uint32_t* counts_dev,
                   uint32_t row_stride) {
     if (ntiles == 0) return IDC_OK;
-    EfDecArgs a{b->d_list_off, b->d_l, b->d_low_off, b->d_high_off, b->d_samp_off, b->d_low, b->d_high, b->d_samples,
-                d_tile_list, d_tile_idx, d_tile_out, out_dev, counts_dev, (uint32_t)ntiles, row_stride};
+    // stage up to 33 groups of max_l words per warp, capped so that 6 CTAs of 8 warps still fit an SM
+    uint32_t stage_words = std::min<uint32_t>(33u * b->max_l + 1u, 768u);
+    stage_words = (stage_words + 3u) & ~3u;
+    EfDecArgs a{b->d_dir, b->d_low, b->d_high, d_sel_desc, d_sel_out, d_row_nos, out_dev, counts_dev, ntiles, row_stride,
+                stage_words};
+    const uint32_t wpb = kDecThreads / 32;
+    const uint32_t grid = (uint32_t)((ntiles + wpb - 1) / wpb);
+    const size_t smem = (size_t)wpb * (2u * kDecTile + 4u * stage_words);
+    IDC_CUDA(cudaFuncSetAttribute(k_ef_decode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IDC_CUDA(cudaFuncSetAttribute(k_ef_decode<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         LaunchScope ls(c, "k_ef_decode");
         if (id_bytes == 8)
-            k_ef_decode<int64_t><<<grid_for(ntiles * 32), kThreads, 0, c->stream>>>(a);
+            k_ef_decode<int64_t><<<grid, kDecThreads, smem, c->stream>>>(a);
         else
-            k_ef_decode<int32_t><<<grid_for(ntiles * 32), kThreads, 0, c->stream>>>(a);
+            k_ef_decode<int32_t><<<grid, kDecThreads, smem, c->stream>>>(a);
     }
     IDC_TRY(check_last_launch("k_ef_decode"));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
@@ -557,62 +671,36 @@ int idc_ef_decode(idc_ctx* c, const idc_ef_blob* b, const uint64_t* list_nos, ui
     IDC_REQUIRE(b->row_stride == 0, IDC_ERR_ARG, "row blob: use idc_ef_decode_rows");
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
-    idc_ef_blob* mb = const_cast<idc_ef_blob*>(b);
-    std::vector<uint32_t> tl, ti;
-    std::vector<uint64_t> to;
-    uint64_t total_out = 0;
-    auto add_list = [&](uint64_t L, uint64_t pos) {
-        uint64_t m = b->list_offsets[L + 1] - b->list_offsets[L];
-        for (uint64_t t = 0; t * kDecTile < m; t++) {
-            tl.push_back((uint32_t)L);
-            ti.push_back((uint32_t)t);
-            to.push_back(pos + t * kDecTile);
-        }
-        return m;
-    };
-    const uint32_t *d_tl, *d_ti;
-    const uint64_t* d_to;
-    uint64_t ntiles;
-    uint32_t *t_tl = nullptr, *t_ti = nullptr;
-    uint64_t* t_to = nullptr;
+    uint64_t total_out = 0, ntiles = 0;
+    uint32_t* t_desc = nullptr;
+    uint64_t* t_out = nullptr;
     if (list_nos == nullptr) {
-        if (!mb->plan_ready) {
-            for (uint64_t L = 0; L < b->nlist; L++) add_list(L, b->list_offsets[L]);
-            mb->ntiles = tl.size();
-            IDC_TRY(dev_alloc(&mb->d_tile_list, tl.size()));
-            IDC_TRY(dev_alloc(&mb->d_tile_idx, tl.size()));
-            IDC_TRY(dev_alloc(&mb->d_tile_out, tl.size()));
-            IDC_TRY(upload(c, mb->d_tile_list, tl));
-            IDC_TRY(upload(c, mb->d_tile_idx, ti));
-            IDC_TRY(upload(c, mb->d_tile_out, to));
-            IDC_CUDA(cudaStreamSynchronize(c->stream));
-            mb->plan_ready = true;
-        }
-        d_tl = b->d_tile_list;
-        d_ti = b->d_tile_idx;
-        d_to = b->d_tile_out;
-        ntiles = b->ntiles;
+        // decode everything: tile i is chunk descriptor i, no per-call planning at all
+        ntiles = b->ndir;
         total_out = b->total_ids;
         if (out_offsets) memcpy(out_offsets, b->list_offsets.data(), (b->nlist + 1) * 8);
     } else {
+        std::vector<uint32_t> td;
+        std::vector<uint64_t> to;
         uint64_t pos = 0;
         for (uint64_t i = 0; i < nsel; i++) {
-            IDC_REQUIRE(list_nos[i] < b->nlist, IDC_ERR_ARG, "list_no out of range");
+            uint64_t L = list_nos[i];
+            IDC_REQUIRE(L < b->nlist, IDC_ERR_ARG, "list_no out of range");
             if (out_offsets) out_offsets[i] = pos;
-            pos += add_list(list_nos[i], pos);
+            for (uint64_t d = b->dir_off[L]; d < b->dir_off[L + 1]; d++) {
+                td.push_back((uint32_t)d);
+                to.push_back(pos);
+            }
+            pos += b->list_offsets[L + 1] - b->list_offsets[L];
         }
         if (out_offsets) out_offsets[nsel] = pos;
         total_out = pos;
-        ntiles = tl.size();
-        IDC_TRY(dev_alloc(&t_tl, ntiles));
-        IDC_TRY(dev_alloc(&t_ti, ntiles));
-        IDC_TRY(dev_alloc(&t_to, ntiles));
-        IDC_TRY(upload(c, t_tl, tl));
-        IDC_TRY(upload(c, t_ti, ti));
-        IDC_TRY(upload(c, t_to, to));
-        d_tl = t_tl;
-        d_ti = t_ti;
-        d_to = t_to;
+        ntiles = td.size();
+        IDC_REQUIRE(b->ndir < (1ull << 32), IDC_ERR_ARG, "too many chunks for subset decode");
+        IDC_TRY(dev_alloc(&t_desc, ntiles));
+        IDC_TRY(dev_alloc(&t_out, ntiles));
+        IDC_TRY(upload(c, t_desc, td));
+        IDC_TRY(upload(c, t_out, to));
     }
     int rc = IDC_OK;
     if (total_out) {
@@ -622,7 +710,7 @@ int idc_ef_decode(idc_ctx* c, const idc_ef_blob* b, const uint64_t* list_nos, ui
             rc = c->stage.reserve(total_out * id_bytes);
             out_dev = c->stage.p;
         }
-        if (rc == IDC_OK) rc = ef_run_decode(c, b, d_tl, d_ti, d_to, ntiles, out_dev, id_bytes, nullptr, 0);
+        if (rc == IDC_OK) rc = ef_run_decode(c, b, t_desc, t_out, nullptr, ntiles, out_dev, id_bytes, nullptr, 0);
         if (rc == IDC_OK && out_mem == IDC_MEM_HOST) {
             cudaError_t e = cudaMemcpyAsync(ids_out, out_dev, total_out * id_bytes, cudaMemcpyDeviceToHost, c->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -634,9 +722,8 @@ int idc_ef_decode(idc_ctx* c, const idc_ef_blob* b, const uint64_t* list_nos, ui
     } else {
         cudaStreamSynchronize(c->stream);
     }
-    cudaFree(t_tl);
-    cudaFree(t_ti);
-    cudaFree(t_to);
+    cudaFree(t_desc);
+    cudaFree(t_out);
     return rc;
 }
 
@@ -651,28 +738,16 @@ int idc_ef_decode_rows(idc_ctx* c, const idc_ef_blob* b, const int32_t* row_nos,
     if (row_nos == nullptr) nsel = b->nlist;
     if (nsel == 0) return IDC_OK;
     IDC_REQUIRE(out != nullptr, IDC_ERR_ARG, "out is NULL");
-    std::vector<int32_t> rows_h;
-    if (row_nos && rows_mem == IDC_MEM_DEVICE) {
-        rows_h.resize(nsel);
-        IDC_CUDA(cudaMemcpyAsync(rows_h.data(), row_nos, nsel * 4, cudaMemcpyDeviceToHost, c->stream));
-        IDC_CUDA(cudaStreamSynchronize(c->stream));
-        row_nos = rows_h.data();
+    IDC_REQUIRE(3ull * K + 2 <= 64ull * kDecChunkWords, IDC_ERR_ARG, "row stride %u too large: a row must fit one 2048-bit chunk", K);
+    // rows are addressed directly by the kernel (list = row number, chunk 0): no tile tables
+    const int32_t* d_rows = row_nos;
+    if (row_nos && rows_mem == IDC_MEM_HOST) {
+        for (uint64_t i = 0; i < nsel; i++)
+            IDC_REQUIRE(row_nos[i] >= 0 && (uint64_t)row_nos[i] < b->nlist, IDC_ERR_ARG, "row %d out of range", row_nos[i]);
+        IDC_TRY(c->meta.reserve(nsel * 4 + 256));
+        IDC_CUDA(cudaMemcpyAsync(c->meta.p, row_nos, nsel * 4, cudaMemcpyHostToDevice, c->stream));
+        d_rows = c->meta.as<int32_t>();
     }
-    std::vector<uint32_t> tl(nsel), ti(nsel, 0);
-    std::vector<uint64_t> to(nsel);
-    for (uint64_t i = 0; i < nsel; i++) {
-        int64_t r = row_nos ? row_nos[i] : (int64_t)i;
-        IDC_REQUIRE(r >= 0 && (uint64_t)r < b->nlist, IDC_ERR_ARG, "row %lld out of range", (long long)r);
-        tl[i] = (uint32_t)r;
-        to[i] = i * K;
-    }
-    IDC_TRY(c->meta.reserve(nsel * 16 + 1024));
-    uint32_t* d_tl = c->meta.as<uint32_t>();
-    uint32_t* d_ti = reinterpret_cast<uint32_t*>(c->meta.as<uint8_t>() + ((nsel * 4 + 255) & ~255ull));
-    uint64_t* d_to = reinterpret_cast<uint64_t*>(c->meta.as<uint8_t>() + 2 * ((nsel * 4 + 255) & ~255ull));
-    IDC_TRY(upload(c, d_tl, tl));
-    IDC_TRY(upload(c, d_ti, ti));
-    IDC_TRY(upload(c, d_to, to));
     int32_t* out_dev = out;
     uint32_t* cnt_dev = counts;
     if (out_mem == IDC_MEM_HOST) {
@@ -680,7 +755,7 @@ int idc_ef_decode_rows(idc_ctx* c, const idc_ef_blob* b, const int32_t* row_nos,
         out_dev = c->stage.as<int32_t>();
         cnt_dev = reinterpret_cast<uint32_t*>(c->stage.as<uint8_t>() + nsel * K * 4);
     }
-    IDC_TRY(ef_run_decode(c, b, d_tl, d_ti, d_to, nsel, out_dev, 4, cnt_dev, K));
+    IDC_TRY(ef_run_decode(c, b, nullptr, nullptr, d_rows, nsel, out_dev, 4, cnt_dev, K));
     if (out_mem == IDC_MEM_HOST) {
         IDC_CUDA(cudaMemcpyAsync(out, out_dev, nsel * K * 4, cudaMemcpyDeviceToHost, c->stream));
         if (counts) IDC_CUDA(cudaMemcpyAsync(counts, cnt_dev, nsel * 4, cudaMemcpyDeviceToHost, c->stream));
