@@ -495,6 +495,11 @@ def e2e_section(args, ctx, offsets, ids, world, dev, barrier):
 
 
 if __name__ == "__main__":
+    # The contract is ONE JSON line on stdout: keep the real stdout for it and send everything else that a
+    # library may print there (e.g. "NCCL version ...") to stderr.
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -66,19 +66,19 @@ struct idc_ef_blob {
     uint64_t* d_tile_out = nullptr;
     uint64_t ntiles = 0;
     ~idc_ef_blob() {
-        cudaFree(d_list_off);
-        cudaFree(d_l);
-        cudaFree(d_low_off);
-        cudaFree(d_high_off);
-        cudaFree(d_samp_off);
-        cudaFree(d_low);
-        cudaFree(d_high);
-        cudaFree(d_samples);
-        cudaFree(d_dir_off);
-        cudaFree(d_dir);
-        cudaFree(d_tile_list);
-        cudaFree(d_tile_idx);
-        cudaFree(d_tile_out);
+        if (ctx) ctx->pool_release(d_list_off);
+        if (ctx) ctx->pool_release(d_l);
+        if (ctx) ctx->pool_release(d_low_off);
+        if (ctx) ctx->pool_release(d_high_off);
+        if (ctx) ctx->pool_release(d_samp_off);
+        if (ctx) ctx->pool_release(d_low);
+        if (ctx) ctx->pool_release(d_high);
+        if (ctx) ctx->pool_release(d_samples);
+        if (ctx) ctx->pool_release(d_dir_off);
+        if (ctx) ctx->pool_release(d_dir);
+        if (ctx) ctx->pool_release(d_tile_list);
+        if (ctx) ctx->pool_release(d_tile_idx);
+        if (ctx) ctx->pool_release(d_tile_out);
     }
 };
 
@@ -438,16 +438,16 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     b->ndir = b->dir_off[nl];
     b->bits_total = bits_total;
     uint64_t acct = 0;
-    IDC_TRY(dev_alloc(&b->d_list_off, nl + 1, &acct));
-    IDC_TRY(dev_alloc(&b->d_l, nl, &acct));
-    IDC_TRY(dev_alloc(&b->d_low_off, nl + 1, &acct));
-    IDC_TRY(dev_alloc(&b->d_high_off, nl + 1, &acct));
-    IDC_TRY(dev_alloc(&b->d_samp_off, nl + 1, &acct));
-    IDC_TRY(dev_alloc(&b->d_dir_off, nl + 1, &acct));
-    IDC_TRY(dev_alloc(&b->d_dir, b->ndir, &acct));
-    IDC_TRY(dev_alloc(&b->d_low, b->low_words + 32, &acct));  // +256 B: the decoder's last group may read past the end
-    IDC_TRY(dev_alloc(&b->d_high, b->high_words, &acct));
-    IDC_TRY(dev_alloc(&b->d_samples, b->nsamples, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_list_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_l, nl, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_low_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_high_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_samp_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_dir_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_dir, b->ndir, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_low, b->low_words + 32, &acct));  // +256 B: the decoder's last group may read past the end
+    IDC_TRY(dev_alloc(c, &b->d_high, b->high_words, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_samples, b->nsamples, &acct));
     IDC_TRY(upload(c, b->d_list_off, b->list_offsets));
     IDC_TRY(upload(c, b->d_l, b->l));
     IDC_TRY(upload(c, b->d_low_off, b->low_off));
@@ -556,6 +556,7 @@ int idc_ef_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const voi
     IDC_REQUIRE(id_bytes == 8 || id_bytes == 4, IDC_ERR_ARG, "id_bytes must be 4 or 8");
     IDC_REQUIRE(nlist < (1ull << 32), IDC_ERR_ARG, "too many lists");
     *out = nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     std::unique_ptr<idc_ef_blob> b(new idc_ef_blob());
@@ -588,6 +589,7 @@ int idc_ef_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* da
     IDC_REQUIRE(K >= 1 && K <= kMaxUnit, IDC_ERR_ARG, "K out of range");
     IDC_REQUIRE(nrows < (1ull << 32), IDC_ERR_ARG, "too many rows");
     *out = nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     std::unique_ptr<idc_ef_blob> b(new idc_ef_blob());
@@ -658,6 +660,7 @@ int idc_ef_blob_export(const idc_ef_blob* b, uint64_t* list_offsets, uint8_t* l,
 
 int idc_ef_blob_free(idc_ef_blob* b) {
     if (b) {
+        std::lock_guard<std::mutex> lock(b->ctx->mu);
         cudaSetDevice(b->ctx->device);
         delete b;
     }
@@ -669,6 +672,7 @@ int idc_ef_decode(idc_ctx* c, const idc_ef_blob* b, const uint64_t* list_nos, ui
     IDC_REQUIRE(c && b, IDC_ERR_ARG, "idc_ef_decode: null argument");
     IDC_REQUIRE(id_bytes == 8 || id_bytes == 4, IDC_ERR_ARG, "id_bytes must be 4 or 8");
     IDC_REQUIRE(b->row_stride == 0, IDC_ERR_ARG, "row blob: use idc_ef_decode_rows");
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     uint64_t total_out = 0, ntiles = 0;
@@ -697,8 +701,8 @@ int idc_ef_decode(idc_ctx* c, const idc_ef_blob* b, const uint64_t* list_nos, ui
         total_out = pos;
         ntiles = td.size();
         IDC_REQUIRE(b->ndir < (1ull << 32), IDC_ERR_ARG, "too many chunks for subset decode");
-        IDC_TRY(dev_alloc(&t_desc, ntiles));
-        IDC_TRY(dev_alloc(&t_out, ntiles));
+        IDC_TRY(dev_alloc(c, &t_desc, ntiles));
+        IDC_TRY(dev_alloc(c, &t_out, ntiles));
         IDC_TRY(upload(c, t_desc, td));
         IDC_TRY(upload(c, t_out, to));
     }
@@ -722,8 +726,8 @@ int idc_ef_decode(idc_ctx* c, const idc_ef_blob* b, const uint64_t* list_nos, ui
     } else {
         cudaStreamSynchronize(c->stream);
     }
-    cudaFree(t_desc);
-    cudaFree(t_out);
+    c->pool_release(t_desc);
+    c->pool_release(t_out);
     return rc;
 }
 
@@ -732,6 +736,7 @@ int idc_ef_decode_rows(idc_ctx* c, const idc_ef_blob* b, const int32_t* row_nos,
     IDC_REQUIRE(c && b, IDC_ERR_ARG, "idc_ef_decode_rows: null argument");
     IDC_REQUIRE(b->row_stride != 0, IDC_ERR_ARG, "not a row blob");
     IDC_REQUIRE(b->row_stride <= kDecTile, IDC_ERR_ARG, "row stride > %u not supported", kDecTile);
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     const uint32_t K = b->row_stride;
@@ -768,6 +773,7 @@ int idc_ef_select(idc_ctx* c, const idc_ef_blob* b, const uint64_t* list_nos, co
                   uint64_t nq, int query_mem, int64_t* ids_out, int out_mem) {
     IDC_REQUIRE(c && b && (nq == 0 || (list_nos && offsets_in_list && ids_out)), IDC_ERR_ARG,
                 "idc_ef_select: null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     if (nq == 0) return IDC_OK;
@@ -802,6 +808,7 @@ int idc_bits_pack(idc_ctx* c, uint64_t n, const void* vals, int val_bytes, int v
     IDC_REQUIRE(val_bytes == 8 || val_bytes == 4, IDC_ERR_ARG, "val_bytes must be 4 or 8");
     IDC_REQUIRE(bits >= 1 && bits <= 8 * val_bytes, IDC_ERR_ARG, "bits out of range");
     IDC_REQUIRE(out_bytes * 8 >= n * (uint64_t)bits, IDC_ERR_ARG, "output too small");
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     if (out_bytes == 0) return IDC_OK;
@@ -835,6 +842,7 @@ int idc_bits_unpack(idc_ctx* c, uint64_t n, const uint8_t* code, uint64_t code_b
     IDC_REQUIRE(val_bytes == 8 || val_bytes == 4, IDC_ERR_ARG, "val_bytes must be 4 or 8");
     IDC_REQUIRE(bits >= 1 && bits <= 8 * val_bytes, IDC_ERR_ARG, "bits out of range");
     IDC_REQUIRE(code_bytes * 8 >= n * (uint64_t)bits, IDC_ERR_ARG, "code too small");
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     if (n == 0) return IDC_OK;

@@ -1,4 +1,5 @@
 // idc_ctx.cu -- context, error reporting and constant tables of libidcodec.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <random>
@@ -52,6 +53,52 @@ void idc_ctx::mark(const char* name) {
 void idc_ctx::mark_end() {
     if (!timing || times.empty()) return;
     cudaEventRecord(times.back().b, stream);
+}
+
+int idc_ctx::pool_alloc(void** p, size_t bytes) {
+    *p = nullptr;
+    bytes = (std::max<size_t>(bytes, 1) + 511) & ~size_t(511);
+    size_t best = pool_free.size();
+    for (size_t i = 0; i < pool_free.size(); i++)
+        if (pool_free[i].second >= bytes && pool_free[i].second <= bytes + bytes / 8 + 4096 &&
+            (best == pool_free.size() || pool_free[i].second < pool_free[best].second))
+            best = i;
+    if (best != pool_free.size()) {
+        *p = pool_free[best].first;
+        pool_live.push_back(pool_free[best]);
+        pool_free.erase(pool_free.begin() + best);
+        return IDC_OK;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_trim();  // give cached blocks back and retry once
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        idc::set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return IDC_ERR_NOMEM;
+    }
+    pool_live.push_back({*p, bytes});
+    return IDC_OK;
+}
+
+void idc_ctx::pool_release(void* p) {
+    if (!p) return;
+    for (size_t i = 0; i < pool_live.size(); i++)
+        if (pool_live[i].first == p) {
+            pool_free.push_back(pool_live[i]);
+            pool_live.erase(pool_live.begin() + i);
+            if (pool_free.size() > 64) pool_trim();
+            return;
+        }
+    cudaFree(p);  // not ours
+}
+
+void idc_ctx::pool_trim() {
+    for (auto& b : pool_free) cudaFree(b.first);
+    pool_free.clear();
 }
 
 int idc_ctx::fork(int n) {
@@ -157,6 +204,9 @@ int idc_ctx_destroy(idc_ctx* c) {
     cudaFree(c->d_mt);
     cudaFree(c->d_rcp64);
     cudaFree(c->d_q31);
+    c->pool_trim();
+    for (auto& b : c->pool_live) cudaFree(b.first);
+    c->pool_live.clear();
     c->ws.release();
     c->scratch.release();
     c->stage.release();

@@ -7,7 +7,9 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/idcodec.h"
@@ -78,6 +80,9 @@ struct KernelTime {
 }  // namespace idc
 
 struct idc_ctx {
+    // One call at a time per context: workspaces, staging buffers and the stream are shared state. The Faiss
+    // virtuals (get_ids ...) are called from OpenMP threads concurrently, so every entry point takes this lock.
+    std::mutex mu;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -97,6 +102,13 @@ struct idc_ctx {
     idc::DevBuf stage;    // host<->device staging of ids
     idc::DevBuf meta;     // per-call unit tables
     idc::DevBuf status;   // per-call status words
+    // device memory pool for blob arrays: cudaMalloc/cudaFree of GB-sized blocks cost tens of ms each, and a
+    // blob is typically rebuilt with the same shapes; freed blocks are kept and reused (exact size class).
+    std::vector<std::pair<void*, size_t>> pool_free;
+    std::vector<std::pair<void*, size_t>> pool_live;
+    int pool_alloc(void** p, size_t bytes);
+    void pool_release(void* p);
+    void pool_trim();
     // auxiliary streams: size classes of one logical kernel run concurrently (fork/join around c->stream)
     std::vector<cudaStream_t> aux;
     std::vector<cudaEvent_t> aux_done;

@@ -17,14 +17,9 @@ using namespace idc;
 constexpr int kThreads = 128;  // 4 warps per CTA
 
 template <typename T>
-int dev_alloc(T** p, size_t count, uint64_t* acct = nullptr) {
-    *p = nullptr;
+int dev_alloc(idc_ctx* c, T** p, size_t count, uint64_t* acct = nullptr) {
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    cudaError_t e = cudaMalloc((void**)p, bytes);
-    if (e != cudaSuccess) {
-        set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-        return IDC_ERR_NOMEM;
-    }
+    IDC_TRY(c->pool_alloc(reinterpret_cast<void**>(p), bytes));
     if (acct) *acct += bytes;
     return IDC_OK;
 }

@@ -61,17 +61,17 @@ struct idc_roc_blob {
     std::vector<uint32_t> plan_ns;   // unit lengths in launch order
 
     ~idc_roc_blob() {
-        cudaFree(d_unit_n);
-        cudaFree(d_unit_prec);
-        cudaFree(d_unit_head);
-        cudaFree(d_word_off);
-        cudaFree(d_words);
-        cudaFree(d_unit_lo);
-        cudaFree(d_unit_hi);
-        cudaFree(d_order);
-        cudaFree(d_plan_unit);
-        cudaFree(d_plan_out);
-        cudaFree(d_plan_ws);
+        if (ctx) ctx->pool_release(d_unit_n);
+        if (ctx) ctx->pool_release(d_unit_prec);
+        if (ctx) ctx->pool_release(d_unit_head);
+        if (ctx) ctx->pool_release(d_word_off);
+        if (ctx) ctx->pool_release(d_words);
+        if (ctx) ctx->pool_release(d_unit_lo);
+        if (ctx) ctx->pool_release(d_unit_hi);
+        if (ctx) ctx->pool_release(d_order);
+        if (ctx) ctx->pool_release(d_plan_unit);
+        if (ctx) ctx->pool_release(d_plan_out);
+        if (ctx) ctx->pool_release(d_plan_ws);
     }
 };
 
@@ -277,13 +277,13 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
                      const std::vector<uint32_t>& unit_posbase, uint64_t id_elems) {
     const uint64_t nu = b->nunits;
     uint64_t acct = 0;
-    IDC_TRY(dev_alloc(&b->d_unit_n, nu, &acct));
-    IDC_TRY(dev_alloc(&b->d_unit_prec, nu, &acct));
-    IDC_TRY(dev_alloc(&b->d_unit_head, nu, &acct));
-    IDC_TRY(dev_alloc(&b->d_word_off, nu + 1, &acct));
-    IDC_TRY(dev_alloc(&b->d_unit_lo, nu, &acct));
-    IDC_TRY(dev_alloc(&b->d_unit_hi, nu, &acct));
-    if (flags & IDC_F_WANT_ORDER) IDC_TRY(dev_alloc(&b->d_order, id_elems, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_n, nu, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_prec, nu, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_head, nu, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_word_off, nu + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_lo, nu, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_hi, nu, &acct));
+    if (flags & IDC_F_WANT_ORDER) IDC_TRY(dev_alloc(c, &b->d_order, id_elems, &acct));
     IDC_TRY(upload(c, b->d_unit_n, b->unit_n));
 
     // per-call tables: unit_src, posbase, perm, ws_off, scratch_off, nwords
@@ -448,7 +448,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
     }
     b->total_words = word_off[nu];
     b->ans_bytes = ans_bytes;
-    IDC_TRY(dev_alloc(&b->d_words, b->total_words, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_words, b->total_words, &acct));
     IDC_TRY(upload(c, b->d_word_off, word_off));
     {
         LaunchScope ls(c, "k_roc_compact");
@@ -511,9 +511,9 @@ int build_decode_plan(idc_ctx* c, const idc_roc_blob* b, const std::vector<uint3
         sw[i] = wsb;
         wsb += ns[perm[i]] ? dec_tree_bytes(ns[perm[i]]) : 0;
     }
-    IDC_TRY(dev_alloc(d_unit, m));
-    IDC_TRY(dev_alloc(d_out, m));
-    IDC_TRY(dev_alloc(d_ws, m));
+    IDC_TRY(dev_alloc(c, d_unit, m));
+    IDC_TRY(dev_alloc(c, d_out, m));
+    IDC_TRY(dev_alloc(c, d_ws, m));
     IDC_TRY(upload(c, *d_unit, su));
     IDC_TRY(upload(c, *d_out, so));
     IDC_TRY(upload(c, *d_ws, sw));
@@ -606,6 +606,7 @@ int idc_roc_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const vo
     IDC_REQUIRE(max_unit <= kMaxUnit, IDC_ERR_ARG,
                 "max_unit %u > 65536: the reference codec does not round-trip larger sets", max_unit);
     *out = nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
@@ -632,6 +633,7 @@ int idc_roc_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* d
     IDC_REQUIRE(K >= 1 && K <= kMaxUnit, IDC_ERR_ARG, "K out of range");
     IDC_REQUIRE(nrows < (1ull << 32), IDC_ERR_ARG, "too many rows");
     *out = nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
@@ -717,6 +719,7 @@ int idc_roc_blob_import(idc_ctx* c, uint64_t nlist, const uint32_t* unit_n, cons
                         idc_roc_blob** out) {
     IDC_REQUIRE(c && out && (nlist == 0 || (unit_n && unit_precision && unit_heads)) && word_offsets, IDC_ERR_ARG,
                 "idc_roc_blob_import: null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     *out = nullptr;
     std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
@@ -748,13 +751,13 @@ int idc_roc_blob_import(idc_ctx* c, uint64_t nlist, const uint32_t* unit_n, cons
     b->total_words = word_offsets[nlist] - word_offsets[0];
     b->ans_bytes = ans;
     uint64_t acct = 0;
-    IDC_TRY(dev_alloc(&b->d_unit_n, nlist, &acct));
-    IDC_TRY(dev_alloc(&b->d_unit_prec, nlist, &acct));
-    IDC_TRY(dev_alloc(&b->d_unit_head, nlist, &acct));
-    IDC_TRY(dev_alloc(&b->d_word_off, nlist + 1, &acct));
-    IDC_TRY(dev_alloc(&b->d_unit_lo, nlist, &acct));
-    IDC_TRY(dev_alloc(&b->d_unit_hi, nlist, &acct));
-    IDC_TRY(dev_alloc(&b->d_words, b->total_words, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_n, nlist, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_prec, nlist, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_head, nlist, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_word_off, nlist + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_lo, nlist, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_hi, nlist, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_words, b->total_words, &acct));
     std::vector<uint64_t> woff(nlist + 1);
     for (uint64_t l = 0; l <= nlist; l++) woff[l] = word_offsets[l] - word_offsets[0];
     cudaStream_t s = c->stream;
@@ -788,6 +791,7 @@ int idc_roc_blob_order(const idc_roc_blob* b, uint32_t* order, int order_mem) {
 
 int idc_roc_blob_free(idc_roc_blob* b) {
     if (b) {
+        std::lock_guard<std::mutex> lock(b->ctx->mu);
         cudaSetDevice(b->ctx->device);
         delete b;
     }
@@ -799,6 +803,7 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
     IDC_REQUIRE(c && b, IDC_ERR_ARG, "idc_roc_decode: null argument");
     IDC_REQUIRE(id_bytes == 8 || id_bytes == 4, IDC_ERR_ARG, "id_bytes must be 4 or 8");
     IDC_REQUIRE(b->row_stride == 0, IDC_ERR_ARG, "row blob: use idc_roc_decode_rows");
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     idc_roc_blob* mb = const_cast<idc_roc_blob*>(b);
@@ -871,9 +876,9 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
             }
         }
     }
-    cudaFree(t_unit);
-    cudaFree(t_out);
-    cudaFree(t_ws);
+    c->pool_release(t_unit);
+    c->pool_release(t_out);
+    c->pool_release(t_ws);
     return rc;
 }
 
@@ -881,6 +886,7 @@ int idc_roc_decode_rows(idc_ctx* c, const idc_roc_blob* b, const int32_t* row_no
                         int32_t* out, uint32_t* counts, int out_mem) {
     IDC_REQUIRE(c && b, IDC_ERR_ARG, "idc_roc_decode_rows: null argument");
     IDC_REQUIRE(b->row_stride != 0, IDC_ERR_ARG, "not a row blob");
+    std::lock_guard<std::mutex> lock(c->mu);
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     const uint32_t K = b->row_stride;
