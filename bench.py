@@ -360,7 +360,7 @@ def run_b200(args):
             "config": workload_config(args, sizes),
             "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "parity": parity,
-            "roc": {"encode_ids_per_s": n_ids / (sum(avg.get(k, 0) for k in ("k_unit_meta", "k_enc_tree_init", "k_roc_encode", "k_roc_compact")) * 1e-3),
+            "roc": {"encode_ids_per_s": n_ids / (sum(avg.get(k, 0) for k in ("k_unit_meta", "k_enc_records", "k_roc_encode", "k_roc_compact")) * 1e-3),
                     "decode_ids_per_s": n_ids / (sum(avg.get(k, 0) for k in ("memset_ws", "k_roc_decode")) * 1e-3),
                     "bits_per_id": 8.0 * info["ans_bytes"] / n_ids, "units": info["nunits"],
                     "wall_ms_per_step": 1e3 * t_wall / args.steps},

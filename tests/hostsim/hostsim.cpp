@@ -25,17 +25,18 @@ int64_t sim_roc_encode(uint32_t n, const uint64_t* ids, int prec, uint64_t* head
                        uint32_t cap, uint32_t* order_out, uint32_t* status_out) {
     uint32_t mt[kMtWords];
     tables(mt);
-    std::vector<uint8_t> ws(enc_tree_bytes(n) + 64, 0);
+    std::vector<uint8_t> ws(enc_tree_bytes(n) + 256, 0);
     std::vector<uint32_t> sm(enc_tree_sm_words(n) + 8, 0);
     EncLane<int64_t> L;
-    L.tree.leaf = reinterpret_cast<uint16_t*>(ws.data());
+    L.tree.rec = reinterpret_cast<uint32_t*>(ws.data());
     L.tree.sm = sm.data();
     L.tree.stride = 1;
     EncTreeLayout lay = enc_tree_layout(n);
-    for (uint32_t e = 0; e < lay.leaf_sectors * 16u; e++) L.tree.leaf[e] = enc_tree_init_leaf(n, e);
+    for (uint32_t r = 0; r < lay.records; r++)
+        for (uint32_t w = 0; w < 32; w++)
+            L.tree.rec[r * 32 + w] = enc_record_word(reinterpret_cast<const int64_t*>(ids), n, r, w);
     enc_tree_init_sm(L.tree, n);
     L.st = EncState{kRansL, words_out, 0, cap, 0, 0};
-    L.src = reinterpret_cast<const int64_t*>(ids);
     L.sort_idx = nullptr;
     L.order = order_out;
     L.pos_base = 0;

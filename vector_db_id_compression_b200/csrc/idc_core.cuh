@@ -137,6 +137,15 @@ IDC_HD void red_and32(uint32_t* p, uint32_t v) {
 #endif
 }
 
+template <typename T>
+IDC_HD T load_id_raw(const T* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
 // ------------------------------------------------ sector-of-16-counts math --
 // A "sector" is 32 bytes = 16 unsigned 16-bit counts = two 16-byte loads.
 
@@ -395,74 +404,205 @@ IDC_HD void dec_push_uniform(DecState& st, uint32_t sym, uint32_t nmax, uint32_t
 
 // ------------------------------------------------- encoder: select-remove --
 // Order statistics over the unit's id-sorted array, replacing
-// FenwickTree::reverse_lookup_then_remove (fenwick_tree.h:96-140): a 16-ary
-// tree of 16-bit counts over a presence bitmap. One 32-byte sector per level:
-//   leaf sector s : 16 masks of 16 bits  -> positions [256 s, 256 s + 256)
-//   L1 sector  t  : 16 counts, entry e = ids left in leaf sector 16 t + e
-//   L2 sector     : 16 counts, entry e = ids left in L1 sector e (n <= 65536)
+// FenwickTree::reverse_lookup_then_remove (fenwick_tree.h:96-140).
+//
+// A random HBM access costs a whole 128-byte line whatever is asked for, so a step may afford ONE: the unit's
+// ids are re-laid as 128-byte RECORDS -- word 0 a presence mask, words 1..31 thirty-one consecutive ids of the
+// sorted unit -- and one line load yields both "which ids of this stretch are still there" and the id itself.
+// Everything that decides WHICH record to touch lives in shared memory, private to the lane:
+//   L0  one word per 6 records: six 5-bit counts of ids still present
+//   L1  per 12 records (two L0 words) an exclusive cumulative 16-bit count, 16 entries (a "sector") per
+//       superblock of 192 records
+//   L2  sixteen 32-bit exclusive cumulative counts over the superblocks (n <= 65536 -> <= 12 of them)
+// Cumulative entries make select a batch of independent compares (no serial prefix scan on the step's
+// critical path); the matching decrements after a removal are independent word updates off that path.
+
+constexpr uint32_t kRecIds = 31;          // ids per record
+constexpr uint32_t kRecPerWord = 6;       // 5-bit counts per L0 word
+constexpr uint32_t kRecPerPair = 12;      // records per L1 entry
+constexpr uint32_t kRecPerSuper = 192;    // records per superblock (16 L1 entries)
 
 struct EncTreeLayout {
-    uint32_t leaf_sectors;  // ceil(n / 256)
-    uint32_t l1_sectors;    // ceil(leaf_sectors / 16)
+    uint32_t records;   // ceil(n / 31)
+    uint32_t l0_words;  // ceil(records / 6), rounded up to even
+    uint32_t supers;    // ceil(records / 192)
 };
 
 IDC_HD EncTreeLayout enc_tree_layout(uint32_t n) {
     EncTreeLayout L;
-    L.leaf_sectors = (n + 255u) / 256u;
-    if (L.leaf_sectors == 0) L.leaf_sectors = 1;
-    L.l1_sectors = (L.leaf_sectors + 15u) / 16u;
+    L.records = (n + kRecIds - 1u) / kRecIds;
+    if (L.records == 0) L.records = 1;
+    L.l0_words = ((L.records + kRecPerWord - 1u) / kRecPerWord + 1u) & ~1u;
+    L.supers = (L.records + kRecPerSuper - 1u) / kRecPerSuper;
     return L;
 }
-// global workspace: the leaf bitmap only
-IDC_HD uint64_t enc_tree_bytes(uint32_t n) { return 32ull * enc_tree_layout(n).leaf_sectors; }
-// shared-memory words per lane: L2 sector (8 words) then the L1 sectors
-IDC_HD uint32_t enc_tree_sm_words(uint32_t n) { return 8u + 8u * enc_tree_layout(n).l1_sectors; }
+// global workspace: the records
+IDC_HD uint64_t enc_tree_bytes(uint32_t n) { return 128ull * enc_tree_layout(n).records; }
+// shared-memory words per lane: [L2: 16][L1: 8 per superblock][L0]
+IDC_HD uint32_t enc_tree_sm_words(uint32_t n) {
+    EncTreeLayout L = enc_tree_layout(n);
+    return 16u + 8u * L.supers + L.l0_words;
+}
 
 struct EncTree {
-    uint16_t* leaf;   // global
+    uint32_t* rec;    // global: records of 32 words
     uint32_t* sm;     // this lane's shared-memory region
     uint32_t stride;
+    uint32_t sm_l0;   // word offset of L0
 };
 
-// value of 16-bit entry `e` (global entry index) of each level for a full tree over n present ids
-IDC_HD uint16_t enc_tree_init_leaf(uint32_t n, uint32_t e) {
-    uint32_t lo = e * 16u;
-    if (lo >= n) return 0;
-    uint32_t c = n - lo;
-    return c >= 16u ? 0xffffu : (uint16_t)((1u << c) - 1u);
-}
-IDC_HD uint32_t enc_tree_init_count(uint32_t n, uint32_t e, uint32_t span) {
-    uint64_t lo = (uint64_t)e * span;
-    if (lo >= n) return 0;
-    uint64_t c = n - lo;
-    return (uint32_t)(c >= span ? span : c);
+// ids present in records [0, r) of a full unit of n ids
+IDC_HD uint32_t enc_full_before(uint32_t n, uint32_t r) {
+    uint64_t c = (uint64_t)r * kRecIds;
+    return (uint32_t)(c < n ? c : n);
 }
 
 // fill this lane's shared-memory levels for a full set of n ids
-IDC_HD void enc_tree_init_sm(const EncTree& t, uint32_t n) {
+IDC_HD void enc_tree_init_sm(EncTree& t, uint32_t n) {
     EncTreeLayout L = enc_tree_layout(n);
-    for (uint32_t w = 0; w < 8u; w++)
-        t.sm[(size_t)w * t.stride] = enc_tree_init_count(n, 2 * w, 4096u) | (enc_tree_init_count(n, 2 * w + 1, 4096u) << 16);
-    for (uint32_t w = 0; w < 8u * L.l1_sectors; w++)
-        t.sm[(size_t)(8u + w) * t.stride] = enc_tree_init_count(n, 2 * w, 256u) | (enc_tree_init_count(n, 2 * w + 1, 256u) << 16);
+    t.sm_l0 = 16u + 8u * L.supers;
+    for (uint32_t w = 0; w < 16u; w++) t.sm[(size_t)w * t.stride] = enc_full_before(n, w * kRecPerSuper);
+    for (uint32_t sb = 0; sb < L.supers; sb++) {
+        uint32_t base = enc_full_before(n, sb * kRecPerSuper);
+        for (uint32_t w = 0; w < 8u; w++) {
+            uint32_t lo = enc_full_before(n, sb * kRecPerSuper + (2 * w) * kRecPerPair) - base;
+            uint32_t hi = enc_full_before(n, sb * kRecPerSuper + (2 * w + 1) * kRecPerPair) - base;
+            t.sm[(size_t)(16u + 8u * sb + w) * t.stride] = lo | (hi << 16);
+        }
+    }
+    for (uint32_t w = 0; w < L.l0_words; w++) {
+        uint32_t word = 0;
+        for (uint32_t q = 0; q < kRecPerWord; q++) {
+            uint32_t r = w * kRecPerWord + q;
+            uint32_t c = enc_full_before(n, r + 1) - enc_full_before(n, r);
+            word |= c << (5u * q);
+        }
+        t.sm[(size_t)(t.sm_l0 + w) * t.stride] = word;
+    }
 }
 
-// returns the position (in the id-sorted unit) of the k-th remaining id and removes it
-IDC_HD uint32_t enc_tree_select_remove(const EncTree& t, uint32_t k) {
-    Sector s2 = ld_sector_sm(t.sm, 0, t.stride);
-    uint32_t j2 = sector_select(s2, k);
-    Sector s1 = ld_sector_sm(t.sm, 8u + 8u * j2, t.stride);
-    uint32_t j1 = sector_select(s1, k);
-    uint32_t leaf_sector = j2 * 16u + j1;
-    Sector s0 = ld_sector(t.leaf, leaf_sector);
-    uint32_t j0 = sector_select_masks(s0, k);
-    uint32_t b = select16(sector_get(s0, j0), k);
-    // removal: clear the bit (fire-and-forget RED.AND), decrement the two counts on the path
-    uint32_t* leaf_word = reinterpret_cast<uint32_t*>(t.leaf) + leaf_sector * 8u + (j0 >> 1);
-    red_and32(leaf_word, ~(1u << (b + 16u * (j0 & 1u))));
-    t.sm[(size_t)(8u + 8u * j2 + (j1 >> 1)) * t.stride] -= 1u << (16u * (j1 & 1u));
-    t.sm[(size_t)(j2 >> 1) * t.stride] -= 1u << (16u * (j2 & 1u));
-    return (leaf_sector * 16u + j0) * 16u + b;
+// record word 0 (mask) and words 1..31 (ids) for record r of a unit of n ascending ids
+template <typename IdT>
+IDC_HD uint32_t enc_record_word(const IdT* src, uint32_t n, uint32_t r, uint32_t w) {
+    uint32_t first = r * kRecIds;
+    uint32_t have = first < n ? (n - first < kRecIds ? n - first : kRecIds) : 0u;
+    if (w == 0) return have ? (0xffffffffu >> (32u - have)) : 0u;
+    return (w - 1u) < have ? (uint32_t)load_id_raw(src + first + (w - 1u)) : 0xffffffffu;
+}
+
+// In a sector of 16 exclusive cumulative counts (E[0] = 0, non-decreasing, padding repeats the total):
+// j = last entry with E[j] <= k.
+IDC_HD uint32_t cum_sector_find(const Sector& s, uint32_t k) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        c += (s.w[w] & 0xffffu) <= k ? 1u : 0u;
+        c += (s.w[w] >> 16) <= k ? 1u : 0u;
+    }
+    return c - 1u;  // entry 0 always counts
+}
+
+// subtract one from every entry above j (the words are already in registers)
+IDC_HD void cum_sector_dec_above(uint32_t* sm, uint32_t word0, uint32_t stride, const Sector& s, uint32_t j) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        uint32_t dec = ((uint32_t)(2 * w) > j ? 1u : 0u) | ((uint32_t)(2 * w + 1) > j ? 0x10000u : 0u);
+        if (dec) sm[(size_t)(word0 + w) * stride] = s.w[w] - dec;
+    }
+}
+
+// position of the r-th (0-based) set bit of a 32-bit mask with more than r ones
+IDC_HD uint32_t select32(uint32_t m, uint32_t r) {
+    uint32_t pos = 0, c;
+    c = (uint32_t)popc32(m & 0xffffu);
+    if (r >= c) { r -= c; pos += 16; m >>= 16; }
+    c = (uint32_t)popc32(m & 0xffu);
+    if (r >= c) { r -= c; pos += 8; m >>= 8; }
+    c = (uint32_t)popc32(m & 0xfu);
+    if (r >= c) { r -= c; pos += 4; m >>= 4; }
+    c = (uint32_t)popc32(m & 0x3u);
+    if (r >= c) { r -= c; pos += 2; m >>= 2; }
+    if (r >= (m & 1u)) pos += 1;
+    return pos;
+}
+
+struct RecLine {
+    uint32_t w[32];
+};
+
+IDC_HD RecLine ld_record(const uint32_t* rec) {
+    RecLine r;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        Sector s = ld_sector(reinterpret_cast<const uint16_t*>(rec), (uint32_t)q);
+#pragma unroll
+        for (int j = 0; j < 8; j++) r.w[8 * q + j] = s.w[j];
+    }
+    return r;
+}
+
+// words[1 + pos] without dynamic register indexing: a 5-level select tree
+IDC_HD uint32_t rec_pick(const RecLine& r, uint32_t pos) {
+    uint32_t idx = pos + 1u;  // 1..31
+    uint32_t a16[16], a8[8], a4[4], a2[2];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a16[i] = (idx & 1u) ? r.w[2 * i + 1] : r.w[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a8[i] = (idx & 2u) ? a16[2 * i + 1] : a16[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a4[i] = (idx & 4u) ? a8[2 * i + 1] : a8[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) a2[i] = (idx & 8u) ? a4[2 * i + 1] : a4[2 * i];
+    return (idx & 16u) ? a2[1] : a2[0];
+}
+
+// Select the k-th remaining id (0-based) of the unit, remove it; returns its position in the sorted unit and
+// the id itself (read from the record line that had to be fetched anyway).
+IDC_HD uint32_t enc_tree_select_remove(const EncTree& t, uint32_t k, uint32_t& id_out) {
+    const uint32_t st = t.stride;
+    // L2: sixteen 32-bit exclusive cumulative counts (entry 0 is 0; entries past the last superblock hold the total)
+    uint32_t e2[16];
+#pragma unroll
+    for (int w = 0; w < 16; w++) e2[w] = t.sm[(size_t)w * st];
+    uint32_t sb = 0;
+#pragma unroll
+    for (int w = 1; w < 16; w++) sb += e2[w] <= k ? 1u : 0u;
+    {
+        uint32_t base = e2[0];
+#pragma unroll
+        for (int w = 1; w < 16; w++) base = (sb == (uint32_t)w) ? e2[w] : base;
+        k -= base;
+    }
+    Sector s1 = ld_sector_sm(t.sm, 16u + 8u * sb, st);
+    const uint32_t p = cum_sector_find(s1, k);
+    k -= sector_get(s1, p);
+    // two L0 words = twelve 5-bit counts: first record whose inclusive prefix exceeds k
+    const uint32_t l0 = t.sm_l0 + (sb * 16u + p) * 2u;
+    const uint32_t wa = t.sm[(size_t)l0 * st], wb = t.sm[(size_t)(l0 + 1u) * st];
+    uint32_t run = 0, r = 0, sub = 0;
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+        uint32_t c = ((q < 6 ? wa : wb) >> (5 * (q % 6))) & 31u;
+        run += c;
+        bool le = run <= k;
+        r += le ? 1u : 0u;
+        sub = le ? run : sub;
+    }
+    k -= sub;
+    r = r < 11u ? r : 11u;
+    const uint32_t rg = (sb * 16u + p) * kRecPerPair + r;  // record index inside the unit
+    uint32_t* rec = t.rec + (size_t)rg * 32u;
+    RecLine line = ld_record(rec);
+    const uint32_t pos = select32(line.w[0], k);
+    id_out = rec_pick(line, pos);
+    // removal
+    red_and32(rec, ~(1u << pos));
+    t.sm[(size_t)(l0 + (r >= 6u ? 1u : 0u)) * st] = (r >= 6u ? wb : wa) - (1u << (5u * (r >= 6u ? r - 6u : r)));
+    cum_sector_dec_above(t.sm, 16u + 8u * sb, st, s1, p);
+#pragma unroll
+    for (int w = 1; w < 16; w++)
+        if ((uint32_t)w > sb) t.sm[(size_t)w * st] = e2[w] - 1u;
+    return rg * kRecIds + pos;
 }
 
 // ---------------------------------------------------- decoder: insert-rank --

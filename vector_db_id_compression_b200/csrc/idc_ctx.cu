@@ -106,7 +106,11 @@ int idc_ctx::fork(int n) {
     while ((int)aux.size() < n) {
         cudaStream_t s;
         cudaEvent_t e;
-        IDC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        // aux[0] carries the longest units, whose serial chains bound the kernel: highest priority first
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        int prio = std::min(least, greatest + (int)aux.size());
+        IDC_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio));
         IDC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         aux.push_back(s);
         aux_done.push_back(e);

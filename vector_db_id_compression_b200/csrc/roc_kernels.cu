@@ -12,7 +12,7 @@
 //   k_unit_meta     per unit min/max id, precision rule, sortedness / width checks
 //   k_row_counts    NSG rows: length = entries before the first -1
 //   k_sort_units    per unit bitonic sort (only when the input is not sorted)
-//   k_enc_tree_init order-statistic tree of the encoder, all ids present
+//   k_enc_records   the unit's ids re-laid as 128-byte records (presence mask + 31 ids)
 //   k_roc_encode    the coder
 //   k_roc_compact   gather the per-unit scratch streams into the packed blob
 //   k_roc_decode    the decoder
@@ -100,37 +100,41 @@ struct EncArgs {
     uint32_t sm_words;           // shared-memory words per lane (upper tree levels)
     uint32_t slot_base;          // this launch covers launch slots [slot_base, slot_end)
     uint32_t slot_end;
+    uint32_t lanes;              // units per warp (32, or fewer for the longest units: less divergence per step)
 };
 
-// one warp per unit, lanes stride over the leaf bitmap's 16-bit entries
-__global__ void __launch_bounds__(kThreads) k_enc_tree_init(EncArgs a) {
+// Re-lay every unit's ascending ids as 128-byte records (mask word + 31 ids, idc_core.cuh): one warp per unit,
+// one record per warp iteration (lane w writes word w: coalesced 128-byte stores, coalesced id reads).
+template <typename IdT>
+__global__ void __launch_bounds__(kThreads) k_enc_records(EncArgs a) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.nunits) return;
     uint32_t n = a.unit_n[warp];
     if (n == 0) return;
-    uint16_t* leaf = reinterpret_cast<uint16_t*>(a.ws + a.ws_off[warp]);
-    EncTreeLayout L = enc_tree_layout(n);
-    for (uint32_t e = lane; e < L.leaf_sectors * 16u; e += 32) leaf[e] = enc_tree_init_leaf(n, e);
+    const IdT* src = reinterpret_cast<const IdT*>(a.ids) + a.unit_src[warp];
+    uint32_t* rec = reinterpret_cast<uint32_t*>(a.ws + a.ws_off[warp]);
+    uint32_t records = enc_tree_layout(n).records;
+    for (uint32_t r = 0; r < records; r++) rec[(size_t)r * 32u + lane] = enc_record_word(src, n, r, lane);
 }
 
 template <typename IdT>
 __global__ void __launch_bounds__(kThreads) k_roc_encode(EncArgs a) {
     extern __shared__ uint32_t smem[];
-    uint32_t slot = a.slot_base + blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = slot < a.slot_end;
+    const uint32_t lane = threadIdx.x & 31, gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t slot = a.slot_base + gwarp * a.lanes + lane;
+    bool valid = lane < a.lanes && slot < a.slot_end;
     uint32_t u = valid ? a.perm[slot] : 0u;
     uint32_t n = valid ? a.unit_n[u] : 0u;
     EncLane<IdT> L;
     L.n = n;
     L.prec = valid ? (int)a.unit_prec[u] : 0;
     uint64_t src_off = valid ? a.unit_src[u] : 0ull;
-    L.src = reinterpret_cast<const IdT*>(a.ids) + src_off;
     L.sort_idx = a.sort_idx ? a.sort_idx + src_off : nullptr;
     L.order = a.order ? a.order + src_off : nullptr;
     L.pos_base = valid ? a.unit_posbase[u] : 0u;
-    L.tree.leaf = reinterpret_cast<uint16_t*>(a.ws + (valid ? a.ws_off[u] : 0ull));
-    L.tree.sm = smem + (threadIdx.x >> 5) * (a.sm_words * 32u) + (threadIdx.x & 31);
-    L.tree.stride = 32u;
+    L.tree.rec = reinterpret_cast<uint32_t*>(a.ws + (valid ? a.ws_off[u] : 0ull));
+    L.tree.sm = smem + (threadIdx.x >> 5) * (a.sm_words * a.lanes) + (valid ? lane : 0u);
+    L.tree.stride = a.lanes;
     if (n) enc_tree_init_sm(L.tree, n);
     L.st.head = kRansL;
     L.st.words = a.scratch + (valid ? a.scratch_off[u] : 0ull);
@@ -185,13 +189,15 @@ struct DecArgs {
     uint32_t sm_words;          // shared-memory words per lane (all count levels)
     uint32_t slot_base;         // this launch covers launch slots [slot_base, slot_end)
     uint32_t slot_end;
+    uint32_t lanes;             // units per warp
 };
 
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
     extern __shared__ uint32_t smem[];
-    uint32_t slot = a.slot_base + blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = slot < a.slot_end;
+    const uint32_t lane = threadIdx.x & 31, gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t slot = a.slot_base + gwarp * a.lanes + lane;
+    bool valid = lane < a.lanes && slot < a.slot_end;
     uint32_t u = valid ? a.sel_unit[slot] : 0u;
     uint32_t n = valid ? a.unit_n[u] : 0u;
     DecLane<OutT> L;
@@ -206,9 +212,10 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
     L.st.has_ov = 0;
     L.st.draws = 0;
     L.st.status = 0;
-    uint32_t* sm = smem + (threadIdx.x >> 5) * (a.sm_words * 32u) + (threadIdx.x & 31);
-    for (uint32_t w = 0; w < a.sm_words; w++) sm[w * 32u] = 0u;
-    L.tree = dec_tree_at(a.ws + (valid ? a.sel_ws[slot] : 0ull), sm, 32u, n ? n : 1u, valid ? a.unit_lo[u] : 0u,
+    uint32_t* sm = smem + (threadIdx.x >> 5) * (a.sm_words * a.lanes) + (valid ? lane : 0u);
+    if (valid)
+        for (uint32_t w = 0; w < a.sm_words; w++) sm[w * a.lanes] = 0u;
+    L.tree = dec_tree_at(a.ws + (valid ? a.sel_ws[slot] : 0ull), sm, a.lanes, n ? n : 1u, valid ? a.unit_lo[u] : 0u,
                          valid ? a.unit_hi[u] : 0u);
     uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
     for (uint32_t i = 0; i < tmax; ++i) {
@@ -264,8 +271,16 @@ std::vector<SizeClass> size_classes(uint64_t nslots, NofSlot n_of_slot) {
 }
 
 // warps per CTA such that several CTAs fit an SM's 227 KB of shared memory
-inline uint32_t warps_for(uint32_t sm_words) {
-    size_t per_warp = (size_t)sm_words * 128;
+inline uint32_t lanes_for(uint32_t max_n) {
+    if (const char* e = getenv("IDC_LONG_LANES")) {
+        int v = atoi(e);
+        if (max_n > 16384 && (v == 4 || v == 8 || v == 16 || v == 32)) return (uint32_t)v;
+    }
+    return 32u;  // measured: fewer units per warp did not shorten the long chains (profiles/README.md)
+}
+
+inline uint32_t warps_for(uint32_t sm_words, uint32_t lanes = 32) {
+    size_t per_warp = (size_t)sm_words * 4 * lanes;
     if (per_warp * 4 <= 56 * 1024) return 4;
     if (per_warp * 2 <= 56 * 1024) return 2;
     return 1;
@@ -397,16 +412,19 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
     for (uint64_t u = 0; u < nu; u++) max_n = std::max(max_n, b->unit_n[u]);
     b->max_n = max_n;
     {
-        LaunchScope ls(c, "k_enc_tree_init");
-        k_enc_tree_init<<<grid_for(nu * 32), kThreads, 0, c->stream>>>(e);
+        LaunchScope ls(c, "k_enc_records");
+        if (enc_id_bytes == 8)
+            k_enc_records<int64_t><<<grid_for(nu * 32), kThreads, 0, c->stream>>>(e);
+        else
+            k_enc_records<uint32_t><<<grid_for(nu * 32), kThreads, 0, c->stream>>>(e);
     }
-    IDC_TRY(check_last_launch("k_enc_tree_init"));
+    IDC_TRY(check_last_launch("k_enc_records"));
     {
         auto cls = size_classes(nu, [&](uint64_t slot) { return b->unit_n[perm[slot]]; });
         size_t max_smem = 0;
         for (auto& k : cls) {
-            uint32_t w = enc_tree_sm_words(k.max_n ? k.max_n : 1u);
-            max_smem = std::max(max_smem, (size_t)w * 128 * warps_for(w));
+            uint32_t w = enc_tree_sm_words(k.max_n ? k.max_n : 1u), ln = lanes_for(k.max_n);
+            max_smem = std::max(max_smem, (size_t)w * 4 * ln * warps_for(w, ln));
         }
         IDC_CUDA(cudaFuncSetAttribute(k_roc_encode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         IDC_CUDA(cudaFuncSetAttribute(k_roc_encode<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
@@ -417,9 +435,11 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
             ek.slot_base = cls[k].slot_base;
             ek.slot_end = cls[k].slot_end;
             ek.sm_words = enc_tree_sm_words(cls[k].max_n ? cls[k].max_n : 1u);
-            uint32_t warps = warps_for(ek.sm_words), threads = warps * 32;
-            uint32_t slots = ek.slot_end - ek.slot_base, grid = (slots + threads - 1) / threads;
-            size_t smem = (size_t)ek.sm_words * 128 * warps;
+            ek.lanes = lanes_for(cls[k].max_n);
+            uint32_t warps = warps_for(ek.sm_words, ek.lanes), threads = warps * 32;
+            uint32_t slots = ek.slot_end - ek.slot_base, nwarps = (slots + ek.lanes - 1) / ek.lanes;
+            uint32_t grid = (nwarps + warps - 1) / warps;
+            size_t smem = (size_t)ek.sm_words * 4 * ek.lanes * warps;
             if (enc_id_bytes == 8)
                 k_roc_encode<int64_t><<<grid, threads, smem, c->aux[k]>>>(ek);
             else
@@ -559,8 +579,8 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
         auto cls = size_classes(nsel, n_of_slot);
         size_t max_smem = 0;
         for (auto& k : cls) {
-            uint32_t w = dec_tree_sm_words(k.max_n ? k.max_n : 1u);
-            max_smem = std::max(max_smem, (size_t)w * 128 * warps_for(w));
+            uint32_t w = dec_tree_sm_words(k.max_n ? k.max_n : 1u), ln = lanes_for(k.max_n);
+            max_smem = std::max(max_smem, (size_t)w * 4 * ln * warps_for(w, ln));
         }
         (void)max_n;
         IDC_CUDA(cudaFuncSetAttribute(k_roc_decode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
@@ -572,9 +592,11 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
             ak.slot_base = cls[k].slot_base;
             ak.slot_end = cls[k].slot_end;
             ak.sm_words = dec_tree_sm_words(cls[k].max_n ? cls[k].max_n : 1u);
-            uint32_t warps = warps_for(ak.sm_words), threads = warps * 32;
-            uint32_t slots = ak.slot_end - ak.slot_base, grid = (slots + threads - 1) / threads;
-            size_t smem = (size_t)ak.sm_words * 128 * warps;
+            ak.lanes = lanes_for(cls[k].max_n);
+            uint32_t warps = warps_for(ak.sm_words, ak.lanes), threads = warps * 32;
+            uint32_t slots = ak.slot_end - ak.slot_base, nwarps = (slots + ak.lanes - 1) / ak.lanes;
+            uint32_t grid = (nwarps + warps - 1) / warps;
+            size_t smem = (size_t)ak.sm_words * 4 * ak.lanes * warps;
             if (id_bytes == 8)
                 k_roc_decode<int64_t><<<grid, threads, smem, c->aux[k]>>>(ak);
             else

@@ -13,7 +13,6 @@ template <typename IdT>
 struct EncLane {
     EncState st;
     EncTree tree;
-    const IdT* src;            // the unit's ids, ascending
     const uint32_t* sort_idx;  // original position of each sorted id inside its list (null: input was sorted)
     uint32_t* order;           // sample order out (null: not wanted)
     uint32_t pos_base;         // position of the unit's first id inside its list
@@ -37,9 +36,9 @@ IDC_HD uint64_t load_id(const IdT* p) {
 template <typename IdT>
 IDC_HD void enc_lane_step(EncLane<IdT>& L, uint32_t nmax, uint64_t rcp, uint32_t q31, const uint32_t* mt) {
     uint32_t k = enc_pop_uniform(L.st, nmax, rcp, q31, mt);
-    uint32_t pos = enc_tree_select_remove(L.tree, k);
-    uint64_t id = load_id(L.src + pos);
-    enc_push_id(L.st, id, L.prec);
+    uint32_t id32;
+    uint32_t pos = enc_tree_select_remove(L.tree, k, id32);
+    enc_push_id(L.st, (uint64_t)id32, L.prec);
     if (L.order) {
         uint32_t o = L.sort_idx ? L.sort_idx[pos] : L.pos_base + pos;
         L.order[L.n - nmax] = o;
