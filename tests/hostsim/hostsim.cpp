@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY. Compiles the lane-level codec functions of
-// vector_db_id_compression_b200/csrc (idc_core.cuh, roc_lane.cuh, ef_core.cuh)
+// vector_db_id_compression_b200/csrc (idc_core.cuh, roc_group.cuh, ef_core.cuh)
 // with g++ so their logic can be checked against the oracle in the CPU test
 // suite (no GPU in the build container). Not part of libidcodec.so; nothing in
 // the product loads it.
@@ -8,7 +8,8 @@
 #include <random>
 #include <vector>
 
-#include "../../vector_db_id_compression_b200/csrc/roc_lane.cuh"
+#include "../../vector_db_id_compression_b200/csrc/roc_group.cuh"
+#include "grp_emu.h"
 #include "../../vector_db_id_compression_b200/csrc/ef_core.cuh"
 
 using namespace idc;
@@ -18,53 +19,77 @@ static void tables(uint32_t* mt) {
     for (int i = 0; i < kMtWords; i++) mt[i] = (uint32_t)g();
 }
 
-extern "C" {
-
-// ids ascending. Returns words used (or -1), fills head/words/order/status.
-int64_t sim_roc_encode(uint32_t n, const uint64_t* ids, int prec, uint64_t* head_out, uint32_t* words_out,
-                       uint32_t cap, uint32_t* order_out, uint32_t* status_out) {
+// ---- the group design of roc_group.cuh: G host threads play the G lanes of the group that owns the unit
+template <int G>
+static int64_t group_encode(uint32_t n, const uint64_t* ids, int prec, uint64_t* head_out, uint32_t* words_out,
+                            uint32_t cap, uint32_t* order_out, uint32_t* status_out) {
     uint32_t mt[kMtWords];
     tables(mt);
     std::vector<uint8_t> ws(enc_tree_bytes(n) + 256, 0);
-    std::vector<uint32_t> sm(enc_tree_sm_words(n) + 8, 0);
-    EncLane<int64_t> L;
-    L.tree.rec = reinterpret_cast<uint32_t*>(ws.data());
-    L.tree.sm = sm.data();
-    L.tree.stride = 1;
+    std::vector<uint32_t> sm(genc_sm_words(n) + 8, 0);
+    uint32_t* rec = reinterpret_cast<uint32_t*>(ws.data());
     EncTreeLayout lay = enc_tree_layout(n);
     for (uint32_t r = 0; r < lay.records; r++)
         for (uint32_t w = 0; w < 32; w++)
-            L.tree.rec[r * 32 + w] = enc_record_word(reinterpret_cast<const int64_t*>(ids), n, r, w);
-    enc_tree_init_sm(L.tree, n);
-    L.st = EncState{kRansL, words_out, 0, cap, 0, 0};
-    L.sort_idx = nullptr;
-    L.order = order_out;
-    L.pos_base = 0;
-    L.n = n;
-    L.prec = prec;
-    for (uint32_t t = n; t >= 1; --t)
-        enc_lane_step(L, t, ~0ull / t, (uint32_t)((1ull << 31) / t), mt);
-    *head_out = L.st.head;
-    *status_out = L.st.status;
-    return L.st.status & kStScratch ? -1 : (int64_t)L.st.sp;
+            rec[r * 32 + w] = enc_record_word(reinterpret_cast<const int64_t*>(ids), n, r, w);
+    int64_t result = 0;
+    run_group(G, [&](const HostGrp& g) {
+        GEncUnit<G, int64_t> U;
+        U.tree.rec = rec;
+        U.tree.sm = SmView{sm.data(), 1, 0};
+        genc_tree_init<G>(g, U.tree, n);
+        g.sync();
+        U.st = EncState{kRansL, words_out, 0, cap, 0, 0, g.sub == 0 ? 1u : 0u};
+        U.sort_idx = nullptr;
+        U.order = order_out;
+        U.pos_base = 0;
+        U.n = n;
+        U.prec = prec;
+        for (uint32_t t = n; t >= 1; --t)
+            genc_step<G>(g, U, t, ~0ull / t, (uint32_t)((1ull << 31) / t), mt, true);
+        if (g.sub == 0) {
+            *head_out = U.st.head;
+            *status_out = U.st.status;
+            result = U.st.status & kStScratch ? -1 : (int64_t)U.st.sp;
+        }
+    });
+    return result;
 }
 
-void sim_roc_decode(uint64_t head, const uint32_t* words, uint32_t nwords, uint32_t n, int prec, uint32_t lo,
-                    uint32_t hi, int64_t* out, uint32_t* status_out, uint32_t force_degenerate) {
+template <int G>
+static void group_decode(uint64_t head, const uint32_t* words, uint32_t nwords, uint32_t n, int prec, uint32_t lo,
+                         uint32_t hi, int64_t* out, uint32_t* status_out, uint32_t force_degenerate) {
     uint32_t mt[kMtWords];
     tables(mt);
-    std::vector<uint8_t> ws(dec_tree_bytes(n) + 64, 0xff);  // bucket slots pre-filled, as the device memset does
+    std::vector<uint8_t> ws(dec_tree_bytes(n) + 64, 0xff);
     std::vector<uint32_t> sm(dec_tree_sm_words(n) + 8, 0);
-    DecLane<int64_t> L;
-    L.tree = dec_tree_at(ws.data(), sm.data(), 1, n, lo, hi);
-    if (force_degenerate) L.tree.ovf_cap = force_degenerate - 1;  // shrink the overflow list to exercise the fallback
-    L.st = DecState{head, words, nwords, 0, 0, 0, 0};
-    L.out = out;
-    L.n = n;
-    L.prec = prec;
-    for (uint32_t i = 0; i < n; i++)
-        dec_lane_step(L, i, (uint32_t)((1ull << 31) / (i + 1)), mt);
-    *status_out = L.st.status;
+    run_group(G, [&](const HostGrp& g) {
+        GDecUnit<int64_t> U;
+        U.tree = gdec_tree_at(ws.data(), SmView{sm.data(), 1, 0}, n, lo, hi);
+        if (force_degenerate) U.tree.ovf_cap = force_degenerate - 1;
+        dec_state_init(U.st, head, words, nwords);
+        U.out = out;
+        U.n = n;
+        U.prec = prec;
+        for (uint32_t i = 0; i < n; i++)
+            gdec_step<G>(g, U, i, (uint32_t)((1ull << 31) / (i + 1)), mt, true);
+        if (g.sub == 0) *status_out = U.st.status;
+    });
+}
+
+extern "C" {
+
+int64_t sim_group_encode(int G, uint32_t n, const uint64_t* ids, int prec, uint64_t* head_out, uint32_t* words_out,
+                         uint32_t cap, uint32_t* order_out, uint32_t* status_out) {
+    return G == 8 ? group_encode<8>(n, ids, prec, head_out, words_out, cap, order_out, status_out)
+                  : group_encode<4>(n, ids, prec, head_out, words_out, cap, order_out, status_out);
+}
+void sim_group_decode(int G, uint64_t head, const uint32_t* words, uint32_t nwords, uint32_t n, int prec, uint32_t lo,
+                      uint32_t hi, int64_t* out, uint32_t* status_out, uint32_t force_degenerate) {
+    if (G == 8)
+        group_decode<8>(head, words, nwords, n, prec, lo, hi, out, status_out, force_degenerate);
+    else
+        group_decode<4>(head, words, nwords, n, prec, lo, hi, out, status_out, force_degenerate);
 }
 
 uint64_t sim_dec_tree_bytes(uint32_t n) { return dec_tree_bytes(n); }

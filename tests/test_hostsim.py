@@ -1,4 +1,4 @@
-"""CPU: the lane-level device code (csrc/idc_core.cuh, roc_lane.cuh, ef_core.cuh), compiled for the host by
+"""CPU: the device code of the codec steps (csrc/idc_core.cuh, roc_group.cuh, ef_core.cuh), compiled for the host by
 tests/hostsim, against the oracle. This checks the exact arithmetic and the order-statistic structures the
 CUDA kernels run per lane -- without a GPU. The GPU parity tests proper are tests/test_gpu_parity.py."""
 import ctypes as C
@@ -20,15 +20,16 @@ i64p = np.ctypeslib.ndpointer(np.int64, flags="C")
 def sim():
     so = HERE / "libhostsim.so"
     cc = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
-    subprocess.run([cc, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(so),
+    subprocess.run([cc, "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-o", str(so),
                     str(HERE / "hostsim.cpp")], check=True)
     lib = C.CDLL(str(so))
-    lib.sim_roc_encode.restype = C.c_int64
-    lib.sim_roc_encode.argtypes = [C.c_uint32, u64p, C.c_int, C.POINTER(C.c_uint64), u32p, C.c_uint32, u32p,
-                                   C.POINTER(C.c_uint32)]
-    lib.sim_roc_decode.restype = None
-    lib.sim_roc_decode.argtypes = [C.c_uint64, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, i64p,
-                                   C.POINTER(C.c_uint32), C.c_uint32]
+    enc_args = [C.c_uint32, u64p, C.c_int, C.POINTER(C.c_uint64), u32p, C.c_uint32, u32p, C.POINTER(C.c_uint32)]
+    dec_args = [C.c_uint64, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, i64p,
+                C.POINTER(C.c_uint32), C.c_uint32]
+    lib.sim_group_encode.restype = C.c_int64
+    lib.sim_group_encode.argtypes = [C.c_int] + enc_args
+    lib.sim_group_decode.restype = None
+    lib.sim_group_decode.argtypes = [C.c_int] + dec_args
     lib.sim_ef_shape.argtypes = [C.c_uint64, C.c_uint64, u64p]
     lib.sim_ef_encode.argtypes = [i64p, C.c_uint64, C.c_uint64, u64p, u64p, u32p]
     lib.sim_ef_select.restype = C.c_uint64
@@ -36,23 +37,23 @@ def sim():
     return lib
 
 
-def sim_enc(lib, ids, p):
+def grp_enc(lib, G, ids, p):
     ids = np.sort(np.asarray(ids, dtype=np.uint64))
     n = ids.size
     w = np.zeros(n + 4, np.uint32)
     o = np.zeros(max(n, 1), np.uint32)
     h, st = C.c_uint64(), C.c_uint32()
-    r = lib.sim_roc_encode(n, ids, p, C.byref(h), w, n + 4, o, C.byref(st))
+    r = lib.sim_group_encode(G, n, ids, p, C.byref(h), w, n + 4, o, C.byref(st))
     assert r >= 0, st.value
     return h.value, w[:r].copy(), o[:n], st.value
 
 
-def sim_dec(lib, h, w, n, p, lo=0, hi=None, force=0):
+def grp_dec(lib, G, h, w, n, p, lo=0, hi=None, force=0):
     if hi is None:
         hi = (1 << p) - 1 if p < 32 else 0xFFFFFFFF
     out = np.zeros(max(n, 1), np.int64)
     st = C.c_uint32()
-    lib.sim_roc_decode(h, w if w.size else np.zeros(1, np.uint32), w.size, n, p, lo, hi, out, C.byref(st), force)
+    lib.sim_group_decode(G, h, w if w.size else np.zeros(1, np.uint32), w.size, n, p, lo, hi, out, C.byref(st), force)
     return out[:n], st.value
 
 
@@ -62,45 +63,50 @@ def rand_set(rng, n, p):
     return np.unique(rng.integers(0, 1 << p, size=n, dtype=np.uint64))
 
 
-def test_lane_codec_random_sets(sim):
-    rng = np.random.default_rng(0)
-    for trial in range(1200):
+@pytest.mark.parametrize("G", [4, 8])
+def test_group_codec_random_sets(sim, G):
+    """csrc/roc_group.cuh (G lanes per unit, lanes emulated by host threads) against the oracle."""
+    rng = np.random.default_rng(10 + G)
+    for trial in range(400):
         p = int(rng.integers(1, 33))
-        n = min(int(rng.integers(1, 700)), 1 << p)
+        n = min(int(rng.integers(1, 900)), 1 << p)
         if rng.random() < 0.3:
             p = max(1, int(np.ceil(np.log2(n + 1))))
         ids = rand_set(rng, n, p)
         n = ids.size
         h, w, o = oracle.port.encode(ids, p, want_order=True)
         d = oracle.port.decode(h, w, n, p)
-        h2, w2, o2, st = sim_enc(sim, ids, p)
-        assert (h, w.tolist()) == (h2, w2.tolist()) and st == 0
+        h2, w2, o2, st = grp_enc(sim, G, ids, p)
+        assert (h, w.tolist()) == (h2, w2.tolist()) and st == 0, (trial, n, p)
         srt = np.sort(ids.astype(np.uint64))
         assert np.array_equal(srt[o2], d)
         mode = trial % 3
         if mode == 0:
-            d2, st = sim_dec(sim, h, w, n, p)
+            d2, st = grp_dec(sim, G, h, w, n, p)
         elif mode == 1:
-            d2, st = sim_dec(sim, h, w, n, p, lo=int(srt[0]), hi=int(srt[-1]))
-        else:  # tiny overflow list: exercises the brute-force fallback
-            d2, st = sim_dec(sim, h, w, n, p, lo=int(srt[0]), hi=int(srt[-1]), force=1 + int(rng.integers(0, 3)))
-        assert np.array_equal(d2.astype(np.uint64), d)
+            d2, st = grp_dec(sim, G, h, w, n, p, lo=int(srt[0]), hi=int(srt[-1]))
+        else:
+            d2, st = grp_dec(sim, G, h, w, n, p, lo=int(srt[0]), hi=int(srt[-1]), force=1 + int(rng.integers(0, 3)))
+        assert np.array_equal(d2.astype(np.uint64), d), (trial, n, p, mode)
         assert st & ~32 == 0
 
 
-@pytest.mark.parametrize("n,p", [(15259, 30), (65536, 17), (65536, 31), (65000, 20), (4097, 13), (4096, 12), (257, 9)])
-def test_lane_codec_large_units(sim, n, p):
+@pytest.mark.parametrize("G,n,p", [(4, 15259, 30), (4, 65536, 17), (8, 65536, 31), (4, 65000, 20), (8, 4097, 13), (4, 2233, 12)])
+def test_group_codec_large_units(sim, G, n, p):
     rng = np.random.default_rng(n + p)
     ids = rng.choice(1 << p, size=n, replace=False) if p <= 24 else rand_set(rng, n, p)
     n = ids.size
     h, w = oracle.port.encode(ids, p)
-    h2, w2, _, st = sim_enc(sim, ids, p)
+    h2, w2, _, st = grp_enc(sim, G, ids, p)
     assert (h, st) == (h2, 0) and np.array_equal(w, w2)
-    d2, st = sim_dec(sim, h, w, n, p)
+    d2, st = grp_dec(sim, G, h, w, n, p)
     assert np.array_equal(d2.astype(np.uint64), oracle.port.decode(h, w, n, p)) and st == 0
 
 
-def test_lane_codec_golden_and_adversarial(sim, roc_golden):
+@pytest.mark.parametrize("G", [4, 8])
+def test_group_codec_golden_and_adversarial(sim, roc_golden, G):
+    sim_enc = lambda lib, ids, p: grp_enc(lib, G, ids, p)
+    sim_dec = lambda lib, h, w, n, p, **kw: grp_dec(lib, G, h, w, n, p, **kw)
     for c in roc_golden:
         if c["p"] > 32:
             continue

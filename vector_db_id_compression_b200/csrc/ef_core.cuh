@@ -14,7 +14,7 @@
 #pragma once
 
 #include "idc_core.cuh"
-#include "roc_lane.cuh"
+#include "idc_core.cuh"
 
 namespace idc {
 

@@ -1,8 +1,9 @@
-// idc_core.cuh -- lane-level building blocks of the ROC codec.
+// idc_core.cuh -- building blocks of the ROC codec: the exact rANS arithmetic of the reference, and the layouts
+// of the order-statistic workspaces. The per-step bodies that use them are in roc_group.cuh.
 //
 // Everything here is written once as IDC_HD (host + device) code: the CUDA
-// kernels in roc_kernels.cu run one rANS stream per lane ("32-way interleaved
-// across lists": 32 independent heads per warp, one per unit), and
+// kernels in roc_kernels.cu run one rANS stream per group of lanes (interleaved
+// across lists: several independent heads per warp, one per unit), and
 // tests/hostsim compiles the very same functions with g++ to check them
 // against the oracle before any GPU time is spent. The host build is test
 // infrastructure only -- the shipped library contains no CPU code path.
@@ -87,6 +88,16 @@ IDC_HD uint32_t ld_ro32(const uint32_t* p) {
     return *p;
 #endif
 }
+// the same, pinned where it is written: the compiler may neither sink it to its first use nor hoist it
+IDC_HD uint32_t ld_ro32_pinned(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
 IDC_HD void prefetch_ro(const void* p) {
 #if defined(__CUDA_ARCH__)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
@@ -146,6 +157,13 @@ IDC_HD T load_id_raw(const T* p) {
 #endif
 }
 
+template <typename IdT>
+IDC_HD uint64_t load_id(const IdT* p) {
+    IdT v = load_id_raw(p);
+    if (sizeof(IdT) == 4) return (uint64_t)(uint32_t)v;
+    return (uint64_t)v;
+}
+
 // ------------------------------------------------ sector-of-16-counts math --
 // A "sector" is 32 bytes = 16 unsigned 16-bit counts = two 16-byte loads.
 
@@ -169,81 +187,6 @@ IDC_HD Sector ld_sector(const uint16_t* base, uint32_t sector_idx) {
     return s;
 }
 
-// The upper tree levels live in shared memory, one private region per lane, interleaved by lane:
-// word w of this lane is sm[w * stride] (stride = 32 on the device: conflict-free; 1 in the host build).
-IDC_HD Sector ld_sector_sm(const uint32_t* sm, uint32_t word0, uint32_t stride) {
-    Sector s;
-#pragma unroll
-    for (int j = 0; j < 8; j++) s.w[j] = sm[(size_t)(word0 + j) * stride];
-    return s;
-}
-
-// sum of entries [0, slot), slot in 0..16
-IDC_HD uint32_t sector_sum_below(const Sector& s, uint32_t slot) {
-    uint32_t incl = (1u << slot) - 1u;  // bit t set <=> entry t counted
-    uint32_t acc = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        uint32_t two = (incl >> (2 * j)) & 3u;
-        uint32_t sel = (two & 1u) | ((two & 2u) << 7);
-        acc = dp2a(s.w[j], sel, acc);
-    }
-    return acc;
-}
-
-// entry at dynamic position slot (0..15)
-IDC_HD uint32_t sector_get(const Sector& s, uint32_t slot) {
-    uint32_t j = slot >> 1, w = s.w[0];
-#pragma unroll
-    for (int t = 1; t < 8; t++)
-        w = (j == (uint32_t)t) ? s.w[t] : w;
-    return (slot & 1u) ? (w >> 16) : (w & 0xffffu);
-}
-
-// Given counts c[0..15] and k < sum(c): the first entry j whose inclusive
-// prefix exceeds k; k is reduced by the exclusive prefix of j.
-IDC_HD uint32_t sector_select(const Sector& s, uint32_t& k) {
-    uint32_t run = 0, j = 0, sub = 0;
-#pragma unroll
-    for (int t = 0; t < 16; t++) {
-        uint32_t c = (t & 1) ? (s.w[t >> 1] >> 16) : (s.w[t >> 1] & 0xffffu);
-        run += c;
-        bool le = run <= k;
-        j += le ? 1u : 0u;
-        sub = le ? run : sub;
-    }
-    k -= sub;
-    return j < 15u ? j : 15u;
-}
-
-// same, where each 16-bit entry is a presence mask and its count is popc
-IDC_HD uint32_t sector_select_masks(const Sector& s, uint32_t& k) {
-    uint32_t run = 0, j = 0, sub = 0;
-#pragma unroll
-    for (int t = 0; t < 16; t++) {
-        uint32_t m = (t & 1) ? (s.w[t >> 1] >> 16) : (s.w[t >> 1] & 0xffffu);
-        run += (uint32_t)popc32(m);
-        bool le = run <= k;
-        j += le ? 1u : 0u;
-        sub = le ? run : sub;
-    }
-    k -= sub;
-    return j < 15u ? j : 15u;
-}
-
-// position of the r-th (0-based) set bit of a 16-bit mask
-IDC_HD uint32_t select16(uint32_t m, uint32_t r) {
-    uint32_t pos = 0, c;
-    c = (uint32_t)popc32(m & 0xffu);
-    if (r >= c) { r -= c; pos += 8; m >>= 8; }
-    c = (uint32_t)popc32(m & 0xfu);
-    if (r >= c) { r -= c; pos += 4; m >>= 4; }
-    c = (uint32_t)popc32(m & 0x3u);
-    if (r >= c) { r -= c; pos += 2; m >>= 2; }
-    if (r >= (m & 1u)) pos += 1;
-    return pos;
-}
-
 // ------------------------------------------------------ encoder rANS state --
 // The encoder's stack is append-only in the codec's valid domain; the rare
 // pop-from-stack cases are still implemented exactly (read back the word just
@@ -256,13 +199,13 @@ struct EncState {
     uint32_t cap;
     uint32_t draws;
     uint32_t status;
+    uint32_t wr;       // this lane stores the words (lane 0 of the group that owns the unit)
 };
 
 IDC_HD void enc_spill(EncState& st, uint32_t w) {
-    if (st.sp < st.cap)
-        st_ws32(st.words + st.sp, w);
-    else
-        st.status |= kStScratch;
+    const bool ok = st.sp < st.cap;
+    if (ok & (st.wr != 0u)) st_ws32(st.words + st.sp, w);
+    st.status |= ok ? 0u : kStScratch;
     st.sp++;
 }
 
@@ -315,14 +258,17 @@ IDC_HD void enc_push_bits(EncState& st, uint32_t start, uint32_t p) {
     st.head = (h << p) + start;
 }
 
-// codec.cpp:92-105
-IDC_HD void enc_push_id(EncState& st, uint64_t id, int precision) {
-#pragma unroll
-    for (int lower = 0; lower < 64; lower += 16) {
-        int p = precision - lower;
-        p = p < 0 ? 0 : (p > 16 ? 16 : p);
-        enc_push_bits(st, (uint32_t)(id >> lower) & 0xffffu, (uint32_t)p);
-    }
+// codec.cpp:92-105 for ids < 2^32 and precision <= 32 (the device domain). The reference pushes four 16-bit
+// slices, low slice first; the slices at lower = 32 and 48 then have precision 0 and add 0, but still run the
+// spill test `head >= 2^63` (codec.cpp:69) -- false after a push of an id < 2^precision, possible only for the
+// mirrored power-of-two-max_id bug, so it is one cold check here (a second one could not fire: after a spill the
+// head is below 2^32).
+IDC_HD void enc_push_id32(EncState& st, uint32_t id, int precision) {
+    const uint32_t p0 = precision < 16 ? (uint32_t)precision : 16u;
+    const uint32_t p1 = (uint32_t)precision - p0;
+    enc_push_bits(st, id & 0xffffu, p0);
+    enc_push_bits(st, id >> 16, p1);
+    if (st.head >> 63) enc_push_bits(st, 0u, 0u);
 }
 
 // ------------------------------------------------------ decoder rANS state --
@@ -332,31 +278,48 @@ IDC_HD void enc_push_id(EncState& st, uint64_t id, int precision) {
 
 struct DecState {
     uint64_t head;
-    const uint32_t* words;
-    uint32_t sp;
-    uint32_t ov;
+    const uint32_t* wp;  // next word of the blob's stack to be popped is wp[-1]
+    uint32_t sp;         // words still on the blob's stack
+    uint32_t nxt;        // wp[-1], fetched one refill ahead of its use (valid while sp > 0)
+    uint32_t ov;         // overlay: the one word the decoder may hold above the blob's stack
     uint32_t has_ov;
     uint32_t draws;
     uint32_t status;
 };
 
+IDC_HD void dec_state_init(DecState& st, uint64_t head, const uint32_t* words, uint32_t nwords) {
+    st.head = head;
+    st.wp = words + nwords;
+    st.sp = nwords;
+    st.nxt = nwords ? ld_ro32(words + nwords - 1u) : 0u;
+    st.ov = 0;
+    st.has_ov = 0;
+    st.draws = 0;
+    st.status = 0;
+}
+
+// pop one word: the overlay if there is one, else the blob's next word (consumed top-down; the word below is
+// requested now and first needed at the next pop), else the mt19937(1234) fallback of codec.h:32-40
 IDC_HD uint32_t dec_refill(DecState& st, const uint32_t* mt) {
-    if (st.has_ov) {
+    uint32_t w;
+    if (st.has_ov | st.sp) {
+        const bool o = st.has_ov != 0u;
+        w = o ? st.ov : st.nxt;
         st.has_ov = 0;
-        return st.ov;
+        if (!o) {
+            st.sp--;
+            st.wp--;
+            if (st.sp) st.nxt = ld_ro32_pinned(st.wp - 1);
+        }
+    } else {
+        uint32_t d = st.draws++;
+        w = 0;
+        if (d >= (uint32_t)kMtWords)
+            st.status |= kStMtDraws;
+        else
+            w = mt[d];
     }
-    if (st.sp) {
-        st.sp--;
-        // the stream is consumed top-down: when a 32-byte sector is entered, ask for the one below it
-        if ((st.sp & 7u) == 7u && st.sp >= 8u) prefetch_ro(st.words + st.sp - 8u);
-        return ld_ro32(st.words + st.sp);
-    }
-    uint32_t d = st.draws++;
-    if (d >= (uint32_t)kMtWords) {
-        st.status |= kStMtDraws;
-        return 0;
-    }
-    return mt[d];
+    return w;
 }
 
 IDC_HD void dec_spill(DecState& st, uint32_t w) {
@@ -377,16 +340,16 @@ IDC_HD uint32_t dec_pop_bits(DecState& st, uint32_t p, const uint32_t* mt) {
     return sym;
 }
 
-// codec.cpp:107-121
-IDC_HD uint64_t dec_pop_id(DecState& st, int precision, const uint32_t* mt) {
-    uint64_t id = 0;
-#pragma unroll
-    for (int lower = 48; lower >= 0; lower -= 16) {
-        int p = precision - lower;
-        p = p < 0 ? 0 : (p > 16 ? 16 : p);
-        id = (id << 16) | dec_pop_bits(st, (uint32_t)p, mt);
-    }
-    return id;
+// codec.cpp:107-121 for precision <= 32: the slices at lower = 48 and 32 have precision 0 -- they pop nothing
+// but still renormalise (codec.cpp:83-87); never needed after a push_with_finer_precision, kept for exactness.
+IDC_HD uint32_t dec_pop_id32(DecState& st, int precision, const uint32_t* mt) {
+    if (st.head < kRansL) st.head = (st.head << 32) | (uint64_t)dec_refill(st, mt);
+    if (st.head < kRansL) st.head = (st.head << 32) | (uint64_t)dec_refill(st, mt);
+    const uint32_t p0 = precision < 16 ? (uint32_t)precision : 16u;
+    const uint32_t p1 = (uint32_t)precision - p0;
+    const uint32_t hi = dec_pop_bits(st, p1, mt);
+    const uint32_t lo = dec_pop_bits(st, p0, mt);
+    return (hi << 16) | lo;
 }
 
 // codec.cpp:44-63; q31 = 2^31/nmax
@@ -444,41 +407,10 @@ IDC_HD uint32_t enc_tree_sm_words(uint32_t n) {
     return 16u + 8u * L.supers + L.l0_words;
 }
 
-struct EncTree {
-    uint32_t* rec;    // global: records of 32 words
-    uint32_t* sm;     // this lane's shared-memory region
-    uint32_t stride;
-    uint32_t sm_l0;   // word offset of L0
-};
-
 // ids present in records [0, r) of a full unit of n ids
 IDC_HD uint32_t enc_full_before(uint32_t n, uint32_t r) {
     uint64_t c = (uint64_t)r * kRecIds;
     return (uint32_t)(c < n ? c : n);
-}
-
-// fill this lane's shared-memory levels for a full set of n ids
-IDC_HD void enc_tree_init_sm(EncTree& t, uint32_t n) {
-    EncTreeLayout L = enc_tree_layout(n);
-    t.sm_l0 = 16u + 8u * L.supers;
-    for (uint32_t w = 0; w < 16u; w++) t.sm[(size_t)w * t.stride] = enc_full_before(n, w * kRecPerSuper);
-    for (uint32_t sb = 0; sb < L.supers; sb++) {
-        uint32_t base = enc_full_before(n, sb * kRecPerSuper);
-        for (uint32_t w = 0; w < 8u; w++) {
-            uint32_t lo = enc_full_before(n, sb * kRecPerSuper + (2 * w) * kRecPerPair) - base;
-            uint32_t hi = enc_full_before(n, sb * kRecPerSuper + (2 * w + 1) * kRecPerPair) - base;
-            t.sm[(size_t)(16u + 8u * sb + w) * t.stride] = lo | (hi << 16);
-        }
-    }
-    for (uint32_t w = 0; w < L.l0_words; w++) {
-        uint32_t word = 0;
-        for (uint32_t q = 0; q < kRecPerWord; q++) {
-            uint32_t r = w * kRecPerWord + q;
-            uint32_t c = enc_full_before(n, r + 1) - enc_full_before(n, r);
-            word |= c << (5u * q);
-        }
-        t.sm[(size_t)(t.sm_l0 + w) * t.stride] = word;
-    }
 }
 
 // record word 0 (mask) and words 1..31 (ids) for record r of a unit of n ascending ids
@@ -488,27 +420,6 @@ IDC_HD uint32_t enc_record_word(const IdT* src, uint32_t n, uint32_t r, uint32_t
     uint32_t have = first < n ? (n - first < kRecIds ? n - first : kRecIds) : 0u;
     if (w == 0) return have ? (0xffffffffu >> (32u - have)) : 0u;
     return (w - 1u) < have ? (uint32_t)load_id_raw(src + first + (w - 1u)) : 0xffffffffu;
-}
-
-// In a sector of 16 exclusive cumulative counts (E[0] = 0, non-decreasing, padding repeats the total):
-// j = last entry with E[j] <= k.
-IDC_HD uint32_t cum_sector_find(const Sector& s, uint32_t k) {
-    uint32_t c = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        c += (s.w[w] & 0xffffu) <= k ? 1u : 0u;
-        c += (s.w[w] >> 16) <= k ? 1u : 0u;
-    }
-    return c - 1u;  // entry 0 always counts
-}
-
-// subtract one from every entry above j (the words are already in registers)
-IDC_HD void cum_sector_dec_above(uint32_t* sm, uint32_t word0, uint32_t stride, const Sector& s, uint32_t j) {
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        uint32_t dec = ((uint32_t)(2 * w) > j ? 1u : 0u) | ((uint32_t)(2 * w + 1) > j ? 0x10000u : 0u);
-        if (dec) sm[(size_t)(word0 + w) * stride] = s.w[w] - dec;
-    }
 }
 
 // position of the r-th (0-based) set bit of a 32-bit mask with more than r ones
@@ -524,85 +435,6 @@ IDC_HD uint32_t select32(uint32_t m, uint32_t r) {
     if (r >= c) { r -= c; pos += 2; m >>= 2; }
     if (r >= (m & 1u)) pos += 1;
     return pos;
-}
-
-struct RecLine {
-    uint32_t w[32];
-};
-
-IDC_HD RecLine ld_record(const uint32_t* rec) {
-    RecLine r;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        Sector s = ld_sector(reinterpret_cast<const uint16_t*>(rec), (uint32_t)q);
-#pragma unroll
-        for (int j = 0; j < 8; j++) r.w[8 * q + j] = s.w[j];
-    }
-    return r;
-}
-
-// words[1 + pos] without dynamic register indexing: a 5-level select tree
-IDC_HD uint32_t rec_pick(const RecLine& r, uint32_t pos) {
-    uint32_t idx = pos + 1u;  // 1..31
-    uint32_t a16[16], a8[8], a4[4], a2[2];
-#pragma unroll
-    for (int i = 0; i < 16; i++) a16[i] = (idx & 1u) ? r.w[2 * i + 1] : r.w[2 * i];
-#pragma unroll
-    for (int i = 0; i < 8; i++) a8[i] = (idx & 2u) ? a16[2 * i + 1] : a16[2 * i];
-#pragma unroll
-    for (int i = 0; i < 4; i++) a4[i] = (idx & 4u) ? a8[2 * i + 1] : a8[2 * i];
-#pragma unroll
-    for (int i = 0; i < 2; i++) a2[i] = (idx & 8u) ? a4[2 * i + 1] : a4[2 * i];
-    return (idx & 16u) ? a2[1] : a2[0];
-}
-
-// Select the k-th remaining id (0-based) of the unit, remove it; returns its position in the sorted unit and
-// the id itself (read from the record line that had to be fetched anyway).
-IDC_HD uint32_t enc_tree_select_remove(const EncTree& t, uint32_t k, uint32_t& id_out) {
-    const uint32_t st = t.stride;
-    // L2: sixteen 32-bit exclusive cumulative counts (entry 0 is 0; entries past the last superblock hold the total)
-    uint32_t e2[16];
-#pragma unroll
-    for (int w = 0; w < 16; w++) e2[w] = t.sm[(size_t)w * st];
-    uint32_t sb = 0;
-#pragma unroll
-    for (int w = 1; w < 16; w++) sb += e2[w] <= k ? 1u : 0u;
-    {
-        uint32_t base = e2[0];
-#pragma unroll
-        for (int w = 1; w < 16; w++) base = (sb == (uint32_t)w) ? e2[w] : base;
-        k -= base;
-    }
-    Sector s1 = ld_sector_sm(t.sm, 16u + 8u * sb, st);
-    const uint32_t p = cum_sector_find(s1, k);
-    k -= sector_get(s1, p);
-    // two L0 words = twelve 5-bit counts: first record whose inclusive prefix exceeds k
-    const uint32_t l0 = t.sm_l0 + (sb * 16u + p) * 2u;
-    const uint32_t wa = t.sm[(size_t)l0 * st], wb = t.sm[(size_t)(l0 + 1u) * st];
-    uint32_t run = 0, r = 0, sub = 0;
-#pragma unroll
-    for (int q = 0; q < 12; q++) {
-        uint32_t c = ((q < 6 ? wa : wb) >> (5 * (q % 6))) & 31u;
-        run += c;
-        bool le = run <= k;
-        r += le ? 1u : 0u;
-        sub = le ? run : sub;
-    }
-    k -= sub;
-    r = r < 11u ? r : 11u;
-    const uint32_t rg = (sb * 16u + p) * kRecPerPair + r;  // record index inside the unit
-    uint32_t* rec = t.rec + (size_t)rg * 32u;
-    RecLine line = ld_record(rec);
-    const uint32_t pos = select32(line.w[0], k);
-    id_out = rec_pick(line, pos);
-    // removal
-    red_and32(rec, ~(1u << pos));
-    t.sm[(size_t)(l0 + (r >= 6u ? 1u : 0u)) * st] = (r >= 6u ? wb : wa) - (1u << (5u * (r >= 6u ? r - 6u : r)));
-    cum_sector_dec_above(t.sm, 16u + 8u * sb, st, s1, p);
-#pragma unroll
-    for (int w = 1; w < 16; w++)
-        if ((uint32_t)w > sb) t.sm[(size_t)w * st] = e2[w] - 1u;
-    return rg * kRecIds + pos;
 }
 
 // ---------------------------------------------------- decoder: insert-rank --
@@ -653,45 +485,6 @@ IDC_HD uint32_t dec_tree_sm_words(uint32_t n) {
     return 4u + 8u * L.l1_sectors + 4u * L.ngroups;
 }
 
-struct DecTree {
-    uint32_t* rec;      // nb buckets of 64 ids
-    uint32_t* ovf;      // pairs (bucket, id)
-    uint32_t* sm;       // this lane's shared-memory region
-    uint32_t stride;
-    uint32_t sm_l0;     // word offset of level 0 inside the region
-    uint32_t nb, ovf_cap, ovf_n;
-    uint32_t lo, hi;    // id range mapped onto the buckets (hint; exactness does not depend on it)
-    uint64_t scale;     // bucket = ((v - lo) * scale) >> 32
-    uint32_t degenerate;
-};
-
-IDC_HD DecTree dec_tree_at(uint8_t* ws, uint32_t* sm, uint32_t stride, uint32_t n, uint32_t lo, uint32_t hi) {
-    DecTreeLayout L = dec_tree_layout(n);
-    DecTree t;
-    t.rec = reinterpret_cast<uint32_t*>(ws);
-    t.ovf = reinterpret_cast<uint32_t*>(ws + 256ull * L.nb);
-    t.sm = sm;
-    t.stride = stride;
-    t.sm_l0 = 4u + 8u * L.l1_sectors;
-    t.nb = L.nb;
-    t.ovf_cap = L.ovf_cap;
-    t.ovf_n = 0;
-    if (hi < lo) hi = lo;
-    t.lo = lo;
-    t.hi = hi;
-    uint64_t range = (uint64_t)hi - lo + 1ull;
-    t.scale = ((uint64_t)L.nb << 32) / range;  // <= nb * 2^32
-    t.degenerate = 0;
-    return t;
-}
-
-IDC_HD uint32_t dec_bucket(const DecTree& t, uint32_t v) {
-    uint32_t c = v < t.lo ? t.lo : (v > t.hi ? t.hi : v);
-    // (c - lo) < range and scale <= nb*2^32/range  =>  product < nb * 2^32: fits 64 bits
-    uint64_t b = ((uint64_t)(c - t.lo) * t.scale) >> 32;
-    return b >= t.nb ? t.nb - 1u : (uint32_t)b;
-}
-
 IDC_HD uint32_t dp4a_u(uint32_t a, uint32_t sel, uint32_t acc) {
 #if defined(__CUDA_ARCH__)
     return __dp4a(a, sel, acc);
@@ -699,87 +492,6 @@ IDC_HD uint32_t dp4a_u(uint32_t a, uint32_t sel, uint32_t acc) {
     for (int k = 0; k < 4; k++) acc += ((a >> (8 * k)) & 0xffu) * ((sel >> (8 * k)) & 0xffu);
     return acc;
 #endif
-}
-
-// out_prev: the ids decoded so far (any order), `decoded` of them. Only touched on the degenerate path.
-template <typename OutT>
-IDC_HD uint32_t dec_tree_insert_rank(DecTree& t, uint32_t v, const OutT* out_prev, uint32_t decoded) {
-    if (t.degenerate) {
-        uint32_t r = 0;
-        for (uint32_t i = 0; i < decoded; i++)
-            r += ((uint32_t)out_prev[i] < v) ? 1u : 0u;
-        return r;
-    }
-    const uint32_t b = dec_bucket(t, v);
-    const uint32_t g = b >> 4, sct = g >> 4, st = t.stride;
-    // this bucket's count first: it decides how many sectors of the bucket are fetched
-    uint32_t w0[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) w0[j] = t.sm[(size_t)(t.sm_l0 + 4u * g + j) * st];
-    uint32_t wsel = w0[0];
-#pragma unroll
-    for (int j = 1; j < 4; j++) wsel = (((b >> 2) & 3u) == (uint32_t)j) ? w0[j] : wsel;
-    const uint32_t cnt = (wsel >> (8u * (b & 3u))) & 0xffu;
-    const uint32_t sv = cnt < kBkSlots ? cnt : kBkSlots;
-    // issue every needed 32-byte load of the bucket before touching the data (one DRAM round trip)
-    const uint16_t* recp = reinterpret_cast<const uint16_t*>(t.rec + (size_t)b * kBkSlots);
-    Sector rs[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-        if (sv > 8u * j) rs[j] = ld_sector(recp, j);
-
-    // prefix counts from shared memory
-    uint32_t rank = 0;
-    {
-        uint32_t incl = (1u << (b & 15u)) - 1u;  // bytes of the group below this bucket
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t nib = (incl >> (4 * j)) & 15u;
-            uint32_t sel = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-            rank = dp4a_u(w0[j], sel, rank);
-        }
-        Sector s1 = ld_sector_sm(t.sm, 4u + 8u * sct, st);
-        rank += sector_sum_below(s1, g & 15u);
-        uint32_t incl2 = (1u << sct) - 1u;  // sct <= 7
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t two = (incl2 >> (2 * j)) & 3u;
-            uint32_t sel = (two & 1u) | ((two & 2u) << 7);
-            rank = dp2a(t.sm[(size_t)j * st], sel, rank);
-        }
-    }
-    // exact tie-break inside the bucket. Unused slots hold 0xffffffff (the workspace is pre-filled), which is
-    // never < v, so one compare per slot suffices; one accumulator per sector keeps the adds independent.
-    uint32_t part[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        part[j] = 0;
-        if (sv > 8u * j) {
-#pragma unroll
-            for (int q = 0; q < 8; q++) part[j] += rs[j].w[q] < v ? 1u : 0u;
-        }
-    }
-    rank += ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
-    if (cnt > kBkSlots) {
-        for (uint32_t e = 0; e < t.ovf_n; e++) {
-            uint64_t pr = ld_ws64(reinterpret_cast<const uint64_t*>(t.ovf) + e);
-            rank += ((uint32_t)pr == b && (uint32_t)(pr >> 32) < v) ? 1u : 0u;
-        }
-    }
-    // insert
-    if (cnt < kBkSlots) {
-        st_ws32(t.rec + (size_t)b * kBkSlots + cnt, v);
-    } else if (cnt < 254u && t.ovf_n < t.ovf_cap) {
-        st_ws64(reinterpret_cast<uint64_t*>(t.ovf) + t.ovf_n, (uint64_t)b | ((uint64_t)v << 32));
-        t.ovf_n++;
-    } else {
-        t.degenerate = 1;  // from now on ranks come from the output array
-        return rank;
-    }
-    t.sm[(size_t)(t.sm_l0 + (b >> 2)) * st] += 1u << (8u * (b & 3u));
-    t.sm[(size_t)(4u + (g >> 1)) * st] += 1u << (16u * (g & 1u));
-    t.sm[(size_t)(sct >> 1) * st] += 1u << (16u * (sct & 1u));
-    return rank;
 }
 
 }  // namespace idc

@@ -8,7 +8,7 @@
 
 #include "idc_core.cuh"
 #include "idc_host.h"
-#include "roc_lane.cuh"
+#include "idc_core.cuh"
 
 namespace {
 

@@ -1,12 +1,14 @@
 // roc_kernels.cu -- ROC (bits-back rANS over sets) encode / decode on sm_100a.
 //
-// Execution model: ONE UNIT PER LANE. The reference stream is a single serial
-// rANS head per list (codec.cpp:131-137,144-151), so the only bit-exact way to
-// interleave 32 coders per warp is across lists: every lane owns one unit's
-// head, stream pointer and order-statistic workspace. Units are sorted by
-// length so the 32 lanes of a warp run in lock step, and the encoder walks
-// them END-ALIGNED so that `nmax` (ids left in the set) is the same in every
-// lane -- the reciprocal used by the uniform pop is then one broadcast load.
+// Execution model: ONE UNIT PER GROUP OF G LANES (G = 4 or 8; roc_group.cuh). The reference
+// stream is a single serial rANS head per list (codec.cpp:131-137,144-151), so the only
+// bit-exact way to interleave coders inside a warp is across lists: a warp runs 32/G units,
+// every group owns one unit's head (replicated in its lanes), stream pointer and
+// order-statistic workspace, and the group's lanes share the work on that workspace (one
+// coalesced 128-byte request per step, ballot searches of the count levels). Units are
+// sorted by length so the groups of a warp run in lock step, and the encoder walks them
+// END-ALIGNED so that `nmax` (ids left in the set) is the same in every group -- the
+// reciprocal used by the uniform pop is then one broadcast load.
 //
 // Kernels (all integer, HBM/L2-latency bound; no tensor cores):
 //   k_unit_meta     per unit min/max id, precision rule, sortedness / width checks
@@ -25,7 +27,7 @@
 
 #include "idc_host.h"
 #include "idc_prep.cuh"
-#include "roc_lane.cuh"
+#include "roc_group.cuh"
 
 using namespace idc;
 
@@ -97,10 +99,9 @@ struct EncArgs {
     const uint64_t* rcp64;
     const uint32_t* q31;
     uint32_t nunits;
-    uint32_t sm_words;           // shared-memory words per lane (upper tree levels)
+    uint32_t sm_words;           // shared-memory words per unit (the count levels), a multiple of 4
     uint32_t slot_base;          // this launch covers launch slots [slot_base, slot_end)
     uint32_t slot_end;
-    uint32_t lanes;              // units per warp (32, or fewer for the longest units: less divergence per step)
 };
 
 // Re-lay every unit's ascending ids as 128-byte records (mask word + 31 ids, idc_core.cuh): one warp per unit,
@@ -117,38 +118,43 @@ __global__ void __launch_bounds__(kThreads) k_enc_records(EncArgs a) {
     for (uint32_t r = 0; r < records; r++) rec[(size_t)r * 32u + lane] = enc_record_word(src, n, r, lane);
 }
 
-template <typename IdT>
+template <int G, typename IdT>
 __global__ void __launch_bounds__(kThreads) k_roc_encode(EncArgs a) {
-    extern __shared__ uint32_t smem[];
-    const uint32_t lane = threadIdx.x & 31, gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    uint32_t slot = a.slot_base + gwarp * a.lanes + lane;
-    bool valid = lane < a.lanes && slot < a.slot_end;
-    uint32_t u = valid ? a.perm[slot] : 0u;
-    uint32_t n = valid ? a.unit_n[u] : 0u;
-    EncLane<IdT> L;
-    L.n = n;
-    L.prec = valid ? (int)a.unit_prec[u] : 0;
-    uint64_t src_off = valid ? a.unit_src[u] : 0ull;
-    L.sort_idx = a.sort_idx ? a.sort_idx + src_off : nullptr;
-    L.order = a.order ? a.order + src_off : nullptr;
-    L.pos_base = valid ? a.unit_posbase[u] : 0u;
-    L.tree.rec = reinterpret_cast<uint32_t*>(a.ws + (valid ? a.ws_off[u] : 0ull));
-    L.tree.sm = smem + (threadIdx.x >> 5) * (a.sm_words * a.lanes) + (valid ? lane : 0u);
-    L.tree.stride = a.lanes;
-    if (n) enc_tree_init_sm(L.tree, n);
-    L.st.head = kRansL;
-    L.st.words = a.scratch + (valid ? a.scratch_off[u] : 0ull);
-    L.st.sp = 0;
-    L.st.cap = n + 4u;
-    L.st.draws = 0;
-    L.st.status = 0;
-    // end-aligned lock step: at warp step t every active lane has nmax == t
-    uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr uint32_t NG = 32 / G;  // units per warp
+    const Grp<G> g;
+    const uint32_t lane_id = threadIdx.x & 31, q = lane_id / G, wic = threadIdx.x >> 5;
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + wic;
+    const uint32_t slot = a.slot_base + gwarp * NG + q;
+    const bool valid = slot < a.slot_end;
+    const uint32_t u = valid ? a.perm[slot] : 0u;
+    const uint32_t n = valid ? a.unit_n[u] : 0u;
+    GEncUnit<G, IdT> U;
+#pragma unroll
+    for (int j = 0; j < 16 / G; j++) U.tree.ea[j] = 0u;
+    U.n = n;
+    U.prec = valid ? (int)a.unit_prec[u] : 0;
+    const uint64_t src_off = valid ? a.unit_src[u] : 0ull;
+    U.sort_idx = a.sort_idx ? a.sort_idx + src_off : nullptr;
+    U.order = a.order ? a.order + src_off : nullptr;
+    U.pos_base = valid ? a.unit_posbase[u] : 0u;
+    U.tree.rec = reinterpret_cast<uint32_t*>(a.ws + (valid ? a.ws_off[u] : 0ull));
+    U.tree.sm = SmView{smem + (size_t)wic * (a.sm_words * NG), NG, q};
+    if (n) genc_tree_init<G>(g, U.tree, n);
+    U.st.head = kRansL;
+    U.st.words = a.scratch + (valid ? a.scratch_off[u] : 0ull);
+    U.st.sp = 0;
+    U.st.cap = n + 4u;
+    U.st.draws = 0;
+    U.st.status = 0;
+    U.st.wr = g.sub == 0 ? 1u : 0u;
+    __syncwarp();
+    // end-aligned lock step: at warp step t every active group has nmax == t
+    const uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
     // Reciprocal tables: every warp of the launch walks the same t at about the same time, so a per-step table
     // load turns one L2 slice into a hot spot (measured: 67 % of all stall samples). Instead each warp fetches 32
     // consecutive entries with one coalesced load per 32 steps (lane j holds entry tb - j), one block ahead, and
     // broadcasts the step's entry with shuffles.
-    const uint32_t lane_id = threadIdx.x & 31;
     auto tab_rcp = [&](uint32_t tb) { return tb >= lane_id ? __ldg(a.rcp64 + (tb - lane_id)) : 0ull; };
     auto tab_q31 = [&](uint32_t tb) { return tb >= lane_id ? __ldg(a.q31 + (tb - lane_id)) : 0u; };
     uint32_t tb = tmax;                       // block covers t = tb, tb-1, ..., tb-31
@@ -164,12 +170,12 @@ __global__ void __launch_bounds__(kThreads) k_roc_encode(EncArgs a) {
         }
         const uint64_t rcp = __shfl_sync(0xffffffffu, rcp_blk, tb - t);
         const uint32_t q31 = __shfl_sync(0xffffffffu, q31_blk, tb - t);
-        if (t <= n) enc_lane_step(L, t, rcp, q31, a.mt);
+        genc_step<G>(g, U, t, rcp, q31, a.mt, t <= n);
     }
-    if (valid) {
-        a.unit_head[u] = L.st.head;
-        a.unit_nwords[u] = L.st.sp;
-        if (L.st.status) atomicOr(a.status, L.st.status);
+    if (valid && g.sub == 0) {
+        a.unit_head[u] = U.st.head;
+        a.unit_nwords[u] = U.st.sp;
+        if (U.st.status) atomicOr(a.status, U.st.status);
     }
 }
 
@@ -203,40 +209,36 @@ struct DecArgs {
     const uint32_t* q31;
     uint32_t nsel;
     uint32_t row_stride;        // rows: pad the slot's output to this many entries with -1
-    uint32_t sm_words;          // shared-memory words per lane (all count levels)
+    uint32_t sm_words;          // shared-memory words per unit (all count levels), a multiple of 4
     uint32_t slot_base;         // this launch covers launch slots [slot_base, slot_end)
     uint32_t slot_end;
-    uint32_t lanes;             // units per warp
 };
 
-template <typename OutT>
+template <int G, typename OutT>
 __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
-    extern __shared__ uint32_t smem[];
-    const uint32_t lane = threadIdx.x & 31, gwarp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    uint32_t slot = a.slot_base + gwarp * a.lanes + lane;
-    bool valid = lane < a.lanes && slot < a.slot_end;
-    uint32_t u = valid ? a.sel_unit[slot] : 0u;
-    uint32_t n = valid ? a.unit_n[u] : 0u;
-    DecLane<OutT> L;
-    L.n = n;
-    L.prec = valid ? (int)a.unit_prec[u] : 0;
-    L.out = reinterpret_cast<OutT*>(a.out) + (valid ? a.sel_out[slot] : 0ull);
-    uint64_t w0 = valid ? a.word_off[u] : 0ull, w1 = valid ? a.word_off[u + 1] : 0ull;
-    L.st.head = valid ? a.unit_head[u] : kRansL;
-    L.st.words = a.words + w0;
-    L.st.sp = (uint32_t)(w1 - w0);
-    L.st.ov = 0;
-    L.st.has_ov = 0;
-    L.st.draws = 0;
-    L.st.status = 0;
-    uint32_t* sm = smem + (threadIdx.x >> 5) * (a.sm_words * a.lanes) + (valid ? lane : 0u);
+    extern __shared__ __align__(16) uint32_t smem[];
+    constexpr uint32_t NG = 32 / G;  // units per warp
+    const Grp<G> g;
+    const uint32_t lane_id = threadIdx.x & 31, q = lane_id / G, wic = threadIdx.x >> 5;
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + wic;
+    const uint32_t slot = a.slot_base + gwarp * NG + q;
+    const bool valid = slot < a.slot_end;
+    const uint32_t u = valid ? a.sel_unit[slot] : 0u;
+    const uint32_t n = valid ? a.unit_n[u] : 0u;
+    GDecUnit<OutT> U;
+    U.n = n;
+    U.prec = valid ? (int)a.unit_prec[u] : 0;
+    U.out = reinterpret_cast<OutT*>(a.out) + (valid ? a.sel_out[slot] : 0ull);
+    const uint64_t w0 = valid ? a.word_off[u] : 0ull, w1 = valid ? a.word_off[u + 1] : 0ull;
+    dec_state_init(U.st, valid ? a.unit_head[u] : kRansL, a.words + w0, (uint32_t)(w1 - w0));
+    const SmView sm{smem + (size_t)wic * (a.sm_words * NG), NG, q};
     if (valid)
-        for (uint32_t w = 0; w < a.sm_words; w++) sm[w * a.lanes] = 0u;
-    L.tree = dec_tree_at(a.ws + (valid ? a.sel_ws[slot] : 0ull), sm, a.lanes, n ? n : 1u, valid ? a.unit_lo[u] : 0u,
-                         valid ? a.unit_hi[u] : 0u);
-    uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
+        for (uint32_t w = g.sub; w < a.sm_words; w += (uint32_t)G) *sm.at(w) = 0u;
+    U.tree = gdec_tree_at(a.ws + (valid ? a.sel_ws[slot] : 0ull), sm, n ? n : 1u, valid ? a.unit_lo[u] : 0u,
+                          valid ? a.unit_hi[u] : 0u);
+    __syncwarp();
+    const uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
     // 2^31 / (i + 1) from the table, 32 entries per coalesced load and one block ahead (see k_roc_encode)
-    const uint32_t lane_id = threadIdx.x & 31;
     auto tab_q31 = [&](uint32_t ib) { uint32_t e = ib + lane_id + 1u; return __ldg(a.q31 + (e <= kMaxUnit ? e : kMaxUnit)); };
     uint32_t ib = 0;                          // block covers i = ib .. ib+31
     uint32_t q31_blk = tab_q31(0), q31_nxt = tab_q31(32);
@@ -247,14 +249,16 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
             q31_nxt = tab_q31(ib + 32u);
         }
         const uint32_t q31 = __shfl_sync(0xffffffffu, q31_blk, i - ib);
-        if (i < n) dec_lane_step(L, i, q31, a.mt);
+        gdec_step<G>(g, U, i, q31, a.mt, i < n);
     }
     if (valid) {
         if (a.row_stride)
-            for (uint32_t t = n; t < a.row_stride; ++t) L.out[t] = (OutT)-1;
-        if (a.counts) a.counts[slot] = n;
-        uint32_t st = L.st.status & ~kStDegenerate;
-        if (st) atomicOr(a.status, st);
+            for (uint32_t t = n + g.sub; t < a.row_stride; t += (uint32_t)G) U.out[t] = (OutT)-1;
+        if (g.sub == 0) {
+            if (a.counts) a.counts[slot] = n;
+            uint32_t st = U.st.status & ~kStDegenerate;
+            if (st) atomicOr(a.status, st);
+        }
     }
 }
 
@@ -297,20 +301,33 @@ std::vector<SizeClass> size_classes(uint64_t nslots, NofSlot n_of_slot) {
     return cls;
 }
 
-// warps per CTA such that several CTAs fit an SM's 227 KB of shared memory
-inline uint32_t lanes_for(uint32_t max_n) {
-    if (const char* e = getenv("IDC_LONG_LANES")) {
+// Lanes per unit. 4 is the default for every size class: 8 units per warp keep the issue cost per id low, and a
+// group of 4 already fetches its line as one request (profiles/r1_lat_bench_b200.txt). IDC_ROC_G=8 /
+// IDC_ROC_G8_MIN_N=<n> select 8 lanes for all classes / for classes whose longest unit exceeds n (experiments).
+inline int group_lanes_for(uint32_t max_n) {
+    int gdef = 4;
+    if (const char* e = getenv("IDC_ROC_G")) {
         int v = atoi(e);
-        if (max_n > 16384 && (v == 4 || v == 8 || v == 16 || v == 32)) return (uint32_t)v;
+        if (v == 4 || v == 8) gdef = v;
     }
-    return 32u;  // measured: fewer units per warp did not shorten the long chains (profiles/README.md)
+    if (const char* e = getenv("IDC_ROC_G8_MIN_N")) {
+        if (max_n > (uint32_t)atoi(e)) return 8;
+    }
+    return gdef;
 }
 
-inline uint32_t warps_for(uint32_t sm_words, uint32_t lanes = 32) {
-    size_t per_warp = (size_t)sm_words * 4 * lanes;
+// warps per CTA such that several CTAs fit an SM's 227 KB of shared memory
+inline uint32_t warps_for(uint32_t sm_words, uint32_t units_per_warp) {
+    size_t per_warp = (size_t)sm_words * 4 * units_per_warp;
     if (per_warp * 4 <= 56 * 1024) return 4;
     if (per_warp * 2 <= 56 * 1024) return 2;
     return 1;
+}
+
+template <typename K>
+int set_max_smem(K kernel, size_t bytes) {
+    IDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return IDC_OK;
 }
 
 // Shared encode driver. ids_dev: device pointer to the caller's ids (CSR or
@@ -448,29 +465,30 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
     IDC_TRY(check_last_launch("k_enc_records"));
     {
         auto cls = size_classes(nu, [&](uint64_t slot) { return b->unit_n[perm[slot]]; });
-        size_t max_smem = 0;
-        for (auto& k : cls) {
-            uint32_t w = enc_tree_sm_words(k.max_n ? k.max_n : 1u), ln = lanes_for(k.max_n);
-            max_smem = std::max(max_smem, (size_t)w * 4 * ln * warps_for(w, ln));
-        }
-        IDC_CUDA(cudaFuncSetAttribute(k_roc_encode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-        IDC_CUDA(cudaFuncSetAttribute(k_roc_encode<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         LaunchScope ls(c, "k_roc_encode");
         IDC_TRY(c->fork((int)cls.size()));
         for (size_t k = 0; k < cls.size(); k++) {
             EncArgs ek = e;
             ek.slot_base = cls[k].slot_base;
             ek.slot_end = cls[k].slot_end;
-            ek.sm_words = enc_tree_sm_words(cls[k].max_n ? cls[k].max_n : 1u);
-            ek.lanes = lanes_for(cls[k].max_n);
-            uint32_t warps = warps_for(ek.sm_words, ek.lanes), threads = warps * 32;
-            uint32_t slots = ek.slot_end - ek.slot_base, nwarps = (slots + ek.lanes - 1) / ek.lanes;
-            uint32_t grid = (nwarps + warps - 1) / warps;
-            size_t smem = (size_t)ek.sm_words * 4 * ek.lanes * warps;
-            if (enc_id_bytes == 8)
-                k_roc_encode<int64_t><<<grid, threads, smem, c->aux[k]>>>(ek);
-            else
-                k_roc_encode<uint32_t><<<grid, threads, smem, c->aux[k]>>>(ek);
+            ek.sm_words = genc_sm_words(cls[k].max_n ? cls[k].max_n : 1u);
+            const int G = group_lanes_for(cls[k].max_n);
+            const uint32_t upw = 32u / (uint32_t)G;  // units per warp
+            const uint32_t warps = warps_for(ek.sm_words, upw), threads = warps * 32;
+            const uint32_t slots = ek.slot_end - ek.slot_base, nwarps = (slots + upw - 1) / upw;
+            const uint32_t grid = (nwarps + warps - 1) / warps;
+            const size_t smem = (size_t)ek.sm_words * 4 * upw * warps;
+#define IDC_LAUNCH_ENC(GG, TT)                                                       \
+    do {                                                                             \
+        IDC_TRY(set_max_smem(k_roc_encode<GG, TT>, smem));                            \
+        k_roc_encode<GG, TT><<<grid, threads, smem, c->aux[k]>>>(ek);                 \
+    } while (0)
+            if (G == 8) {
+                if (enc_id_bytes == 8) IDC_LAUNCH_ENC(8, int64_t); else IDC_LAUNCH_ENC(8, uint32_t);
+            } else {
+                if (enc_id_bytes == 8) IDC_LAUNCH_ENC(4, int64_t); else IDC_LAUNCH_ENC(4, uint32_t);
+            }
+#undef IDC_LAUNCH_ENC
             c->launches++;
         }
         c->launches--;  // LaunchScope counted one already
@@ -604,14 +622,7 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     a.row_stride = row_stride;
     {
         auto cls = size_classes(nsel, n_of_slot);
-        size_t max_smem = 0;
-        for (auto& k : cls) {
-            uint32_t w = dec_tree_sm_words(k.max_n ? k.max_n : 1u), ln = lanes_for(k.max_n);
-            max_smem = std::max(max_smem, (size_t)w * 4 * ln * warps_for(w, ln));
-        }
         (void)max_n;
-        IDC_CUDA(cudaFuncSetAttribute(k_roc_decode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-        IDC_CUDA(cudaFuncSetAttribute(k_roc_decode<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
         LaunchScope ls(c, "k_roc_decode");
         IDC_TRY(c->fork((int)cls.size()));
         for (size_t k = 0; k < cls.size(); k++) {
@@ -619,15 +630,23 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
             ak.slot_base = cls[k].slot_base;
             ak.slot_end = cls[k].slot_end;
             ak.sm_words = dec_tree_sm_words(cls[k].max_n ? cls[k].max_n : 1u);
-            ak.lanes = lanes_for(cls[k].max_n);
-            uint32_t warps = warps_for(ak.sm_words, ak.lanes), threads = warps * 32;
-            uint32_t slots = ak.slot_end - ak.slot_base, nwarps = (slots + ak.lanes - 1) / ak.lanes;
-            uint32_t grid = (nwarps + warps - 1) / warps;
-            size_t smem = (size_t)ak.sm_words * 4 * ak.lanes * warps;
-            if (id_bytes == 8)
-                k_roc_decode<int64_t><<<grid, threads, smem, c->aux[k]>>>(ak);
-            else
-                k_roc_decode<int32_t><<<grid, threads, smem, c->aux[k]>>>(ak);
+            const int G = group_lanes_for(cls[k].max_n);
+            const uint32_t upw = 32u / (uint32_t)G;
+            const uint32_t warps = warps_for(ak.sm_words, upw), threads = warps * 32;
+            const uint32_t slots = ak.slot_end - ak.slot_base, nwarps = (slots + upw - 1) / upw;
+            const uint32_t grid = (nwarps + warps - 1) / warps;
+            const size_t smem = (size_t)ak.sm_words * 4 * upw * warps;
+#define IDC_LAUNCH_DEC(GG, TT)                                                       \
+    do {                                                                             \
+        IDC_TRY(set_max_smem(k_roc_decode<GG, TT>, smem));                            \
+        k_roc_decode<GG, TT><<<grid, threads, smem, c->aux[k]>>>(ak);                 \
+    } while (0)
+            if (G == 8) {
+                if (id_bytes == 8) IDC_LAUNCH_DEC(8, int64_t); else IDC_LAUNCH_DEC(8, int32_t);
+            } else {
+                if (id_bytes == 8) IDC_LAUNCH_DEC(4, int64_t); else IDC_LAUNCH_DEC(4, int32_t);
+            }
+#undef IDC_LAUNCH_DEC
             c->launches++;
         }
         c->launches--;
