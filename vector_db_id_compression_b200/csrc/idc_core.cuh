@@ -187,6 +187,33 @@ IDC_HD Sector ld_sector(const uint16_t* base, uint32_t sector_idx) {
     return s;
 }
 
+// predicated memory operations: straight-line code in every lane. A data-dependent `if` around a store or a
+// load makes the groups of a warp take different paths; each divergence costs a branch resolve and a reconvergence
+// barrier on the step's critical path (measured: 40 % of the rANS push).
+IDC_HD void st_ws32_if(uint32_t* p, uint32_t v, bool cond) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.global.cg.u32 [%0], %1; }" ::"l"(p), "r"(v), "r"((uint32_t)cond)
+                 : "memory");
+#else
+    if (cond) *p = v;
+#endif
+}
+// v = cond ? *p : v, pinned where it is written (neither sunk to the first use nor hoisted)
+IDC_HD void ld_ro32_if(const uint32_t* p, uint32_t& v, bool cond) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.global.nc.u32 %0, [%1]; }" : "+r"(v) : "l"(p), "r"((uint32_t)cond));
+#else
+    if (cond) v = *p;
+#endif
+}
+IDC_HD void prefetch_ro_if(const void* p, bool cond) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q prefetch.global.L1 [%0]; }" ::"l"(p), "r"((uint32_t)cond));
+#else
+    (void)p, (void)cond;
+#endif
+}
+
 // ------------------------------------------------------ encoder rANS state --
 // The encoder's stack is append-only in the codec's valid domain; the rare
 // pop-from-stack cases are still implemented exactly (read back the word just
@@ -202,11 +229,12 @@ struct EncState {
     uint32_t wr;       // this lane stores the words (lane 0 of the group that owns the unit)
 };
 
-IDC_HD void enc_spill(EncState& st, uint32_t w) {
+// push w if `cond`
+IDC_HD void enc_spill_if(EncState& st, uint32_t w, bool cond) {
     const bool ok = st.sp < st.cap;
-    if (ok & (st.wr != 0u)) st_ws32(st.words + st.sp, w);
-    st.status |= ok ? 0u : kStScratch;
-    st.sp++;
+    st_ws32_if(st.words + st.sp, w, cond & ok & (st.wr != 0u));
+    st.status |= (cond & !ok) ? kStScratch : 0u;
+    st.sp += cond ? 1u : 0u;
 }
 
 IDC_HD uint32_t enc_refill(EncState& st, const uint32_t* mt) {
@@ -227,34 +255,31 @@ IDC_HD uint32_t enc_refill(EncState& st, const uint32_t* mt) {
 // word because the threshold's lower word is zero.
 IDC_HD uint32_t enc_pop_uniform(EncState& st, uint32_t nmax, uint64_t rcp, uint32_t q31, const uint32_t* mt) {
     uint64_t h = st.head;
-    bool spill = (uint32_t)(h >> 32) >= nmax * q31;  // nmax*q31 <= 2^31: no overflow
-    uint32_t low = (uint32_t)h;
-    if (spill)
-        h >>= 32;
+    const uint32_t hi = (uint32_t)(h >> 32), low = (uint32_t)h;
+    const bool spill = hi >= nmax * q31;  // nmax*q31 <= 2^31: no overflow
+    h = spill ? (uint64_t)hi : h;
     uint64_t q = mulhi64(h, rcp);
     uint64_t r = h - q * nmax;
-    if (r >= nmax) { q++; r -= nmax; }
-    bool refill = h < kRansL;
-    if (spill && refill) {
-        // the word just spilled is popped straight back: the stack is unchanged
-        q = (uint64_t)low | (q << 32);
-    } else {
-        if (spill)
-            enc_spill(st, low);
-        if (refill)
-            q = (uint64_t)enc_refill(st, mt) | (q << 32);
-    }
-    st.head = q;
+    const bool fix = r >= nmax;
+    q += fix ? 1u : 0u;
+    r -= fix ? nmax : 0u;
+    const bool refill = h < kRansL;
+    // spill && refill: the word just spilled is popped straight back, the stack is unchanged.
+    // refill without spill needs head < 2^31 on entry: never inside the codec's valid domain (kept exact, cold).
+    enc_spill_if(st, low, spill & !refill);
+    uint32_t w = low;
+    if (refill & !spill) w = enc_refill(st, mt);
+    st.head = refill ? ((uint64_t)w | (q << 32)) : q;
     return (uint32_t)r;
 }
 
 // codec.cpp:65-76, start added unmasked; p in 0..16
 IDC_HD void enc_push_bits(EncState& st, uint32_t start, uint32_t p) {
     uint64_t h = st.head;
-    if ((uint32_t)(h >> 32) >= (uint32_t)(kRansL >> p)) {
-        enc_spill(st, (uint32_t)h);
-        h >>= 32;
-    }
+    const uint32_t hi = (uint32_t)(h >> 32);
+    const bool spill = hi >= (0x80000000u >> p);
+    enc_spill_if(st, (uint32_t)h, spill);
+    h = spill ? (uint64_t)hi : h;
     st.head = (h << p) + start;
 }
 
@@ -292,59 +317,54 @@ IDC_HD void dec_state_init(DecState& st, uint64_t head, const uint32_t* words, u
     st.wp = words + nwords;
     st.sp = nwords;
     st.nxt = nwords ? ld_ro32(words + nwords - 1u) : 0u;
+    if (nwords > 8u) prefetch_ro(words + nwords - 9u);
     st.ov = 0;
     st.has_ov = 0;
     st.draws = 0;
     st.status = 0;
 }
 
-// pop one word: the overlay if there is one, else the blob's next word (consumed top-down; the word below is
-// requested now and first needed at the next pop), else the mt19937(1234) fallback of codec.h:32-40
-IDC_HD uint32_t dec_refill(DecState& st, const uint32_t* mt) {
-    uint32_t w;
-    if (st.has_ov | st.sp) {
-        const bool o = st.has_ov != 0u;
-        w = o ? st.ov : st.nxt;
-        st.has_ov = 0;
-        if (!o) {
-            st.sp--;
-            st.wp--;
-            if (st.sp) st.nxt = ld_ro32_pinned(st.wp - 1);
-        }
-    } else {
+// `if (h < 2^31) h = (h << 32) | pop()` of codec.cpp:83-87 / :56-60 as straight-line code. pop() = the overlay if
+// there is one, else the blob's next word (consumed top-down; the word below is requested now and first needed
+// at the next pop; the sector below that is prefetched into L1 when a sector is entered), else the
+// mt19937(1234) fallback of codec.h:32-40 (only at the very bottom of a stream: the one cold branch).
+IDC_HD uint64_t dec_renorm(DecState& st, uint64_t h, const uint32_t* mt) {
+    const bool rf = h < kRansL;
+    const bool o = st.has_ov != 0u;
+    const bool blob = rf & !o;
+    uint32_t w = o ? st.ov : st.nxt;
+    if (blob & (st.sp == 0u)) {
         uint32_t d = st.draws++;
         w = 0;
         if (d >= (uint32_t)kMtWords)
             st.status |= kStMtDraws;
         else
             w = mt[d];
+    } else {
+        const uint32_t dec = blob ? 1u : 0u;
+        st.sp -= dec;
+        st.wp -= dec;
+        const bool more = blob & (st.sp != 0u);
+        ld_ro32_if(st.wp - 1, st.nxt, more);
+        prefetch_ro_if(st.wp - 9, more & (((uint32_t)(uintptr_t)(st.wp - 1) & 31u) == 28u) & (st.sp > 8u));
     }
-    return w;
-}
-
-IDC_HD void dec_spill(DecState& st, uint32_t w) {
-    if (st.has_ov)
-        st.status |= kStOverlay;
-    st.ov = w;
-    st.has_ov = 1;
+    st.has_ov = rf ? 0u : st.has_ov;
+    return rf ? ((h << 32) | (uint64_t)w) : h;
 }
 
 // codec.cpp:78-90; p in 0..16
 IDC_HD uint32_t dec_pop_bits(DecState& st, uint32_t p, const uint32_t* mt) {
-    uint64_t h = st.head;
-    uint32_t sym = (uint32_t)h & ((1u << p) - 1u);
-    h >>= p;
-    if (h < kRansL)
-        h = (h << 32) | (uint64_t)dec_refill(st, mt);
-    st.head = h;
+    const uint64_t h = st.head;
+    const uint32_t sym = (uint32_t)h & ((1u << p) - 1u);
+    st.head = dec_renorm(st, h >> p, mt);
     return sym;
 }
 
 // codec.cpp:107-121 for precision <= 32: the slices at lower = 48 and 32 have precision 0 -- they pop nothing
 // but still renormalise (codec.cpp:83-87); never needed after a push_with_finer_precision, kept for exactness.
 IDC_HD uint32_t dec_pop_id32(DecState& st, int precision, const uint32_t* mt) {
-    if (st.head < kRansL) st.head = (st.head << 32) | (uint64_t)dec_refill(st, mt);
-    if (st.head < kRansL) st.head = (st.head << 32) | (uint64_t)dec_refill(st, mt);
+    if (st.head < kRansL) st.head = dec_renorm(st, st.head, mt);
+    if (st.head < kRansL) st.head = dec_renorm(st, st.head, mt);
     const uint32_t p0 = precision < 16 ? (uint32_t)precision : 16u;
     const uint32_t p1 = (uint32_t)precision - p0;
     const uint32_t hi = dec_pop_bits(st, p1, mt);
@@ -355,14 +375,15 @@ IDC_HD uint32_t dec_pop_id32(DecState& st, int precision, const uint32_t* mt) {
 // codec.cpp:44-63; q31 = 2^31/nmax
 IDC_HD void dec_push_uniform(DecState& st, uint32_t sym, uint32_t nmax, uint32_t q31, const uint32_t* mt) {
     uint64_t h = st.head;
-    if ((uint32_t)(h >> 32) >= q31) {
-        dec_spill(st, (uint32_t)h);
-        h >>= 32;
-    }
+    const uint32_t hi = (uint32_t)(h >> 32);
+    const bool spill = hi >= q31;
+    // the spilled word goes to the overlay; a second word above the blob's stack is flagged, not assumed away
+    st.status |= (spill & (st.has_ov != 0u)) ? kStOverlay : 0u;
+    st.ov = spill ? (uint32_t)h : st.ov;
+    st.has_ov = spill ? 1u : st.has_ov;
+    h = spill ? (uint64_t)hi : h;
     h = h * nmax + sym;
-    if (h < kRansL)
-        h = (uint64_t)dec_refill(st, mt) | (h << 32);
-    st.head = h;
+    st.head = dec_renorm(st, h, mt);
 }
 
 // ------------------------------------------------- encoder: select-remove --

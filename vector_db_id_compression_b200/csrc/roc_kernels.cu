@@ -274,11 +274,38 @@ void length_sorted_order(const uint32_t* n, uint64_t count, std::vector<uint32_t
 }
 
 // Size classes. Units are launched in descending length; a class is a contiguous slot range whose shared
-// memory footprint is set by its first (longest) unit. Classes run concurrently on auxiliary streams, so the
-// long units (which bound the kernel's duration) start first and the short ones fill the rest of the chip.
+// memory footprint is set by its first (longest) unit. The longest class bounds the kernel's duration (its units
+// are serial chains of up to 65 536 steps). A class's duration is about (its longest unit) x (step latency), so the
+// classes are spread over a few (3) streams by longest-processing-time-first on that estimate and run one
+// after the other inside a stream: the longest class keeps a stream to itself, the short ones queue up in its
+// shadow. Measured: all classes at once slow the long chains by 25 % (they share the issue slots); everything but
+// the longest class on ONE stream makes that stream the critical path.
 struct SizeClass {
     uint32_t slot_base, slot_end, max_n;
 };
+
+constexpr int kMaxClassStreams = 8;
+
+inline int class_stream_count() {
+    int n = 3;
+    if (const char* e = getenv("IDC_CLASS_STREAMS")) n = atoi(e);  // experiments
+    return n < 1 ? 1 : (n > kMaxClassStreams ? kMaxClassStreams : n);
+}
+
+// stream of each class: greedy LPT on max_n (classes come in descending max_n)
+inline std::vector<int> class_streams(const std::vector<SizeClass>& cls) {
+    std::vector<int> out(cls.size(), 0);
+    const int kClassStreams = class_stream_count();
+    uint64_t load[kMaxClassStreams] = {0};
+    for (size_t k = 0; k < cls.size(); k++) {
+        int best = 0;
+        for (int j = 1; j < kClassStreams; j++)
+            if (load[j] < load[best]) best = j;
+        out[k] = best;
+        load[best] += cls[k].max_n ? cls[k].max_n : 1u;
+    }
+    return out;
+}
 
 template <typename NofSlot>
 std::vector<SizeClass> size_classes(uint64_t nslots, NofSlot n_of_slot) {
@@ -327,6 +354,10 @@ inline uint32_t warps_for(uint32_t sm_words, uint32_t units_per_warp) {
 template <typename K>
 int set_max_smem(K kernel, size_t bytes) {
     IDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // All size classes ask for the maximum shared-memory carve-out: an SM keeps one carve-out while a kernel runs
+    // on it, and with the driver's per-launch choice a class that needs more shared memory than the running class
+    // left over could not become co-resident (measured: decode 146 ms -> 117 ms with the classes overlapping).
+    IDC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     return IDC_OK;
 }
 
@@ -466,7 +497,8 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
     {
         auto cls = size_classes(nu, [&](uint64_t slot) { return b->unit_n[perm[slot]]; });
         LaunchScope ls(c, "k_roc_encode");
-        IDC_TRY(c->fork((int)cls.size()));
+        const std::vector<int> cstream = class_streams(cls);
+        IDC_TRY(c->fork(class_stream_count()));
         for (size_t k = 0; k < cls.size(); k++) {
             EncArgs ek = e;
             ek.slot_base = cls[k].slot_base;
@@ -481,7 +513,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
 #define IDC_LAUNCH_ENC(GG, TT)                                                       \
     do {                                                                             \
         IDC_TRY(set_max_smem(k_roc_encode<GG, TT>, smem));                            \
-        k_roc_encode<GG, TT><<<grid, threads, smem, c->aux[k]>>>(ek);                 \
+        k_roc_encode<GG, TT><<<grid, threads, smem, c->aux[cstream[k]]>>>(ek);                 \
     } while (0)
             if (G == 8) {
                 if (enc_id_bytes == 8) IDC_LAUNCH_ENC(8, int64_t); else IDC_LAUNCH_ENC(8, uint32_t);
@@ -492,7 +524,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
             c->launches++;
         }
         c->launches--;  // LaunchScope counted one already
-        IDC_TRY(c->join((int)cls.size()));
+        IDC_TRY(c->join(class_stream_count()));
     }
     IDC_TRY(check_last_launch("k_roc_encode"));
 
@@ -624,7 +656,8 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
         auto cls = size_classes(nsel, n_of_slot);
         (void)max_n;
         LaunchScope ls(c, "k_roc_decode");
-        IDC_TRY(c->fork((int)cls.size()));
+        const std::vector<int> cstream = class_streams(cls);
+        IDC_TRY(c->fork(class_stream_count()));
         for (size_t k = 0; k < cls.size(); k++) {
             DecArgs ak = a;
             ak.slot_base = cls[k].slot_base;
@@ -639,7 +672,7 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
 #define IDC_LAUNCH_DEC(GG, TT)                                                       \
     do {                                                                             \
         IDC_TRY(set_max_smem(k_roc_decode<GG, TT>, smem));                            \
-        k_roc_decode<GG, TT><<<grid, threads, smem, c->aux[k]>>>(ak);                 \
+        k_roc_decode<GG, TT><<<grid, threads, smem, c->aux[cstream[k]]>>>(ak);                 \
     } while (0)
             if (G == 8) {
                 if (id_bytes == 8) IDC_LAUNCH_DEC(8, int64_t); else IDC_LAUNCH_DEC(8, int32_t);
@@ -650,7 +683,7 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
             c->launches++;
         }
         c->launches--;
-        IDC_TRY(c->join((int)cls.size()));
+        IDC_TRY(c->join(class_stream_count()));
     }
     IDC_TRY(check_last_launch("k_roc_decode"));
     uint32_t st = 0;
