@@ -305,7 +305,8 @@ struct DecState {
     uint64_t head;
     const uint32_t* wp;  // next word of the blob's stack to be popped is wp[-1]
     uint32_t sp;         // words still on the blob's stack
-    uint32_t nxt;        // wp[-1], fetched one refill ahead of its use (valid while sp > 0)
+    uint32_t nxt;        // wp[-1] (valid while sp > 0) and
+    uint32_t nx2;        // wp[-2] (valid while sp > 1): fetched two pops ahead of their use, straight from L2
     uint32_t ov;         // overlay: the one word the decoder may hold above the blob's stack
     uint32_t has_ov;
     uint32_t draws;
@@ -317,7 +318,7 @@ IDC_HD void dec_state_init(DecState& st, uint64_t head, const uint32_t* words, u
     st.wp = words + nwords;
     st.sp = nwords;
     st.nxt = nwords ? ld_ro32(words + nwords - 1u) : 0u;
-    if (nwords > 8u) prefetch_ro(words + nwords - 9u);
+    st.nx2 = nwords > 1u ? ld_ro32(words + nwords - 2u) : 0u;
     st.ov = 0;
     st.has_ov = 0;
     st.draws = 0;
@@ -325,9 +326,10 @@ IDC_HD void dec_state_init(DecState& st, uint64_t head, const uint32_t* words, u
 }
 
 // `if (h < 2^31) h = (h << 32) | pop()` of codec.cpp:83-87 / :56-60 as straight-line code. pop() = the overlay if
-// there is one, else the blob's next word (consumed top-down; the word below is requested now and first needed
-// at the next pop; the sector below that is prefetched into L1 when a sector is entered), else the
-// mt19937(1234) fallback of codec.h:32-40 (only at the very bottom of a stream: the one cold branch).
+// there is one, else the blob's next word (consumed top-down; two words are kept in registers and the word two
+// below is requested at every pop -- two pops of one step can be 100 cycles apart, and the kernels leave next to
+// no L1 to prefetch into), else the mt19937(1234) fallback of codec.h:32-40 (only at the very bottom of a
+// stream: the one cold branch).
 IDC_HD uint64_t dec_renorm(DecState& st, uint64_t h, const uint32_t* mt) {
     const bool rf = h < kRansL;
     const bool o = st.has_ov != 0u;
@@ -344,9 +346,8 @@ IDC_HD uint64_t dec_renorm(DecState& st, uint64_t h, const uint32_t* mt) {
         const uint32_t dec = blob ? 1u : 0u;
         st.sp -= dec;
         st.wp -= dec;
-        const bool more = blob & (st.sp != 0u);
-        ld_ro32_if(st.wp - 1, st.nxt, more);
-        prefetch_ro_if(st.wp - 9, more & (((uint32_t)(uintptr_t)(st.wp - 1) & 31u) == 28u) & (st.sp > 8u));
+        st.nxt = blob ? st.nx2 : st.nxt;
+        ld_ro32_if(st.wp - 2, st.nx2, blob & (st.sp > 1u));
     }
     st.has_ov = rf ? 0u : st.has_ov;
     return rf ? ((h << 32) | (uint64_t)w) : h;
