@@ -392,14 +392,10 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     IDC_TRY(upload(c, d_n, n32));
     const bool sorted_in = (flags & IDC_F_SORTED) != 0;
     {
-        MetaArgs m{ids_dev, d_src, d_n, (uint32_t)nl, sorted_in ? 1u : 0u, 0u, d_prec, d_lo, d_hi, d_status};
-        LaunchScope ls(c, "k_unit_meta");
-        if (id_bytes == 8)
-            k_unit_meta<int64_t><<<grid_for(nl * 32), kThreads, 0, c->stream>>>(m);
-        else
-            k_unit_meta<uint32_t><<<grid_for(nl * 32), kThreads, 0, c->stream>>>(m);
+        MetaArgs m{ids_dev, d_src, d_n, (uint32_t)nl, sorted_in ? 1u : 0u, 0u, d_prec, d_lo, d_hi, d_status,
+                   nullptr, nullptr, 0u};
+        IDC_TRY(run_unit_meta(c, m, n32, id_bytes));
     }
-    IDC_TRY(check_last_launch("k_unit_meta"));
     std::vector<uint32_t> hi(nl);
     uint32_t st = 0;
     if (nl) IDC_CUDA(cudaMemcpyAsync(hi.data(), d_hi, nl * 4, cudaMemcpyDeviceToHost, c->stream));

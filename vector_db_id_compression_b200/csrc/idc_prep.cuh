@@ -44,23 +44,30 @@ struct MetaArgs {
     uint32_t* unit_lo;
     uint32_t* unit_hi;
     uint32_t* status;  // single word, OR of per-unit flags
+    // tiles of kMetaTile ids: a unit (an Elias-Fano "unit" is a whole list, possibly 10^8 ids) is scanned by as
+    // many warps as it has tiles
+    const uint32_t* tile_unit;
+    const uint32_t* tile_idx;
+    uint32_t ntiles;
 };
+
+constexpr uint32_t kMetaTile = 4096;
 
 __device__ __forceinline__ uint32_t bit_length64(uint64_t x) { return x ? 64u - (uint32_t)__clzll((long long)x) : 0u; }
 
-// One warp per unit: min / max id, ascending check, 32-bit width check and the
-// reference precision rule (uint64_t)ceil(log2((int)max_id))
-// (custom_invlists_impl.cpp:163-164, altid_impl.cpp:124-125) restated in
-// integers: ceil(log2(m)) = bit_length(m - 1) for m >= 1.
+// One warp per tile: min / max id, ascending check (including the pair that straddles the tile's end) and 32-bit
+// width check, merged into the unit's slots with atomics (unit_lo starts at 0xffffffff, unit_hi at 0).
 template <typename IdT>
 __global__ void __launch_bounds__(kThreads) k_unit_meta(MetaArgs a) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= a.nunits) return;
-    const IdT* src = reinterpret_cast<const IdT*>(a.ids) + a.unit_src[warp];
-    uint32_t n = a.unit_n[warp];
+    if (warp >= a.ntiles) return;
+    const uint32_t u = a.tile_unit[warp];
+    const IdT* src = reinterpret_cast<const IdT*>(a.ids) + a.unit_src[u];
+    const uint32_t n = a.unit_n[u];
+    const uint32_t i0 = a.tile_idx[warp] * kMetaTile, i1 = i0 + kMetaTile < n ? i0 + kMetaTile : n;
     uint64_t mx = 0, mn = ~0ull;
     uint32_t bad = 0;
-    for (uint32_t i = lane; i < n; i += 32) {
+    for (uint32_t i = i0 + lane; i < i1; i += 32) {
         uint64_t v = load_id(src + i);
         if (sizeof(IdT) == 8 && (v >> 32)) bad |= kStWide;
         if (a.expect_sorted && i + 1 < n && load_id(src + i + 1) < v) bad |= kStUnsorted;
@@ -74,18 +81,29 @@ __global__ void __launch_bounds__(kThreads) k_unit_meta(MetaArgs a) {
         bad |= __shfl_xor_sync(0xffffffffu, bad, o);
     }
     if (lane == 0) {
-        uint32_t p;
-        if (n == 0)
-            p = 0;
-        else if (a.precision_safe)
-            p = bit_length64(mx);
-        else
-            p = mx ? bit_length64(mx - 1) : 0;  // max_id == 0 is undefined in the reference; 0 here
-        a.unit_prec[warp] = (uint8_t)p;
-        a.unit_lo[warp] = n ? (uint32_t)mn : 0u;
-        a.unit_hi[warp] = n ? (uint32_t)mx : 0u;
+        atomicMin(a.unit_lo + u, (uint32_t)(mn > 0xffffffffull ? 0xffffffffull : mn));
+        atomicMax(a.unit_hi + u, (uint32_t)(mx > 0xffffffffull ? 0xffffffffull : mx));
         if (bad) atomicOr(a.status, bad);
     }
+}
+
+// One thread per unit: the reference precision rule (uint64_t)ceil(log2((int)max_id))
+// (custom_invlists_impl.cpp:163-164, altid_impl.cpp:124-125) restated in integers:
+// ceil(log2(m)) = bit_length(m - 1) for m >= 1.
+__global__ void __launch_bounds__(kThreads) k_unit_meta_finish(MetaArgs a) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= a.nunits) return;
+    const uint32_t n = a.unit_n[u];
+    const uint64_t mx = a.unit_hi[u];
+    uint32_t p;
+    if (n == 0)
+        p = 0;
+    else if (a.precision_safe)
+        p = bit_length64(mx);
+    else
+        p = mx ? bit_length64(mx - 1) : 0;  // max_id == 0 is undefined in the reference; 0 here
+    a.unit_prec[u] = (uint8_t)p;
+    if (n == 0) a.unit_lo[u] = 0u, a.unit_hi[u] = 0u;
 }
 
 // NSG rows: number of entries before the first -1 (altid_impl.cpp:110-117)
@@ -165,6 +183,45 @@ __global__ void __launch_bounds__(256) k_sort_units(SortArgs a) {
 
 
 inline uint32_t grid_for(uint64_t threads) { return (uint32_t)((threads + kThreads - 1) / kThreads); }
+
+// Per-unit metadata for the units described by (m.unit_src, m.unit_n); unit_n_host mirrors m.unit_n. The tile
+// tables live in c->scratch (free at this point of every encode call).
+inline int run_unit_meta(idc_ctx* c, MetaArgs m, const std::vector<uint32_t>& unit_n_host, int id_bytes) {
+    const uint64_t nu = unit_n_host.size();
+    if (nu == 0) return IDC_OK;
+    std::vector<uint32_t> tile_unit, tile_idx;
+    for (uint64_t u = 0; u < nu; u++)
+        for (uint32_t t = 0; (uint64_t)t * kMetaTile < unit_n_host[u]; t++) {
+            tile_unit.push_back((uint32_t)u);
+            tile_idx.push_back(t);
+        }
+    const uint64_t nt = tile_unit.size();
+    IDC_REQUIRE(nt < (1ull << 32), IDC_ERR_ARG, "too many metadata tiles");
+    IDC_TRY(c->scratch.reserve(nt * 8 + 256));
+    uint32_t* d_tu = c->scratch.as<uint32_t>();
+    uint32_t* d_ti = d_tu + nt;
+    IDC_TRY(upload(c, d_tu, tile_unit));
+    IDC_TRY(upload(c, d_ti, tile_idx));
+    IDC_CUDA(cudaMemsetAsync(m.unit_lo, 0xff, nu * 4, c->stream));
+    IDC_CUDA(cudaMemsetAsync(m.unit_hi, 0, nu * 4, c->stream));
+    m.tile_unit = d_tu;
+    m.tile_idx = d_ti;
+    m.ntiles = (uint32_t)nt;
+    {
+        LaunchScope ls(c, "k_unit_meta");
+        if (nt) {
+            if (id_bytes == 8)
+                k_unit_meta<int64_t><<<grid_for(nt * 32), kThreads, 0, c->stream>>>(m);
+            else
+                k_unit_meta<uint32_t><<<grid_for(nt * 32), kThreads, 0, c->stream>>>(m);
+        }
+        k_unit_meta_finish<<<grid_for(nu), kThreads, 0, c->stream>>>(m);
+    }
+    IDC_TRY(check_last_launch("k_unit_meta"));
+    // the upload sources are stack vectors: finish before they go away
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    return IDC_OK;
+}
 
 
 int status_to_error(uint32_t st, const char* what) {

@@ -414,14 +414,10 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
     // 1. unit metadata
     {
         MetaArgs m{ids_dev, d_unit_src, b->d_unit_n, (uint32_t)nu, sorted_in ? 1u : 0u,
-                   (flags & IDC_F_PRECISION_SAFE) ? 1u : 0u, b->d_unit_prec, b->d_unit_lo, b->d_unit_hi, d_status};
-        LaunchScope ls(c, "k_unit_meta");
-        if (id_bytes == 8)
-            k_unit_meta<int64_t><<<grid_for(nu * 32), kThreads, 0, c->stream>>>(m);
-        else
-            k_unit_meta<uint32_t><<<grid_for(nu * 32), kThreads, 0, c->stream>>>(m);
+                   (flags & IDC_F_PRECISION_SAFE) ? 1u : 0u, b->d_unit_prec, b->d_unit_lo, b->d_unit_hi, d_status,
+                   nullptr, nullptr, 0u};
+        IDC_TRY(run_unit_meta(c, m, b->unit_n, id_bytes));
     }
-    IDC_TRY(check_last_launch("k_unit_meta"));
     {
         uint32_t st = 0;
         IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
