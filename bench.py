@@ -61,6 +61,20 @@ def measured_peak_gbs():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str, n_ids: int, zipf_s: float):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py), summed over the kernel's size-class launches.
+    Only reported when the capture was made on this very workload."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        t = json.load(open(p))
+        if int(t["n_ids"]) == int(n_ids) and abs(float(t["zipf_s"]) - float(zipf_s)) < 1e-9 and kernel in t["kernels"]:
+            return float(t["kernels"][kernel]["dram_bytes"]), t.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -332,8 +346,9 @@ def run_b200(args):
     dom = max(("k_roc_encode", "k_roc_decode"), key=lambda k: avg.get(k, 0.0))
     dom_bytes = enc_bytes if dom == "k_roc_encode" else dec_bytes
     achieved = dom_bytes / (avg[dom] * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(dom, n_ids, args.zipf_s)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": avg[dom],
                 "other": {k: {"ms": avg[k]} for k in avg if k != dom}}
     for k, b in (("k_roc_encode", enc_bytes), ("k_roc_decode", dec_bytes)):
