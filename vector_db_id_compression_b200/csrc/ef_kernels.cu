@@ -3,7 +3,7 @@
 // codec: every id is read once and every packed word is written once, with
 // coalesced 8-byte stores; there is no contraction, hence no tensor cores.
 //
-//   k_ef_encode   one thread per OUTPUT word (gather formulation, ef_core.cuh)
+//   k_ef_encode   one warp per tile of 1024 ids: read once, transposed, lane-local packing of both bit vectors
 //   k_ef_decode   one warp per tile of 1024 ids: popcount + warp prefix scan over
 //                 the upper-bit words, upper parts staged in shared memory, then a
 //                 coalesced pass that merges the lower bits and stores the ids
@@ -22,7 +22,8 @@ using namespace idc;
 
 namespace {
 
-constexpr uint32_t kEncTileWords = 1024;  // output words per warp in k_ef_encode
+constexpr uint32_t kEncTileIds = 1024;    // ids per warp in k_ef_encode (a multiple of 64: tiles own whole lower-bits words)
+constexpr uint32_t kEncWinWords = 256;    // 32-bit words of the shared-memory window over the upper bits (8192 bits)
 constexpr uint32_t kDecChunkWords = 16;   // 64-bit high words per warp in k_ef_decode (1024 bits, <= 1024 ids)
 constexpr uint32_t kDecTile = 1024;       // max ids of one chunk
 constexpr int kDecThreads = 256;          // 8 warps per CTA in k_ef_decode
@@ -103,117 +104,148 @@ struct EfEncArgs {
     uint32_t ntiles;
 };
 
-// first index i in [lo, hi] with ef_high_pos(i) >= P (hi if none); hp is strictly increasing in i. A 32-ary
-// search by the whole warp: five rounds of one coalesced-ish probe per lane instead of ~27 dependent loads.
-template <typename IdT>
-__device__ __forceinline__ uint64_t warp_search_high(const IdT* ids, uint32_t l, uint64_t lo, uint64_t hi, uint64_t P,
-                                                     uint32_t lane) {
-    while (hi > lo) {
-        const uint64_t len = hi - lo, stride = (len + 31) / 32;
-        const uint64_t p = lo + (uint64_t)lane * stride;
-        const bool less = p < hi && ef_high_pos(ids, p, l) < P;
-        const uint32_t c = (uint32_t)__popc(__ballot_sync(0xffffffffu, less));
-        if (c == 0) {
-            hi = lo;
-        } else {
-            const uint64_t pc = lo + (uint64_t)c * stride;  // first probe that is not `less` (or past the end)
-            lo = lo + (uint64_t)(c - 1) * stride + 1;
-            hi = pc < hi ? pc : hi;
-        }
-    }
-    return lo;
+// One warp per tile of 1024 consecutive ids of a list. Every id is read exactly once (32 coalesced rows, all
+// requested before the first is used) and transposed through shared memory so that lane j holds the 32
+// CONSECUTIVE ids 32 j .. 32 j + 31 of the tile; everything after that is lane-local:
+//   lower bits: a lane's 32 fields are exactly l consecutive 32-bit words (1024 l bits per tile = a whole number of
+//               64-bit words, so tiles own their lower-bits words): packed through a 64-bit accumulator, staged in
+//               shared memory, stored coalesced.
+//   upper bits: a lane's ones are strictly increasing and ~96 bits apart from the next lane's, so setting them in
+//               an 8192-bit shared-memory window is an atomicOr without conflicts. Words strictly between the tile's
+//               first and last one belong to the tile alone (plain stores); its first and last word may be shared
+//               with the neighbouring tiles (atomicOr on the pre-zeroed array).
+//   chunk descriptors for the decoder: id e announces the chunk boundaries between the previous id's one and its
+//               own (ids before such a boundary = e); the list's last tile adds the trailing ones.
+__device__ __forceinline__ void ef_emit_chunk(const EfEncArgs& a, uint32_t L, uint32_t l, uint64_t m, uint64_t hw,
+                                              uint64_t C, uint64_t before) {
+    const uint64_t W = C * kDecChunkWords;
+    if (W >= hw) return;
+    const bool last = W + kDecChunkWords >= hw;
+    const uint64_t cntc = last ? m - before : 0x7ffull;  // 0x7ff: k_ef_finish_chunks takes it from the next descriptor
+    const uint64_t rest = hw - W;
+    const uint64_t nw32 = 2 * (rest < kDecChunkWords ? rest : kDecChunkWords);
+    EfChunk d;
+    d.a = (2 * (a.high_off[L] + W)) | (cntc << 40) | ((uint64_t)l << 51) | (nw32 << 56);
+    d.low32 = 2 * a.low_off[L] + (before >> 5) * l;
+    d.out_base = a.list_off[L];
+    d.b = before | ((W * 64 - before) << 32);
+    a.dir[a.dir_off[L] + C] = d;
 }
 
-// One warp per tile of 1024 output words of a list (lower-bits words first, then upper-bits words).
-//   lower bits: gather -- a word collects the ceil(64/l)+1 fields that overlap it (ef_low_word)
-//   upper bits: the tile covers bit positions [P0, P1); the warp finds the ids whose ones fall there with two
-//               32-ary searches, reads them once, coalesced, and ORs their bits into the tile in shared memory;
-//               popcounts of the finished words give the decoder's chunk descriptors; the words leave with
-//               coalesced 8-byte stores.
 template <typename IdT>
-__global__ void __launch_bounds__(kThreads) k_ef_encode(EfEncArgs a) {
-    __shared__ unsigned long long tile_sm[kThreads / 32][kEncTileWords];
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(kThreads, 4) k_ef_encode(EfEncArgs a) {
+    __shared__ uint32_t tile_sm[kThreads / 32][kEncTileIds + 32];
+    __shared__ uint32_t win_sm[kThreads / 32][kEncWinWords];
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.ntiles) return;
-    uint32_t L = a.tile_list[warp];
-    uint64_t m = a.list_off[L + 1] - a.list_off[L];
+    const uint32_t L = a.tile_list[warp];
+    const uint64_t m = a.list_off[L + 1] - a.list_off[L];
     if (m == 0) return;
     const IdT* ids = reinterpret_cast<const IdT*>(a.ids) + a.list_src[L];
-    uint32_t l = a.l[L];
-    uint64_t universe = a.list_hi[L];
-    uint64_t lw = a.low_off[L + 1] - a.low_off[L], hw = a.high_off[L + 1] - a.high_off[L];
-    uint64_t w0 = (uint64_t)a.tile_idx[warp] * kEncTileWords;
-    uint64_t w1 = w0 + kEncTileWords < lw + hw ? w0 + kEncTileWords : lw + hw;
-    uint64_t* low = a.low + a.low_off[L];
-    uint64_t* high = a.high + a.high_off[L];
-    uint32_t* samples = a.samples + a.samp_off[L];
-    // ---- lower-bits words of the tile
-    for (uint64_t w = w0 + lane; w < w1 && w < lw; w += 32) low[w] = ef_low_word(ids, m, l, w);
-    if (w1 <= lw) return;
-    // ---- upper-bits words [h0, h1) of the list
-    const uint64_t h0 = (w0 > lw ? w0 : lw) - lw, h1 = w1 - lw;
-    const uint32_t nw = (uint32_t)(h1 - h0);
-    const uint64_t P0 = h0 * 64, P1 = h1 * 64;
-    unsigned long long* tile = tile_sm[threadIdx.x >> 5];
-    for (uint32_t j = lane; j < nw; j += 32) tile[j] = 0ull;
-    // ids i with P0 <= hp(i) < P1; i <= hp(i) <= i + (universe >> l) bounds both searches
-    const uint64_t span = universe >> l;
-    uint64_t lo0 = P0 > span ? P0 - span : 0, hi0 = P0 < m ? P0 : m;
-    if (lo0 > hi0) lo0 = hi0;
-    const uint64_t ia = warp_search_high(ids, l, lo0, hi0, P0, lane);
-    uint64_t hi1 = P1 < m ? P1 : m;
-    const uint64_t ib = warp_search_high(ids, l, ia, hi1 > ia ? hi1 : ia, P1, lane);
+    const uint32_t l = a.l[L];
+    const uint64_t hw = a.high_off[L + 1] - a.high_off[L];
+    const uint64_t i0 = (uint64_t)a.tile_idx[warp] * kEncTileIds;
+    const uint32_t cnt = (uint32_t)(m - i0 < kEncTileIds ? m - i0 : kEncTileIds);
+    const bool last_tile = i0 + cnt == m;
+    uint32_t* low32 = reinterpret_cast<uint32_t*>(a.low + a.low_off[L]) + (i0 * l) / 32;
+    uint32_t* high32 = reinterpret_cast<uint32_t*>(a.high + a.high_off[L]);
+    uint32_t* ts = tile_sm[threadIdx.x >> 5];
+    uint32_t* win = win_sm[threadIdx.x >> 5];
+    // ---- coalesced rows -> shared memory (element e at e + e / 32: both access patterns are conflict-free)
+    {
+        uint32_t row[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            row[r] = (uint32_t)r * 32u + lane < cnt ? (uint32_t)load_id(ids + i0 + (uint32_t)r * 32u + lane) : 0u;
+#pragma unroll
+        for (int r = 0; r < 32; r++) ts[33u * (uint32_t)r + lane] = row[r];
+    }
+    // the one before this tile's first one (-1: none)
+    const int64_t hp_prev_tile = i0 ? (int64_t)ef_high_pos(ids, i0 - 1, l) : -1;
     __syncwarp();
-    // 32 consecutive ids per round, one per lane. Their ones are strictly increasing and dense (at least one id
-    // per three upper bits), so a round touches two to four 32-bit words: for each of them the lanes' bits are
-    // OR-reduced across the warp and lane 0 merges the result -- no shared-memory atomics (a 32-way conflict on
-    // one word per round, measured 3x slower than the gather formulation).
-    uint32_t* tile32 = reinterpret_cast<uint32_t*>(tile);
-    for (uint64_t base = ia; base < ib; base += 32) {
-        const uint64_t i = base + lane;
-        const bool on = i < ib;
-        uint64_t hp = 0;
-        if (on) {
-            hp = ef_high_pos(ids, i, l);
-            if ((i & (kEfSample - 1)) == 0) samples[i >> kEfSampleLog] = (uint32_t)hp;
-        }
-        const uint32_t w32 = on ? (uint32_t)((hp - P0) >> 5) : 0u, bit = on ? 1u << (hp & 31) : 0u;
-        const uint32_t wlo = __shfl_sync(0xffffffffu, w32, 0), whi = __reduce_max_sync(0xffffffffu, w32);
-        for (uint32_t cur = wlo; cur <= whi; cur++) {
-            const uint32_t v = __reduce_or_sync(0xffffffffu, w32 == cur ? bit : 0u);
-            if (lane == 0) tile32[cur] |= v;
-        }
-    }
+    uint32_t v[32];  // lane-major: v[r] = id of element 32 * lane + r
+#pragma unroll
+    for (int r = 0; r < 32; r++) v[r] = ts[33u * lane + (uint32_t)r];
+    const uint64_t hpF = (uint64_t)(ts[0] >> l) + i0;
+    const uint64_t hpL = (uint64_t)(ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0 + cnt - 1u;
     __syncwarp();
-    // ---- ids before each word: lane j owns words [32 j, 32 j + 32) of the tile
-    uint32_t mine = 0;
-    for (uint32_t j = lane * 32; j < lane * 32 + 32 && j < nw; j++) mine += (uint32_t)__popcll(tile[j]);
-    uint32_t incl = mine;
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += v;
-    }
-    uint64_t before = ia + (incl - mine);
-    for (uint32_t j = lane * 32; j < lane * 32 + 32 && j < nw; j++) {
-        const uint64_t hwi = h0 + j;
-        if ((hwi & (kDecChunkWords - 1)) == 0) {
-            // a chunk boundary: the descriptor the decoder reads. Ids in the chunk are known here for a list's last
-            // chunk, otherwise next chunk's r0 - r0, filled in by k_ef_finish_chunks (0x7ff = "take it from the
-            // next descriptor")
-            const bool last = hwi + kDecChunkWords >= hw;
-            const uint64_t cnt = last ? m - before : 0x7ffull;
-            uint64_t rest = hw - hwi;
-            uint64_t nw32 = 2 * (rest < kDecChunkWords ? rest : kDecChunkWords);
-            EfChunk d;
-            d.a = (2 * (a.high_off[L] + hwi)) | (cnt << 40) | ((uint64_t)l << 51) | (nw32 << 56);
-            d.low32 = 2 * a.low_off[L] + (before >> 5) * l;
-            d.out_base = a.list_off[L];
-            d.b = before | ((hwi * 64 - before) << 32);
-            a.dir[a.dir_off[L] + hwi / kDecChunkWords] = d;
+    // ---- lower bits
+    if (l) {
+        const uint32_t nlw = ((cnt * l + 63u) / 64u) * 2u;  // 32-bit words, a whole number of 64-bit words
+        const uint32_t fmask = (1u << l) - 1u;             // l <= 31 for ids < 2^32
+        uint64_t acc = 0;
+        uint32_t fill = 0, wq = lane * l;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            acc |= (uint64_t)(v[r] & fmask) << fill;  // ids past the end of the list were loaded as 0
+            fill += l;
+            if (fill >= 32u) {
+                ts[wq++] = (uint32_t)acc;
+                acc >>= 32;
+                fill -= 32u;
+            }
         }
-        before += (uint64_t)__popcll(tile[j]);
+        __syncwarp();
+        for (uint32_t q = lane; q < nlw; q += 32) low32[q] = ts[q];
     }
-    for (uint32_t j = lane; j < nw; j += 32) high[h0 + j] = tile[j];
+    // ---- upper bits
+    const uint64_t gF = hpF >> 5, gL = hpL >> 5;  // the tile's first / last 32-bit word of the high vector
+    if (lane % 8u == 0u && 32u * lane < cnt) (a.samples + a.samp_off[L])[(i0 + 32u * lane) >> kEfSampleLog] = (uint32_t)((v[0] >> l) + i0 + 32u * lane);
+    uint64_t wb = hpF & ~31ull;  // window base (a bit position)
+    for (;;) {
+        for (uint32_t q = lane; q < kEncWinWords; q += 32) win[q] = 0u;
+        __syncwarp();
+        const bool more = hpL >= wb + 32ull * kEncWinWords;  // warp-uniform: some ones lie past this window
+        uint64_t next = ~0ull;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const uint32_t e = 32u * lane + (uint32_t)r;
+            const uint64_t hp = (uint64_t)(v[r] >> l) + i0 + e;
+            const uint64_t rel = hp - wb;  // wraps (huge) for positions below the window: handled in an earlier pass
+            if (e < cnt && rel < 32ull * kEncWinWords) atomicOr(win + (uint32_t)(rel >> 5), 1u << (hp & 31));
+            if (more && e < cnt && hp >= wb + 32ull * kEncWinWords && hp < next) next = hp;
+        }
+        __syncwarp();
+        for (uint32_t q = lane; q < kEncWinWords; q += 32) {
+            const uint64_t g = (wb >> 5) + q;
+            if (g < gF || g > gL) continue;
+            const uint32_t val = win[q];
+            if (g == gF || g == gL) {
+                if (val) atomicOr(high32 + g, val);
+            } else {
+                high32[g] = val;
+            }
+        }
+        if (!more) break;
+        for (int o = 16; o; o >>= 1) {
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, next, o);
+            next = other < next ? other : next;
+        }
+        wb = next & ~31ull;
+        __syncwarp();
+    }
+    // ---- chunk descriptors (a chunk = kDecChunkWords 64-bit words = 1024 bits of the high vector)
+    {
+        const uint32_t e_last = 32u * lane + 31u;
+        const int64_t my_last = (int64_t)((uint64_t)(v[31] >> l) + i0 + e_last);
+        int64_t prev = __shfl_up_sync(0xffffffffu, my_last, 1);
+        if (lane == 0) prev = hp_prev_tile;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const uint32_t e = 32u * lane + (uint32_t)r;
+            const int64_t hp = (int64_t)((uint64_t)(v[r] >> l) + i0 + e);
+            if (e < cnt) {
+                // chunks C with prev < 1024 C <= hp: id e is the first one at or past their first bit
+                const int64_t c_hi = hp >> 10;
+                for (int64_t C = prev < 0 ? 0 : (prev >> 10) + 1; C <= c_hi; C++) ef_emit_chunk(a, L, l, m, hw, (uint64_t)C, i0 + e);
+            }
+            prev = hp;
+        }
+        if (last_tile) {
+            const uint64_t nchunks = (hw + kDecChunkWords - 1) / kDecChunkWords;
+            for (uint64_t C = (hpL >> 10) + 1 + lane; C < nchunks; C += 32) ef_emit_chunk(a, L, l, m, hw, C, m);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) k_ef_finish_chunks(EfChunk* dir, uint64_t n) {
@@ -476,8 +508,7 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
         b->samp_off[i + 1] = b->samp_off[i] + s.samples;
         b->dir_off[i + 1] = b->dir_off[i] + std::max<uint64_t>(1, (s.high_words + kDecChunkWords - 1) / kDecChunkWords);
         bits_total += s.low_bits + s.high_bits;
-        uint64_t words = s.low_words + s.high_words;
-        for (uint64_t t = 0; t * kEncTileWords < words; t++) {
+        for (uint64_t t = 0; t * kEncTileIds < n32[i]; t++) {
             tile_list.push_back((uint32_t)i);
             tile_idx.push_back((uint32_t)t);
         }
@@ -550,6 +581,8 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
         enc_id_bytes = 4;
     }
     IDC_TRY(check_last_launch("k_sort_units"));
+    // tiles OR their first / last upper-bits word into the array: it starts out zero
+    IDC_CUDA(cudaMemsetAsync(b->d_high, 0, std::max<uint64_t>(b->high_words, 1) * 8, c->stream));
     if (ntiles) {
         EfEncArgs e{enc_ids, d_src, b->d_list_off, b->d_l, d_hi, b->d_low_off, b->d_high_off, b->d_samp_off,
                     b->d_low, b->d_high, b->d_samples, b->d_dir_off, b->d_dir, d_tile_list, d_tile_idx, (uint32_t)ntiles};
