@@ -178,6 +178,23 @@ int idc_roc_decode(
         int out_mem,
         uint64_t* out_offsets);
 
+/* The id-translation step of search_IVF_defer_id_decoding
+ * (custom_invlists_impl.cpp:464-525): labels hold (list_no << 32 | offset)
+ * pairs as written by search_preassigned(store_pairs = true); `offset` counts
+ * in the list's decode order (= the order of its re-laid codes). Every distinct
+ * hit list is decoded ONCE, in one bulk launch (the reference groups the hits
+ * by list and decodes the hit lists under OpenMP, :477-525), then the ids are
+ * gathered on the device. Negative labels pass through unchanged. labels and
+ * ids_out are n int64 values, HOST or DEVICE per their *_mem arguments. */
+int idc_roc_translate(
+        idc_ctx* ctx,
+        const idc_roc_blob* blob,
+        const int64_t* labels,
+        int labels_mem,
+        uint64_t n,
+        int64_t* ids_out,
+        int out_mem);
+
 /* ROCNSGGraph::get_neighbors (altid_impl.cpp:153-165) for many rows at once:
  * out is nsel x K int32; entries past the row's length are set to -1;
  * counts (may be NULL) receives the true neighbour count per row (the

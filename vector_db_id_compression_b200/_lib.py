@@ -44,6 +44,7 @@ SYMBOLS = {
     "idc_roc_blob_order": (C.c_int, [vp, vp, C.c_int]),
     "idc_roc_blob_free": (C.c_int, [vp]),
     "idc_roc_decode": (C.c_int, [vp, vp, vp, u64, vp, C.c_int, C.c_int, vp]),
+    "idc_roc_translate": (C.c_int, [vp, vp, vp, C.c_int, u64, vp, C.c_int]),
     "idc_roc_decode_rows": (C.c_int, [vp, vp, vp, C.c_int, u64, vp, vp, C.c_int]),
     "idc_ef_encode": (C.c_int, [vp, u64, vp, vp, C.c_int, C.c_int, u32, C.POINTER(vp)]),
     "idc_ef_encode_rows": (C.c_int, [vp, u64, u32, vp, C.c_int, u32, C.POINTER(vp)]),

@@ -272,6 +272,17 @@ class RocBlob:
         _check(self._l.idc_roc_decode(self.ctx._h, self._h, lp, nsel, p, id_bytes, mem, out_off.ctypes.data))
         return out[:total], out_off
 
+    def translate(self, labels, *, device=None):
+        """(list_no << 32 | offset) labels -> ids; negative labels pass through (idc_roc_translate)."""
+        if not _is_torch(labels):
+            labels = np.ascontiguousarray(labels, dtype=np.int64)
+        n = int(labels.numel() if _is_torch(labels) else labels.size)
+        out = _alloc_like(None, n, np.int64, device)
+        pl, ml = _ptr(labels)
+        po, mo = _ptr(out)
+        _check(self._l.idc_roc_translate(self.ctx._h, self._h, pl, ml, n, po, mo))
+        return out[:n]
+
     def export_list_offsets(self) -> np.ndarray:
         lo = np.zeros(self.nlist + 1, np.uint64)
         _check(self._l.idc_roc_blob_export(self._h, lo.ctypes.data, None, None, None, None, None, None))

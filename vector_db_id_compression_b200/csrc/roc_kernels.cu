@@ -190,6 +190,15 @@ __global__ void __launch_bounds__(kThreads) k_roc_compact(const uint32_t* scratc
     for (uint32_t i = lane; i < cnt; i += 32) words[d0 + i] = __ldcs(src + i);
 }
 
+// ids_out[i] = labels[i] < 0 ? labels[i] : decoded[src[i]]
+__global__ void __launch_bounds__(kThreads) k_translate_gather(const int64_t* labels, const uint64_t* src,
+                                                               const int64_t* decoded, int64_t* out, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t lab = labels[i];
+    out[i] = lab < 0 ? lab : decoded[src[i]];
+}
+
 struct DecArgs {
     const uint32_t* sel_unit;   // launch slot -> blob unit, by descending n
     const uint64_t* sel_out;    // launch slot -> element offset in out
@@ -971,6 +980,104 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
                 set_error("D2H copy failed: %s", cudaGetErrorString(e));
                 rc = IDC_ERR_CUDA;
             }
+        }
+    }
+    c->pool_release(t_unit);
+    c->pool_release(t_out);
+    c->pool_release(t_ws);
+    return rc;
+}
+
+int idc_roc_translate(idc_ctx* c, const idc_roc_blob* b, const int64_t* labels, int labels_mem, uint64_t n,
+                      int64_t* ids_out, int out_mem) {
+    IDC_REQUIRE(c && b, IDC_ERR_ARG, "idc_roc_translate: null argument");
+    IDC_REQUIRE(b->row_stride == 0, IDC_ERR_ARG, "row blob: labels address inverted lists");
+    if (n == 0) return IDC_OK;
+    IDC_REQUIRE(labels && ids_out, IDC_ERR_ARG, "idc_roc_translate: null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    // labels on the host: grouping the hits by list is metadata work (custom_invlists_impl.cpp:477-502)
+    std::vector<int64_t> lab_h;
+    const int64_t* lab = labels;
+    if (labels_mem == IDC_MEM_DEVICE) {
+        lab_h.resize(n);
+        IDC_CUDA(cudaMemcpyAsync(lab_h.data(), labels, n * 8, cudaMemcpyDeviceToHost, c->stream));
+        IDC_CUDA(cudaStreamSynchronize(c->stream));
+        lab = lab_h.data();
+    }
+    std::vector<uint64_t> hit;  // distinct hit lists, ascending
+    hit.reserve(n);
+    for (uint64_t i = 0; i < n; i++) {
+        if (lab[i] < 0) continue;
+        const uint64_t l = (uint64_t)lab[i] >> 32, o = (uint64_t)lab[i] & 0xffffffffull;
+        IDC_REQUIRE(l < b->nlist, IDC_ERR_ARG, "label %llu: list_no %llu out of range", (unsigned long long)i,
+                    (unsigned long long)l);
+        IDC_REQUIRE(o < b->list_offsets[l + 1] - b->list_offsets[l], IDC_ERR_ARG,
+                    "label %llu: offset %llu past the end of list %llu", (unsigned long long)i, (unsigned long long)o,
+                    (unsigned long long)l);
+        hit.push_back(l);
+    }
+    std::sort(hit.begin(), hit.end());
+    hit.erase(std::unique(hit.begin(), hit.end()), hit.end());
+    // decode plan for the hit lists; pos_of[list] = element offset of the list in the decoded buffer
+    std::vector<uint32_t> units;
+    std::vector<uint64_t> out_off, list_pos(hit.size());
+    uint64_t pos = 0;
+    for (size_t h = 0; h < hit.size(); h++) {
+        list_pos[h] = pos;
+        for (uint64_t u = b->unit_offsets[hit[h]]; u < b->unit_offsets[hit[h] + 1]; u++) {
+            units.push_back((uint32_t)u);
+            out_off.push_back(pos);
+            pos += b->unit_n[u];
+        }
+    }
+    std::vector<uint64_t> src(n, 0);
+    for (uint64_t i = 0; i < n; i++) {
+        if (lab[i] < 0) continue;
+        const uint64_t l = (uint64_t)lab[i] >> 32, o = (uint64_t)lab[i] & 0xffffffffull;
+        const size_t h = std::lower_bound(hit.begin(), hit.end(), l) - hit.begin();
+        src[i] = list_pos[h] + o;
+    }
+    // device buffers: decoded ids | src | labels (when they came from the host) | out (when it goes to the host)
+    const size_t off_src = (pos * 8 + 255) & ~size_t(255), off_lab = off_src + ((n * 8 + 255) & ~size_t(255));
+    const size_t off_out = off_lab + ((n * 8 + 255) & ~size_t(255));
+    IDC_TRY(c->stage.reserve(off_out + n * 8 + 256));
+    uint8_t* st = c->stage.as<uint8_t>();
+    int64_t* d_dec = reinterpret_cast<int64_t*>(st);
+    uint64_t* d_src = reinterpret_cast<uint64_t*>(st + off_src);
+    const int64_t* d_lab = labels;
+    if (labels_mem == IDC_MEM_HOST) {
+        IDC_CUDA(cudaMemcpyAsync(st + off_lab, labels, n * 8, cudaMemcpyHostToDevice, c->stream));
+        d_lab = reinterpret_cast<const int64_t*>(st + off_lab);
+    }
+    int64_t* d_out = out_mem == IDC_MEM_HOST ? reinterpret_cast<int64_t*>(st + off_out) : ids_out;
+    IDC_TRY(upload(c, d_src, src));
+    int rc = IDC_OK;
+    uint32_t* t_unit = nullptr;
+    uint64_t *t_out = nullptr, *t_ws = nullptr;
+    if (!units.empty()) {
+        uint64_t ws_bytes = 0;
+        std::vector<uint32_t> t_ns;
+        rc = build_decode_plan(c, b, units, out_off, &t_unit, &t_out, &t_ws, &ws_bytes, &t_ns);
+        if (rc == IDC_OK)
+            rc = run_decode(c, b, t_unit, t_out, t_ws, ws_bytes, units.size(), d_dec, 8, nullptr, 0, t_ns.empty() ? 0u : t_ns[0],
+                            [&](uint64_t slot) { return t_ns[slot]; });
+    }
+    if (rc == IDC_OK) {
+        {
+            LaunchScope ls(c, "k_translate_gather");
+            k_translate_gather<<<grid_for(n), kThreads, 0, c->stream>>>(d_lab, d_src, d_dec, d_out, n);
+        }
+        rc = check_last_launch("k_translate_gather");
+    }
+    if (rc == IDC_OK) {
+        cudaError_t e = cudaSuccess;
+        if (out_mem == IDC_MEM_HOST) e = cudaMemcpyAsync(ids_out, d_out, n * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            set_error("idc_roc_translate: %s", cudaGetErrorString(e));
+            rc = IDC_ERR_CUDA;
         }
     }
     c->pool_release(t_unit);

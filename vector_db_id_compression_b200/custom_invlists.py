@@ -240,6 +240,9 @@ def translate_labels(invlists: InvertedListsArrayCodes, labels: np.ndarray, deco
         else:
             out[valid] = [invlists.get_single_id(int(l), int(o)) for l, o in zip(lists, offs)]
         return out.reshape(labels.shape)
+    if isinstance(invlists, CompressedIDInvertedListsFenwickTree):
+        # one C-ABI call: distinct hit lists decoded once on the GPU, ids gathered on the device
+        return invlists.blob.translate(labels.ravel()).reshape(labels.shape)
     invlists.prefetch(np.unique(lists))
     for l in np.unique(lists):
         m = lists == l
