@@ -34,6 +34,7 @@ int check_last_launch(const char* what) {
 void idc_ctx::begin_call() {
     times.clear();
     events_used = 0;
+    sync_used = 0;
 }
 
 void idc_ctx::mark(const char* name) {
@@ -99,6 +100,22 @@ void idc_ctx::pool_release(void* p) {
 void idc_ctx::pool_trim() {
     for (auto& b : pool_free) cudaFree(b.first);
     pool_free.clear();
+}
+
+int idc_ctx::copy_stream_get(cudaStream_t* s) {
+    if (!copy_stream) IDC_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    *s = copy_stream;
+    return IDC_OK;
+}
+
+int idc_ctx::sync_event(cudaEvent_t* e) {
+    if (sync_used == sync_events.size()) {
+        cudaEvent_t ev;
+        IDC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        sync_events.push_back(ev);
+    }
+    *e = sync_events[sync_used++];
+    return IDC_OK;
 }
 
 int idc_ctx::fork(int n) {
@@ -205,6 +222,8 @@ int idc_ctx_destroy(idc_ctx* c) {
     for (auto s : c->aux) cudaStreamDestroy(s);
     for (auto e : c->aux_done) cudaEventDestroy(e);
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
+    for (auto e : c->sync_events) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->d_mt);
     cudaFree(c->d_rcp64);
     cudaFree(c->d_q31);

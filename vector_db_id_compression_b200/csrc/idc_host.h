@@ -113,6 +113,12 @@ struct idc_ctx {
     std::vector<cudaStream_t> aux;
     std::vector<cudaEvent_t> aux_done;
     cudaEvent_t fork_ev = nullptr;
+    // copy engine stream + reusable ordering events (host<->device copies overlapped with the kernels)
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> sync_events;
+    size_t sync_used = 0;
+    int copy_stream_get(cudaStream_t* s);
+    int sync_event(cudaEvent_t* e);  // an event for ordering only; recycled at the next begin_call()
     int fork(int n);              // make aux[0..n) wait for everything queued on `stream`
     int join(int n);              // make `stream` wait for aux[0..n)
 

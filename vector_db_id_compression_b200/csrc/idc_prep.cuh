@@ -48,7 +48,10 @@ struct MetaArgs {
     // many warps as it has tiles
     const uint32_t* tile_unit;
     const uint32_t* tile_idx;
-    uint32_t ntiles;
+    uint32_t ntiles;      // tiles of this launch: [tile_base, tile_base + ntiles)
+    uint32_t tile_base;
+    uint32_t unit_base;   // k_unit_meta_finish: units [unit_base, unit_base + unit_count)
+    uint32_t unit_count;
 };
 
 constexpr uint32_t kMetaTile = 4096;
@@ -61,6 +64,7 @@ template <typename IdT>
 __global__ void __launch_bounds__(kThreads) k_unit_meta(MetaArgs a) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.ntiles) return;
+    warp += a.tile_base;
     const uint32_t u = a.tile_unit[warp];
     const IdT* src = reinterpret_cast<const IdT*>(a.ids) + a.unit_src[u];
     const uint32_t n = a.unit_n[u];
@@ -92,7 +96,8 @@ __global__ void __launch_bounds__(kThreads) k_unit_meta(MetaArgs a) {
 // ceil(log2(m)) = bit_length(m - 1) for m >= 1.
 __global__ void __launch_bounds__(kThreads) k_unit_meta_finish(MetaArgs a) {
     uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= a.nunits) return;
+    if (u >= a.unit_count) return;
+    u += a.unit_base;
     const uint32_t n = a.unit_n[u];
     const uint64_t mx = a.unit_hi[u];
     uint32_t p;
@@ -184,45 +189,67 @@ __global__ void __launch_bounds__(256) k_sort_units(SortArgs a) {
 
 inline uint32_t grid_for(uint64_t threads) { return (uint32_t)((threads + kThreads - 1) / kThreads); }
 
-// Per-unit metadata for the units described by (m.unit_src, m.unit_n); unit_n_host mirrors m.unit_n. The tile
-// tables live in c->scratch (free at this point of every encode call).
+// Per-unit metadata for the units described by (m.unit_src, m.unit_n).
+struct MetaPlan {
+    std::vector<uint32_t> tile_unit, tile_idx;
+    std::vector<uint64_t> tile_first;  // per unit (nunits + 1): index of its first tile
+};
+
+inline void plan_unit_meta(const std::vector<uint32_t>& unit_n, MetaPlan& p) {
+    p.tile_unit.clear();
+    p.tile_idx.clear();
+    p.tile_first.assign(unit_n.size() + 1, 0);
+    for (uint64_t u = 0; u < unit_n.size(); u++) {
+        p.tile_first[u] = p.tile_unit.size();
+        for (uint32_t t = 0; (uint64_t)t * kMetaTile < unit_n[u]; t++) {
+            p.tile_unit.push_back((uint32_t)u);
+            p.tile_idx.push_back(t);
+        }
+    }
+    p.tile_first[unit_n.size()] = p.tile_unit.size();
+}
+
+// the kernels for units [u0, u1); m.tile_unit / m.tile_idx are the uploaded tables of the whole plan, unit_lo /
+// unit_hi hold 0xffffffff / 0 for these units
+template <int kDummy = 0>
+int launch_unit_meta(idc_ctx* c, MetaArgs m, int id_bytes, uint64_t u0, uint64_t u1, const MetaPlan& p) {
+    if (u1 <= u0) return IDC_OK;
+    m.tile_base = (uint32_t)p.tile_first[u0];
+    m.ntiles = (uint32_t)(p.tile_first[u1] - p.tile_first[u0]);
+    m.unit_base = (uint32_t)u0;
+    m.unit_count = (uint32_t)(u1 - u0);
+    LaunchScope ls(c, "k_unit_meta");
+    if (m.ntiles) {
+        if (id_bytes == 8)
+            k_unit_meta<int64_t><<<grid_for((uint64_t)m.ntiles * 32), kThreads, 0, c->stream>>>(m);
+        else
+            k_unit_meta<uint32_t><<<grid_for((uint64_t)m.ntiles * 32), kThreads, 0, c->stream>>>(m);
+    }
+    k_unit_meta_finish<<<grid_for(m.unit_count), kThreads, 0, c->stream>>>(m);
+    return check_last_launch("k_unit_meta");
+}
+
+// everything at once; the tile tables go to c->scratch (free at this point of an Elias-Fano encode call)
 inline int run_unit_meta(idc_ctx* c, MetaArgs m, const std::vector<uint32_t>& unit_n_host, int id_bytes) {
     const uint64_t nu = unit_n_host.size();
     if (nu == 0) return IDC_OK;
-    std::vector<uint32_t> tile_unit, tile_idx;
-    for (uint64_t u = 0; u < nu; u++)
-        for (uint32_t t = 0; (uint64_t)t * kMetaTile < unit_n_host[u]; t++) {
-            tile_unit.push_back((uint32_t)u);
-            tile_idx.push_back(t);
-        }
-    const uint64_t nt = tile_unit.size();
+    MetaPlan p;
+    plan_unit_meta(unit_n_host, p);
+    const uint64_t nt = p.tile_unit.size();
     IDC_REQUIRE(nt < (1ull << 32), IDC_ERR_ARG, "too many metadata tiles");
     IDC_TRY(c->scratch.reserve(nt * 8 + 256));
     uint32_t* d_tu = c->scratch.as<uint32_t>();
     uint32_t* d_ti = d_tu + nt;
-    IDC_TRY(upload(c, d_tu, tile_unit));
-    IDC_TRY(upload(c, d_ti, tile_idx));
+    IDC_TRY(upload(c, d_tu, p.tile_unit));
+    IDC_TRY(upload(c, d_ti, p.tile_idx));
     IDC_CUDA(cudaMemsetAsync(m.unit_lo, 0xff, nu * 4, c->stream));
     IDC_CUDA(cudaMemsetAsync(m.unit_hi, 0, nu * 4, c->stream));
     m.tile_unit = d_tu;
     m.tile_idx = d_ti;
-    m.ntiles = (uint32_t)nt;
-    {
-        LaunchScope ls(c, "k_unit_meta");
-        if (nt) {
-            if (id_bytes == 8)
-                k_unit_meta<int64_t><<<grid_for(nt * 32), kThreads, 0, c->stream>>>(m);
-            else
-                k_unit_meta<uint32_t><<<grid_for(nt * 32), kThreads, 0, c->stream>>>(m);
-        }
-        k_unit_meta_finish<<<grid_for(nu), kThreads, 0, c->stream>>>(m);
-    }
-    IDC_TRY(check_last_launch("k_unit_meta"));
-    // the upload sources are stack vectors: finish before they go away
+    IDC_TRY(launch_unit_meta(c, m, id_bytes, 0, nu, p));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
     return IDC_OK;
 }
-
 
 int status_to_error(uint32_t st, const char* what) {
     if (st & kStWide) {

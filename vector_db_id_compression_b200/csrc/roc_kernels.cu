@@ -102,6 +102,8 @@ struct EncArgs {
     uint32_t sm_words;           // shared-memory words per unit (the count levels), a multiple of 4
     uint32_t slot_base;          // this launch covers launch slots [slot_base, slot_end)
     uint32_t slot_end;
+    uint32_t rec_base;           // k_enc_records: units [rec_base, rec_base + rec_count)
+    uint32_t rec_count;
 };
 
 // Re-lay every unit's ascending ids as 128-byte records (mask word + 31 ids, idc_core.cuh): one warp per unit,
@@ -109,7 +111,8 @@ struct EncArgs {
 template <typename IdT>
 __global__ void __launch_bounds__(kThreads) k_enc_records(EncArgs a) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= a.nunits) return;
+    if (warp >= a.rec_count) return;
+    warp += a.rec_base;
     uint32_t n = a.unit_n[warp];
     if (n == 0) return;
     const IdT* src = reinterpret_cast<const IdT*>(a.ids) + a.unit_src[warp];
@@ -372,8 +375,12 @@ int set_max_smem(K kernel, size_t bytes) {
 
 // Shared encode driver. ids_dev: device pointer to the caller's ids (CSR or
 // row-strided); blob has list_offsets / unit tables filled in already.
-int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_bytes, uint32_t flags,
-                     const std::vector<uint32_t>& unit_posbase, uint64_t id_elems) {
+// ids_host != nullptr: the ids are still on the host and ids_dev is the device staging buffer they go to. With
+// ascending input the upload is cut into chunks of whole units on the copy stream; metadata and record kernels
+// follow chunk by chunk, and a size class starts as soon as the chunk holding its last unit has arrived (Zipf-length
+// lists in CSR order: the longest class, which bounds the kernel, is complete after 72 % of the upload).
+int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const void* ids_host, int id_bytes,
+                     uint32_t flags, const std::vector<uint32_t>& unit_posbase, uint64_t id_elems) {
     const uint64_t nu = b->nunits;
     uint64_t acct = 0;
     IDC_TRY(dev_alloc(c, &b->d_unit_n, nu, &acct));
@@ -396,7 +403,11 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
         scratch_off[u] = scratch_words;
         scratch_words += b->unit_n[u] ? (uint64_t)b->unit_n[u] + 4u : 0;
     }
-    size_t meta_bytes = nu * (8 + 4 + 4 + 8 + 8 + 4) + 64;
+    MetaPlan mplan;
+    plan_unit_meta(b->unit_n, mplan);
+    const uint64_t ntile = mplan.tile_unit.size();
+    IDC_REQUIRE(ntile < (1ull << 32), IDC_ERR_ARG, "too many metadata tiles");
+    size_t meta_bytes = nu * (8 + 4 + 4 + 8 + 8 + 4) + ntile * 8 + 256;
     IDC_TRY(c->meta.reserve(meta_bytes + 256));
     uint8_t* mp = c->meta.as<uint8_t>();
     auto carve = [&](size_t bytes) {
@@ -410,6 +421,8 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
     uint32_t* d_posbase = (uint32_t*)carve(nu * 4);
     uint32_t* d_perm = (uint32_t*)carve(nu * 4);
     uint32_t* d_nwords = (uint32_t*)carve(nu * 4);
+    uint32_t* d_tile_unit = (uint32_t*)carve(ntile * 4);
+    uint32_t* d_tile_idx = (uint32_t*)carve(ntile * 4);
     IDC_TRY(c->status.reserve(64));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
@@ -418,23 +431,31 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
     IDC_TRY(upload(c, d_scratch_off, scratch_off));
     IDC_TRY(upload(c, d_posbase, unit_posbase));
     IDC_TRY(upload(c, d_perm, perm));
+    IDC_TRY(upload(c, d_tile_unit, mplan.tile_unit));
+    IDC_TRY(upload(c, d_tile_idx, mplan.tile_idx));
+    if (nu) {
+        IDC_CUDA(cudaMemsetAsync(b->d_unit_lo, 0xff, nu * 4, c->stream));
+        IDC_CUDA(cudaMemsetAsync(b->d_unit_hi, 0, nu * 4, c->stream));
+    }
 
     const bool sorted_in = (flags & IDC_F_SORTED) != 0;
-    // 1. unit metadata
-    {
-        MetaArgs m{ids_dev, d_unit_src, b->d_unit_n, (uint32_t)nu, sorted_in ? 1u : 0u,
-                   (flags & IDC_F_PRECISION_SAFE) ? 1u : 0u, b->d_unit_prec, b->d_unit_lo, b->d_unit_hi, d_status,
-                   nullptr, nullptr, 0u};
-        IDC_TRY(run_unit_meta(c, m, b->unit_n, id_bytes));
+    // chunks of whole units: [cu[j], cu[j+1])
+    const bool pipelined = ids_host != nullptr && sorted_in && nu >= 64 && id_elems >= (1ull << 22);
+    std::vector<uint64_t> cu{0};
+    if (pipelined) {
+        const uint64_t first = b->unit_src[0], span = id_elems - first, target = (span + 15) / 16;
+        for (uint64_t u = 1; u < nu; u++)
+            if (b->unit_src[u] - b->unit_src[cu.back()] >= target) cu.push_back(u);
     }
-    {
-        uint32_t st = 0;
-        IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
-        IDC_CUDA(cudaStreamSynchronize(c->stream));
-        IDC_TRY(status_to_error(st, "roc_encode"));
-    }
+    cu.push_back(nu);
+    const size_t nchunk = cu.size() - 1;
+    auto chunk_of_unit = [&](uint64_t u) { return (size_t)(std::upper_bound(cu.begin(), cu.end(), u) - cu.begin()) - 1; };
+    cudaStream_t copy_s = nullptr;
+    if (pipelined) IDC_TRY(c->copy_stream_get(&copy_s));
+    if (ids_host && !pipelined && id_elems)
+        IDC_CUDA(cudaMemcpyAsync(const_cast<void*>(ids_dev), ids_host, id_elems * id_bytes, cudaMemcpyHostToDevice, c->stream));
 
-    // 2. sort when needed
+    // workspaces (the sort, when needed, works on a 32-bit copy of the ids)
     const void* enc_ids = ids_dev;
     int enc_id_bytes = id_bytes;
     uint32_t* d_sort_idx = nullptr;
@@ -452,25 +473,9 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
     }
     IDC_TRY(c->ws.reserve(ws_need + 256));
     IDC_TRY(c->scratch.reserve(scratch_words * 4 + 256));
-    if (!sorted_in) {
-        uint32_t* d_sorted = (uint32_t*)(c->ws.as<uint8_t>() + sorted_off);
-        d_sort_idx = (uint32_t*)(c->ws.as<uint8_t>() + sortidx_off);
-        SortArgs s{ids_dev, d_unit_src, b->d_unit_n, d_posbase, (uint32_t)nu, d_sorted, d_sort_idx,
-                   (uint64_t*)(c->ws.as<uint8_t>() + big_off)};
-        LaunchScope ls(c, "k_sort_units");
-        if (id_bytes == 8)
-            k_sort_units<int64_t><<<sort_grid, 256, 0, c->stream>>>(s);
-        else
-            k_sort_units<uint32_t><<<sort_grid, 256, 0, c->stream>>>(s);
-        enc_ids = d_sorted;
-        enc_id_bytes = 4;
-    }
-    IDC_TRY(check_last_launch("k_sort_units"));
 
-    // 3. encode
     EncArgs e{};
     e.ids = enc_ids;
-    e.sort_idx = d_sort_idx;
     e.unit_src = d_unit_src;
     e.unit_n = b->d_unit_n;
     e.unit_posbase = d_posbase;
@@ -491,19 +496,73 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
     uint32_t max_n = 0;
     for (uint64_t u = 0; u < nu; u++) max_n = std::max(max_n, b->unit_n[u]);
     b->max_n = max_n;
-    {
-        LaunchScope ls(c, "k_enc_records");
-        if (enc_id_bytes == 8)
-            k_enc_records<int64_t><<<grid_for(nu * 32), kThreads, 0, c->stream>>>(e);
-        else
-            k_enc_records<uint32_t><<<grid_for(nu * 32), kThreads, 0, c->stream>>>(e);
+
+    // the class streams wait for what has been queued so far (tables, memsets), not for the chunks
+    auto cls = size_classes(nu, [&](uint64_t slot) { return b->unit_n[perm[slot]]; });
+    const std::vector<int> cstream = class_streams(cls);
+    IDC_TRY(c->fork(class_stream_count()));
+
+    // 1. per chunk: upload, unit metadata, [sort], records
+    MetaArgs m{ids_dev, d_unit_src, b->d_unit_n, (uint32_t)nu, sorted_in ? 1u : 0u,
+               (flags & IDC_F_PRECISION_SAFE) ? 1u : 0u, b->d_unit_prec, b->d_unit_lo, b->d_unit_hi, d_status,
+               d_tile_unit, d_tile_idx, 0u, 0u, 0u, 0u};
+    std::vector<cudaEvent_t> ev_ready(nchunk);
+    for (size_t j = 0; j < nchunk; j++) {
+        const uint64_t u0 = cu[j], u1 = cu[j + 1];
+        if (pipelined) {
+            const uint64_t e0 = j == 0 ? 0 : b->unit_src[u0], e1 = u1 < nu ? b->unit_src[u1] : id_elems;
+            cudaEvent_t ev;
+            IDC_TRY(c->sync_event(&ev));
+            IDC_CUDA(cudaMemcpyAsync((uint8_t*)const_cast<void*>(ids_dev) + e0 * id_bytes, (const uint8_t*)ids_host + e0 * id_bytes,
+                                     (e1 - e0) * id_bytes, cudaMemcpyHostToDevice, copy_s));
+            IDC_CUDA(cudaEventRecord(ev, copy_s));
+            IDC_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
+        }
+        IDC_TRY(launch_unit_meta(c, m, id_bytes, u0, u1, mplan));
+        if (!pipelined) {
+            // input errors surface before the heavy work (the pipelined path checks at the end: the kernels are
+            // memory-safe on unsorted or too wide ids, their output is then discarded)
+            uint32_t st = 0;
+            IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+            IDC_CUDA(cudaStreamSynchronize(c->stream));
+            IDC_TRY(status_to_error(st, "roc_encode"));
+        }
+        if (!sorted_in) {
+            uint32_t* d_sorted = (uint32_t*)(c->ws.as<uint8_t>() + sorted_off);
+            d_sort_idx = (uint32_t*)(c->ws.as<uint8_t>() + sortidx_off);
+            SortArgs s{ids_dev, d_unit_src, b->d_unit_n, d_posbase, (uint32_t)nu, d_sorted, d_sort_idx,
+                       (uint64_t*)(c->ws.as<uint8_t>() + big_off)};
+            LaunchScope ls(c, "k_sort_units");
+            if (id_bytes == 8)
+                k_sort_units<int64_t><<<sort_grid, 256, 0, c->stream>>>(s);
+            else
+                k_sort_units<uint32_t><<<sort_grid, 256, 0, c->stream>>>(s);
+            enc_ids = d_sorted;
+            enc_id_bytes = 4;
+            e.ids = enc_ids;
+            IDC_TRY(check_last_launch("k_sort_units"));
+        }
+        e.sort_idx = d_sort_idx;
+        {
+            EncArgs er = e;
+            er.rec_base = (uint32_t)u0;
+            er.rec_count = (uint32_t)(u1 - u0);
+            LaunchScope ls(c, "k_enc_records");
+            if (er.rec_count) {
+                if (enc_id_bytes == 8)
+                    k_enc_records<int64_t><<<grid_for((uint64_t)er.rec_count * 32), kThreads, 0, c->stream>>>(er);
+                else
+                    k_enc_records<uint32_t><<<grid_for((uint64_t)er.rec_count * 32), kThreads, 0, c->stream>>>(er);
+            }
+        }
+        IDC_TRY(check_last_launch("k_enc_records"));
+        IDC_TRY(c->sync_event(&ev_ready[j]));
+        IDC_CUDA(cudaEventRecord(ev_ready[j], c->stream));
     }
-    IDC_TRY(check_last_launch("k_enc_records"));
+
+    // 3. encode: a class starts when the chunk with its last unit is ready
     {
-        auto cls = size_classes(nu, [&](uint64_t slot) { return b->unit_n[perm[slot]]; });
         LaunchScope ls(c, "k_roc_encode");
-        const std::vector<int> cstream = class_streams(cls);
-        IDC_TRY(c->fork(class_stream_count()));
         for (size_t k = 0; k < cls.size(); k++) {
             EncArgs ek = e;
             ek.slot_base = cls[k].slot_base;
@@ -515,10 +574,13 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, int id_by
             const uint32_t slots = ek.slot_end - ek.slot_base, nwarps = (slots + upw - 1) / upw;
             const uint32_t grid = (nwarps + warps - 1) / warps;
             const size_t smem = (size_t)ek.sm_words * 4 * upw * warps;
+            uint32_t last_unit = 0;
+            for (uint32_t sl = ek.slot_base; sl < ek.slot_end; sl++) last_unit = std::max(last_unit, perm[sl]);
+            IDC_CUDA(cudaStreamWaitEvent(c->aux[cstream[k]], ev_ready[nchunk ? chunk_of_unit(last_unit) : 0], 0));
 #define IDC_LAUNCH_ENC(GG, TT)                                                       \
     do {                                                                             \
         IDC_TRY(set_max_smem(k_roc_encode<GG, TT>, smem));                            \
-        k_roc_encode<GG, TT><<<grid, threads, smem, c->aux[cstream[k]]>>>(ek);                 \
+        k_roc_encode<GG, TT><<<grid, threads, smem, c->aux[cstream[k]]>>>(ek);       \
     } while (0)
             if (G == 8) {
                 if (enc_id_bytes == 8) IDC_LAUNCH_ENC(8, int64_t); else IDC_LAUNCH_ENC(8, uint32_t);
@@ -626,10 +688,31 @@ int build_decode_plan(idc_ctx* c, const idc_roc_blob* b, const std::vector<uint3
     return IDC_OK;
 }
 
+// For a caller that overlaps the device->host copy of the output with the kernels: one event per size class,
+// recorded when that class is done, and the class's shortest unit (classes are ranges of unit lengths).
+struct DecodeOverlap {
+    std::vector<cudaEvent_t> class_done;
+    std::vector<uint32_t> class_min_n;
+};
+
+int finish_decode(idc_ctx* c) {
+    uint32_t st = 0;
+    IDC_CUDA(cudaMemcpyAsync(&st, c->status.as<uint32_t>(), 4, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    return status_to_error(st, "roc_decode");
+}
+
+// ov == nullptr: launches, waits and checks. ov != nullptr: launches only; the caller runs finish_decode().
 int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const uint64_t* d_out, const uint64_t* d_ws,
                uint64_t ws_bytes, uint64_t nsel, void* out_dev, int id_bytes, uint32_t* counts_dev, uint32_t row_stride,
-               uint32_t max_n, const std::function<uint32_t(uint64_t)>& n_of_slot) {
-    if (nsel == 0) return IDC_OK;
+               uint32_t max_n, const std::function<uint32_t(uint64_t)>& n_of_slot, DecodeOverlap* ov = nullptr) {
+    if (nsel == 0) {
+        if (ov) {
+            IDC_TRY(c->status.reserve(64));
+            IDC_CUDA(cudaMemsetAsync(c->status.p, 0, 4, c->stream));
+        }
+        return IDC_OK;
+    }
     IDC_TRY(c->ws.reserve(ws_bytes + 256));
     IDC_TRY(c->status.reserve(64));
     uint32_t* d_status = c->status.as<uint32_t>();
@@ -686,15 +769,20 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
             }
 #undef IDC_LAUNCH_DEC
             c->launches++;
+            if (ov) {
+                cudaEvent_t ev;
+                IDC_TRY(c->sync_event(&ev));
+                IDC_CUDA(cudaEventRecord(ev, c->aux[cstream[k]]));
+                ov->class_done.push_back(ev);
+                ov->class_min_n.push_back(n_of_slot(cls[k].slot_end - 1));
+            }
         }
         c->launches--;
         IDC_TRY(c->join(class_stream_count()));
     }
     IDC_TRY(check_last_launch("k_roc_decode"));
-    uint32_t st = 0;
-    IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
-    IDC_CUDA(cudaStreamSynchronize(c->stream));
-    return status_to_error(st, "roc_decode");
+    if (ov) return IDC_OK;
+    return finish_decode(c);
 }
 
 }  // namespace
@@ -722,13 +810,14 @@ int idc_roc_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const vo
     uint64_t first = offsets[0], elems = offsets[nlist];
     IDC_REQUIRE(ids != nullptr || elems == 0, IDC_ERR_ARG, "ids is NULL");
     const void* ids_dev = ids;
+    const void* ids_host = nullptr;
     if (ids_mem == IDC_MEM_HOST && elems) {
         IDC_TRY(c->stage.reserve(elems * id_bytes));
-        IDC_CUDA(cudaMemcpyAsync(c->stage.p, ids, elems * id_bytes, cudaMemcpyHostToDevice, c->stream));
         ids_dev = c->stage.p;
+        ids_host = ids;  // uploaded inside, overlapped with the kernels
     }
     (void)first;
-    IDC_TRY(roc_encode_units(c, b.get(), ids_dev, id_bytes, flags, posbase, elems));
+    IDC_TRY(roc_encode_units(c, b.get(), ids_dev, ids_host, id_bytes, flags, posbase, elems));
     *out = b.release();
     return IDC_OK;
 }
@@ -782,7 +871,7 @@ int idc_roc_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* d
     b->list_offsets[nrows] = total;
     b->unit_offsets[nrows] = nrows;
     b->total_ids = total;
-    IDC_TRY(roc_encode_units(c, b.get(), d_data, 4, flags & ~IDC_F_SORTED, posbase, elems));
+    IDC_TRY(roc_encode_units(c, b.get(), d_data, nullptr, 4, flags & ~IDC_F_SORTED, posbase, elems));
     *out = b.release();
     return IDC_OK;
 }
@@ -967,18 +1056,72 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
             rc = c->stage.reserve(total_out * id_bytes);
             out_dev = c->stage.p;
         }
-        {
-            const std::vector<uint32_t>& ns = list_nos == nullptr ? b->plan_ns : t_ns;
+        const std::vector<uint32_t>& ns = list_nos == nullptr ? b->plan_ns : t_ns;
+        const bool overlap = out_mem == IDC_MEM_HOST && list_nos == nullptr && total_out >= (1ull << 22) && rc == IDC_OK;
+        if (overlap) {
+            // Decode everything into host memory: the output is copied in 16 chunks of whole units on the copy
+            // stream, each as soon as the size classes of its units are done (Zipf-length lists in CSR order: the
+            // short lists at the end of the array are finished, and on their way, long before the longest class).
+            DecodeOverlap ov;
+            rc = run_decode(c, b, d_unit, d_out, d_ws, ws_bytes, nunits_sel, out_dev, id_bytes, nullptr, 0,
+                            ns.empty() ? 0u : ns[0], [&](uint64_t slot) { return ns[slot]; }, &ov);
+            cudaStream_t copy_s = nullptr;
+            if (rc == IDC_OK) rc = c->copy_stream_get(&copy_s);
+            if (rc == IDC_OK) {
+                auto class_of = [&](uint32_t n) {
+                    size_t k = 0;
+                    while (k + 1 < ov.class_min_n.size() && n < ov.class_min_n[k]) k++;
+                    return k;
+                };
+                const uint64_t first = b->list_offsets[0], target = (total_out + 15) / 16;
+                struct Chunk {
+                    uint64_t e0, e1;
+                    uint32_t mask;
+                };
+                std::vector<Chunk> chunks;
+                for (uint64_t u0 = 0; u0 < b->nunits;) {
+                    uint64_t u1 = u0;
+                    Chunk ch{b->unit_src[u0] - first, b->unit_src[u0] - first, 0u};
+                    while (u1 < b->nunits && ch.e1 - ch.e0 < target) {
+                        if (b->unit_n[u1]) ch.mask |= 1u << class_of(b->unit_n[u1]);
+                        ch.e1 = b->unit_src[u1] - first + b->unit_n[u1];
+                        u1++;
+                    }
+                    if (ch.e1 > ch.e0) chunks.push_back(ch);
+                    u0 = u1;
+                }
+                // the copy stream is in order: chunks that only need the short classes (done early) go first
+                auto longest_class = [](uint32_t m) { return m ? (uint32_t)__builtin_ctz(m) : 32u; };
+                std::stable_sort(chunks.begin(), chunks.end(),
+                                 [&](const Chunk& x, const Chunk& y) { return longest_class(x.mask) > longest_class(y.mask); });
+                cudaError_t e = cudaSuccess;
+                for (const Chunk& ch : chunks) {
+                    for (size_t k = 0; k < ov.class_done.size() && e == cudaSuccess; k++)
+                        if (ch.mask >> k & 1u) e = cudaStreamWaitEvent(copy_s, ov.class_done[k], 0);
+                    if (e == cudaSuccess)
+                        e = cudaMemcpyAsync((uint8_t*)ids_out + ch.e0 * id_bytes, (const uint8_t*)out_dev + ch.e0 * id_bytes,
+                                            (ch.e1 - ch.e0) * id_bytes, cudaMemcpyDeviceToHost, copy_s);
+                    if (e != cudaSuccess) break;
+                }
+                if (e != cudaSuccess) {
+                    set_error("D2H copy failed: %s", cudaGetErrorString(e));
+                    rc = IDC_ERR_CUDA;
+                }
+            }
+            int rc2 = finish_decode(c);
+            if (copy_s) cudaStreamSynchronize(copy_s);
+            if (rc == IDC_OK) rc = rc2;
+        } else {
             if (rc == IDC_OK)
                 rc = run_decode(c, b, d_unit, d_out, d_ws, ws_bytes, nunits_sel, out_dev, id_bytes, nullptr, 0,
                                 ns.empty() ? 0u : ns[0], [&](uint64_t slot) { return ns[slot]; });
-        }
-        if (rc == IDC_OK && out_mem == IDC_MEM_HOST) {
-            cudaError_t e = cudaMemcpyAsync(ids_out, out_dev, total_out * id_bytes, cudaMemcpyDeviceToHost, c->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-            if (e != cudaSuccess) {
-                set_error("D2H copy failed: %s", cudaGetErrorString(e));
-                rc = IDC_ERR_CUDA;
+            if (rc == IDC_OK && out_mem == IDC_MEM_HOST) {
+                cudaError_t e = cudaMemcpyAsync(ids_out, out_dev, total_out * id_bytes, cudaMemcpyDeviceToHost, c->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+                if (e != cudaSuccess) {
+                    set_error("D2H copy failed: %s", cudaGetErrorString(e));
+                    rc = IDC_ERR_CUDA;
+                }
             }
         }
     }
