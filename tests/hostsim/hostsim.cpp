@@ -63,11 +63,13 @@ static void group_decode(uint64_t head, const uint32_t* words, uint32_t nwords, 
     tables(mt);
     std::vector<uint8_t> ws(dec_tree_bytes(n) + 64, 0xff);
     std::vector<uint32_t> sm(dec_tree_sm_words(n) + 8, 0);
+    std::vector<uint32_t> ring(kDecRing, 0);
     run_group(G, [&](const HostGrp& g) {
         GDecUnit<int64_t> U;
         U.tree = gdec_tree_at(ws.data(), SmView{sm.data(), 1, 0}, n, lo, hi);
         if (force_degenerate) U.tree.ovf_cap = force_degenerate - 1;
-        dec_state_init(U.st, head, words, nwords);
+        dec_state_init(U.st, head, words, nwords, DecRing{ring.data(), 4u}, g.sub == 0);
+        g.sync();
         U.out = out;
         U.n = n;
         U.prec = prec;

@@ -301,40 +301,101 @@ IDC_HD void enc_push_id32(EncState& st, uint32_t id, int precision) {
 // (the decoder never holds more than one word above its low-water mark inside
 // the codec's valid domain -- violations are flagged, not assumed away).
 
+// The blob's words are consumed top-down through a ring of kDecRing words in SHARED memory that is kept full by
+// asynchronous copies (cp.async: global -> shared without a destination register). Why not registers: a warp's
+// scoreboard is per register, not per lane -- with 8 units per warp some group re-loads its look-ahead register at
+// almost every pop, and every other group's next read of "its" copy of that register then waits for that load
+// (measured: 570 of the decoder's 3 100 cycles per step, with one and with two words of look-ahead).
+constexpr uint32_t kDecRing = 16;      // words of look-ahead
+constexpr uint32_t kDecRingWait = 8;   // copies allowed in flight when a word is read (it was issued 16 pops ago)
+
+struct DecRing {
+    uint32_t* base;       // this unit's ring in shared memory: word i at base[(i >> 2) * chunk_stride + (i & 3)]
+    uint32_t chunk_stride;
+    IDC_HD uint32_t* at(uint32_t i) const { return base + (size_t)(i >> 2) * chunk_stride + (i & 3u); }
+};
+
+IDC_HD void ring_fetch_if(uint32_t* dst_smem, const uint32_t* src, bool cond) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q cp.async.ca.shared.global [%0], [%1], 4; }" ::"r"(d), "l"(src),
+                 "r"((uint32_t)cond)
+                 : "memory");
+#else
+    if (cond) *dst_smem = *src;
+#endif
+}
+IDC_HD void ring_commit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+IDC_HD void ring_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 struct DecState {
     uint64_t head;
-    const uint32_t* wp;  // next word of the blob's stack to be popped is wp[-1]
-    uint32_t sp;         // words still on the blob's stack
-    uint32_t nxt;        // wp[-1] (valid while sp > 0) and
-    uint32_t nx2;        // wp[-2] (valid while sp > 1): fetched two pops ahead of their use, straight from L2
+    const uint32_t* words;  // the unit's words (read directly only by the host emulation, see dec_ring_word)
+    const uint32_t* fp;  // next word to FETCH into the ring is fp[-1]
+    uint32_t fleft;      // words of the blob's stack not fetched yet
+    uint32_t sp;         // words of the blob's stack not popped yet
+    uint32_t rpos;       // ring slot of the next word to pop
+    DecRing ring;
+    uint32_t fetcher;    // this lane issues the copies (lane 0 of the group that owns the unit)
     uint32_t ov;         // overlay: the one word the decoder may hold above the blob's stack
     uint32_t has_ov;
     uint32_t draws;
     uint32_t status;
 };
 
-IDC_HD void dec_state_init(DecState& st, uint64_t head, const uint32_t* words, uint32_t nwords) {
+// every lane of the group calls this; afterwards the caller synchronises the group (the fetching lane has waited
+// for the copies, the other lanes see them after the rendezvous)
+IDC_HD void dec_state_init(DecState& st, uint64_t head, const uint32_t* words, uint32_t nwords, DecRing ring, bool fetcher) {
     st.head = head;
-    st.wp = words + nwords;
+    st.words = words;
     st.sp = nwords;
-    st.nxt = nwords ? ld_ro32(words + nwords - 1u) : 0u;
-    st.nx2 = nwords > 1u ? ld_ro32(words + nwords - 2u) : 0u;
+    st.rpos = 0;
+    st.ring = ring;
+    st.fetcher = fetcher ? 1u : 0u;
+    const uint32_t first = nwords < kDecRing ? nwords : kDecRing;
+    for (uint32_t i = 0; i < first; i++) ring_fetch_if(ring.at(i), words + nwords - 1u - i, fetcher);
+    ring_commit();
+    ring_wait<0>();
+    st.fp = words + nwords - first;
+    st.fleft = nwords - first;
     st.ov = 0;
     st.has_ov = 0;
     st.draws = 0;
     st.status = 0;
 }
 
+// The word the next pop returns. Device: the ring slot (every lane of the warp reads it in the same instruction,
+// before the fetching lane's asynchronous refill of that slot can land). The host emulation's lanes are free-running
+// threads, so there the fetching lane's refill could overtake a slower lane's read: it reads the blob itself.
+IDC_HD uint32_t dec_ring_word(const DecState& st, const uint32_t* slot) {
+#if defined(__CUDA_ARCH__)
+    return *slot;
+#else
+    (void)slot;
+    return st.sp ? st.words[st.sp - 1u] : 0u;
+#endif
+}
+
 // `if (h < 2^31) h = (h << 32) | pop()` of codec.cpp:83-87 / :56-60 as straight-line code. pop() = the overlay if
-// there is one, else the blob's next word (consumed top-down; two words are kept in registers and the word two
-// below is requested at every pop -- two pops of one step can be 100 cycles apart, and the kernels leave next to
-// no L1 to prefetch into), else the mt19937(1234) fallback of codec.h:32-40 (only at the very bottom of a
-// stream: the one cold branch).
+// there is one, else the blob's next word (from the ring; its slot is refilled at once with the word kDecRing
+// below), else the mt19937(1234) fallback of codec.h:32-40 (only at the very bottom of a stream: the one cold
+// branch).
 IDC_HD uint64_t dec_renorm(DecState& st, uint64_t h, const uint32_t* mt) {
     const bool rf = h < kRansL;
     const bool o = st.has_ov != 0u;
     const bool blob = rf & !o;
-    uint32_t w = o ? st.ov : st.nxt;
+    ring_wait<kDecRingWait>();
+    uint32_t* slot = st.ring.at(st.rpos);
+    uint32_t w = o ? st.ov : dec_ring_word(st, slot);
     if (blob & (st.sp == 0u)) {
         uint32_t d = st.draws++;
         w = 0;
@@ -344,11 +405,14 @@ IDC_HD uint64_t dec_renorm(DecState& st, uint64_t h, const uint32_t* mt) {
             w = mt[d];
     } else {
         const uint32_t dec = blob ? 1u : 0u;
+        const bool more = blob & (st.fleft != 0u);
+        ring_fetch_if(slot, st.fp - 1, more & (st.fetcher != 0u));
         st.sp -= dec;
-        st.wp -= dec;
-        st.nxt = blob ? st.nx2 : st.nxt;
-        ld_ro32_if(st.wp - 2, st.nx2, blob & (st.sp > 1u));
+        st.rpos = (st.rpos + dec) & (kDecRing - 1u);
+        st.fp -= more ? 1 : 0;
+        st.fleft -= more ? 1u : 0u;
     }
+    ring_commit();
     st.has_ov = rf ? 0u : st.has_ov;
     return rf ? ((h << 32) | (uint64_t)w) : h;
 }

@@ -242,10 +242,12 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
     U.prec = valid ? (int)a.unit_prec[u] : 0;
     U.out = reinterpret_cast<OutT*>(a.out) + (valid ? a.sel_out[slot] : 0ull);
     const uint64_t w0 = valid ? a.word_off[u] : 0ull, w1 = valid ? a.word_off[u + 1] : 0ull;
-    dec_state_init(U.st, valid ? a.unit_head[u] : kRansL, a.words + w0, (uint32_t)(w1 - w0));
+    // the stream ring sits behind the count levels in the unit's shared-memory region
     const SmView sm{smem + (size_t)wic * (a.sm_words * NG), NG, q};
+    dec_state_init(U.st, valid ? a.unit_head[u] : kRansL, a.words + w0, valid ? (uint32_t)(w1 - w0) : 0u,
+                   DecRing{sm.at(a.sm_words - kDecRing), NG * 4u}, g.sub == 0);
     if (valid)
-        for (uint32_t w = g.sub; w < a.sm_words; w += (uint32_t)G) *sm.at(w) = 0u;
+        for (uint32_t w = g.sub; w < a.sm_words - kDecRing; w += (uint32_t)G) *sm.at(w) = 0u;
     U.tree = gdec_tree_at(a.ws + (valid ? a.sel_ws[slot] : 0ull), sm, n ? n : 1u, valid ? a.unit_lo[u] : 0u,
                           valid ? a.unit_hi[u] : 0u);
     __syncwarp();
@@ -750,7 +752,7 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
             DecArgs ak = a;
             ak.slot_base = cls[k].slot_base;
             ak.slot_end = cls[k].slot_end;
-            ak.sm_words = dec_tree_sm_words(cls[k].max_n ? cls[k].max_n : 1u);
+            ak.sm_words = dec_tree_sm_words(cls[k].max_n ? cls[k].max_n : 1u) + kDecRing;
             const int G = group_lanes_for(cls[k].max_n);
             const uint32_t upw = 32u / (uint32_t)G;
             const uint32_t warps = warps_for(ak.sm_words, upw), threads = warps * 32;
