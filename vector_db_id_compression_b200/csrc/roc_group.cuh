@@ -43,7 +43,7 @@ struct Grp {
     }
     __device__ __forceinline__ uint32_t shfl_xor(uint32_t v, uint32_t m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
-    __device__ __forceinline__ void host_sync() const {}  // lanes run in lock step here; the host emulation needs a rendezvous
+    __device__ __forceinline__ void host_sync() const { __syncwarp(); }  // off the critical path where it is used
 };
 #endif
 
@@ -252,7 +252,7 @@ IDC_HD uint32_t genc_select_remove(const GR& g, GEncTree<G>& t, uint32_t k, uint
     }
     issue_fence();
     // ---- the count updates ride in the shadow of the line fetch; every lane updates its own entries only
-    g.host_sync();  // (host emulation: all lanes have read the C words)
+    g.host_sync();  // all lanes have read the C words before lane 0 rewrites one (racecheck: warp-level WAR)
     if (act) {
 #pragma unroll
         for (int j = 0; j < EA; j++) t.ea[j] -= (g.sub * EA + (uint32_t)j > sb) ? 1u : 0u;
