@@ -37,6 +37,7 @@ constexpr uint32_t kStUnsorted = 4u;     // ids not ascending although IDC_F_SOR
 constexpr uint32_t kStWide = 8u;         // id does not fit 32 bits
 constexpr uint32_t kStScratch = 16u;     // encoder ran out of scratch words (cannot happen within the bound)
 constexpr uint32_t kStDegenerate = 32u;  // decoder fell back to brute-force ranks (informational)
+constexpr uint32_t kStRange = 64u;       // a row number on the device was out of range
 
 struct uint4x {  // 16 bytes; uint4 on device
     uint32_t x, y, z, w;

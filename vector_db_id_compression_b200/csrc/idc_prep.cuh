@@ -260,6 +260,10 @@ int status_to_error(uint32_t st, const char* what) {
         set_error("%s: IDC_F_SORTED was given but a list is not ascending", what);
         return IDC_ERR_DOMAIN;
     }
+    if (st & kStRange) {
+        set_error("%s: row number out of range", what);
+        return IDC_ERR_ARG;
+    }
     if (st & (kStOverlay | kStMtDraws | kStScratch)) {
         set_error("%s: stream invariant violated (status 0x%x)", what, st);
         return IDC_ERR_STREAM;

@@ -224,6 +224,12 @@ struct DecArgs {
     uint32_t sm_words;          // shared-memory words per unit (all count levels), a multiple of 4
     uint32_t slot_base;         // this launch covers launch slots [slot_base, slot_end)
     uint32_t slot_end;
+    // row mode (sel_out == nullptr): slot s decodes row rows[s] (s itself when rows == nullptr) into out + s *
+    // row_stride with the workspace slot s * slot_ws -- no per-slot tables, the row numbers may live on the device
+    const int32_t* rows;
+    uint64_t slot_ws;
+    uint32_t nrows;
+    uint32_t row_base;          // rows == nullptr: slot s decodes row row_base + s
 };
 
 template <int G, typename OutT>
@@ -234,13 +240,27 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
     const uint32_t lane_id = threadIdx.x & 31, q = lane_id / G, wic = threadIdx.x >> 5;
     const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + wic;
     const uint32_t slot = a.slot_base + gwarp * NG + q;
-    const bool valid = slot < a.slot_end;
-    const uint32_t u = valid ? a.sel_unit[slot] : 0u;
+    bool valid = slot < a.slot_end;
+    const bool row_mode = a.sel_out == nullptr;
+    uint32_t u = 0;
+    if (valid) {
+        if (!row_mode) {
+            u = a.sel_unit[slot];
+        } else {
+            const int64_t r = a.rows ? (int64_t)a.rows[slot] : (int64_t)a.row_base + slot;
+            if (r < 0 || r >= (int64_t)a.nrows) {
+                if (g.sub == 0) atomicOr(a.status, kStRange);
+                valid = false;
+            } else {
+                u = (uint32_t)r;
+            }
+        }
+    }
     const uint32_t n = valid ? a.unit_n[u] : 0u;
     GDecUnit<OutT> U;
     U.n = n;
     U.prec = valid ? (int)a.unit_prec[u] : 0;
-    U.out = reinterpret_cast<OutT*>(a.out) + (valid ? a.sel_out[slot] : 0ull);
+    U.out = reinterpret_cast<OutT*>(a.out) + (row_mode ? (uint64_t)slot * a.row_stride : (valid ? a.sel_out[slot] : 0ull));
     const uint64_t w0 = valid ? a.word_off[u] : 0ull, w1 = valid ? a.word_off[u + 1] : 0ull;
     // the stream ring sits behind the count levels in the unit's shared-memory region
     const SmView sm{smem + (size_t)wic * (a.sm_words * NG), NG, q};
@@ -248,8 +268,8 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
                    DecRing{sm.at(a.sm_words - kDecRing), NG * 4u}, g.sub == 0);
     if (valid)
         for (uint32_t w = g.sub; w < a.sm_words - kDecRing; w += (uint32_t)G) *sm.at(w) = 0u;
-    U.tree = gdec_tree_at(a.ws + (valid ? a.sel_ws[slot] : 0ull), sm, n ? n : 1u, valid ? a.unit_lo[u] : 0u,
-                          valid ? a.unit_hi[u] : 0u);
+    U.tree = gdec_tree_at(a.ws + (row_mode ? (uint64_t)slot * a.slot_ws : (valid ? a.sel_ws[slot] : 0ull)), sm, n ? n : 1u,
+                          valid ? a.unit_lo[u] : 0u, valid ? a.unit_hi[u] : 0u);
     __syncwarp();
     const uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
     // 2^31 / (i + 1) from the table, 32 entries per coalesced load and one block ahead (see k_roc_encode)
@@ -707,7 +727,8 @@ int finish_decode(idc_ctx* c) {
 // ov == nullptr: launches, waits and checks. ov != nullptr: launches only; the caller runs finish_decode().
 int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const uint64_t* d_out, const uint64_t* d_ws,
                uint64_t ws_bytes, uint64_t nsel, void* out_dev, int id_bytes, uint32_t* counts_dev, uint32_t row_stride,
-               uint32_t max_n, const std::function<uint32_t(uint64_t)>& n_of_slot, DecodeOverlap* ov = nullptr) {
+               uint32_t max_n, const std::function<uint32_t(uint64_t)>& n_of_slot, DecodeOverlap* ov = nullptr,
+               const int32_t* rows_dev = nullptr, uint64_t slot_ws = 0, uint64_t row_base = 0) {
     if (nsel == 0) {
         if (ov) {
             IDC_TRY(c->status.reserve(64));
@@ -742,6 +763,10 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     a.q31 = c->d_q31;
     a.nsel = (uint32_t)nsel;
     a.row_stride = row_stride;
+    a.rows = rows_dev;
+    a.slot_ws = slot_ws;
+    a.nrows = (uint32_t)b->nlist;
+    a.row_base = (uint32_t)row_base;
     {
         auto cls = size_classes(nsel, n_of_slot);
         (void)max_n;
@@ -1242,14 +1267,9 @@ int idc_roc_decode_rows(idc_ctx* c, const idc_roc_blob* b, const int32_t* row_no
     if (row_nos == nullptr) nsel = b->nlist;
     if (nsel == 0) return IDC_OK;
     IDC_REQUIRE(out != nullptr, IDC_ERR_ARG, "out is NULL");
-    // rows are short and near-uniform in length: no length sort, one fixed-size workspace slot per row
-    std::vector<int32_t> rows_h;
-    if (row_nos && rows_mem == IDC_MEM_DEVICE) {
-        rows_h.resize(nsel);
-        IDC_CUDA(cudaMemcpyAsync(rows_h.data(), row_nos, nsel * 4, cudaMemcpyDeviceToHost, c->stream));
-        IDC_CUDA(cudaStreamSynchronize(c->stream));
-        row_nos = rows_h.data();
-    }
+    // rows are short and near-uniform in length: no length sort, one fixed-size workspace slot per row, and the
+    // kernel derives everything from the slot number (row mode of k_roc_decode): no host-side tables, the row
+    // numbers stay where they are when they live on the device
     const uint64_t slot_ws = dec_tree_bytes(K);
     const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(nsel, (4ull << 30) / slot_ws));
     int32_t* out_dev = out;
@@ -1259,27 +1279,18 @@ int idc_roc_decode_rows(idc_ctx* c, const idc_roc_blob* b, const int32_t* row_no
         out_dev = c->stage.as<int32_t>();
         cnt_dev = reinterpret_cast<uint32_t*>(c->stage.as<uint8_t>() + chunk * K * 4);
     }
+    const int32_t* rows_dev = row_nos;
+    if (row_nos && rows_mem == IDC_MEM_HOST) {
+        IDC_TRY(c->meta.reserve(nsel * 4 + 256));
+        IDC_CUDA(cudaMemcpyAsync(c->meta.p, row_nos, nsel * 4, cudaMemcpyHostToDevice, c->stream));
+        rows_dev = c->meta.as<int32_t>();
+    }
     for (uint64_t s = 0; s < nsel; s += chunk) {
-        uint64_t m = std::min(chunk, nsel - s);
-        std::vector<uint32_t> su(m);
-        std::vector<uint64_t> so(m), sw(m);
-        for (uint64_t i = 0; i < m; i++) {
-            int64_t r = row_nos ? row_nos[s + i] : (int64_t)(s + i);
-            IDC_REQUIRE(r >= 0 && (uint64_t)r < b->nlist, IDC_ERR_ARG, "row %lld out of range", (long long)r);
-            su[i] = (uint32_t)r;
-            so[i] = (out_mem == IDC_MEM_HOST ? i : s + i) * K;
-            sw[i] = i * slot_ws;
-        }
-        IDC_TRY(c->meta.reserve(m * 20 + 256));
-        uint32_t* d_unit = c->meta.as<uint32_t>();
-        uint64_t* d_out = reinterpret_cast<uint64_t*>(c->meta.as<uint8_t>() + ((m * 4 + 15) & ~15ull));
-        uint64_t* d_ws = d_out + m;
-        IDC_TRY(upload(c, d_unit, su));
-        IDC_TRY(upload(c, d_out, so));
-        IDC_TRY(upload(c, d_ws, sw));
+        const uint64_t m = std::min(chunk, nsel - s);
+        int32_t* od = out_mem == IDC_MEM_HOST ? out_dev : out_dev + s * K;
         uint32_t* cd = cnt_dev ? (out_mem == IDC_MEM_HOST ? cnt_dev : cnt_dev + s) : nullptr;
-        IDC_TRY(run_decode(c, b, d_unit, d_out, d_ws, m * slot_ws, m, out_dev, 4, cd, K, K,
-                           [&](uint64_t) { return K; }));
+        IDC_TRY(run_decode(c, b, nullptr, nullptr, nullptr, m * slot_ws, m, od, 4, cd, K, K, [&](uint64_t) { return K; },
+                           nullptr, rows_dev ? rows_dev + s : nullptr, slot_ws, s));
         if (out_mem == IDC_MEM_HOST) {
             IDC_CUDA(cudaMemcpyAsync(out + s * K, out_dev, m * K * 4, cudaMemcpyDeviceToHost, c->stream));
             if (counts) IDC_CUDA(cudaMemcpyAsync(counts + s, cnt_dev, m * 4, cudaMemcpyDeviceToHost, c->stream));
