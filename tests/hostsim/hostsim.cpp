@@ -83,13 +83,16 @@ extern "C" {
 
 int64_t sim_group_encode(int G, uint32_t n, const uint64_t* ids, int prec, uint64_t* head_out, uint32_t* words_out,
                          uint32_t cap, uint32_t* order_out, uint32_t* status_out) {
-    return G == 8 ? group_encode<8>(n, ids, prec, head_out, words_out, cap, order_out, status_out)
-                  : group_encode<4>(n, ids, prec, head_out, words_out, cap, order_out, status_out);
+    return G == 8   ? group_encode<8>(n, ids, prec, head_out, words_out, cap, order_out, status_out)
+           : G == 2 ? group_encode<2>(n, ids, prec, head_out, words_out, cap, order_out, status_out)
+                    : group_encode<4>(n, ids, prec, head_out, words_out, cap, order_out, status_out);
 }
 void sim_group_decode(int G, uint64_t head, const uint32_t* words, uint32_t nwords, uint32_t n, int prec, uint32_t lo,
                       uint32_t hi, int64_t* out, uint32_t* status_out, uint32_t force_degenerate) {
     if (G == 8)
         group_decode<8>(head, words, nwords, n, prec, lo, hi, out, status_out, force_degenerate);
+    else if (G == 2)
+        group_decode<2>(head, words, nwords, n, prec, lo, hi, out, status_out, force_degenerate);
     else
         group_decode<4>(head, words, nwords, n, prec, lo, hi, out, status_out, force_degenerate);
 }

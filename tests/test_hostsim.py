@@ -63,7 +63,7 @@ def rand_set(rng, n, p):
     return np.unique(rng.integers(0, 1 << p, size=n, dtype=np.uint64))
 
 
-@pytest.mark.parametrize("G", [4, 8])
+@pytest.mark.parametrize("G", [2, 4, 8])
 def test_group_codec_random_sets(sim, G):
     """csrc/roc_group.cuh (G lanes per unit, lanes emulated by host threads) against the oracle."""
     rng = np.random.default_rng(10 + G)
@@ -91,7 +91,7 @@ def test_group_codec_random_sets(sim, G):
         assert st & ~32 == 0
 
 
-@pytest.mark.parametrize("G,n,p", [(4, 15259, 30), (4, 65536, 17), (8, 65536, 31), (4, 65000, 20), (8, 4097, 13), (4, 2233, 12)])
+@pytest.mark.parametrize("G,n,p", [(4, 15259, 30), (4, 65536, 17), (8, 65536, 31), (4, 65000, 20), (8, 4097, 13), (4, 2233, 12), (2, 65536, 30), (2, 15259, 20)])
 def test_group_codec_large_units(sim, G, n, p):
     rng = np.random.default_rng(n + p)
     ids = rng.choice(1 << p, size=n, replace=False) if p <= 24 else rand_set(rng, n, p)
@@ -103,7 +103,7 @@ def test_group_codec_large_units(sim, G, n, p):
     assert np.array_equal(d2.astype(np.uint64), oracle.port.decode(h, w, n, p)) and st == 0
 
 
-@pytest.mark.parametrize("G", [4, 8])
+@pytest.mark.parametrize("G", [2, 4, 8])
 def test_group_codec_golden_and_adversarial(sim, roc_golden, G):
     sim_enc = lambda lib, ids, p: grp_enc(lib, G, ids, p)
     sim_dec = lambda lib, h, w, n, p, **kw: grp_dec(lib, G, h, w, n, p, **kw)

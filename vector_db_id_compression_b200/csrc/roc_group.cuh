@@ -1,4 +1,4 @@
-// roc_group.cuh -- one ROC unit per GROUP of G lanes (G = 4 or 8): the per-step encode / decode bodies.
+// roc_group.cuh -- one ROC unit per GROUP of G lanes (G = 2, 4 or 8): the per-step encode / decode bodies.
 //
 // Why groups (profiles/README.md, r1_lat_bench_b200.txt): with one unit per lane every step makes each lane
 // fetch its own 128-byte line; 32 different lines per warp instruction cost 990 ns instead of 465 ns, the
@@ -90,6 +90,37 @@ template <class GR>
 IDC_HD uint32_t group_sum(const GR& g, uint32_t v, int G) {
     for (int m = G >> 1; m; m >>= 1) v += g.shfl_xor(v, (uint32_t)m);
     return v;
+}
+
+// this lane's slice of a 128-byte line: words [sub * W, (sub + 1) * W), W = 32 / G = 4, 8 or 16
+template <int W>
+IDC_HD void ld_line_slice(const uint32_t* line, uint32_t sub, uint32_t (&v)[W]) {
+    if (W == 4) {
+        uint4x s = ld_ws16(line + sub * 4u);
+        v[0] = s.x, v[1 % W] = s.y, v[2 % W] = s.z, v[3 % W] = s.w;
+    } else {
+#pragma unroll
+        for (int h = 0; h < W / 8; h++) {
+            Sector s = ld_sector(reinterpret_cast<const uint16_t*>(line), sub * (uint32_t)(W / 8) + (uint32_t)h);
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[(8 * h + j) % W] = s.w[j];
+        }
+    }
+}
+
+// v[idx % W] as a select tree (dynamic indexing of a register array would turn into divergent branches)
+template <int W>
+IDC_HD uint32_t pick_word(const uint32_t (&v)[W], uint32_t idx) {
+    uint32_t a[W];
+#pragma unroll
+    for (int j = 0; j < W; j++) a[j] = v[j];
+#pragma unroll
+    for (int span = W / 2, bit = 0; span >= 1; span >>= 1, bit++) {
+        const bool b = (idx >> bit) & 1u;
+#pragma unroll
+        for (int j = 0; j < span; j++) a[j] = b ? a[2 * j + 1] : a[2 * j];
+    }
+    return a[0];
 }
 
 // later memory operations are not scheduled before this point (keeps a long-latency load the first thing issued)
@@ -240,16 +271,7 @@ IDC_HD uint32_t genc_select_remove(const GR& g, GEncTree<G>& t, uint32_t k, uint
     uint32_t lw[WL];
 #pragma unroll
     for (int j = 0; j < WL; j++) lw[j] = 0u;
-    if (act) {
-        if (WL == 8) {
-            Sector s = ld_sector(reinterpret_cast<const uint16_t*>(rec), g.sub);
-#pragma unroll
-            for (int j = 0; j < WL; j++) lw[j] = s.w[j % 8];
-        } else {
-            uint4x s = ld_ws16(rec + g.sub * 4u);
-            lw[0] = s.x, lw[1 % WL] = s.y, lw[2 % WL] = s.z, lw[3 % WL] = s.w;
-        }
-    }
+    if (act) ld_line_slice<WL>(rec, g.sub, lw);
     issue_fence();
     // ---- the count updates ride in the shadow of the line fetch; every lane updates its own entries only
     g.host_sync();  // all lanes have read the C words before lane 0 rewrites one (racecheck: warp-level WAR)
@@ -271,21 +293,7 @@ IDC_HD uint32_t genc_select_remove(const GR& g, GEncTree<G>& t, uint32_t k, uint
     const uint32_t mask = g.shfl(lw[0], 0u);
     const uint32_t pos = select32(mask, k);
     const uint32_t idx = pos + 1u;  // word of the record that holds the id
-    // lw[idx % WL] as a select tree (dynamic indexing of a register array would turn into divergent branches)
-    uint32_t mine;
-    {
-        const bool b0 = idx & 1u, b1 = idx & 2u;
-        if (WL == 8) {
-            const bool b2 = idx & 4u;
-            const uint32_t a0 = b0 ? lw[1 % WL] : lw[0], a1 = b0 ? lw[3 % WL] : lw[2 % WL];
-            const uint32_t a2 = b0 ? lw[5 % WL] : lw[4 % WL], a3 = b0 ? lw[7 % WL] : lw[6 % WL];
-            const uint32_t c0 = b1 ? a1 : a0, c1 = b1 ? a3 : a2;
-            mine = b2 ? c1 : c0;
-        } else {
-            const uint32_t a0 = b0 ? lw[1 % WL] : lw[0], a1 = b0 ? lw[3 % WL] : lw[2 % WL];
-            mine = b1 ? a1 : a0;
-        }
-    }
+    const uint32_t mine = pick_word<WL>(lw, idx);
     id_out = g.shfl(mine, idx / (uint32_t)WL);
     if (act && g.sub == 0) st_ws32(rec, mask & ~(1u << pos));
     return rg * kRecIds + pos;
@@ -396,37 +404,22 @@ IDC_HD uint32_t gdec_rank(const GR& g, const GDecTree& t, uint32_t v, const OutT
         const uint32_t* bk = t.rec + (size_t)b * kBkSlots;
         uint32_t s0[SL], s1[SL];
         const bool need0 = sv > g.sub * SL, need1 = sv > 32u + g.sub * SL;
-        if (SL == 8) {
-            if (need0) {
-                Sector s = ld_sector(reinterpret_cast<const uint16_t*>(bk), g.sub);
-#pragma unroll
-                for (int j = 0; j < SL; j++) s0[j] = s.w[j % 8];
-            }
-            if (need1) {
-                Sector s = ld_sector(reinterpret_cast<const uint16_t*>(bk), 4u + g.sub);
-#pragma unroll
-                for (int j = 0; j < SL; j++) s1[j] = s.w[j % 8];
-            }
-        } else {
-            if (need0) {
-                uint4x s = ld_ws16(bk + g.sub * 4u);
-                s0[0] = s.x, s0[1 % SL] = s.y, s0[2 % SL] = s.z, s0[3 % SL] = s.w;
-            }
-            if (need1) {
-                uint4x s = ld_ws16(bk + 32u + g.sub * 4u);
-                s1[0] = s.x, s1[1 % SL] = s.y, s1[2 % SL] = s.z, s1[3 % SL] = s.w;
-            }
-        }
+        if (need0) ld_line_slice<SL>(bk, g.sub, s0);
+        if (need1) ld_line_slice<SL>(bk + 32u, g.sub, s1);
         issue_fence();  // the bucket fetch is in flight before the count levels are read
         // ---- counts below the bucket, one slice per lane
-        if (g.sub < 4u) {
-            // level 0: the 16 bucket bytes of this group, word g.sub
-            uint32_t nib = (((1u << (b & 15u)) - 1u) >> (4u * g.sub)) & 15u;
-            uint32_t sel = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-            part = dp4a_u(*t.sm.at(t.sm_l0 + 4u * grp + g.sub), sel, part);
-            // level 2: eight u16 entries, word g.sub
-            uint32_t two = (((1u << sct) - 1u) >> (2u * g.sub)) & 3u;
-            part = dp2a(*t.sm.at(g.sub), (two & 1u) | ((two & 2u) << 7), part);
+#pragma unroll
+        for (uint32_t j0 = 0; j0 < 4u; j0 += (uint32_t)G) {
+            const uint32_t j = j0 + g.sub;  // the four words of levels 0 and 2 are dealt round the group
+            if (j < 4u) {
+                // level 0: the 16 bucket bytes of this group of buckets, word j
+                uint32_t nib = (((1u << (b & 15u)) - 1u) >> (4u * j)) & 15u;
+                uint32_t sel = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                part = dp4a_u(*t.sm.at(t.sm_l0 + 4u * grp + j), sel, part);
+                // level 2: eight u16 entries, word j
+                uint32_t two = (((1u << sct) - 1u) >> (2u * j)) & 3u;
+                part = dp2a(*t.sm.at(j), (two & 1u) | ((two & 2u) << 7), part);
+            }
         }
         {
             // level 1: sixteen u16 entries of sector sct, 8 / G words per lane

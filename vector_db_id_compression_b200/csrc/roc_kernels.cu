@@ -362,19 +362,26 @@ std::vector<SizeClass> size_classes(uint64_t nslots, NofSlot n_of_slot) {
     return cls;
 }
 
-// Lanes per unit. 4 is the default for every size class: 8 units per warp keep the issue cost per id low, and a
-// group of 4 already fetches its line as one request (profiles/r1_lat_bench_b200.txt). IDC_ROC_G=8 /
-// IDC_ROC_G8_MIN_N=<n> select 8 lanes for all classes / for classes whose longest unit exceeds n (experiments).
+// Lanes per unit, per size class.
+//   4 for the classes with long units: their serial chains bound the kernel, and 4 lanes give the shortest step
+//     (one coalesced line request, 4 count entries per lane);
+//   2 for the classes of short units (n <= kG2MaxN): those are many and cheap, what counts there is the issue
+//     cost per id -- 16 units per warp need ~30 instead of ~49 warp instructions per id.
+// IDC_ROC_G=2|4|8 forces one width for all classes, IDC_ROC_G8_MIN_N=<n> selects 8 lanes for classes whose longest
+// unit exceeds n, IDC_ROC_G2_MAX_N=<n> moves the 2-lane threshold (experiments; profiles/README.md has the results).
+constexpr uint32_t kG2MaxN = 16384;
+
 inline int group_lanes_for(uint32_t max_n) {
-    int gdef = 4;
     if (const char* e = getenv("IDC_ROC_G")) {
         int v = atoi(e);
-        if (v == 4 || v == 8) gdef = v;
+        if (v == 2 || v == 4 || v == 8) return v;
     }
     if (const char* e = getenv("IDC_ROC_G8_MIN_N")) {
         if (max_n > (uint32_t)atoi(e)) return 8;
     }
-    return gdef;
+    uint32_t g2 = kG2MaxN;
+    if (const char* e = getenv("IDC_ROC_G2_MAX_N")) g2 = (uint32_t)atoi(e);
+    return max_n <= g2 ? 2 : 4;
 }
 
 // warps per CTA such that several CTAs fit an SM's 227 KB of shared memory
@@ -606,6 +613,8 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
     } while (0)
             if (G == 8) {
                 if (enc_id_bytes == 8) IDC_LAUNCH_ENC(8, int64_t); else IDC_LAUNCH_ENC(8, uint32_t);
+            } else if (G == 2) {
+                if (enc_id_bytes == 8) IDC_LAUNCH_ENC(2, int64_t); else IDC_LAUNCH_ENC(2, uint32_t);
             } else {
                 if (enc_id_bytes == 8) IDC_LAUNCH_ENC(4, int64_t); else IDC_LAUNCH_ENC(4, uint32_t);
             }
@@ -791,6 +800,8 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     } while (0)
             if (G == 8) {
                 if (id_bytes == 8) IDC_LAUNCH_DEC(8, int64_t); else IDC_LAUNCH_DEC(8, int32_t);
+            } else if (G == 2) {
+                if (id_bytes == 8) IDC_LAUNCH_DEC(2, int64_t); else IDC_LAUNCH_DEC(2, int32_t);
             } else {
                 if (id_bytes == 8) IDC_LAUNCH_DEC(4, int64_t); else IDC_LAUNCH_DEC(4, int32_t);
             }
