@@ -116,7 +116,7 @@ struct EfEncArgs {
 //               with the neighbouring tiles (atomicOr on the pre-zeroed array).
 //   chunk descriptors for the decoder: id e announces the chunk boundaries between the previous id's one and its
 //               own (ids before such a boundary = e); the list's last tile adds the trailing ones.
-__device__ __forceinline__ void ef_emit_chunk(const EfEncArgs& a, uint32_t L, uint32_t l, uint64_t m, uint64_t hw,
+__device__ __noinline__ void ef_emit_chunk(const EfEncArgs& a, uint32_t L, uint32_t l, uint64_t m, uint64_t hw,
                                               uint64_t C, uint64_t before) {
     const uint64_t W = C * kDecChunkWords;
     if (W >= hw) return;
