@@ -70,6 +70,7 @@ static void group_decode(uint64_t head, const uint32_t* words, uint32_t nwords, 
         if (force_degenerate) U.tree.ovf_cap = force_degenerate - 1;
         dec_state_init(U.st, head, words, nwords, DecRing{ring.data(), 4u}, g.sub == 0);
         g.sync();
+        dec_ring_prime(U.st);
         U.out = out;
         U.n = n;
         U.prec = prec;

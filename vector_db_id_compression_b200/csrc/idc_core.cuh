@@ -345,6 +345,7 @@ struct DecState {
     uint32_t fleft;      // words of the blob's stack not fetched yet
     uint32_t sp;         // words of the blob's stack not popped yet
     uint32_t rpos;       // ring slot of the next word to pop
+    uint32_t peek;       // that word, read from the ring right after the previous pop (off the critical path)
     DecRing ring;
     uint32_t fetcher;    // this lane issues the copies (lane 0 of the group that owns the unit)
     uint32_t ov;         // overlay: the one word the decoder may hold above the blob's stack
@@ -372,19 +373,28 @@ IDC_HD void dec_state_init(DecState& st, uint64_t head, const uint32_t* words, u
     st.has_ov = 0;
     st.draws = 0;
     st.status = 0;
+    st.peek = 0;  // set by dec_ring_prime() once the group has met
 }
 
-// The word the next pop returns. Device: the ring slot (every lane of the warp reads it in the same instruction,
-// before the fetching lane's asynchronous refill of that slot can land). The host emulation's lanes are free-running
-// threads, so there the fetching lane's refill could overtake a slower lane's read: it reads the blob itself.
-IDC_HD uint32_t dec_ring_word(const DecState& st, const uint32_t* slot) {
+// after dec_state_init and a rendezvous of the group
+IDC_HD void dec_ring_prime(DecState& st);
+
+// The word the next pop returns. Device: the ring slot st.rpos (every lane of the warp reads it in the same
+// instruction, long after the copy that filled it has landed). The host emulation's lanes are free-running
+// threads, so there the fetching lane's refill of a slot could overtake a slower lane's read: it reads the blob
+// itself.
+IDC_HD uint32_t dec_ring_word(const DecState& st) {
 #if defined(__CUDA_ARCH__)
-    return *slot;
+    return *st.ring.at(st.rpos);
 #else
-    (void)slot;
     return st.sp ? st.words[st.sp - 1u] : 0u;
 #endif
 }
+
+// Once per step, before the first pop: all but the kDecRingWait most recent copy groups have landed. A word is
+// popped kDecRing pops after its copy was issued, at most three pops (= groups) happen per step, and every step ends
+// with a rendezvous of the group, so the word every lane reads is complete and visible.
+IDC_HD void dec_ring_sync() { ring_wait<kDecRingWait>(); }
 
 // `if (h < 2^31) h = (h << 32) | pop()` of codec.cpp:83-87 / :56-60 as straight-line code. pop() = the overlay if
 // there is one, else the blob's next word (from the ring; its slot is refilled at once with the word kDecRing
@@ -394,9 +404,8 @@ IDC_HD uint64_t dec_renorm(DecState& st, uint64_t h, const uint32_t* mt) {
     const bool rf = h < kRansL;
     const bool o = st.has_ov != 0u;
     const bool blob = rf & !o;
-    ring_wait<kDecRingWait>();
     uint32_t* slot = st.ring.at(st.rpos);
-    uint32_t w = o ? st.ov : dec_ring_word(st, slot);
+    uint32_t w = o ? st.ov : st.peek;
     if (blob & (st.sp == 0u)) {
         uint32_t d = st.draws++;
         w = 0;
@@ -412,11 +421,14 @@ IDC_HD uint64_t dec_renorm(DecState& st, uint64_t h, const uint32_t* mt) {
         st.rpos = (st.rpos + dec) & (kDecRing - 1u);
         st.fp -= more ? 1 : 0;
         st.fleft -= more ? 1u : 0u;
+        st.peek = dec_ring_word(st);  // (same slot again when nothing was popped)
     }
     ring_commit();
     st.has_ov = rf ? 0u : st.has_ov;
     return rf ? ((h << 32) | (uint64_t)w) : h;
 }
+
+IDC_HD void dec_ring_prime(DecState& st) { st.peek = dec_ring_word(st); }
 
 // codec.cpp:78-90; p in 0..16
 IDC_HD uint32_t dec_pop_bits(DecState& st, uint32_t p, const uint32_t* mt) {

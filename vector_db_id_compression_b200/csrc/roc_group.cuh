@@ -488,6 +488,7 @@ struct GDecUnit {
 template <int G, class GR, typename OutT>
 IDC_HD void gdec_step(const GR& g, GDecUnit<OutT>& U, uint32_t i, uint32_t q31, const uint32_t* mt, bool act) {
     uint32_t id = 0;
+    dec_ring_sync();
     if (act) id = dec_pop_id32(U.st, U.prec, mt);
     GDecHit hit;
     const uint32_t rank = gdec_rank<G>(g, U.tree, id, U.out + (U.n - i), i, act, hit);

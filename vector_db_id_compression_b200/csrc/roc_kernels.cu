@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
     U.tree = gdec_tree_at(a.ws + (row_mode ? (uint64_t)slot * a.slot_ws : (valid ? a.sel_ws[slot] : 0ull)), sm, n ? n : 1u,
                           valid ? a.unit_lo[u] : 0u, valid ? a.unit_hi[u] : 0u);
     __syncwarp();
+    dec_ring_prime(U.st);
     const uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
     // 2^31 / (i + 1) from the table, 32 entries per coalesced load and one block ahead (see k_roc_encode)
     auto tab_q31 = [&](uint32_t ib) { uint32_t e = ib + lane_id + 1u; return __ldg(a.q31 + (e <= kMaxUnit ? e : kMaxUnit)); };
