@@ -81,31 +81,6 @@ IDC_HD uint4x ld_ws16(const void* p) {
     return *reinterpret_cast<const uint4x*>(p);
 #endif
 }
-// read-only inputs (id arrays, compressed streams): normal cached loads
-IDC_HD uint32_t ld_ro32(const uint32_t* p) {
-#if defined(__CUDA_ARCH__)
-    return __ldg(p);
-#else
-    return *p;
-#endif
-}
-// the same, pinned where it is written: the compiler may neither sink it to its first use nor hoist it
-IDC_HD uint32_t ld_ro32_pinned(const uint32_t* p) {
-#if defined(__CUDA_ARCH__)
-    uint32_t v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-#else
-    return *p;
-#endif
-}
-IDC_HD void prefetch_ro(const void* p) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
 IDC_HD uint32_t ld_ws32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
     return __ldcg(p);
@@ -134,21 +109,6 @@ IDC_HD void st_ws64(uint64_t* p, uint64_t v) {
     *p = v;
 #endif
 }
-IDC_HD void red_add32(uint32_t* p, uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    atomicAdd(p, v);  // result unused -> RED.ADD
-#else
-    *p += v;
-#endif
-}
-IDC_HD void red_and32(uint32_t* p, uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    atomicAnd(p, v);  // result unused -> RED.AND
-#else
-    *p &= v;
-#endif
-}
-
 template <typename T>
 IDC_HD T load_id_raw(const T* p) {
 #if defined(__CUDA_ARCH__)
@@ -199,22 +159,6 @@ IDC_HD void st_ws32_if(uint32_t* p, uint32_t v, bool cond) {
     if (cond) *p = v;
 #endif
 }
-// v = cond ? *p : v, pinned where it is written (neither sunk to the first use nor hoisted)
-IDC_HD void ld_ro32_if(const uint32_t* p, uint32_t& v, bool cond) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.global.nc.u32 %0, [%1]; }" : "+r"(v) : "l"(p), "r"((uint32_t)cond));
-#else
-    if (cond) v = *p;
-#endif
-}
-IDC_HD void prefetch_ro_if(const void* p, bool cond) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q prefetch.global.L1 [%0]; }" ::"l"(p), "r"((uint32_t)cond));
-#else
-    (void)p, (void)cond;
-#endif
-}
-
 // ------------------------------------------------------ encoder rANS state --
 // The encoder's stack is append-only in the codec's valid domain; the rare
 // pop-from-stack cases are still implemented exactly (read back the word just
