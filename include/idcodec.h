@@ -87,6 +87,10 @@ int idc_version(void);
  *
  * offsets: HOST array of nlist+1 element offsets (CSR) into ids.
  * ids:     int64 (id_bytes = 8, faiss::idx_t) or int32 (id_bytes = 4), host or device.
+ *          IDC_MEM_HOST with IDC_F_SORTED: the upload is cut into chunks of whole units and
+ *          overlapped with the kernels (a size class of units starts when its chunk is there);
+ *          page-locked host memory makes the copies asynchronous. Input errors (an id >= 2^32,
+ *          unsorted ids behind IDC_F_SORTED) are reported by the return code in every case.
  */
 int idc_roc_encode(
         idc_ctx* ctx,
@@ -216,7 +220,9 @@ int idc_roc_decode_rows(
  *   CompressedIDInvertedListsEliasFano ctor custom_invlists_impl.cpp:229-284
  *   EliasFanoNSGGraph ctor                altid_impl.cpp:53-90
  * Per list: l = msb(max_id / m), low bits m*l, high bits (m+1)+(max_id>>l)+1,
- * both LSB-first in 64-bit words (succinct bit_vector layout).
+ * both LSB-first in 64-bit words (succinct bit_vector layout). A list whose
+ * high-bits vector would reach 2^32 bits (more than ~1.4e9 ids) is rejected
+ * with IDC_ERR_DOMAIN.
  */
 int idc_ef_encode(
         idc_ctx* ctx,
