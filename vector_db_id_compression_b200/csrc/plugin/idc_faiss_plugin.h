@@ -128,6 +128,14 @@ struct CompressedIDInvertedListsFenwickTree : InvertedListsArrayCodes {
         for (size_t i = 0; i < n; i++) cache_[ln[i]].assign(ids.begin() + off[i], ids.begin() + off[i + 1]);
     }
 
+    /// the id-translation step of search_IVF_defer_id_decoding (:464-525), in place: labels hold
+    /// (list_no << 32 | offset) from search_preassigned(store_pairs = true), -1 for empty slots
+    void translate_labels(idx_t* labels, size_t n) const {
+        static_assert(sizeof(idx_t) == 8, "faiss::idx_t is int64");
+        idc_plugin::check(idc_roc_translate(idc_plugin::context(), blob, reinterpret_cast<const int64_t*>(labels), IDC_MEM_HOST, n,
+                                            reinterpret_cast<int64_t*>(labels), IDC_MEM_HOST));
+    }
+
     const idx_t* get_ids(size_t list_no) const override {  // :210-219
         size_t ls = list_size(list_no);
         if (ls == 0) return nullptr;
