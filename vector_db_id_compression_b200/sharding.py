@@ -52,6 +52,16 @@ def shard_csr(offsets: np.ndarray, lists: np.ndarray):
     return loc, sizes
 
 
+def _gather_index(goff: np.ndarray, lists: np.ndarray) -> np.ndarray:
+    """Element indices of the given lists, concatenated in the given order (vectorised: no per-list loop)."""
+    if lists.size == 0:
+        return np.zeros(0, np.int64)
+    starts = goff[lists].astype(np.int64)
+    sizes = (goff[lists + 1] - goff[lists]).astype(np.int64)
+    out_start = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    return np.repeat(starts - out_start, sizes) + np.arange(int(sizes.sum()), dtype=np.int64)
+
+
 def scatter_lists(offsets, ids, device, src: int = 0, group=None):
     """Rank `src` owns (offsets, ids); every rank gets (its list numbers, local offsets, its ids on `device`).
 
@@ -78,8 +88,7 @@ def scatter_lists(offsets, ids, device, src: int = 0, group=None):
         blocks = []
         for r in range(world):
             lists = parts[r]
-            idx = (np.concatenate([np.arange(goff[l], goff[l + 1]) for l in lists]) if lists.size
-                   else np.zeros(0, np.int64))
+            idx = _gather_index(goff, lists)
             blk = ids_t[torch.as_tensor(idx, device=device)] if idx.size else torch.empty(0, dtype=torch.int64, device=device)
             if r == src:
                 recv.copy_(blk)
