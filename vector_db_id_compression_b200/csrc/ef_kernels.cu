@@ -166,8 +166,42 @@ __global__ void __launch_bounds__(kThreads, 4) k_ef_encode(EfEncArgs a) {
     uint32_t v[32];  // lane-major: v[r] = id of element 32 * lane + r
 #pragma unroll
     for (int r = 0; r < 32; r++) v[r] = ts[33u * lane + (uint32_t)r];
-    const uint64_t hpF = (uint64_t)(ts[0] >> l) + i0;
-    const uint64_t hpL = (uint64_t)(ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0 + cnt - 1u;
+    // positions in the high bit vector fit 32 bits (ef_build rejects lists whose vector is longer)
+    const uint32_t i0w = (uint32_t)i0;
+    const uint32_t hpF = (ts[0] >> l) + i0w;
+    const uint32_t hpL = (ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0w + cnt - 1u;
+    // ---- chunk descriptors (a chunk = kDecChunkWords 64-bit words = 1024 bits of the high vector). Id e announces
+    // the chunks C with prev < 1024 C <= hp(e), prev = the one before it: it is the first id at or past their first
+    // bit, so `ids before the chunk` = e. A straight-line pass marks the announcing ids (a few per tile); the
+    // descriptors are written in a rolled loop that re-reads those ids from shared memory (still intact here).
+    {
+        const uint32_t my_last = (v[31] >> l) + i0w + 32u * lane + 31u;
+        int64_t prev = (int64_t)__shfl_up_sync(0xffffffffu, my_last, 1);
+        if (lane == 0) prev = hp_prev_tile;
+        uint32_t c_lo = prev < 0 ? 0u : (uint32_t)(prev >> 10) + 1u;  // first chunk not announced yet
+        uint32_t bm = 0;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const uint32_t e = 32u * lane + (uint32_t)r;
+            const uint32_t c_hi = ((v[r] >> l) + i0w + e) >> 10;
+            if (e < cnt) {
+                bm |= c_hi >= c_lo ? 1u << r : 0u;
+                c_lo = c_hi + 1u;
+            }
+        }
+        while (bm) {
+            const uint32_t r = (uint32_t)__ffs((int)bm) - 1u;
+            bm &= bm - 1u;
+            const uint32_t e = 32u * lane + r;
+            const uint32_t c_hi = ((ts[33u * lane + r] >> l) + i0w + e) >> 10;
+            const int64_t pp = r ? (int64_t)((ts[33u * lane + r - 1u] >> l) + i0w + e - 1u) : prev;
+            for (uint32_t C = pp < 0 ? 0u : (uint32_t)(pp >> 10) + 1u; C <= c_hi; C++) ef_emit_chunk(a, L, l, m, hw, C, i0 + e);
+        }
+        if (last_tile) {
+            const uint64_t nchunks = (hw + kDecChunkWords - 1) / kDecChunkWords;
+            for (uint64_t C = (uint64_t)(hpL >> 10) + 1 + lane; C < nchunks; C += 32) ef_emit_chunk(a, L, l, m, hw, C, m);
+        }
+    }
     __syncwarp();
     // ---- lower bits
     if (l) {
@@ -189,25 +223,25 @@ __global__ void __launch_bounds__(kThreads, 4) k_ef_encode(EfEncArgs a) {
         for (uint32_t q = lane; q < nlw; q += 32) low32[q] = ts[q];
     }
     // ---- upper bits
-    const uint64_t gF = hpF >> 5, gL = hpL >> 5;  // the tile's first / last 32-bit word of the high vector
-    if (lane % 8u == 0u && 32u * lane < cnt) (a.samples + a.samp_off[L])[(i0 + 32u * lane) >> kEfSampleLog] = (uint32_t)((v[0] >> l) + i0 + 32u * lane);
-    uint64_t wb = hpF & ~31ull;  // window base (a bit position)
+    const uint32_t gF = hpF >> 5, gL = hpL >> 5;  // the tile's first / last 32-bit word of the high vector
+    if (lane % 8u == 0u && 32u * lane < cnt) (a.samples + a.samp_off[L])[(i0 + 32u * lane) >> kEfSampleLog] = (v[0] >> l) + i0w + 32u * lane;
+    uint32_t wb = hpF & ~31u;  // window base (a bit position)
     for (;;) {
         for (uint32_t q = lane; q < kEncWinWords; q += 32) win[q] = 0u;
         __syncwarp();
-        const bool more = hpL >= wb + 32ull * kEncWinWords;  // warp-uniform: some ones lie past this window
-        uint64_t next = ~0ull;
+        const bool more = hpL - wb >= 32u * kEncWinWords;  // warp-uniform: some ones lie past this window
+        uint32_t next = 0xffffffffu;
 #pragma unroll
         for (int r = 0; r < 32; r++) {
             const uint32_t e = 32u * lane + (uint32_t)r;
-            const uint64_t hp = (uint64_t)(v[r] >> l) + i0 + e;
-            const uint64_t rel = hp - wb;  // wraps (huge) for positions below the window: handled in an earlier pass
-            if (e < cnt && rel < 32ull * kEncWinWords) atomicOr(win + (uint32_t)(rel >> 5), 1u << (hp & 31));
-            if (more && e < cnt && hp >= wb + 32ull * kEncWinWords && hp < next) next = hp;
+            const uint32_t hp = (v[r] >> l) + i0w + e;
+            const uint32_t rel = hp - wb;  // wraps (huge) for positions below the window: handled in an earlier pass
+            if (e < cnt && rel < 32u * kEncWinWords) atomicOr(win + (rel >> 5), 1u << (hp & 31u));
+            if (more && e < cnt && hp >= wb && rel >= 32u * kEncWinWords && hp < next) next = hp;
         }
         __syncwarp();
         for (uint32_t q = lane; q < kEncWinWords; q += 32) {
-            const uint64_t g = (wb >> 5) + q;
+            const uint32_t g = (wb >> 5) + q;
             if (g < gF || g > gL) continue;
             const uint32_t val = win[q];
             if (g == gF || g == gL) {
@@ -217,34 +251,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_ef_encode(EfEncArgs a) {
             }
         }
         if (!more) break;
-        for (int o = 16; o; o >>= 1) {
-            const uint64_t other = __shfl_xor_sync(0xffffffffu, next, o);
-            next = other < next ? other : next;
-        }
-        wb = next & ~31ull;
+        next = __reduce_min_sync(0xffffffffu, next);
+        wb = next & ~31u;
         __syncwarp();
-    }
-    // ---- chunk descriptors (a chunk = kDecChunkWords 64-bit words = 1024 bits of the high vector)
-    {
-        const uint32_t e_last = 32u * lane + 31u;
-        const int64_t my_last = (int64_t)((uint64_t)(v[31] >> l) + i0 + e_last);
-        int64_t prev = __shfl_up_sync(0xffffffffu, my_last, 1);
-        if (lane == 0) prev = hp_prev_tile;
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            const uint32_t e = 32u * lane + (uint32_t)r;
-            const int64_t hp = (int64_t)((uint64_t)(v[r] >> l) + i0 + e);
-            if (e < cnt) {
-                // chunks C with prev < 1024 C <= hp: id e is the first one at or past their first bit
-                const int64_t c_hi = hp >> 10;
-                for (int64_t C = prev < 0 ? 0 : (prev >> 10) + 1; C <= c_hi; C++) ef_emit_chunk(a, L, l, m, hw, (uint64_t)C, i0 + e);
-            }
-            prev = hp;
-        }
-        if (last_tile) {
-            const uint64_t nchunks = (hw + kDecChunkWords - 1) / kDecChunkWords;
-            for (uint64_t C = (hpL >> 10) + 1 + lane; C < nchunks; C += 32) ef_emit_chunk(a, L, l, m, hw, C, m);
-        }
     }
 }
 
@@ -500,6 +509,9 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     uint64_t bits_total = 0;
     for (uint64_t i = 0; i < nl; i++) {
         EfShape s = ef_shape(hi[i], n32[i]);
+        IDC_REQUIRE(s.high_bits < (1ull << 32), IDC_ERR_DOMAIN,
+                    "list %llu: upper-bits vector of %llu bits; the device path handles up to 2^32 - 1",
+                    (unsigned long long)i, (unsigned long long)s.high_bits);
         b->l[i] = (uint8_t)s.l;
         b->max_l = std::max<uint32_t>(b->max_l, s.l);
         b->universe[i] = hi[i];
@@ -572,11 +584,9 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
         IDC_CUDA(cudaMemsetAsync(d_posbase, 0, nl * 4, c->stream));
         SortArgs s{ids_dev, d_src, d_n, d_posbase, (uint32_t)nl, d_sorted, d_sort_idx,
                    (uint64_t*)(c->ws.as<uint8_t>() + big_off)};
-        LaunchScope ls(c, "k_sort_units");
-        if (id_bytes == 8)
-            k_sort_units<int64_t><<<sort_grid, 256, 0, c->stream>>>(s);
-        else
-            k_sort_units<uint32_t><<<sort_grid, 256, 0, c->stream>>>(s);
+        bool any_big = false;
+        for (uint64_t i = 0; i < nl && !any_big; i++) any_big = n32[i] > kSortWarp;
+        IDC_TRY(launch_sorts(c, s, id_bytes, sort_grid, any_big));
         enc_ids = d_sorted;
         enc_id_bytes = 4;
     }

@@ -145,13 +145,60 @@ struct SortArgs {
 };
 
 constexpr uint32_t kSortSmem = 4096;
+constexpr uint32_t kSortWarp = 64;  // units up to this size are sorted by one warp in registers (k_sort_small)
+
+// Units of <= 64 ids (NSG rows: K <= 64): one warp per unit, two keys per lane, bitonic network over shuffles --
+// no shared memory, no block barriers (the CTA-wide sort below pays 21 __syncthreads per 64-id row).
+template <typename IdT>
+__global__ void __launch_bounds__(kThreads) k_sort_small(SortArgs a) {
+    const uint32_t u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (u >= a.nunits) return;
+    const uint32_t n = a.unit_n[u];
+    if (n == 0 || n > kSortWarp) return;
+    const uint64_t src_off = a.unit_src[u];
+    const IdT* src = reinterpret_cast<const IdT*>(a.ids) + src_off;
+    const uint32_t base = a.unit_posbase[u];
+    uint64_t key[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint32_t i = (uint32_t)r * 32u + lane;
+        key[r] = i < n ? ((load_id(src + i) << 32) | (uint64_t)(base + i)) : ~0ull;
+    }
+#pragma unroll
+    for (uint32_t k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            if (j == 32) {  // partner = the lane's other key; k == 64: ascending
+                const uint64_t lo = key[0] < key[1] ? key[0] : key[1], hi = key[0] < key[1] ? key[1] : key[0];
+                key[0] = lo, key[1] = hi;
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const uint32_t i = (uint32_t)r * 32u + lane;
+                    const uint64_t other = __shfl_xor_sync(0xffffffffu, key[r], j);
+                    const bool up = (i & k) == 0, lower = (lane & j) == 0;
+                    const uint64_t mn = key[r] < other ? key[r] : other, mx = key[r] < other ? other : key[r];
+                    key[r] = (lower == up) ? mn : mx;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint32_t i = (uint32_t)r * 32u + lane;
+        if (i < n) {
+            a.sorted_ids[src_off + i] = (uint32_t)(key[r] >> 32);
+            a.sort_idx[src_off + i] = (uint32_t)key[r];
+        }
+    }
+}
 
 template <typename IdT>
 __global__ void __launch_bounds__(256) k_sort_units(SortArgs a) {
     __shared__ uint64_t skeys[kSortSmem];
     for (uint32_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
         uint32_t n = a.unit_n[u];
-        if (n == 0) continue;
+        if (n <= kSortWarp) continue;  // empty, or sorted by k_sort_small
         uint64_t src_off = a.unit_src[u];
         const IdT* src = reinterpret_cast<const IdT*>(a.ids) + src_off;
         uint32_t npad = 1;
@@ -188,6 +235,25 @@ __global__ void __launch_bounds__(256) k_sort_units(SortArgs a) {
 
 
 inline uint32_t grid_for(uint64_t threads) { return (uint32_t)((threads + kThreads - 1) / kThreads); }
+
+// both sort kernels: units of <= 64 ids by one warp each, longer ones by one CTA each (only launched when there
+// are any: `any_big`)
+inline int launch_sorts(idc_ctx* c, const SortArgs& s, int id_bytes, uint32_t sort_grid, bool any_big) {
+    LaunchScope ls(c, "k_sort_units");
+    if (s.nunits) {
+        if (id_bytes == 8)
+            k_sort_small<int64_t><<<grid_for((uint64_t)s.nunits * 32), kThreads, 0, c->stream>>>(s);
+        else
+            k_sort_small<uint32_t><<<grid_for((uint64_t)s.nunits * 32), kThreads, 0, c->stream>>>(s);
+    }
+    if (any_big) {
+        if (id_bytes == 8)
+            k_sort_units<int64_t><<<sort_grid, 256, 0, c->stream>>>(s);
+        else
+            k_sort_units<uint32_t><<<sort_grid, 256, 0, c->stream>>>(s);
+    }
+    return IDC_OK;
+}
 
 // Per-unit metadata for the units described by (m.unit_src, m.unit_n).
 struct MetaPlan {

@@ -562,11 +562,9 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
             d_sort_idx = (uint32_t*)(c->ws.as<uint8_t>() + sortidx_off);
             SortArgs s{ids_dev, d_unit_src, b->d_unit_n, d_posbase, (uint32_t)nu, d_sorted, d_sort_idx,
                        (uint64_t*)(c->ws.as<uint8_t>() + big_off)};
-            LaunchScope ls(c, "k_sort_units");
-            if (id_bytes == 8)
-                k_sort_units<int64_t><<<sort_grid, 256, 0, c->stream>>>(s);
-            else
-                k_sort_units<uint32_t><<<sort_grid, 256, 0, c->stream>>>(s);
+            bool any_big = false;
+            for (uint64_t u = 0; u < nu && !any_big; u++) any_big = b->unit_n[u] > kSortWarp;
+            IDC_TRY(launch_sorts(c, s, id_bytes, sort_grid, any_big));
             enc_ids = d_sorted;
             enc_id_bytes = 4;
             e.ids = enc_ids;
