@@ -173,12 +173,23 @@ IDC_HD uint32_t genc_sm_init_word(uint32_t n, const EncTreeLayout& L, uint32_t w
     return word;
 }
 
+// Levels A and B can be searched by the group (each lane 16/G entries, a ballot and two shuffles per level) or by
+// every lane on its own (all 16 entries in registers / loaded by every lane: more instructions, no collectives).
+// Measured (profiles/README.md): the 2-lane classes gain 8 % from the local search (equal-length control: encode
+// 66.7 -> 61.3 ms), the 4-lane classes lose 5 % (Zipf: 103.9 -> 108.7 ms) -- so it follows the lane count.
+template <int G>
+struct EncSearch {
+    static constexpr bool kLocal = G == 2;
+    static constexpr int kEa = kLocal ? 16 : 16 / G;  // level-A entries held by a lane
+};
+
 template <int G>
 struct GEncTree {
     uint32_t* rec;        // global: records of 32 words
     SmView sm;
     uint32_t sm_l0;       // logical word offset of level C
-    uint32_t ea[16 / G];  // level A: this lane's entries [sub * 16/G, (sub + 1) * 16/G)
+    // level A: all 16 entries (local search) or this lane's entries [sub * 16/G, (sub + 1) * 16/G)
+    uint32_t ea[EncSearch<G>::kEa];
 };
 
 template <int G, class GR>
@@ -187,8 +198,24 @@ IDC_HD void genc_tree_init(const GR& g, GEncTree<G>& t, uint32_t n) {
     t.sm_l0 = 8u * L.supers;
     const uint32_t total = t.sm_l0 + L.l0_words;
     for (uint32_t w = g.sub; w < total; w += (uint32_t)G) *t.sm.at(w) = genc_sm_init_word(n, L, w);
+    constexpr bool kEncLocalSearch = EncSearch<G>::kLocal;
+    if (kEncLocalSearch) {
 #pragma unroll
-    for (int j = 0; j < 16 / G; j++) t.ea[j] = enc_full_before(n, (g.sub * (16 / G) + (uint32_t)j) * kRecPerSuper);
+        for (int j = 0; j < 16; j++) t.ea[j % EncSearch<G>::kEa] = enc_full_before(n, (uint32_t)j * kRecPerSuper);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16 / G; j++) t.ea[j] = enc_full_before(n, (g.sub * (16 / G) + (uint32_t)j) * kRecPerSuper);
+    }
+}
+
+// 16 non-decreasing exclusive cumulative entries, all held by the calling lane (entry 0 is 0): index of the last
+// entry <= k and its value
+IDC_HD uint32_t local_cum_find(const uint32_t (&e)[16], uint32_t k, uint32_t& base) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 1; j < 16; j++) c += e[j] <= k ? 1u : 0u;
+    base = pick_word<16>(e, c);
+    return c;
 }
 
 // Six 5-bit counts c0..c5 of one C word -> inclusive prefix sums in 10-bit fields:
@@ -233,23 +260,62 @@ IDC_HD uint32_t group_cum_find(const GR& g, const uint32_t (&e)[EL], uint32_t k,
 // no memory.
 template <int G, class GR>
 IDC_HD uint32_t genc_select_remove(const GR& g, GEncTree<G>& t, uint32_t k, uint32_t& id_out, bool act) {
-    constexpr int EA = 16 / G;   // level-A entries per lane
+    constexpr bool kEncLocalSearch = EncSearch<G>::kLocal;
+    constexpr int EA = 16 / G;   // level-A entries per lane (group search)
     constexpr int WB = 8 / G;    // level-B words per lane (two entries each)
     constexpr int WL = 32 / G;   // record words per lane
-    // ---- level A (registers)
-    uint32_t base;
-    const uint32_t sb = group_cum_find<EA>(g, t.ea, k, base);
-    k -= base;
-    // ---- level B
-    uint32_t wb[WB], eb[2 * WB];
+    uint32_t base, sb, p;
+    uint32_t wb[kEncLocalSearch ? 8 : WB];
+    uint32_t* pb;
+    if (kEncLocalSearch) {
+        // ---- level A (registers, every lane all 16 entries)
+        uint32_t ea16[16];
 #pragma unroll
-    for (int j = 0; j < WB; j++) wb[j] = 0u;
-    uint32_t* pb = t.sm.at(8u * sb + g.sub * WB);
-    if (act) sm_load<WB>(pb, wb);
+        for (int j = 0; j < 16; j++) ea16[j] = t.ea[j % EncSearch<G>::kEa];
+        sb = local_cum_find(ea16, k, base);
+        k -= base;
+        // ---- level B (every lane loads the superblock's 8 words)
 #pragma unroll
-    for (int j = 0; j < WB; j++) eb[2 * j] = wb[j] & 0xffffu, eb[2 * j + 1] = wb[j] >> 16;
-    const uint32_t p = group_cum_find<2 * WB>(g, eb, k, base);
-    k -= base;
+        for (int j = 0; j < 8; j++) wb[j % (kEncLocalSearch ? 8 : WB)] = 0u;
+        pb = t.sm.at(8u * sb);
+        if (act) {
+            uint32_t h0[4], h1[4];
+            sm_load<4>(pb, h0);
+            sm_load<4>(t.sm.at(8u * sb + 4u), h1);
+#pragma unroll
+            for (int j = 0; j < 4; j++) wb[j % (kEncLocalSearch ? 8 : WB)] = h0[j], wb[(4 + j) % (kEncLocalSearch ? 8 : WB)] = h1[j];
+        }
+        uint32_t eb16[16];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            eb16[2 * j] = wb[j % (kEncLocalSearch ? 8 : WB)] & 0xffffu;
+            eb16[2 * j + 1] = wb[j % (kEncLocalSearch ? 8 : WB)] >> 16;
+        }
+        p = local_cum_find(eb16, k, base);
+        k -= base;
+    } else {
+        // ---- level A (registers, 16/G entries per lane)
+        uint32_t eal[EA];
+#pragma unroll
+        for (int j = 0; j < EA; j++) eal[j] = t.ea[j];
+        sb = group_cum_find<EA>(g, eal, k, base);
+        k -= base;
+        // ---- level B
+        uint32_t eb[2 * WB];
+#pragma unroll
+        for (int j = 0; j < WB; j++) wb[j] = 0u;
+        pb = t.sm.at(8u * sb + g.sub * WB);
+        uint32_t wl[WB];
+        if (act) {
+            sm_load<WB>(pb, wl);
+#pragma unroll
+            for (int j = 0; j < WB; j++) wb[j] = wl[j];
+        }
+#pragma unroll
+        for (int j = 0; j < WB; j++) eb[2 * j] = wb[j] & 0xffffu, eb[2 * j + 1] = wb[j] >> 16;
+        p = group_cum_find<2 * WB>(g, eb, k, base);
+        k -= base;
+    }
     // ---- level C: twelve 5-bit counts, replicated in every lane
     const uint32_t l0 = t.sm_l0 + (sb * 16u + p) * 2u;
     uint32_t wc[2] = {0u, 0u};
@@ -276,14 +342,31 @@ IDC_HD uint32_t genc_select_remove(const GR& g, GEncTree<G>& t, uint32_t k, uint
     // ---- the count updates ride in the shadow of the line fetch; every lane updates its own entries only
     g.host_sync();  // all lanes have read the C words before lane 0 rewrites one (racecheck: warp-level WAR)
     if (act) {
+        if (kEncLocalSearch) {
 #pragma unroll
-        for (int j = 0; j < EA; j++) t.ea[j] -= (g.sub * EA + (uint32_t)j > sb) ? 1u : 0u;
+            for (int j = 1; j < 16; j++) t.ea[j % EncSearch<G>::kEa] -= ((uint32_t)j > sb) ? 1u : 0u;
+            if (g.sub == 0) {  // one lane rewrites the superblock's 8 words
+                uint32_t h0[4], h1[4];
 #pragma unroll
-        for (int j = 0; j < WB; j++) {
-            uint32_t i0 = (g.sub * WB + (uint32_t)j) * 2u;
-            wb[j] -= (i0 > p ? 1u : 0u) | (i0 + 1u > p ? 0x10000u : 0u);
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t i0 = (uint32_t)j * 2u;
+                    const uint32_t w = wb[j % (kEncLocalSearch ? 8 : WB)] - ((i0 > p ? 1u : 0u) | (i0 + 1u > p ? 0x10000u : 0u));
+                    if (j < 4) h0[j % 4] = w; else h1[j % 4] = w;
+                }
+                sm_store<4>(pb, h0);
+                sm_store<4>(t.sm.at(8u * sb + 4u), h1);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < EA; j++) t.ea[j] -= (g.sub * EA + (uint32_t)j > sb) ? 1u : 0u;
+            uint32_t wl[WB];
+#pragma unroll
+            for (int j = 0; j < WB; j++) {
+                uint32_t i0 = (g.sub * WB + (uint32_t)j) * 2u;
+                wl[j] = wb[j] - ((i0 > p ? 1u : 0u) | (i0 + 1u > p ? 0x10000u : 0u));
+            }
+            sm_store<WB>(pb, wl);
         }
-        sm_store<WB>(pb, wb);
         if (g.sub == 0) {
             const uint32_t wsel = second ? wc[1] : wc[0];
             *(second ? pc + 1 : pc) = wsel - (1u << (5u * (second ? rb : ra)));
