@@ -163,16 +163,25 @@ __global__ void __launch_bounds__(kThreads) k_roc_encode(EncArgs a) {
     uint32_t tb = tmax;                       // block covers t = tb, tb-1, ..., tb-31
     uint64_t rcp_blk = tab_rcp(tb), rcp_nxt = tb >= 32u ? tab_rcp(tb - 32u) : 0ull;
     uint32_t q31_blk = tab_q31(tb), q31_nxt = tb >= 32u ? tab_q31(tb - 32u) : 0u;
+    // the step's table entries are broadcast one step ahead: the shuffles for step t - 1 are issued at the top of
+    // step t, so their latency is off the dependent chain
+    uint64_t rcp_next = __shfl_sync(0xffffffffu, rcp_blk, 0);
+    uint32_t q31_next = __shfl_sync(0xffffffffu, q31_blk, 0);
     for (uint32_t t = tmax; t >= 1u; --t) {
-        if (tb - t == 32u) {
-            tb -= 32u;
-            rcp_blk = rcp_nxt;
-            q31_blk = q31_nxt;
-            rcp_nxt = tb >= 32u ? tab_rcp(tb - 32u) : 0ull;
-            q31_nxt = tb >= 32u ? tab_q31(tb - 32u) : 0u;
+        const uint64_t rcp = rcp_next;
+        const uint32_t q31 = q31_next;
+        if (t > 1u) {
+            const uint32_t tn = t - 1u;
+            if (tb - tn == 32u) {
+                tb -= 32u;
+                rcp_blk = rcp_nxt;
+                q31_blk = q31_nxt;
+                rcp_nxt = tb >= 32u ? tab_rcp(tb - 32u) : 0ull;
+                q31_nxt = tb >= 32u ? tab_q31(tb - 32u) : 0u;
+            }
+            rcp_next = __shfl_sync(0xffffffffu, rcp_blk, tb - tn);
+            q31_next = __shfl_sync(0xffffffffu, q31_blk, tb - tn);
         }
-        const uint64_t rcp = __shfl_sync(0xffffffffu, rcp_blk, tb - t);
-        const uint32_t q31 = __shfl_sync(0xffffffffu, q31_blk, tb - t);
         genc_step<G>(g, U, t, rcp, q31, a.mt, t <= n);
     }
     if (valid && g.sub == 0) {
@@ -277,13 +286,18 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
     auto tab_q31 = [&](uint32_t ib) { uint32_t e = ib + lane_id + 1u; return __ldg(a.q31 + (e <= kMaxUnit ? e : kMaxUnit)); };
     uint32_t ib = 0;                          // block covers i = ib .. ib+31
     uint32_t q31_blk = tab_q31(0), q31_nxt = tab_q31(32);
+    uint32_t q31_next = __shfl_sync(0xffffffffu, q31_blk, 0);  // one step ahead, see k_roc_encode
     for (uint32_t i = 0; i < tmax; ++i) {
-        if (i - ib == 32u) {
-            ib += 32u;
-            q31_blk = q31_nxt;
-            q31_nxt = tab_q31(ib + 32u);
+        const uint32_t q31 = q31_next;
+        {
+            const uint32_t in = i + 1u;
+            if (in - ib == 32u) {
+                ib += 32u;
+                q31_blk = q31_nxt;
+                q31_nxt = tab_q31(ib + 32u);
+            }
+            q31_next = __shfl_sync(0xffffffffu, q31_blk, in - ib);
         }
-        const uint32_t q31 = __shfl_sync(0xffffffffu, q31_blk, i - ib);
         gdec_step<G>(g, U, i, q31, a.mt, i < n);
     }
     if (valid) {
