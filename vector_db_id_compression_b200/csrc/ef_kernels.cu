@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(kThreads) k_bits_unpack(const uint8_t* code, u
 int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint32_t flags,
              const std::vector<uint64_t>& list_src, uint64_t id_elems) {
     const uint64_t nl = b->nlist;
+    HostTrace tr("ef_build");
     // per-list metadata via the shared unit kernel (a list is one "unit" here)
     std::vector<uint32_t> n32(nl);
     for (uint64_t i = 0; i < nl; i++) {
@@ -497,6 +498,7 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
     IDC_TRY(status_to_error(st, "ef_encode"));
+    tr.mark("unit metadata");
 
     // shapes
     b->l.resize(nl);
@@ -525,6 +527,7 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
             tile_idx.push_back((uint32_t)t);
         }
     }
+    tr.mark("shapes + tile tables");
     b->low_words = b->low_off[nl];
     b->high_words = b->high_off[nl];
     b->nsamples = b->samp_off[nl];
@@ -549,6 +552,7 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     IDC_TRY(upload(c, b->d_dir_off, b->dir_off));
     IDC_CUDA(cudaMemsetAsync(b->d_dir, 0, std::max<uint64_t>(b->ndir, 1) * sizeof(EfChunk), c->stream));  // empty lists: count 0
 
+    tr.mark("alloc + uploads");
     // sort when needed (ids < 2^32 was checked by the metadata kernel)
     const void* enc_ids = ids_dev;
     int enc_id_bytes = id_bytes;
@@ -609,6 +613,7 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     }
     IDC_TRY(check_last_launch("k_ef_finish_chunks"));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
+    tr.mark("sort + encode kernels");
     b->device_bytes = acct;
     return IDC_OK;
 }

@@ -14,9 +14,27 @@
 
 #include "../../include/idcodec.h"
 
+#include <chrono>
+#include <cstdlib>
+
 namespace idc {
 
 void set_error(const char* fmt, ...);
+
+// IDC_TRACE_HOST=1: wall-clock time of the host-side phases of a call on stderr (where the milliseconds of a call
+// with a million tiny units go)
+struct HostTrace {
+    bool on;
+    const char* what;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostTrace(const char* w) : on(getenv("IDC_TRACE_HOST") != nullptr), what(w), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* phase) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[idc host] %s: %-28s %8.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 #define IDC_CUDA(call)                                                                          \
     do {                                                                                        \

@@ -65,10 +65,11 @@ __global__ void __launch_bounds__(kThreads) k_unit_meta(MetaArgs a) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.ntiles) return;
     warp += a.tile_base;
-    const uint32_t u = a.tile_unit[warp];
+    // null tables: every unit has at most one tile (tile t = unit t, empty units included)
+    const uint32_t u = a.tile_unit ? a.tile_unit[warp] : warp;
     const IdT* src = reinterpret_cast<const IdT*>(a.ids) + a.unit_src[u];
     const uint32_t n = a.unit_n[u];
-    const uint32_t i0 = a.tile_idx[warp] * kMetaTile, i1 = i0 + kMetaTile < n ? i0 + kMetaTile : n;
+    const uint32_t i0 = (a.tile_idx ? a.tile_idx[warp] : 0u) * kMetaTile, i1 = i0 + kMetaTile < n ? i0 + kMetaTile : n;
     uint64_t mx = 0, mn = ~0ull;
     uint32_t bad = 0;
     for (uint32_t i = i0 + lane; i < i1; i += 32) {
@@ -259,12 +260,22 @@ inline int launch_sorts(idc_ctx* c, const SortArgs& s, int id_bytes, uint32_t so
 struct MetaPlan {
     std::vector<uint32_t> tile_unit, tile_idx;
     std::vector<uint64_t> tile_first;  // per unit (nunits + 1): index of its first tile
+    bool identity = false;             // every unit <= kMetaTile ids: tile t = unit t, no tables
 };
 
 inline void plan_unit_meta(const std::vector<uint32_t>& unit_n, MetaPlan& p) {
     p.tile_unit.clear();
     p.tile_idx.clear();
+    p.identity = true;
+    for (uint64_t u = 0; u < unit_n.size() && p.identity; u++) p.identity = unit_n[u] <= kMetaTile;
+    if (p.identity) {  // a million graph rows: no per-tile tables to build or upload
+        p.tile_first.resize(unit_n.size() + 1);
+        for (uint64_t u = 0; u <= unit_n.size(); u++) p.tile_first[u] = u;
+        return;
+    }
     p.tile_first.assign(unit_n.size() + 1, 0);
+    p.tile_unit.reserve(unit_n.size() + unit_n.size() / 4);
+    p.tile_idx.reserve(unit_n.size() + unit_n.size() / 4);
     for (uint64_t u = 0; u < unit_n.size(); u++) {
         p.tile_first[u] = p.tile_unit.size();
         for (uint32_t t = 0; (uint64_t)t * kMetaTile < unit_n[u]; t++) {
@@ -303,11 +314,14 @@ inline int run_unit_meta(idc_ctx* c, MetaArgs m, const std::vector<uint32_t>& un
     plan_unit_meta(unit_n_host, p);
     const uint64_t nt = p.tile_unit.size();
     IDC_REQUIRE(nt < (1ull << 32), IDC_ERR_ARG, "too many metadata tiles");
-    IDC_TRY(c->scratch.reserve(nt * 8 + 256));
-    uint32_t* d_tu = c->scratch.as<uint32_t>();
-    uint32_t* d_ti = d_tu + nt;
-    IDC_TRY(upload(c, d_tu, p.tile_unit));
-    IDC_TRY(upload(c, d_ti, p.tile_idx));
+    uint32_t *d_tu = nullptr, *d_ti = nullptr;
+    if (!p.identity) {
+        IDC_TRY(c->scratch.reserve(nt * 8 + 256));
+        d_tu = c->scratch.as<uint32_t>();
+        d_ti = d_tu + nt;
+        IDC_TRY(upload(c, d_tu, p.tile_unit));
+        IDC_TRY(upload(c, d_ti, p.tile_idx));
+    }
     IDC_CUDA(cudaMemsetAsync(m.unit_lo, 0xff, nu * 4, c->stream));
     IDC_CUDA(cudaMemsetAsync(m.unit_hi, 0, nu * 4, c->stream));
     m.tile_unit = d_tu;

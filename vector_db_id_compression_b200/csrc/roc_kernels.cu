@@ -427,6 +427,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
                      uint32_t flags, const std::vector<uint32_t>& unit_posbase, uint64_t id_elems) {
     const uint64_t nu = b->nunits;
     uint64_t acct = 0;
+    HostTrace tr("roc_encode");
     IDC_TRY(dev_alloc(c, &b->d_unit_n, nu, &acct));
     IDC_TRY(dev_alloc(c, &b->d_unit_prec, nu, &acct));
     IDC_TRY(dev_alloc(c, &b->d_unit_head, nu, &acct));
@@ -447,6 +448,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
         scratch_off[u] = scratch_words;
         scratch_words += b->unit_n[u] ? (uint64_t)b->unit_n[u] + 4u : 0;
     }
+    tr.mark("alloc + order + offsets");
     MetaPlan mplan;
     plan_unit_meta(b->unit_n, mplan);
     const uint64_t ntile = mplan.tile_unit.size();
@@ -482,6 +484,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
         IDC_CUDA(cudaMemsetAsync(b->d_unit_hi, 0, nu * 4, c->stream));
     }
 
+    tr.mark("meta plan + uploads");
     const bool sorted_in = (flags & IDC_F_SORTED) != 0;
     // chunks of whole units: [cu[j], cu[j+1])
     const bool pipelined = ids_host != nullptr && sorted_in && nu >= 64 && id_elems >= (1ull << 22);
@@ -549,7 +552,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
     // 1. per chunk: upload, unit metadata, [sort], records
     MetaArgs m{ids_dev, d_unit_src, b->d_unit_n, (uint32_t)nu, sorted_in ? 1u : 0u,
                (flags & IDC_F_PRECISION_SAFE) ? 1u : 0u, b->d_unit_prec, b->d_unit_lo, b->d_unit_hi, d_status,
-               d_tile_unit, d_tile_idx, 0u, 0u, 0u, 0u};
+               mplan.identity ? nullptr : d_tile_unit, mplan.identity ? nullptr : d_tile_idx, 0u, 0u, 0u, 0u};
     std::vector<cudaEvent_t> ev_ready(nchunk);
     for (size_t j = 0; j < nchunk; j++) {
         const uint64_t u0 = cu[j], u1 = cu[j + 1];
@@ -602,6 +605,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
         IDC_CUDA(cudaEventRecord(ev_ready[j], c->stream));
     }
 
+    tr.mark("chunks: meta, sort, records");
     // 3. encode: a class starts when the chunk with its last unit is ready
     {
         LaunchScope ls(c, "k_roc_encode");
@@ -639,6 +643,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
     }
     IDC_TRY(check_last_launch("k_roc_encode"));
 
+    tr.mark("class launches");
     // 4. sizes -> packed offsets -> compaction
     std::vector<uint32_t> nwords(nu);
     uint32_t st = 0;
@@ -646,6 +651,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
     IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
     IDC_TRY(status_to_error(st, "roc_encode"));
+    tr.mark("wait for the kernels");
     std::vector<uint64_t> word_off(nu + 1);
     word_off[0] = 0;
     uint64_t ans_bytes = 0;
@@ -665,6 +671,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
     }
     IDC_TRY(check_last_launch("k_roc_compact"));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
+    tr.mark("word offsets + compaction");
     b->device_bytes = acct;
     return IDC_OK;
 }
@@ -884,6 +891,7 @@ int idc_roc_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* d
     c->begin_call();
     std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
     b->ctx = c;
+    HostTrace tr("roc_encode_rows");
     b->row_stride = K;
     b->nlist = nrows;
     b->nunits = nrows;
@@ -922,6 +930,7 @@ int idc_roc_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* d
     b->list_offsets[nrows] = total;
     b->unit_offsets[nrows] = nrows;
     b->total_ids = total;
+    tr.mark("row counts + tables");
     IDC_TRY(roc_encode_units(c, b.get(), d_data, nullptr, 4, flags & ~IDC_F_SORTED, posbase, elems));
     *out = b.release();
     return IDC_OK;
