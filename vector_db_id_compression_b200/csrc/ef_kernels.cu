@@ -508,6 +508,8 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     b->samp_off.assign(nl + 1, 0);
     b->dir_off.assign(nl + 1, 0);
     std::vector<uint32_t> tile_list, tile_idx;
+    tile_list.reserve(nl + b->total_ids / kEncTileIds);
+    tile_idx.reserve(nl + b->total_ids / kEncTileIds);
     uint64_t bits_total = 0;
     for (uint64_t i = 0; i < nl; i++) {
         EfShape s = ef_shape(hi[i], n32[i]);
