@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [_nvcc(), "-shared", "-o", str(LIB), *objs, "-lcudart"]
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
     return LIB
 
