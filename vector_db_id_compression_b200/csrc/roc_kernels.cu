@@ -1,6 +1,6 @@
 // roc_kernels.cu -- ROC (bits-back rANS over sets) encode / decode on sm_100a.
 //
-// Execution model: ONE UNIT PER GROUP OF G LANES (G = 4 or 8; roc_group.cuh). The reference
+// Execution model: ONE UNIT PER GROUP OF G LANES (G = 2, 4 or 8; roc_group.cuh). The reference
 // stream is a single serial rANS head per list (codec.cpp:131-137,144-151), so the only
 // bit-exact way to interleave coders inside a warp is across lists: a warp runs 32/G units,
 // every group owns one unit's head (replicated in its lanes), stream pointer and
@@ -11,13 +11,15 @@
 // reciprocal used by the uniform pop is then one broadcast load.
 //
 // Kernels (all integer, HBM/L2-latency bound; no tensor cores):
-//   k_unit_meta     per unit min/max id, precision rule, sortedness / width checks
+//   k_unit_meta     per 4096-id tile min/max id, sortedness / width checks; k_unit_meta_finish: precision rule
 //   k_row_counts    NSG rows: length = entries before the first -1
-//   k_sort_units    per unit bitonic sort (only when the input is not sorted)
+//   k_sort_small / k_sort_units   per unit bitonic sort by a warp (<= 64 ids) / a CTA (only for unsorted input)
 //   k_enc_records   the unit's ids re-laid as 128-byte records (presence mask + 31 ids)
-//   k_roc_encode    the coder
+//   k_roc_encode    the coder (one launch per size class, classes spread over 3 streams)
 //   k_roc_compact   gather the per-unit scratch streams into the packed blob
-//   k_roc_decode    the decoder
+//   k_roc_decode    the decoder (also the row mode: slot-derived tables for NSG rows)
+//   k_translate_gather   ids of (list_no << 32 | offset) labels from the decoded hit lists
+// Host buffers (IDC_MEM_HOST) are uploaded / downloaded in chunks on a copy stream, overlapped with the kernels.
 #include <algorithm>
 #include <cstring>
 #include <numeric>
