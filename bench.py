@@ -477,10 +477,14 @@ def ef_section(args, ctx, offsets, ids, dev, peak):
     eb.free()
     del out
     e, d = float(np.mean(enc_ms)), float(np.mean(dec_ms))
+    pm = float(np.mean(meta_ms))
     return {
         "bit_exact_roundtrip": exact, "bits_per_id": 8.0 * comp / n_ids,
-        "encode": {"kernel_ms": e, "prep_ms": float(np.mean(meta_ms)), "ids_per_s": n_ids / (e * 1e-3),
-                   "achieved_GBs": (8.0 * n_ids + comp) / (e * 1e-3) / 1e9, "frac": (8.0 * n_ids + comp) / (e * 1e-3) / 1e9 / peak},
+        # prep = the metadata kernel in front of k_ef_encode (list ends for ascending input: the order / width check
+        # of the ids happens inside k_ef_encode); frac_with_prep charges it to the encode
+        "encode": {"kernel_ms": e, "prep_ms": pm, "ids_per_s": n_ids / (e * 1e-3),
+                   "achieved_GBs": (8.0 * n_ids + comp) / (e * 1e-3) / 1e9, "frac": (8.0 * n_ids + comp) / (e * 1e-3) / 1e9 / peak,
+                   "frac_with_prep": (8.0 * n_ids + comp) / ((e + pm) * 1e-3) / 1e9 / peak},
         "decode": {"kernel_ms": d, "ids_per_s": n_ids / (d * 1e-3),
                    "achieved_GBs": (8.0 * n_ids + comp) / (d * 1e-3) / 1e9, "frac": (8.0 * n_ids + comp) / (d * 1e-3) / 1e9 / peak},
     }

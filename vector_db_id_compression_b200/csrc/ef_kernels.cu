@@ -102,7 +102,24 @@ struct EfEncArgs {
     const uint32_t* tile_list;
     const uint32_t* tile_idx;
     uint32_t ntiles;
+    uint32_t check_input;       // ascending input taken on trust so far: verify order and width while encoding
+    uint32_t* status;
 };
+
+// Ascending input: a list's universe (max id) is its last id, no pass over the ids needed for it. One thread per
+// list; the order / width of the ids is verified by k_ef_encode, which reads every id anyway.
+template <typename IdT>
+__global__ void __launch_bounds__(kThreads) k_list_ends(const void* ids, const uint64_t* list_src, const uint32_t* list_n,
+                                                        uint32_t nlist, uint32_t* lo, uint32_t* hi, uint32_t* status) {
+    uint32_t L = blockIdx.x * blockDim.x + threadIdx.x;
+    if (L >= nlist) return;
+    const uint32_t n = list_n[L];
+    const IdT* src = reinterpret_cast<const IdT*>(ids) + list_src[L];
+    const uint64_t first = n ? load_id(src) : 0, last = n ? load_id(src + n - 1) : 0;
+    if (sizeof(IdT) == 8 && ((first | last) >> 32)) atomicOr(status, kStWide);
+    lo[L] = (uint32_t)first;
+    hi[L] = (uint32_t)last;
+}
 
 // One warp per tile of 1024 consecutive ids of a list. Every id is read exactly once (32 coalesced rows, all
 // requested before the first is used) and transposed through shared memory so that lane j holds the 32
@@ -152,20 +169,41 @@ __global__ void __launch_bounds__(kThreads, 4) k_ef_encode(EfEncArgs a) {
     uint32_t* ts = tile_sm[threadIdx.x >> 5];
     uint32_t* win = win_sm[threadIdx.x >> 5];
     // ---- coalesced rows -> shared memory (element e at e + e / 32: both access patterns are conflict-free)
+    uint32_t bad = 0;
     {
         uint32_t row[32];
 #pragma unroll
-        for (int r = 0; r < 32; r++)
-            row[r] = (uint32_t)r * 32u + lane < cnt ? (uint32_t)load_id(ids + i0 + (uint32_t)r * 32u + lane) : 0u;
+        for (int r = 0; r < 32; r++) {
+            const uint64_t id = (uint32_t)r * 32u + lane < cnt ? load_id(ids + i0 + (uint32_t)r * 32u + lane) : 0ull;
+            if (sizeof(IdT) == 8 && (id >> 32)) bad |= kStWide;
+            row[r] = (uint32_t)id;
+        }
 #pragma unroll
         for (int r = 0; r < 32; r++) ts[33u * (uint32_t)r + lane] = row[r];
     }
     // the one before this tile's first one (-1: none)
-    const int64_t hp_prev_tile = i0 ? (int64_t)ef_high_pos(ids, i0 - 1, l) : -1;
+    const uint64_t id_prev_tile = i0 ? load_id(ids + i0 - 1) : 0ull;
+    const int64_t hp_prev_tile = i0 ? (int64_t)((id_prev_tile >> l) + i0 - 1) : -1;
     __syncwarp();
     uint32_t v[32];  // lane-major: v[r] = id of element 32 * lane + r
 #pragma unroll
     for (int r = 0; r < 32; r++) v[r] = ts[33u * lane + (uint32_t)r];
+    if (a.check_input) {
+        // ascending? inside the lane, across lanes, across the tile's start (ids past the list's end were loaded as 0)
+#pragma unroll
+        for (int r = 0; r + 1 < 32; r++)
+            if (32u * lane + (uint32_t)r + 1u < cnt && v[r + 1] < v[r]) bad |= kStUnsorted;
+        const uint32_t next_first = __shfl_down_sync(0xffffffffu, v[0], 1);
+        if (lane < 31u && 32u * (lane + 1u) < cnt && next_first < v[31]) bad |= kStUnsorted;
+        if (lane == 0 && i0 && (uint64_t)v[0] < id_prev_tile) bad |= kStUnsorted;
+        // The list's shapes were derived from its LAST id. If this tile is ascending its largest position is its
+        // last one; should that lie outside the list's bit vector (only possible when the list as a whole is not
+        // ascending), or the tile itself be out of order, nothing of it is written: the call fails anyway.
+        const uint64_t last_pos = (uint64_t)(ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0 + cnt - 1u;
+        if (last_pos >= hw * 64) bad |= kStUnsorted;
+        if (bad) atomicOr(a.status, bad);
+        if (__any_sync(0xffffffffu, (bad & kStUnsorted) != 0)) return;
+    }
     // positions in the high bit vector fit 32 bits (ef_build rejects lists whose vector is longer)
     const uint32_t i0w = (uint32_t)i0;
     const uint32_t hpF = (ts[0] >> l) + i0w;
@@ -487,11 +525,20 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     IDC_TRY(upload(c, d_src, list_src));
     IDC_TRY(upload(c, d_n, n32));
     const bool sorted_in = (flags & IDC_F_SORTED) != 0;
-    {
-        MetaArgs m{ids_dev, d_src, d_n, (uint32_t)nl, sorted_in ? 1u : 0u, 0u, d_prec, d_lo, d_hi, d_status,
-                   nullptr, nullptr, 0u};
+    if (sorted_in) {
+        // the universe of an ascending list is its last id; order and width are verified by the encode kernel
+        LaunchScope ls(c, "k_unit_meta");
+        if (nl) {
+            if (id_bytes == 8)
+                k_list_ends<int64_t><<<grid_for(nl), kThreads, 0, c->stream>>>(ids_dev, d_src, d_n, (uint32_t)nl, d_lo, d_hi, d_status);
+            else
+                k_list_ends<uint32_t><<<grid_for(nl), kThreads, 0, c->stream>>>(ids_dev, d_src, d_n, (uint32_t)nl, d_lo, d_hi, d_status);
+        }
+    } else {
+        MetaArgs m{ids_dev, d_src, d_n, (uint32_t)nl, 0u, 0u, d_prec, d_lo, d_hi, d_status, nullptr, nullptr, 0u};
         IDC_TRY(run_unit_meta(c, m, n32, id_bytes));
     }
+    IDC_TRY(check_last_launch("k_unit_meta"));
     std::vector<uint32_t> hi(nl);
     uint32_t st = 0;
     if (nl) IDC_CUDA(cudaMemcpyAsync(hi.data(), d_hi, nl * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -601,7 +648,8 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     IDC_CUDA(cudaMemsetAsync(b->d_high, 0, std::max<uint64_t>(b->high_words, 1) * 8, c->stream));
     if (ntiles) {
         EfEncArgs e{enc_ids, d_src, b->d_list_off, b->d_l, d_hi, b->d_low_off, b->d_high_off, b->d_samp_off,
-                    b->d_low, b->d_high, b->d_samples, b->d_dir_off, b->d_dir, d_tile_list, d_tile_idx, (uint32_t)ntiles};
+                    b->d_low, b->d_high, b->d_samples, b->d_dir_off, b->d_dir, d_tile_list, d_tile_idx, (uint32_t)ntiles,
+                    sorted_in ? 1u : 0u, d_status};
         LaunchScope ls(c, "k_ef_encode");
         if (enc_id_bytes == 8)
             k_ef_encode<int64_t><<<grid_for(ntiles * 32), kThreads, 0, c->stream>>>(e);
@@ -614,7 +662,12 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
         k_ef_finish_chunks<<<grid_for(b->ndir), kThreads, 0, c->stream>>>(b->d_dir, b->ndir);
     }
     IDC_TRY(check_last_launch("k_ef_finish_chunks"));
-    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    {
+        uint32_t st2 = 0;
+        IDC_CUDA(cudaMemcpyAsync(&st2, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+        IDC_CUDA(cudaStreamSynchronize(c->stream));
+        IDC_TRY(status_to_error(st2, "ef_encode"));
+    }
     tr.mark("sort + encode kernels");
     b->device_bytes = acct;
     return IDC_OK;
