@@ -305,6 +305,86 @@ int idc_ef_select(
         int64_t* ids_out,
         int out_mem);
 
+/* ---------------------------------------------------------- wavelet tree ----
+ * Replaces CompressedIDInvertedListsWaveletTree
+ * (custom_invlist_cpp/custom_invlists_impl.cpp:346-397, .h:100-124): ONE
+ * structure over the sequence S[id] = list_no, id in [0, ntotal) (:354-362),
+ * answering get_single_id(list_no, offset) = wt.select(offset + 1, list_no)
+ * (:377-379) and get_ids = all offsets of a list (:381-392).
+ *
+ * The lists must partition [0, ntotal), ntotal = offsets[nlist] - offsets[0],
+ * each list strictly ascending -- the reference's asserts (:358-359) -- else
+ * IDC_ERR_DOMAIN. wt_type 0 = sdsl::wt_int<> with plain bit vectors; wt_type 1
+ * (rrr_vector<63>) is rejected with IDC_ERR_ARG: not implemented.
+ * SDSL is a third-party dependency absent from the reference tree, so the word
+ * layout and size_in_bytes() of its wt_int are not reproduced:
+ * select values are exact, the structure is a wavelet matrix of
+ * bit_length(nlist - 1) levels x ntotal bits plus rank / select directories.
+ */
+typedef struct idc_wt_blob idc_wt_blob;
+
+int idc_wt_encode(
+        idc_ctx* ctx,
+        uint64_t nlist,
+        const uint64_t* offsets,
+        const void* ids,
+        int id_bytes,
+        int ids_mem,
+        int wt_type,
+        idc_wt_blob** out);
+
+typedef struct {
+    uint64_t nlist;
+    uint64_t total_ids;
+    uint64_t bits_bytes;       /* levels x ntotal bits, padded to 512-bit blocks */
+    uint64_t aux_bytes;        /* rank directory, select samples, list start table */
+    uint64_t device_bytes;
+    uint32_t levels;
+    uint32_t wt_type;
+} idc_wt_info;
+
+int idc_wt_blob_info(const idc_wt_blob* blob, idc_wt_info* info);
+
+/* HOST export (any pointer may be NULL): list_offsets[nlist+1];
+ * bits[levels * words] with words = 8 * ceil(ntotal / 512), level after level, LSB first;
+ * rank[levels * (words / 8 + 1)]: ones before each 512-bit block, last entry = ones of the level;
+ * sel1 / sel0[levels * (ntotal / 2048 + 2)]: block of one / zero number m * 2048;
+ * start[nlist]: position of the list's first id below the last level. */
+int idc_wt_blob_export(
+        const idc_wt_blob* blob,
+        uint64_t* list_offsets,
+        uint64_t* bits,
+        uint32_t* rank,
+        uint32_t* sel1,
+        uint32_t* sel0,
+        uint32_t* start);
+
+int idc_wt_blob_free(idc_wt_blob* blob);
+
+/* get_single_id (custom_invlists_impl.cpp:377-379) for nq (list_no, offset)
+ * pairs; a pair outside the index yields -1. */
+int idc_wt_select(
+        idc_ctx* ctx,
+        const idc_wt_blob* blob,
+        const uint64_t* list_nos,
+        const uint64_t* offsets_in_list,
+        uint64_t nq,
+        int query_mem,
+        int64_t* ids_out,
+        int out_mem);
+
+/* get_ids (custom_invlists_impl.cpp:381-392) for nsel lists (list_nos HOST,
+ * NULL = all lists in order); same output convention as idc_ef_decode. */
+int idc_wt_decode(
+        idc_ctx* ctx,
+        const idc_wt_blob* blob,
+        const uint64_t* list_nos,
+        uint64_t nsel,
+        void* ids_out,
+        int id_bytes,
+        int out_mem,
+        uint64_t* out_offsets);
+
 /* ------------------------------------------------------- fixed-width packing
  * CompressedIDInvertedListsPackedBits (custom_invlists_impl.cpp:62-118),
  * CompactBitNSGGraph (altid_impl.cpp:20-51): values LSB-first, `bits` each. */

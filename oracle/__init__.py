@@ -3,7 +3,7 @@
 ctypes front-end for the CPU oracles:
 
 * ``oracle.port``  -- the in-repo C restatement (``roc_oracle.c``, ``ef_oracle.c``,
-  ``bits_oracle.c`` -> ``liboracle.so``).
+  ``bits_oracle.c``, ``wt_oracle.c`` -> ``liboracle.so``).
 * ``oracle.ref``   -- the UNMODIFIED reference ROC codec compiled in place from
   ``/root/reference`` (``ref_shim.cpp`` + the reference's ``codec.cpp`` ->
   ``_ref/libref_roc.so``); ``None`` when that library has not been built.
@@ -31,7 +31,9 @@ _i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so and (if /root/reference is present) _ref/libref_roc.so."""
-    if force or not (_HERE / "liboracle.so").exists() or (
+    so = _HERE / "liboracle.so"
+    stale = so.exists() and any(c.stat().st_mtime > so.stat().st_mtime for c in _HERE.glob("*_oracle.c"))
+    if force or stale or not so.exists() or (
         Path("/root/reference/custom_invlist_cpp/codec.cpp").exists()
         and not (_HERE / "_ref" / "libref_roc.so").exists()
     ):
@@ -386,6 +388,63 @@ class BitsCodec:
         return int(self.lib.oracle_bits_get(np.ascontiguousarray(code, dtype=np.uint8), int(k), bits))
 
 
+class WtCodec:
+    """Wavelet-tree id index restatement (port only; SDSL cannot be built here)."""
+
+    def __init__(self, lib: C.CDLL):
+        self.lib = lib
+        lib.oracle_wt_levels.restype = C.c_uint32
+        lib.oracle_wt_levels.argtypes = [C.c_uint64]
+        lib.oracle_wt_sequence.restype = C.c_int
+        lib.oracle_wt_sequence.argtypes = [C.c_uint64, _u64p, _i64p, _u32p]
+        lib.oracle_wt_select_seq.restype = C.c_int64
+        lib.oracle_wt_select_seq.argtypes = [C.c_uint64, _u32p, C.c_uint32, C.c_uint64]
+        lib.oracle_wt_build.restype = None
+        lib.oracle_wt_build.argtypes = [C.c_uint64, C.c_uint64, _u32p, _u64p, _u32p, _u32p, _u32p, _u32p]
+        lib.oracle_wt_select.restype = C.c_int64
+        lib.oracle_wt_select.argtypes = [C.c_uint64, C.c_uint64, _u64p, _u32p, _u32p, C.c_uint32, C.c_uint64]
+
+    def levels(self, nlist: int) -> int:
+        return int(self.lib.oracle_wt_levels(int(nlist)))
+
+    def sequence(self, offsets, ids) -> np.ndarray:
+        """S[id] = list_no; raises when the lists do not partition [0, ntotal) in ascending order."""
+        offsets = _as_u64(offsets)
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        n = int(offsets[-1] - offsets[0])
+        S = np.zeros(max(n, 1), dtype=np.uint32)
+        if self.lib.oracle_wt_sequence(offsets.size - 1, offsets, ids if ids.size else np.zeros(1, np.int64), S) != 0:
+            raise ValueError("lists must be ascending and partition [0, ntotal)")
+        return S[:n]
+
+    def select_seq(self, S, c: int, k: int) -> int:
+        S = np.ascontiguousarray(S, dtype=np.uint32)
+        return int(self.lib.oracle_wt_select_seq(S.size, S if S.size else np.zeros(1, np.uint32), int(c), int(k)))
+
+    def build(self, nlist: int, S):
+        """-> dict(levels, n, nblk, bits[levels, words], rank[levels, nblk+1], sel1, sel0, start[nlist])"""
+        S = np.ascontiguousarray(S, dtype=np.uint32)
+        n = S.size
+        levels = self.levels(nlist)
+        nblk = (n + 511) // 512
+        samp = (n >> 11) + 2
+        bits = np.zeros((levels, max(nblk * 8, 1)), dtype=np.uint64)
+        rank = np.zeros((levels, nblk + 1), dtype=np.uint32)
+        sel1 = np.zeros((levels, samp), dtype=np.uint32)
+        sel0 = np.zeros((levels, samp), dtype=np.uint32)
+        start = np.zeros(max(nlist, 1), dtype=np.uint32)
+        self.lib.oracle_wt_build(int(nlist), n, S if n else np.zeros(1, np.uint32), bits.reshape(-1), rank.reshape(-1),
+                                 sel1.reshape(-1), sel0.reshape(-1), start)
+        return dict(levels=levels, n=n, nblk=nblk, nlist=int(nlist), bits=bits[:, : nblk * 8], rank=rank, sel1=sel1,
+                    sel0=sel0, start=start[:nlist])
+
+    def select(self, wt, c: int, k: int) -> int:
+        bits = np.ascontiguousarray(wt["bits"]).reshape(-1)
+        return int(self.lib.oracle_wt_select(wt["nlist"], wt["n"], bits if bits.size else np.zeros(1, np.uint64),
+                                             np.ascontiguousarray(wt["rank"]).reshape(-1),
+                                             np.ascontiguousarray(wt["start"]), int(c), int(k)))
+
+
 def mt1234(count: int = 8) -> np.ndarray:
     out = np.zeros(count, dtype=np.uint32)
     _port_lib.oracle_mt1234.argtypes = [_u32p, C.c_int]
@@ -398,6 +457,7 @@ _port_lib = C.CDLL(str(_HERE / "liboracle.so"))
 port = RocCodec(_port_lib, "port")
 ef = EfCodec(_port_lib)
 bits = BitsCodec(_port_lib)
+wt = WtCodec(_port_lib)
 multiset_port = lambda: _MultisetPort(_port_lib)
 
 _ref_path = _HERE / "_ref" / "libref_roc.so"

@@ -3,6 +3,7 @@
 // with g++ so their logic can be checked against the oracle in the CPU test
 // suite (no GPU in the build container). Not part of libidcodec.so; nothing in
 // the product loads it.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <random>
@@ -11,6 +12,7 @@
 #include "../../vector_db_id_compression_b200/csrc/roc_group.cuh"
 #include "grp_emu.h"
 #include "../../vector_db_id_compression_b200/csrc/ef_core.cuh"
+#include "../../vector_db_id_compression_b200/csrc/wt_core.cuh"
 
 using namespace idc;
 
@@ -116,6 +118,100 @@ void sim_ef_encode(const int64_t* ids, uint64_t m, uint64_t universe, uint64_t* 
 }
 uint64_t sim_ef_select(const uint64_t* low, const uint64_t* high, const uint32_t* samples, uint32_t l, uint64_t k) {
     return ef_select(low, high, samples, l, k);
+}
+
+
+// Wavelet matrix: the build passes of wt_kernels.cu lane by lane (a ballot = a loop over the 32 lanes), with the
+// directory and destination formulas of wt_core.cuh; queries through wt_select / wt_access themselves.
+uint32_t sim_wt_levels(uint64_t nlist, uint64_t n) { return wt_shape(nlist, n).levels; }
+void sim_wt_build(uint64_t nlist, uint64_t n, const uint32_t* S, uint64_t* bits, uint32_t* rank, uint32_t* sel1,
+                  uint32_t* sel0, uint32_t* start, const uint64_t* list_size) {
+    WtShape sh = wt_shape(nlist, n);
+    std::vector<uint32_t> seq(S, S + n), next(n);
+    std::vector<uint32_t> ones(sh.nblk + 1);
+    for (uint32_t lev = 0; lev < sh.levels; lev++) {
+        uint32_t shift = sh.levels - 1 - lev;
+        uint32_t* B32 = reinterpret_cast<uint32_t*>(bits + (uint64_t)lev * sh.words);
+        uint32_t* R = rank + (uint64_t)lev * sh.rank_stride;
+        for (uint64_t blk = 0; blk < sh.nblk; blk++) {  // k_wt_level_bits
+            uint32_t cnt = 0;
+            for (int t = 0; t < 16; t++) {
+                uint32_t m = 0;
+                for (uint32_t lane = 0; lane < 32; lane++) {
+                    uint64_t i = (blk << kWtBlockLog) + (uint64_t)t * 32 + lane;
+                    uint32_t v = i < n ? seq[i] : 0u;
+                    m |= ((v >> shift) & 1u) << lane;
+                }
+                B32[blk * 16 + t] = m;
+                cnt += (uint32_t)__builtin_popcount(m);
+            }
+            ones[blk] = cnt;
+        }
+        ones[sh.nblk] = 0;
+        uint32_t acc = 0;  // the scan kernels: exclusive prefix, entry nblk = total
+        for (uint64_t j = 0; j <= sh.nblk; j++) {
+            uint32_t c = ones[j];
+            ones[j] = acc;
+            acc += c;
+        }
+        for (uint64_t j = 0; j <= sh.nblk; j++) {  // k_wt_directory
+            R[j] = ones[j];
+            if (j == sh.nblk) break;
+            WtDirEntry d = wt_dir_entry(j, sh.nblk, n, ones[j], ones[j + 1]);
+            if (d.has1) sel1[(uint64_t)lev * sh.samp_stride + d.m1] = (uint32_t)j;
+            if (d.has0) sel0[(uint64_t)lev * sh.samp_stride + d.m0] = (uint32_t)j;
+        }
+        if (lev + 1 == sh.levels) break;
+        uint64_t z = n - R[sh.nblk];
+        for (uint64_t blk = 0; blk < sh.nblk; blk++) {  // k_wt_level_scatter
+            uint64_t r1 = R[blk];
+            for (int t = 0; t < 16; t++) {
+                uint32_t m = 0;
+                for (uint32_t lane = 0; lane < 32; lane++) {
+                    uint64_t i = (blk << kWtBlockLog) + (uint64_t)t * 32 + lane;
+                    if (i < n && ((seq[i] >> shift) & 1u)) m |= 1u << lane;
+                }
+                for (uint32_t lane = 0; lane < 32; lane++) {
+                    uint64_t i = (blk << kWtBlockLog) + (uint64_t)t * 32 + lane;
+                    if (i >= n) continue;
+                    uint32_t b = (seq[i] >> shift) & 1u;
+                    uint64_t before = r1 + (uint32_t)__builtin_popcount(m & ((1u << lane) - 1u));
+                    next[wt_partition_dest(i, b, z, before)] = seq[i];
+                }
+                r1 += (uint32_t)__builtin_popcount(m);
+            }
+        }
+        seq.swap(next);
+    }
+    // list starts as idc_wt_encode computes them: prefix of the sizes in bit-reversed order
+    std::vector<uint64_t> key(nlist);
+    for (uint64_t l = 0; l < nlist; l++) key[l] = ((uint64_t)wt_bitrev((uint32_t)l, sh.levels) << 32) | l;
+    std::sort(key.begin(), key.end());
+    uint64_t a = 0;
+    for (uint64_t i = 0; i < nlist; i++) {
+        uint32_t l = (uint32_t)key[i];
+        start[l] = (uint32_t)a;
+        a += list_size[l];
+    }
+}
+static WtView wt_view_of(uint64_t nlist, uint64_t n, const uint64_t* bits, const uint32_t* rank, const uint32_t* sel1,
+                         const uint32_t* sel0, const uint32_t* start) {
+    return WtView{bits, rank, sel1, sel0, start, wt_shape(nlist, n)};
+}
+uint64_t sim_wt_select(uint64_t nlist, uint64_t n, const uint64_t* bits, const uint32_t* rank, const uint32_t* sel1,
+                       const uint32_t* sel0, const uint32_t* start, uint32_t c, uint64_t k) {
+    return wt_select(wt_view_of(nlist, n, bits, rank, sel1, sel0, start), c, k);
+}
+uint32_t sim_wt_access(uint64_t nlist, uint64_t n, const uint64_t* bits, const uint32_t* rank, const uint32_t* sel1,
+                       const uint32_t* sel0, const uint32_t* start, uint64_t i) {
+    return wt_access(wt_view_of(nlist, n, bits, rank, sel1, sel0, start), i);
+}
+// every id of every list in one call (list_off = CSR of the list sizes)
+void sim_wt_decode_all(uint64_t nlist, uint64_t n, const uint64_t* bits, const uint32_t* rank, const uint32_t* sel1,
+                       const uint32_t* sel0, const uint32_t* start, const uint64_t* list_off, int64_t* out) {
+    WtView v = wt_view_of(nlist, n, bits, rank, sel1, sel0, start);
+    for (uint64_t l = 0; l < nlist; l++)
+        for (uint64_t k = 0; k < list_off[l + 1] - list_off[l]; k++) out[list_off[l] + k] = (int64_t)wt_select(v, (uint32_t)l, k);
 }
 
 }  // extern "C"

@@ -34,6 +34,17 @@ def sim():
     lib.sim_ef_encode.argtypes = [i64p, C.c_uint64, C.c_uint64, u64p, u64p, u32p]
     lib.sim_ef_select.restype = C.c_uint64
     lib.sim_ef_select.argtypes = [u64p, u64p, u32p, C.c_uint32, C.c_uint64]
+    wt_arrays = [C.c_uint64, C.c_uint64, u64p, u32p, u32p, u32p, u32p]
+    lib.sim_wt_levels.restype = C.c_uint32
+    lib.sim_wt_levels.argtypes = [C.c_uint64, C.c_uint64]
+    lib.sim_wt_build.restype = None
+    lib.sim_wt_build.argtypes = [C.c_uint64, C.c_uint64, u32p, u64p, u32p, u32p, u32p, u32p, u64p]
+    lib.sim_wt_select.restype = C.c_uint64
+    lib.sim_wt_select.argtypes = wt_arrays + [C.c_uint32, C.c_uint64]
+    lib.sim_wt_access.restype = C.c_uint32
+    lib.sim_wt_access.argtypes = wt_arrays + [C.c_uint64]
+    lib.sim_wt_decode_all.restype = None
+    lib.sim_wt_decode_all.argtypes = wt_arrays + [u64p, i64p]
     return lib
 
 
@@ -141,3 +152,48 @@ def test_ef_gather_words(sim):
         assert np.array_equal(low[: int(sh[3])], enc["low"]) and np.array_equal(high[: int(sh[4])], enc["high"])
         for k in rng.integers(0, m, size=8):
             assert sim.sim_ef_select(low, high, smp, enc["l"], int(k)) == int(ids[k])
+
+
+@pytest.mark.parametrize("nlist,n,skew", [(1, 700, 0), (2, 512, 0), (7, 5000, 0), (256, 100_000, 0), (1000, 70_000, 1),
+                                          (65, 20_481, 2)])
+def test_wavelet_matrix_build_and_select(sim, nlist, n, skew):
+    """csrc/wt_core.cuh + the lane-level build passes of wt_kernels.cu against oracle/wt_oracle.c: every array of
+    the structure word for word, then wt_select / wt_access for every id."""
+    from test_oracle_wt import make_lists
+
+    rng = np.random.default_rng(n + nlist)
+    if skew == 0:
+        offsets, ids, lab = make_lists(rng, nlist, n, empty=(2,) if nlist > 3 else ())
+    else:
+        # skewed list sizes (long runs of one bit value: blocks without ones / zeros, sparse samples)
+        lab = np.minimum((rng.pareto(0.7, size=n)).astype(np.int64), nlist - 1)
+        if skew == 2:
+            lab = np.sort(lab)  # ids of a list are consecutive: whole blocks of equal bits
+        order = np.argsort(lab, kind="stable")
+        offsets = np.zeros(nlist + 1, np.uint64)
+        offsets[1:] = np.cumsum(np.bincount(lab, minlength=nlist))
+        ids, lab = order.astype(np.int64), lab.astype(np.uint32)
+    S = oracle.wt.sequence(offsets, ids)
+    want = oracle.wt.build(nlist, S)
+    levels, nblk, samp = want["levels"], want["nblk"], (n >> 11) + 2
+    assert sim.sim_wt_levels(nlist, n) == levels
+    bits = np.zeros(levels * nblk * 8, np.uint64)
+    rank = np.zeros(levels * (nblk + 1), np.uint32)
+    sel1 = np.zeros(levels * samp, np.uint32)
+    sel0 = np.zeros(levels * samp, np.uint32)
+    start = np.zeros(nlist, np.uint32)
+    sizes = np.diff(offsets.astype(np.int64)).astype(np.uint64)
+    sim.sim_wt_build(nlist, n, np.ascontiguousarray(S), bits, rank, sel1, sel0, start, np.ascontiguousarray(sizes))
+    assert np.array_equal(bits.reshape(levels, -1), want["bits"])
+    assert np.array_equal(rank.reshape(levels, -1), want["rank"])
+    assert np.array_equal(sel1.reshape(levels, -1), want["sel1"])
+    assert np.array_equal(sel0.reshape(levels, -1), want["sel0"])
+    assert np.array_equal(start, want["start"])
+    out = np.zeros(n, np.int64)
+    sim.sim_wt_decode_all(nlist, n, bits, rank, sel1, sel0, start, offsets, out)
+    assert np.array_equal(out, ids)
+    for i in rng.integers(0, n, size=300):
+        assert sim.sim_wt_access(nlist, n, bits, rank, sel1, sel0, start, int(i)) == int(S[i])
+    for c, k in [(0, 0), (nlist - 1, 0)]:
+        if offsets[c + 1] > offsets[c]:
+            assert sim.sim_wt_select(nlist, n, bits, rank, sel1, sel0, start, c, k) == int(ids[int(offsets[c]) + k])

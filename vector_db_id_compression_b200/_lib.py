@@ -24,6 +24,11 @@ class EfInfo(C.Structure):
                 ("device_bytes", u64), ("row_stride", u32)]
 
 
+class WtInfo(C.Structure):
+    _fields_ = [("nlist", u64), ("total_ids", u64), ("bits_bytes", u64), ("aux_bytes", u64), ("device_bytes", u64),
+                ("levels", u32), ("wt_type", u32)]
+
+
 # every symbol include/idcodec.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "idc_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
@@ -54,6 +59,12 @@ SYMBOLS = {
     "idc_ef_decode": (C.c_int, [vp, vp, vp, u64, vp, C.c_int, C.c_int, vp]),
     "idc_ef_decode_rows": (C.c_int, [vp, vp, vp, C.c_int, u64, vp, vp, C.c_int]),
     "idc_ef_select": (C.c_int, [vp, vp, vp, vp, u64, C.c_int, vp, C.c_int]),
+    "idc_wt_encode": (C.c_int, [vp, u64, vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "idc_wt_blob_info": (C.c_int, [vp, C.POINTER(WtInfo)]),
+    "idc_wt_blob_export": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "idc_wt_blob_free": (C.c_int, [vp]),
+    "idc_wt_select": (C.c_int, [vp, vp, vp, vp, u64, C.c_int, vp, C.c_int]),
+    "idc_wt_decode": (C.c_int, [vp, vp, vp, u64, vp, C.c_int, C.c_int, vp]),
     "idc_bits_pack": (C.c_int, [vp, u64, vp, C.c_int, C.c_int, C.c_int, vp, u64, C.c_int]),
     "idc_bits_unpack": (C.c_int, [vp, u64, vp, u64, C.c_int, C.c_int, vp, C.c_int, C.c_int]),
 }

@@ -15,7 +15,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libidcodec.so"
-SOURCES = ["idc_ctx.cu", "roc_kernels.cu", "ef_kernels.cu"]
+SOURCES = ["idc_ctx.cu", "roc_kernels.cu", "ef_kernels.cu", "wt_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import EfInfo, RocInfo
+from ._lib import EfInfo, RocInfo, WtInfo
 
 MEM_HOST, MEM_DEVICE = 0, 1
 F_SORTED, F_PRECISION_SAFE, F_WANT_ORDER = 1, 2, 4
@@ -160,6 +160,16 @@ class Context:
         h = C.c_void_p()
         _check(self._l.idc_ef_encode_rows(self._h, n, k, p, mem, 0, C.byref(h)))
         return EfBlob(self, h)
+
+    # ---------------------------------------------------- wavelet tree ----
+    def wt_encode(self, offsets, ids, *, wt_type: int = 0) -> "WtBlob":
+        offsets = _host_u64(offsets)
+        ids, idb = _ids_array(ids)
+        p, mem = _ptr(ids)
+        h = C.c_void_p()
+        _check(self._l.idc_wt_encode(self._h, offsets.size - 1, offsets.ctypes.data, p, idb, mem, int(wt_type),
+                                     C.byref(h)))
+        return WtBlob(self, h)
 
     # ------------------------------------------------------------ bits ----
     def bits_pack(self, vals, bits: int, nbytes: Optional[int] = None):
@@ -397,4 +407,87 @@ class EfBlob:
         pq, _ = _ptr(qo)
         po, mo = _ptr(out)
         _check(self._l.idc_ef_select(self.ctx._h, self._h, pl, pq, nq, mq, po, mo))
+        return out[:nq]
+
+
+
+class WtBlob:
+    """Device-resident wavelet structure over S[id] = list_no (idc_wt_blob)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._l = ctx._l
+        self._h = handle
+        info = WtInfo()
+        _check(self._l.idc_wt_blob_info(self._h, C.byref(info)))
+        self.info = info
+
+    def free(self) -> None:
+        if getattr(self, "_h", None):
+            self._l.idc_wt_blob_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    nlist = property(lambda s: int(s.info.nlist))
+    total_ids = property(lambda s: int(s.info.total_ids))
+    levels = property(lambda s: int(s.info.levels))
+    bits_bytes = property(lambda s: int(s.info.bits_bytes))
+    aux_bytes = property(lambda s: int(s.info.aux_bytes))
+
+    def export(self) -> dict:
+        n, levels, nlist = self.total_ids, self.levels, self.nlist
+        nblk = (n + 511) // 512
+        samp = (n >> 11) + 2
+        d = dict(
+            list_offsets=np.zeros(nlist + 1, np.uint64), bits=np.zeros((levels, max(nblk * 8, 1)), np.uint64),
+            rank=np.zeros((levels, nblk + 1), np.uint32), sel1=np.zeros((levels, samp), np.uint32),
+            sel0=np.zeros((levels, samp), np.uint32), start=np.zeros(max(nlist, 1), np.uint32),
+        )
+        if nblk == 0:
+            d["bits"] = np.zeros((levels, 0), np.uint64)
+            _check(self._l.idc_wt_blob_export(self._h, d["list_offsets"].ctypes.data, None, None, None, None, None))
+        else:
+            _check(self._l.idc_wt_blob_export(self._h, *(d[k].ctypes.data for k in (
+                "list_offsets", "bits", "rank", "sel1", "sel0", "start"))))
+        d["start"] = d["start"][:nlist]
+        d.update(levels=levels, n=n, nblk=nblk, nlist=nlist)
+        return d
+
+    def decode(self, list_nos=None, *, id_bytes: int = 8, device=None):
+        if list_nos is None:
+            nsel, lp, total = self.nlist, None, self.total_ids
+        else:
+            ln = _host_u64(list_nos)
+            nsel, lp = ln.size, ln.ctypes.data
+            lo = np.zeros(self.nlist + 1, np.uint64)
+            _check(self._l.idc_wt_blob_export(self._h, lo.ctypes.data, None, None, None, None, None))
+            total = int(sum(int(lo[int(l) + 1] - lo[int(l)]) for l in ln))
+        out_off = np.zeros(nsel + 1, np.uint64)
+        out = _alloc_like(None, total, np.int64 if id_bytes == 8 else np.int32, device)
+        p, mem = _ptr(out)
+        _check(self._l.idc_wt_decode(self.ctx._h, self._h, lp, nsel, p, id_bytes, mem, out_off.ctypes.data))
+        return out[:total], out_off
+
+    def select(self, list_nos, offsets_in_list, *, device=None):
+        if device is not None:
+            import torch
+
+            ql = torch.as_tensor(list_nos, dtype=torch.int64, device=device).contiguous()
+            qo = torch.as_tensor(offsets_in_list, dtype=torch.int64, device=device).contiguous()
+            out = torch.empty(max(ql.numel(), 1), dtype=torch.int64, device=device)
+            nq = ql.numel()
+        else:
+            ql = _host_u64(list_nos)
+            qo = _host_u64(offsets_in_list)
+            out = np.empty(max(ql.size, 1), np.int64)
+            nq = ql.size
+        pl, mq = _ptr(ql)
+        pq, _ = _ptr(qo)
+        po, mo = _ptr(out)
+        _check(self._l.idc_wt_select(self.ctx._h, self._h, pl, pq, nq, mq, po, mo))
         return out[:nq]

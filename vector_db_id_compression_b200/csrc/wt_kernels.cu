@@ -1,0 +1,585 @@
+// wt_kernels.cu -- the wavelet-tree flavour of the IVF plugin surface on sm_100a
+// (CompressedIDInvertedListsWaveletTree, custom_invlist_cpp/custom_invlists_impl.cpp:346-397).
+//
+// Build = `levels` streaming passes over the sequence "list number of id i" (4 bytes per id, ping-pong in the
+// context workspace). Per level:
+//   k_wt_level_bits     one warp per 512-id rank block: 16 coalesced 128-byte reads, __ballot_sync packs the
+//                       level's bit of 32 symbols per instruction, lanes 0..15 store the block's 64 bytes, the
+//                       block's popcount goes to the directory scratch
+//   k_wt_scan_tiles / k_wt_scan_parts   exclusive prefix sum of the block popcounts (warp shuffles)
+//   k_wt_directory      final rank directory + the select samples for ones and zeros
+//   k_wt_level_scatter  the stable partition: destination = zeros-before (bit 0) or zeros + ones-before (bit 1),
+//                       ones-before = directory entry + running ballot popcount
+// Queries:
+//   k_wt_select         one thread per (list, offset): wt_select of wt_core.cuh
+//   k_wt_decode         whole lists: one thread per output id
+// All HBM-bound integer work; no tensor cores.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "idc_host.h"
+#include "wt_core.cuh"
+
+using namespace idc;
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kWtStHole = 1u;      // an id of [0, ntotal) belongs to no list (or two lists share one)
+constexpr uint32_t kWtStRange = 2u;     // id >= ntotal (custom_invlists_impl.cpp:359 assert)
+constexpr uint32_t kWtStUnsorted = 4u;  // list not strictly ascending (custom_invlists_impl.cpp:358 assert)
+constexpr uint32_t kWtStCorrupt = 8u;   // a select walked off the directory
+constexpr uint32_t kScanThreads = 256;
+constexpr uint32_t kScanPerThread = 4;
+constexpr uint32_t kScanTile = kScanThreads * kScanPerThread;
+
+inline uint32_t grid_for(uint64_t threads, uint32_t per_cta = kThreads) {
+    return (uint32_t)((threads + per_cta - 1) / per_cta);
+}
+
+template <typename T>
+int dev_alloc(idc_ctx* c, T** p, size_t count, uint64_t* acct) {
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    IDC_TRY(c->pool_alloc(reinterpret_cast<void**>(p), bytes));
+    if (acct) *acct += bytes;
+    return IDC_OK;
+}
+
+// ---- S[id] = list_no (custom_invlists_impl.cpp:354-362), with the reference's asserts as status bits
+template <typename IdT>
+__global__ void __launch_bounds__(kThreads) k_wt_fill(const IdT* __restrict__ ids, const uint64_t* __restrict__ list_off,
+                                                      uint32_t nlist, uint64_t n, uint32_t* __restrict__ seq,
+                                                      uint32_t* status) {
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    uint32_t lo = 0, hi = nlist - 1;  // the list that owns element e: largest l with list_off[l] <= e
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo + 1) / 2;
+        if (__ldg(list_off + mid) <= e)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    uint64_t id = load_id(ids + e);  // a negative int64 id becomes >= 2^63: out of range
+    uint32_t st = 0;
+    if (id >= n)
+        st |= kWtStRange;
+    else
+        seq[id] = lo;
+    if (e > __ldg(list_off + lo) && load_id(ids + e - 1) >= id) st |= kWtStUnsorted;
+    if (st) atomicOr(status, st);
+}
+
+// ---- one level: bits of every rank block + its popcount
+__global__ void __launch_bounds__(kThreads) k_wt_level_bits(const uint32_t* __restrict__ seq, uint64_t n, uint64_t nblk,
+                                                            uint32_t shift, uint32_t check_holes,
+                                                            uint64_t* __restrict__ bits, uint32_t* __restrict__ ones,
+                                                            uint32_t* status) {
+    const uint64_t blk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp-uniform
+    const uint32_t lane = threadIdx.x & 31u;
+    if (blk >= nblk) return;
+    const uint64_t base = blk << kWtBlockLog;
+    uint32_t v[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t i = base + (uint64_t)t * 32 + lane;
+        v[t] = i < n ? __ldg(seq + i) : 0u;
+    }
+    uint32_t mine = 0, cnt = 0;
+    bool hole = false;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t i = base + (uint64_t)t * 32 + lane;
+        hole |= check_holes && i < n && v[t] == kWtHole;
+        uint32_t m = __ballot_sync(kFull, (v[t] >> shift) & 1u);
+        if (lane == (uint32_t)t) mine = m;
+        cnt += (uint32_t)__popc(m);
+    }
+    // 16 32-bit words = the block's 8 little-endian 64-bit words
+    if (lane < 16) reinterpret_cast<uint32_t*>(bits)[blk * 16 + lane] = mine;
+    if (lane == 0) ones[blk] = cnt;
+    if (hole) atomicOr(status, kWtStHole);
+}
+
+__device__ __forceinline__ uint32_t warp_inclusive(uint32_t x, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(kFull, x, d);
+        if (lane >= (uint32_t)d) x += t;
+    }
+    return x;
+}
+
+// data[0..E) -> tile-local exclusive prefix, part[tile] = tile total (tiles of 1024 entries)
+__global__ void __launch_bounds__(kScanThreads) k_wt_scan_tiles(uint32_t* __restrict__ data, uint64_t E,
+                                                                uint32_t* __restrict__ part) {
+    __shared__ uint32_t wsum[kScanThreads / 32];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPerThread;
+    uint32_t v[kScanPerThread], s = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kScanPerThread; k++) {
+        v[k] = base + k < E ? data[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t inc = warp_inclusive(s, lane);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t x = lane < kScanThreads / 32 ? wsum[lane] : 0u;
+        uint32_t xi = warp_inclusive(x, lane);
+        if (lane < kScanThreads / 32) wsum[lane] = xi - x;
+    }
+    __syncthreads();
+    uint32_t off = wsum[w] + inc - s;
+#pragma unroll
+    for (uint32_t k = 0; k < kScanPerThread; k++) {
+        if (base + k < E) data[base + k] = off;
+        off += v[k];
+    }
+    if (threadIdx.x == kScanThreads - 1) part[blockIdx.x] = off;
+}
+
+// exclusive prefix sum of the tile totals, one CTA
+__global__ void __launch_bounds__(1024) k_wt_scan_parts(uint32_t* part, uint32_t P) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t total_s;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < P; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t x = i < P ? part[i] : 0u;
+        uint32_t inc = warp_inclusive(x, lane);
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t y = wsum[lane];
+            uint32_t yi = warp_inclusive(y, lane);
+            wsum[lane] = yi - y;
+            if (lane == 31) total_s = yi;
+        }
+        __syncthreads();
+        if (i < P) part[i] = carry + wsum[w] + inc - x;
+        carry += total_s;
+        __syncthreads();
+    }
+}
+
+// final directory of a level: rank[j] = ones before block j (j = nblk: all ones), and the select samples
+__global__ void __launch_bounds__(kThreads) k_wt_directory(const uint32_t* __restrict__ local, const uint32_t* __restrict__ part,
+                                                           uint64_t nblk, uint64_t n, uint32_t* __restrict__ rank,
+                                                           uint32_t* __restrict__ sel1, uint32_t* __restrict__ sel0) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > nblk) return;
+    uint32_t o0 = local[j] + part[j / kScanTile];
+    rank[j] = o0;
+    if (j == nblk) return;
+    uint32_t o1 = local[j + 1] + part[(j + 1) / kScanTile];
+    WtDirEntry d = wt_dir_entry(j, nblk, n, o0, o1);
+    if (d.has1) sel1[d.m1] = (uint32_t)j;
+    if (d.has0) sel0[d.m0] = (uint32_t)j;
+}
+
+// stable partition of a level by its bit: zeros keep their order in [0, z), ones theirs in [z, n)
+__global__ void __launch_bounds__(kThreads) k_wt_level_scatter(const uint32_t* __restrict__ seq, uint64_t n, uint64_t nblk,
+                                                               uint32_t shift, const uint32_t* __restrict__ rank,
+                                                               uint32_t* __restrict__ next) {
+    const uint64_t blk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (blk >= nblk) return;
+    const uint64_t base = blk << kWtBlockLog;
+    const uint64_t z = n - __ldg(rank + nblk);
+    uint64_t r1 = __ldg(rank + blk);
+    uint32_t v[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t i = base + (uint64_t)t * 32 + lane;
+        v[t] = i < n ? __ldg(seq + i) : 0u;
+    }
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t i = base + (uint64_t)t * 32 + lane;
+        bool valid = i < n;
+        uint32_t b = (v[t] >> shift) & 1u;
+        uint32_t m = __ballot_sync(kFull, valid && b);
+        uint64_t ones_before = r1 + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (valid) next[wt_partition_dest(i, b, z, ones_before)] = v[t];
+        r1 += (uint32_t)__popc(m);
+    }
+}
+
+struct WtSelArgs {
+    WtView v;
+    const uint64_t* list_off;
+    uint64_t nlist;
+    const uint64_t* q_list;
+    const uint64_t* q_off;
+    int64_t* out;
+    uint64_t nq;
+};
+
+__global__ void __launch_bounds__(kThreads) k_wt_select(WtSelArgs a) {
+    uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.nq) return;
+    uint64_t L = a.q_list[q], k = a.q_off[q];
+    int64_t r = -1;
+    if (L < a.nlist && k < a.list_off[L + 1] - a.list_off[L]) r = (int64_t)wt_select(a.v, (uint32_t)L, k);
+    a.out[q] = r;
+}
+
+struct WtDecArgs {
+    WtView v;
+    const uint64_t* sel;      // selected list numbers (NULL = all lists in order)
+    const uint64_t* out_off;  // nsel + 1 offsets of the output
+    uint64_t nsel, total;
+    void* out;
+    uint32_t* status;
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads) k_wt_decode(WtDecArgs a) {
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.total) return;
+    uint64_t lo = 0, hi = a.nsel - 1;  // largest s with out_off[s] <= e (skips empty lists)
+    while (lo < hi) {
+        uint64_t mid = lo + (hi - lo + 1) / 2;
+        if (__ldg(a.out_off + mid) <= e)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    uint64_t L = a.sel ? __ldg(a.sel + lo) : lo;
+    uint64_t id = wt_select(a.v, (uint32_t)L, e - __ldg(a.out_off + lo));
+    if (id == ~0ull) atomicOr(a.status, kWtStCorrupt);
+    reinterpret_cast<OutT*>(a.out)[e] = (OutT)id;
+}
+
+}  // namespace
+
+struct idc_wt_blob {
+    idc_ctx* ctx = nullptr;
+    uint64_t nlist = 0, total_ids = 0;
+    int wt_type = 0;
+    WtShape sh{};
+    std::vector<uint64_t> list_offsets;
+    uint64_t* d_list_off = nullptr;
+    uint64_t* d_bits = nullptr;
+    uint32_t* d_rank = nullptr;
+    uint32_t* d_sel1 = nullptr;
+    uint32_t* d_sel0 = nullptr;
+    uint32_t* d_start = nullptr;
+    uint64_t device_bytes = 0;
+    WtView view() const { return WtView{d_bits, d_rank, d_sel1, d_sel0, d_start, sh}; }
+    ~idc_wt_blob() {
+        if (!ctx) return;
+        ctx->pool_release(d_list_off);
+        ctx->pool_release(d_bits);
+        ctx->pool_release(d_rank);
+        ctx->pool_release(d_sel1);
+        ctx->pool_release(d_sel0);
+        ctx->pool_release(d_start);
+    }
+};
+
+namespace {
+
+int wt_status_to_error(uint32_t st, const char* what) {
+    if (st & kWtStRange) {
+        set_error("%s: an id is negative or >= ntotal (the reference asserts ids < ntotal)", what);
+        return IDC_ERR_DOMAIN;
+    }
+    if (st & kWtStUnsorted) {
+        set_error("%s: a list is not strictly ascending (the reference asserts ordered ids)", what);
+        return IDC_ERR_DOMAIN;
+    }
+    if (st & kWtStHole) {
+        set_error("%s: the lists do not partition [0, ntotal): an id is missing or appears twice", what);
+        return IDC_ERR_DOMAIN;
+    }
+    if (st & kWtStCorrupt) {
+        set_error("%s: select left the directory (corrupt blob)", what);
+        return IDC_ERR_STREAM;
+    }
+    return IDC_OK;
+}
+
+template <typename IdT>
+int wt_build(idc_ctx* c, idc_wt_blob* b, const IdT* ids_dev) {
+    const WtShape sh = b->sh;
+    const uint64_t n = sh.n;
+    cudaStream_t s = c->stream;
+    // workspaces: two copies of the sequence (ping-pong), block popcounts + tile totals
+    const uint64_t seq_elems = sh.nblk << kWtBlockLog;
+    IDC_TRY(c->ws.reserve(2 * seq_elems * sizeof(uint32_t)));
+    uint32_t* seq = c->ws.as<uint32_t>();
+    uint32_t* next = seq + seq_elems;
+    const uint64_t E = sh.nblk + 1;
+    const uint32_t P = (uint32_t)((E + kScanTile - 1) / kScanTile);
+    const uint64_t Epad = (E + 31) & ~uint64_t(31);
+    IDC_TRY(c->scratch.reserve((Epad + P + 64) * sizeof(uint32_t)));
+    uint32_t* local = c->scratch.as<uint32_t>();
+    uint32_t* part = local + Epad;
+    IDC_TRY(c->status.reserve(64));
+    uint32_t* d_status = c->status.as<uint32_t>();
+    IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, s));
+    IDC_CUDA(cudaMemsetAsync(seq, 0xff, n * sizeof(uint32_t), s));
+    {
+        LaunchScope ls(c, "k_wt_fill");
+        k_wt_fill<IdT><<<grid_for(n), kThreads, 0, s>>>(ids_dev, b->d_list_off, (uint32_t)b->nlist, n, seq, d_status);
+    }
+    IDC_TRY(check_last_launch("k_wt_fill"));
+    const uint32_t warp_grid = grid_for(sh.nblk * 32);
+    for (uint32_t lev = 0; lev < sh.levels; lev++) {
+        const uint32_t shift = sh.levels - 1 - lev;
+        uint64_t* bits = b->d_bits + (uint64_t)lev * sh.words;
+        uint32_t* rank = b->d_rank + (uint64_t)lev * sh.rank_stride;
+        IDC_CUDA(cudaMemsetAsync(local + sh.nblk, 0, 4, s));  // entry nblk of the scan input: becomes the level's ones
+        {
+            LaunchScope ls(c, "k_wt_level_bits");
+            k_wt_level_bits<<<warp_grid, kThreads, 0, s>>>(seq, n, sh.nblk, shift, lev == 0 ? 1u : 0u, bits, local, d_status);
+        }
+        {
+            LaunchScope ls(c, "k_wt_scan");
+            k_wt_scan_tiles<<<P, kScanThreads, 0, s>>>(local, E, part);
+        }
+        {
+            LaunchScope ls(c, "k_wt_scan");
+            k_wt_scan_parts<<<1, 1024, 0, s>>>(part, P);
+        }
+        {
+            LaunchScope ls(c, "k_wt_directory");
+            k_wt_directory<<<grid_for(E), kThreads, 0, s>>>(local, part, sh.nblk, n, rank,
+                                                            b->d_sel1 + (uint64_t)lev * sh.samp_stride,
+                                                            b->d_sel0 + (uint64_t)lev * sh.samp_stride);
+        }
+        if (lev + 1 < sh.levels) {
+            LaunchScope ls(c, "k_wt_level_scatter");
+            k_wt_level_scatter<<<warp_grid, kThreads, 0, s>>>(seq, n, sh.nblk, shift, rank, next);
+            std::swap(seq, next);
+        }
+        IDC_TRY(check_last_launch("wavelet level"));
+    }
+    uint32_t st = 0;
+    IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, s));
+    IDC_CUDA(cudaStreamSynchronize(s));
+    return wt_status_to_error(st, "wt_encode");
+}
+
+}  // namespace
+
+extern "C" {
+
+int idc_wt_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const void* ids, int id_bytes, int ids_mem,
+                  int wt_type, idc_wt_blob** out) {
+    IDC_REQUIRE(c && offsets && out, IDC_ERR_ARG, "idc_wt_encode: null argument");
+    IDC_REQUIRE(id_bytes == 8 || id_bytes == 4, IDC_ERR_ARG, "id_bytes must be 4 or 8");
+    IDC_REQUIRE(wt_type == 0 || wt_type == 1, IDC_ERR_ARG, "wt_type must be 0 or 1 (custom_invlists_impl.cpp:349)");
+    IDC_REQUIRE(wt_type == 0, IDC_ERR_ARG,
+                "wt_type 1 (sdsl rrr_vector<63> bit vectors) is not implemented: only the plain wt_int flavour is");
+    IDC_REQUIRE(nlist <= (1ull << 31), IDC_ERR_ARG, "too many lists");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    std::unique_ptr<idc_wt_blob> b(new idc_wt_blob());
+    b->ctx = c;
+    b->nlist = nlist;
+    b->wt_type = wt_type;
+    b->list_offsets.resize(nlist + 1);
+    for (uint64_t l = 0; l <= nlist; l++) {
+        IDC_REQUIRE(l == 0 || offsets[l] >= offsets[l - 1], IDC_ERR_ARG, "offsets must be non-decreasing");
+        b->list_offsets[l] = offsets[l] - offsets[0];
+    }
+    const uint64_t n = b->list_offsets[nlist];
+    IDC_REQUIRE(n < (1ull << 32) - 4096, IDC_ERR_ARG, "ntotal must be below 2^32 - 4096 (32-bit positions)");
+    IDC_REQUIRE(ids != nullptr || n == 0, IDC_ERR_ARG, "ids is NULL");
+    b->total_ids = n;
+    b->sh = wt_shape(nlist, n);
+    if (n == 0) {  // nothing to index: every list is empty
+        b->sh.levels = 0;
+        *out = b.release();
+        return IDC_OK;
+    }
+    const WtShape sh = b->sh;
+    IDC_TRY(dev_alloc(c, &b->d_list_off, nlist + 1, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_bits, sh.levels * sh.words, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_rank, sh.levels * sh.rank_stride, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_sel1, sh.levels * sh.samp_stride, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_sel0, sh.levels * sh.samp_stride, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_start, nlist, &b->device_bytes));
+    IDC_CUDA(cudaMemcpyAsync(b->d_list_off, b->list_offsets.data(), (nlist + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    IDC_CUDA(cudaMemsetAsync(b->d_sel1, 0, sh.levels * sh.samp_stride * 4, c->stream));
+    IDC_CUDA(cudaMemsetAsync(b->d_sel0, 0, sh.levels * sh.samp_stride * 4, c->stream));
+    // lists sit below the last level in bit-reversed order of their numbers
+    std::vector<uint32_t> start(nlist);
+    {
+        std::vector<uint64_t> key(nlist);
+        for (uint64_t l = 0; l < nlist; l++) key[l] = ((uint64_t)wt_bitrev((uint32_t)l, sh.levels) << 32) | l;
+        std::sort(key.begin(), key.end());
+        uint64_t acc = 0;
+        for (uint64_t i = 0; i < nlist; i++) {
+            uint32_t l = (uint32_t)key[i];
+            start[l] = (uint32_t)acc;
+            acc += b->list_offsets[l + 1] - b->list_offsets[l];
+        }
+    }
+    IDC_CUDA(cudaMemcpyAsync(b->d_start, start.data(), nlist * 4, cudaMemcpyHostToDevice, c->stream));
+    const uint8_t* src = static_cast<const uint8_t*>(ids) + offsets[0] * (uint64_t)id_bytes;
+    const void* ids_dev = src;
+    if (ids_mem == IDC_MEM_HOST) {
+        IDC_TRY(c->stage.reserve(n * id_bytes));
+        IDC_CUDA(cudaMemcpyAsync(c->stage.p, src, n * id_bytes, cudaMemcpyHostToDevice, c->stream));
+        ids_dev = c->stage.p;
+    }
+    if (id_bytes == 8)
+        IDC_TRY(wt_build<int64_t>(c, b.get(), static_cast<const int64_t*>(ids_dev)));
+    else
+        IDC_TRY(wt_build<uint32_t>(c, b.get(), static_cast<const uint32_t*>(ids_dev)));
+    *out = b.release();
+    return IDC_OK;
+}
+
+int idc_wt_blob_info(const idc_wt_blob* b, idc_wt_info* info) {
+    IDC_REQUIRE(b && info, IDC_ERR_ARG, "null argument");
+    info->nlist = b->nlist;
+    info->total_ids = b->total_ids;
+    info->bits_bytes = (uint64_t)b->sh.levels * b->sh.words * 8;
+    info->aux_bytes = b->total_ids ? (uint64_t)b->sh.levels * (b->sh.rank_stride + 2 * b->sh.samp_stride) * 4 + b->nlist * 4 : 0;
+    info->device_bytes = b->device_bytes;
+    info->levels = b->sh.levels;
+    info->wt_type = (uint32_t)b->wt_type;
+    return IDC_OK;
+}
+
+int idc_wt_blob_export(const idc_wt_blob* b, uint64_t* list_offsets, uint64_t* bits, uint32_t* rank, uint32_t* sel1,
+                       uint32_t* sel0, uint32_t* start) {
+    IDC_REQUIRE(b, IDC_ERR_ARG, "null blob");
+    IDC_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    if (list_offsets) memcpy(list_offsets, b->list_offsets.data(), (b->nlist + 1) * 8);
+    if (b->total_ids) {
+        const WtShape& sh = b->sh;
+        if (bits) IDC_CUDA(cudaMemcpyAsync(bits, b->d_bits, sh.levels * sh.words * 8, cudaMemcpyDeviceToHost, s));
+        if (rank) IDC_CUDA(cudaMemcpyAsync(rank, b->d_rank, sh.levels * sh.rank_stride * 4, cudaMemcpyDeviceToHost, s));
+        if (sel1) IDC_CUDA(cudaMemcpyAsync(sel1, b->d_sel1, sh.levels * sh.samp_stride * 4, cudaMemcpyDeviceToHost, s));
+        if (sel0) IDC_CUDA(cudaMemcpyAsync(sel0, b->d_sel0, sh.levels * sh.samp_stride * 4, cudaMemcpyDeviceToHost, s));
+        if (start && b->nlist) IDC_CUDA(cudaMemcpyAsync(start, b->d_start, b->nlist * 4, cudaMemcpyDeviceToHost, s));
+    }
+    IDC_CUDA(cudaStreamSynchronize(s));
+    return IDC_OK;
+}
+
+int idc_wt_blob_free(idc_wt_blob* b) {
+    if (b) {
+        std::lock_guard<std::mutex> lock(b->ctx->mu);
+        cudaSetDevice(b->ctx->device);
+        delete b;
+    }
+    return IDC_OK;
+}
+
+int idc_wt_select(idc_ctx* c, const idc_wt_blob* b, const uint64_t* list_nos, const uint64_t* offsets_in_list,
+                  uint64_t nq, int query_mem, int64_t* ids_out, int out_mem) {
+    IDC_REQUIRE(c && b && (nq == 0 || (list_nos && offsets_in_list && ids_out)), IDC_ERR_ARG,
+                "idc_wt_select: null argument");
+    std::lock_guard<std::mutex> lock(c->mu);
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    if (nq == 0) return IDC_OK;
+    if (b->total_ids == 0) {  // every query is out of range
+        if (out_mem == IDC_MEM_HOST)
+            for (uint64_t q = 0; q < nq; q++) ids_out[q] = -1;
+        else
+            IDC_CUDA(cudaMemsetAsync(ids_out, 0xff, nq * 8, c->stream));
+        IDC_CUDA(cudaStreamSynchronize(c->stream));
+        return IDC_OK;
+    }
+    const uint64_t *d_ql = list_nos, *d_qo = offsets_in_list;
+    size_t need = (query_mem == IDC_MEM_HOST ? nq * 16 : 0) + (out_mem == IDC_MEM_HOST ? nq * 8 : 0);
+    IDC_TRY(c->stage.reserve(need + 256));
+    uint8_t* sp = c->stage.as<uint8_t>();
+    if (query_mem == IDC_MEM_HOST) {
+        IDC_CUDA(cudaMemcpyAsync(sp, list_nos, nq * 8, cudaMemcpyHostToDevice, c->stream));
+        IDC_CUDA(cudaMemcpyAsync(sp + nq * 8, offsets_in_list, nq * 8, cudaMemcpyHostToDevice, c->stream));
+        d_ql = reinterpret_cast<uint64_t*>(sp);
+        d_qo = reinterpret_cast<uint64_t*>(sp + nq * 8);
+        sp += nq * 16;
+    }
+    int64_t* out_dev = out_mem == IDC_MEM_HOST ? reinterpret_cast<int64_t*>(sp) : ids_out;
+    WtSelArgs a{b->view(), b->d_list_off, b->nlist, d_ql, d_qo, out_dev, nq};
+    {
+        LaunchScope ls(c, "k_wt_select");
+        k_wt_select<<<grid_for(nq), kThreads, 0, c->stream>>>(a);
+    }
+    IDC_TRY(check_last_launch("k_wt_select"));
+    if (out_mem == IDC_MEM_HOST)
+        IDC_CUDA(cudaMemcpyAsync(ids_out, out_dev, nq * 8, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    return IDC_OK;
+}
+
+int idc_wt_decode(idc_ctx* c, const idc_wt_blob* b, const uint64_t* list_nos, uint64_t nsel, void* ids_out, int id_bytes,
+                  int out_mem, uint64_t* out_offsets) {
+    IDC_REQUIRE(c && b, IDC_ERR_ARG, "idc_wt_decode: null argument");
+    IDC_REQUIRE(id_bytes == 8 || id_bytes == 4, IDC_ERR_ARG, "id_bytes must be 4 or 8");
+    std::lock_guard<std::mutex> lock(c->mu);
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    uint64_t total = 0;
+    const uint64_t* d_sel = nullptr;
+    const uint64_t* d_off = nullptr;
+    if (list_nos == nullptr) {
+        nsel = b->nlist;
+        total = b->total_ids;
+        d_off = b->d_list_off;
+        if (out_offsets) memcpy(out_offsets, b->list_offsets.data(), (b->nlist + 1) * 8);
+    } else {
+        std::vector<uint64_t> tab(2 * nsel + 1);  // selected lists, then their output offsets
+        for (uint64_t i = 0; i < nsel; i++) {
+            uint64_t L = list_nos[i];
+            IDC_REQUIRE(L < b->nlist, IDC_ERR_ARG, "list_no out of range");
+            tab[i] = L;
+            tab[nsel + i] = total;
+            total += b->list_offsets[L + 1] - b->list_offsets[L];
+        }
+        tab[2 * nsel] = total;
+        if (out_offsets) memcpy(out_offsets, tab.data() + nsel, (nsel + 1) * 8);
+        if (total) {
+            IDC_TRY(c->meta.reserve(tab.size() * 8));
+            IDC_CUDA(cudaMemcpyAsync(c->meta.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, c->stream));
+            IDC_CUDA(cudaStreamSynchronize(c->stream));  // tab goes out of scope
+            d_sel = c->meta.as<uint64_t>();
+            d_off = d_sel + nsel;
+        }
+    }
+    if (total == 0) return IDC_OK;
+    IDC_REQUIRE(ids_out != nullptr, IDC_ERR_ARG, "ids_out is NULL");
+    void* out_dev = ids_out;
+    if (out_mem == IDC_MEM_HOST) {
+        IDC_TRY(c->stage.reserve(total * id_bytes));
+        out_dev = c->stage.p;
+    }
+    IDC_TRY(c->status.reserve(64));
+    uint32_t* d_status = c->status.as<uint32_t>();
+    IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    WtDecArgs a{b->view(), d_sel, d_off, nsel, total, out_dev, d_status};
+    {
+        LaunchScope ls(c, "k_wt_decode");
+        if (id_bytes == 8)
+            k_wt_decode<int64_t><<<grid_for(total), kThreads, 0, c->stream>>>(a);
+        else
+            k_wt_decode<int32_t><<<grid_for(total), kThreads, 0, c->stream>>>(a);
+    }
+    IDC_TRY(check_last_launch("k_wt_decode"));
+    uint32_t st = 0;
+    IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_mem == IDC_MEM_HOST)
+        IDC_CUDA(cudaMemcpyAsync(ids_out, out_dev, total * id_bytes, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    return wt_status_to_error(st, "wt_decode");
+}
+
+}  // extern "C"

@@ -216,6 +216,35 @@ class CompressedIDInvertedListsPackedBits(InvertedListsArrayCodes):
         return v
 
 
+class CompressedIDInvertedListsWaveletTree(InvertedListsArrayCodes):
+    """Wavelet-tree ids (custom_invlists_impl.h:100-124, .cpp:346-397): ONE structure over S[id] = list_no;
+    get_single_id(list_no, offset) = wt.select(offset + 1, list_no). wt_type 0 = sdsl::wt_int<> (plain bit
+    vectors); wt_type 1 (rrr_vector<63>) is not implemented and raises. Sizes are those of this repository's
+    wavelet matrix (bits + rank / select directories), not sdsl::size_in_bytes (SDSL absent: unpinned)."""
+
+    def __init__(self, il: InvertedLists, wt_type: int = 0, ctx: Optional[capi.Context] = None):
+        super().__init__(il)
+        assert wt_type in (0, 1)  # custom_invlists_impl.cpp:349
+        self.wt_type = int(wt_type)
+        self.ctx = ctx or default_context()
+        offsets, ids = il.csr()
+        # ids must be ascending per list and < ntotal (asserts :358-359): the codec verifies it on the device
+        self.blob = self.ctx.wt_encode(offsets, ids, wt_type=wt_type)
+        self.codes_all = [c.copy() for c in il.codes]  # codes stay in list order (:363-364)
+        self.compressed_ids_size_in_bytes = self.blob.bits_bytes + self.blob.aux_bytes  # :368,371 size_in_bytes(wt)
+        self.codes_size_in_bytes = int(sum(c.size for c in self.codes_all))
+        self.overhead_in_bytes = 0
+
+    def _decode_lists(self, list_nos):
+        return self.blob.decode(list_nos)
+
+    def get_single_id(self, list_no: int, offset: int) -> int:  # :377-379
+        return int(self.blob.select([list_no], [offset])[0])
+
+    def get_single_ids(self, list_nos, offsets) -> np.ndarray:
+        return self.blob.select(list_nos, offsets)
+
+
 def lo_listno(label):
     return np.asarray(label, dtype=np.int64) >> 32
 
