@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ef", action="store_true")
+    ap.add_argument("--no-wt", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
@@ -383,6 +384,14 @@ def run_b200(args):
         else:
             e2e = {"value": None, "unit": "ids/s", "error": "pinned host memory for the e2e leg not available on every rank"}
 
+    # ---------------- wavelet tree (the third id index of the plugin surface) on the same lists (last: a failure here cannot touch the legs above)
+    wt = None
+    if not args.no_wt:
+        try:
+            wt = wt_section(args, ctx, offsets, ids, sizes, dev, peak)
+        except Exception as ex:  # noqa: BLE001 -- never takes the headline numbers down with it
+            wt = {"error": str(ex)}
+
     if rank == 0:
         line = {
             "metric": "ROC encode+decode ids/s (bit-exact round trip)", "value": value, "unit": "ids/s",
@@ -395,7 +404,7 @@ def run_b200(args):
                     "decode_ids_per_s": n_ids / (sum(avg.get(k, 0) for k in ("memset_ws", "k_roc_decode")) * 1e-3),
                     "bits_per_id": 8.0 * info["ans_bytes"] / n_ids, "units": info["nunits"],
                     "wall_ms_per_step": 1e3 * t_wall / args.steps},
-            "ef": ef,
+            "ef": ef, "wt": wt,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -487,6 +496,56 @@ def ef_section(args, ctx, offsets, ids, dev, peak):
                    "frac_with_prep": (8.0 * n_ids + comp) / ((e + pm) * 1e-3) / 1e9 / peak},
         "decode": {"kernel_ms": d, "ids_per_s": n_ids / (d * 1e-3),
                    "achieved_GBs": (8.0 * n_ids + comp) / (d * 1e-3) / 1e9, "frac": (8.0 * n_ids + comp) / (d * 1e-3) / 1e9 / peak},
+    }
+
+
+def wt_section(args, ctx, offsets, ids, sizes, dev, peak):
+    """CompressedIDInvertedListsWaveletTree on the same lists (the workload's ids partition [0, N)): build, get_ids
+    of every list, 10 M random get_single_id calls."""
+    import torch
+
+    n_ids = int(ids.numel())
+    nlist = int(offsets.size - 1)
+    enc_ms, dec_ms, sel_ms = [], [], []
+    wb = None
+    for it in range(2 + min(args.steps, 3)):
+        if wb is not None:
+            wb.free()
+        wb = ctx.wt_encode(offsets, ids)
+        if it >= 2:
+            enc_ms.append(ctx.last_kernel_ms())
+    struct_bytes = float(wb.bits_bytes + wb.aux_bytes)
+    for it in range(2):
+        out, _ = wb.decode(device=dev)
+        dec_ms.append(ctx.last_kernel_ms())
+    exact = bool(torch.equal(out, ids))
+    del out
+    g = torch.Generator(device=dev).manual_seed(11)
+    nq = 10_000_000
+    sz = torch.as_tensor(np.asarray(sizes, dtype=np.int64), device=dev)
+    off = torch.as_tensor(offsets[:-1].astype(np.int64), device=dev)
+    ql = torch.randint(0, nlist, (nq,), device=dev, generator=g)
+    ql = ql[sz[ql] > 0]
+    qo = torch.minimum((torch.rand(ql.numel(), device=dev, generator=g) * sz[ql]).long(), sz[ql] - 1)
+    for it in range(2):
+        got = wb.select(ql, qo, device=dev)
+        sel_ms.append(ctx.last_kernel_ms())
+    exact = exact and bool(torch.equal(got, ids[off[ql] + qo]))
+    levels = wb.levels
+    wb.free()
+    e, d, q = float(np.mean(enc_ms)), dec_ms[-1], sel_ms[-1]
+    return {
+        "bit_exact_roundtrip": exact, "levels": levels, "bits_per_id": 8.0 * struct_bytes / n_ids,
+        # algorithmic bytes: the ids in, the structure out (build) / the structure in, the ids out (decode)
+        "encode": {"kernel_ms": e, "ids_per_s": n_ids / (e * 1e-3),
+                   "achieved_GBs": (8.0 * n_ids + struct_bytes) / (e * 1e-3) / 1e9,
+                   "frac": (8.0 * n_ids + struct_bytes) / (e * 1e-3) / 1e9 / peak,
+                   # what the level passes really stream: 4 B read for the bits + 4 B read and 4 B written by the partition
+                   "pass_GBs": (8.0 * n_ids + 4.0 * n_ids * (3 * levels - 2) + struct_bytes) / (e * 1e-3) / 1e9},
+        "decode": {"kernel_ms": d, "ids_per_s": n_ids / (d * 1e-3),
+                   "achieved_GBs": (8.0 * n_ids + struct_bytes) / (d * 1e-3) / 1e9,
+                   "frac": (8.0 * n_ids + struct_bytes) / (d * 1e-3) / 1e9 / peak},
+        "select": {"queries": int(ql.numel()), "kernel_ms": q, "queries_per_s": ql.numel() / (q * 1e-3)},
     }
 
 

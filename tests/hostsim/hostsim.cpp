@@ -206,6 +206,33 @@ uint32_t sim_wt_access(uint64_t nlist, uint64_t n, const uint64_t* bits, const u
                        const uint32_t* sel0, const uint32_t* start, uint64_t i) {
     return wt_access(wt_view_of(nlist, n, bits, rank, sel1, sel0, start), i);
 }
+// k_wt_replay + k_wt_emit lane by lane: the partitions replayed on the ids, bits read back from the structure
+void sim_wt_replay_all(uint64_t nlist, uint64_t n, const uint64_t* bits, const uint32_t* rank, const uint32_t* start,
+                       const uint64_t* list_off, int64_t* out) {
+    WtShape sh = wt_shape(nlist, n);
+    std::vector<uint32_t> in(n), nxt(n);
+    for (uint64_t i = 0; i < n; i++) in[i] = (uint32_t)i;
+    for (uint32_t lev = 0; lev < sh.levels; lev++) {
+        const uint32_t* B32 = reinterpret_cast<const uint32_t*>(bits + (uint64_t)lev * sh.words);
+        const uint32_t* R = rank + (uint64_t)lev * sh.rank_stride;
+        uint64_t z = n - R[sh.nblk];
+        for (uint64_t blk = 0; blk < sh.nblk; blk++) {
+            uint64_t r1 = R[blk];
+            for (int t = 0; t < 16; t++) {
+                uint32_t m = B32[blk * 16 + t];
+                for (uint32_t lane = 0; lane < 32; lane++) {
+                    uint64_t i = (blk << kWtBlockLog) + (uint64_t)t * 32 + lane;
+                    uint64_t before = r1 + (uint32_t)__builtin_popcount(m & ((1u << lane) - 1u));
+                    if (i < n) nxt[wt_partition_dest(i, (m >> lane) & 1u, z, before)] = in[i];
+                }
+                r1 += (uint32_t)__builtin_popcount(m);
+            }
+        }
+        in.swap(nxt);
+    }
+    for (uint64_t l = 0; l < nlist; l++)
+        for (uint64_t k = 0; k < list_off[l + 1] - list_off[l]; k++) out[list_off[l] + k] = in[start[l] + k];
+}
 // every id of every list in one call (list_off = CSR of the list sizes)
 void sim_wt_decode_all(uint64_t nlist, uint64_t n, const uint64_t* bits, const uint32_t* rank, const uint32_t* sel1,
                        const uint32_t* sel0, const uint32_t* start, const uint64_t* list_off, int64_t* out) {

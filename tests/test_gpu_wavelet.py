@@ -34,8 +34,13 @@ CASES = [(1, 700, 0), (2, 512, 0), (7, 5000, 0), (256, 100_000, 0), (1000, 70_00
          (1024, 1_000_000, 0), (5000, 1_300_001, 1)]
 
 
+@pytest.mark.parametrize("path", ["replay", "select"])
 @pytest.mark.parametrize("nlist,n,skew", CASES)
-def test_wt_structure_and_selects_vs_oracle(ctx, nlist, n, skew):
+def test_wt_structure_and_selects_vs_oracle(ctx, monkeypatch, nlist, n, skew, path):
+    monkeypatch.setenv("IDC_WT_DECODE", path)  # whole-list decode: streaming replay of the partitions / select walks
+    # S[id] = list_no: through id-range buckets (the path of sequences beyond L2; 2^10-id buckets here) / direct stores
+    monkeypatch.setenv("IDC_WT_FILL", "bucket" if path == "replay" else "direct")
+    monkeypatch.setenv("IDC_WT_BUCKET_LOG", "10" if n < 500_000 else "14")
     rng = np.random.default_rng(n + nlist)
     if skew == 0:
         offsets, ids, lab = make_lists(rng, nlist, n, empty=(2,) if nlist > 3 else ())
@@ -88,14 +93,30 @@ def test_wt_device_buffers_and_int32_ids(ctx):
     assert np.array_equal(got.cpu().numpy(), ids[offsets[ql].astype(np.int64) + qo])
 
 
-def test_wt_rejects_what_the_reference_asserts(ctx):
+@pytest.mark.parametrize("fill", ["direct", "bucket"])
+def test_wt_rejects_what_the_reference_asserts_and_level_counts(ctx, monkeypatch, fill):
     from vector_db_id_compression_b200.capi import IdcError
 
+    monkeypatch.setenv("IDC_WT_FILL", fill)
+    monkeypatch.setenv("IDC_WT_BUCKET_LOG", "4")
     for bad in ([1, 0, 2, 3], [0, 1, 2, 4], [0, 1, 1, 3], [0, 1, -2, 3]):  # order, range, duplicate / hole, negative
         with pytest.raises(IdcError):
             ctx.wt_encode([0, 2, 4], np.array(bad, dtype=np.int64))
+    rng = np.random.default_rng(9)
+    offsets, ids, _ = make_lists(rng, 50, 40_000)
+    for pos, val in ((777, None), (20_000, 40_000), (31_000, "dup")):  # the same inside a larger index
+        bad = ids.copy()
+        bad[pos] = bad[pos - 1] if val is None else (bad[5] if val == "dup" else val)
+        with pytest.raises(IdcError):
+            ctx.wt_encode(offsets, bad)
     with pytest.raises(IdcError):
         ctx.wt_encode([0, 2, 4], np.array([0, 3, 1, 2], dtype=np.int64), wt_type=1)  # rrr_vector<63>: not implemented
+    many = ctx.wt_encode(np.arange(0, 200_001, 2), np.arange(200_000))  # 100 000 lists: 17 levels, 16-bit symbols after level 0
+    wide = ctx.wt_encode(np.arange(0, 300_001, 2), np.arange(300_000))  # 150 000 lists: 18 levels, 32-bit symbols
+    for bl, m in ((many, 200_000), (wide, 300_000)):
+        assert bl.levels == (m // 2 - 1).bit_length()
+        assert np.array_equal(bl.decode()[0], np.arange(m))
+        assert bl.select([m // 2 - 1, 7], [1, 0]).tolist() == [m - 1, 14]
     blob = ctx.wt_encode([0, 2, 4], np.array([0, 3, 1, 2], dtype=np.int64))  # the context is still usable
     assert blob.decode()[0].tolist() == [0, 3, 1, 2]
     empty = ctx.wt_encode([0, 0, 0], np.zeros(0, np.int64))

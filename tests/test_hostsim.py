@@ -43,6 +43,8 @@ def sim():
     lib.sim_wt_select.argtypes = wt_arrays + [C.c_uint32, C.c_uint64]
     lib.sim_wt_access.restype = C.c_uint32
     lib.sim_wt_access.argtypes = wt_arrays + [C.c_uint64]
+    lib.sim_wt_replay_all.restype = None
+    lib.sim_wt_replay_all.argtypes = [C.c_uint64, C.c_uint64, u64p, u32p, u32p, u64p, i64p]
     lib.sim_wt_decode_all.restype = None
     lib.sim_wt_decode_all.argtypes = wt_arrays + [u64p, i64p]
     return lib
@@ -192,6 +194,9 @@ def test_wavelet_matrix_build_and_select(sim, nlist, n, skew):
     out = np.zeros(n, np.int64)
     sim.sim_wt_decode_all(nlist, n, bits, rank, sel1, sel0, start, offsets, out)
     assert np.array_equal(out, ids)
+    out2 = np.zeros(n, np.int64)
+    sim.sim_wt_replay_all(nlist, n, bits, rank, start, offsets, out2)
+    assert np.array_equal(out2, ids)
     for i in rng.integers(0, n, size=300):
         assert sim.sim_wt_access(nlist, n, bits, rank, sel1, sel0, start, int(i)) == int(S[i])
     for c, k in [(0, 0), (nlist - 1, 0)]:

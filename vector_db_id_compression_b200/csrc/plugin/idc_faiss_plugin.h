@@ -211,6 +211,49 @@ struct CompressedIDInvertedListsEliasFano : InvertedListsArrayCodes {
     }
 };
 
+/// Wavelet-tree ids. custom_invlists_impl.h:100-124, .cpp:346-397: one structure over S[id] = list_no,
+/// get_single_id(list_no, offset) = wt.select(offset + 1, list_no). wt_type 1 (rrr_vector<63>) throws: not implemented.
+struct CompressedIDInvertedListsWaveletTree : InvertedListsArrayCodes {
+    idc_wt_blob* blob = nullptr;
+    int wt_type = 0;
+    size_t overhead_in_bytes = 0;
+    size_t compressed_ids_size_in_bytes = 0;
+    size_t codes_size_in_bytes = 0;
+
+    explicit CompressedIDInvertedListsWaveletTree(const faiss::InvertedLists& il, int wt_type = 0)
+            : InvertedListsArrayCodes(il), wt_type(wt_type) {
+        idc_plugin::Csr csr(il);  // ids ascending per list and < ntotal (asserts :358-359): verified on the device
+        codes_all.resize(nlist);
+        for (size_t l = 0; l < nlist; l++) {
+            take_codes(il, l, nullptr);  // :363-364
+            codes_size_in_bytes += codes_all[l].size();
+        }
+        idc_plugin::check(idc_wt_encode(idc_plugin::context(), nlist, csr.offsets.data(), csr.ids.data(), 8, IDC_MEM_HOST,
+                                        wt_type, &blob));
+        idc_wt_info info;
+        idc_plugin::check(idc_wt_blob_info(blob, &info));
+        compressed_ids_size_in_bytes = info.bits_bytes + info.aux_bytes;  // :368,371 size_in_bytes(wt), this layout's
+    }
+    ~CompressedIDInvertedListsWaveletTree() override { idc_wt_blob_free(blob); }
+
+    idx_t get_single_id(size_t list_no, size_t offset) const override {  // :377-379
+        uint64_t ln = list_no, of = offset;
+        int64_t id = -1;
+        idc_plugin::check(idc_wt_select(idc_plugin::context(), blob, &ln, &of, 1, IDC_MEM_HOST, &id, IDC_MEM_HOST));
+        return id;
+    }
+    const idx_t* get_ids(size_t list_no) const override {  // :381-392, one bulk call instead of ls selects
+        size_t ls = list_size(list_no);
+        idx_t* the_ids = new idx_t[ls];
+        uint64_t ln = list_no;
+        idc_plugin::check(idc_wt_decode(idc_plugin::context(), blob, &ln, 1, the_ids, 8, IDC_MEM_HOST, nullptr));
+        return the_ids;
+    }
+    void get_single_ids(const uint64_t* list_nos, const uint64_t* offsets, size_t n, int64_t* out) const {
+        idc_plugin::check(idc_wt_select(idc_plugin::context(), blob, list_nos, offsets, n, IDC_MEM_HOST, out, IDC_MEM_HOST));
+    }
+};
+
 /// altid_impl.h:42-50, .cpp:53-101
 struct EliasFanoNSGGraph : faiss::nsg::Graph<int32_t> {
     idc_ef_blob* blob = nullptr;

@@ -12,9 +12,11 @@
 //                       ones-before = directory entry + running ballot popcount
 // Queries:
 //   k_wt_select         one thread per (list, offset): wt_select of wt_core.cuh
-//   k_wt_decode         whole lists: one thread per output id
+//   k_wt_decode         a few whole lists: one thread per output id
+//   k_wt_replay / k_wt_emit   most of the index: the partitions replayed on the ids themselves (streaming passes)
 // All HBM-bound integer work; no tensor cores.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -48,33 +50,159 @@ int dev_alloc(idc_ctx* c, T** p, size_t count, uint64_t* acct) {
     return IDC_OK;
 }
 
-// ---- S[id] = list_no (custom_invlists_impl.cpp:354-362), with the reference's asserts as status bits
-template <typename IdT>
-__global__ void __launch_bounds__(kThreads) k_wt_fill(const IdT* __restrict__ ids, const uint64_t* __restrict__ list_off,
-                                                      uint32_t nlist, uint64_t n, uint32_t* __restrict__ seq,
-                                                      uint32_t* status) {
-    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    uint32_t lo = 0, hi = nlist - 1;  // the list that owns element e: largest l with list_off[l] <= e
+// largest s in [0, cnt) with off[s] <= e (off has cnt + 1 ascending entries, off[cnt] > e); skips empty lists
+__device__ __forceinline__ uint64_t find_owner(const uint64_t* __restrict__ off, uint64_t cnt, uint64_t e) {
+    uint64_t lo = 0, hi = cnt - 1;
     while (lo < hi) {
-        uint32_t mid = lo + (hi - lo + 1) / 2;
-        if (__ldg(list_off + mid) <= e)
+        uint64_t mid = lo + (hi - lo + 1) / 2;
+        if (__ldg(off + mid) <= e)
             lo = mid;
         else
             hi = mid - 1;
     }
-    uint64_t id = load_id(ids + e);  // a negative int64 id becomes >= 2^63: out of range
+    return lo;
+}
+
+// Owners of the 512 consecutive elements [base, base + 512) of a warp's tile, 32 per round (element of lane j in
+// round t: base + 32 t + j, clamped to last): ONE binary search per tile; after that a lane only checks that it is
+// still inside the list of the element before its round (lists are long compared to a round), else it searches.
+__device__ __forceinline__ void tile_owners(const uint64_t* __restrict__ off, uint64_t cnt, uint64_t base, uint64_t last,
+                                            uint32_t lane, uint32_t (&own)[16]) {
+    uint64_t s = 0;
+    if (lane == 0) s = find_owner(off, cnt, base);
+    s = __shfl_sync(kFull, s, 0);
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t e = base + (uint64_t)t * 32 + lane;
+        if (e > last) e = last;
+        uint64_t o = e < __ldg(off + s + 1) ? s : find_owner(off, cnt, e);
+        own[t] = (uint32_t)o;
+        s = __shfl_sync(kFull, o, 31);
+    }
+}
+
+// ---- S[id] = list_no (custom_invlists_impl.cpp:354-362), with the reference's asserts as status bits.
+// One warp per tile of 512 elements of the CSR id array.
+template <typename IdT>
+__global__ void __launch_bounds__(kThreads) k_wt_fill(const IdT* __restrict__ ids, const uint64_t* __restrict__ list_off,
+                                                      uint32_t nlist, uint64_t n, uint32_t* __restrict__ seq,
+                                                      uint32_t* status) {
+    const uint64_t tile = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t base = tile << 9;
+    if (base >= n) return;
+    uint64_t id[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t e = base + (uint64_t)t * 32 + lane;
+        id[t] = e < n ? load_id(ids + e) : 0;  // a negative int64 id becomes >= 2^63: out of range
+    }
+    uint32_t own[16];
+    tile_owners(list_off, nlist, base, n - 1, lane, own);
+    uint64_t before = base ? load_id(ids + base - 1) : 0;  // the id in front of the round's first element
     uint32_t st = 0;
-    if (id >= n)
-        st |= kWtStRange;
-    else
-        seq[id] = lo;
-    if (e > __ldg(list_off + lo) && load_id(ids + e - 1) >= id) st |= kWtStUnsorted;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t e = base + (uint64_t)t * 32 + lane;
+        uint64_t prev = __shfl_up_sync(kFull, id[t], 1);
+        if (lane == 0) prev = before;
+        before = __shfl_sync(kFull, id[t], 31);
+        if (e < n) {
+            if (id[t] >= n)
+                st |= kWtStRange;
+            else
+                seq[id[t]] = own[t];
+            if (e > __ldg(list_off + own[t]) && prev >= id[t]) st |= kWtStUnsorted;
+        }
+    }
     if (st) atomicOr(status, st);
 }
 
+// ---- the same through id-range buckets, for sequences that do not fit L2: a scattered 4-byte store costs a whole
+// DRAM sector (measured 22 G stores/s), so the (id, list) pairs are first distributed into buckets of 2^bucket_log
+// consecutive ids -- the lists partition [0, n), hence bucket b receives exactly its 2^bucket_log pairs and owns
+// the slots [b << bucket_log, ...) of the pair array, no histogram pass -- and then applied bucket after bucket,
+// every store of a bucket landing in one L2-resident window of the sequence.
+constexpr int kDistThreads = 256;      // 8 warps = 8 tiles of 512 elements per CTA
+constexpr uint32_t kMaxBuckets = 2048;
+
+template <typename IdT>
+__global__ void __launch_bounds__(kDistThreads) k_wt_distribute(const IdT* __restrict__ ids, const uint64_t* __restrict__ list_off,
+                                                                uint32_t nlist, uint64_t n, uint32_t bucket_log,
+                                                                uint32_t nbuckets, unsigned long long* __restrict__ cursor,
+                                                                uint64_t* __restrict__ pairs, uint32_t* status) {
+    __shared__ uint32_t s_cnt[kMaxBuckets];
+    __shared__ unsigned long long s_base[kMaxBuckets];
+    for (uint32_t b = threadIdx.x; b < nbuckets; b += kDistThreads) s_cnt[b] = 0;
+    __syncthreads();
+    const uint64_t tile = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t base = tile << 9;
+    const bool live = base < n;  // warp-uniform; dead warps still reach the barriers
+    uint64_t id[16];
+    uint32_t own[16], rank[16];
+    uint32_t st = 0;
+    if (live) {
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            uint64_t e = base + (uint64_t)t * 32 + lane;
+            id[t] = e < n ? load_id(ids + e) : ~0ull;
+        }
+        tile_owners(list_off, nlist, base, n - 1, lane, own);
+        uint64_t before = base ? load_id(ids + base - 1) : 0;
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            uint64_t e = base + (uint64_t)t * 32 + lane;
+            uint64_t prev = __shfl_up_sync(kFull, id[t], 1);
+            if (lane == 0) prev = before;
+            before = __shfl_sync(kFull, id[t], 31);
+            rank[t] = 0;
+            if (e < n) {
+                const bool bad = id[t] >= n;
+                if (bad)
+                    st |= kWtStRange;
+                else if (e > __ldg(list_off + own[t]) && prev >= id[t])
+                    st |= kWtStUnsorted;
+                if (bad)
+                    id[t] = ~0ull;  // dropped
+                else
+                    rank[t] = atomicAdd(&s_cnt[id[t] >> bucket_log], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbuckets; b += kDistThreads)
+        s_base[b] = s_cnt[b] ? atomicAdd(cursor + b, (unsigned long long)s_cnt[b]) : 0ull;
+    __syncthreads();
+    if (live) {
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+            if (id[t] == ~0ull) continue;
+            uint64_t b = id[t] >> bucket_log;
+            uint64_t slot = s_base[b] + rank[t];                     // offset inside the bucket
+            uint64_t cap = min((uint64_t)1 << bucket_log, n - (b << bucket_log));
+            if (slot < cap)
+                pairs[(b << bucket_log) + slot] = (id[t] << 32) | own[t];
+            else
+                st |= kWtStHole;  // more ids than the bucket has room for: some id appears twice
+        }
+    }
+    if (st) atomicOr(status, st);
+}
+
+__global__ void __launch_bounds__(kThreads) k_wt_apply(const uint64_t* __restrict__ pairs, const unsigned long long* __restrict__ cursor,
+                                                       uint64_t n, uint32_t bucket_log, uint32_t* __restrict__ seq) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t b = i >> bucket_log;
+    if (i - (b << bucket_log) >= cursor[b]) return;  // slot never filled (invalid input; reported as a hole)
+    const uint64_t p = __ldg(pairs + i);
+    seq[p >> 32] = (uint32_t)p;
+}
+
 // ---- one level: bits of every rank block + its popcount
-__global__ void __launch_bounds__(kThreads) k_wt_level_bits(const uint32_t* __restrict__ seq, uint64_t n, uint64_t nblk,
+template <typename SymT>
+__global__ void __launch_bounds__(kThreads) k_wt_level_bits(const SymT* __restrict__ seq, uint64_t n, uint64_t nblk,
                                                             uint32_t shift, uint32_t check_holes,
                                                             uint64_t* __restrict__ bits, uint32_t* __restrict__ ones,
                                                             uint32_t* status) {
@@ -86,14 +214,14 @@ __global__ void __launch_bounds__(kThreads) k_wt_level_bits(const uint32_t* __re
 #pragma unroll
     for (int t = 0; t < 16; t++) {
         uint64_t i = base + (uint64_t)t * 32 + lane;
-        v[t] = i < n ? __ldg(seq + i) : 0u;
+        v[t] = i < n ? (uint32_t)__ldg(seq + i) : 0u;
     }
     uint32_t mine = 0, cnt = 0;
     bool hole = false;
 #pragma unroll
     for (int t = 0; t < 16; t++) {
         uint64_t i = base + (uint64_t)t * 32 + lane;
-        hole |= check_holes && i < n && v[t] == kWtHole;
+        hole |= sizeof(SymT) == 4 && check_holes && i < n && v[t] == kWtHole;
         uint32_t m = __ballot_sync(kFull, (v[t] >> shift) & 1u);
         if (lane == (uint32_t)t) mine = m;
         cnt += (uint32_t)__popc(m);
@@ -184,9 +312,10 @@ __global__ void __launch_bounds__(kThreads) k_wt_directory(const uint32_t* __res
 }
 
 // stable partition of a level by its bit: zeros keep their order in [0, z), ones theirs in [z, n)
-__global__ void __launch_bounds__(kThreads) k_wt_level_scatter(const uint32_t* __restrict__ seq, uint64_t n, uint64_t nblk,
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(kThreads) k_wt_level_scatter(const InT* __restrict__ seq, uint64_t n, uint64_t nblk,
                                                                uint32_t shift, const uint32_t* __restrict__ rank,
-                                                               uint32_t* __restrict__ next) {
+                                                               OutT* __restrict__ next) {
     const uint64_t blk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     if (blk >= nblk) return;
@@ -197,7 +326,7 @@ __global__ void __launch_bounds__(kThreads) k_wt_level_scatter(const uint32_t* _
 #pragma unroll
     for (int t = 0; t < 16; t++) {
         uint64_t i = base + (uint64_t)t * 32 + lane;
-        v[t] = i < n ? __ldg(seq + i) : 0u;
+        v[t] = i < n ? (uint32_t)__ldg(seq + i) : 0u;
     }
 #pragma unroll
     for (int t = 0; t < 16; t++) {
@@ -206,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) k_wt_level_scatter(const uint32_t* _
         uint32_t b = (v[t] >> shift) & 1u;
         uint32_t m = __ballot_sync(kFull, valid && b);
         uint64_t ones_before = r1 + (uint32_t)__popc(m & ((1u << lane) - 1u));
-        if (valid) next[wt_partition_dest(i, b, z, ones_before)] = v[t];
+        if (valid) next[wt_partition_dest(i, b, z, ones_before)] = (OutT)v[t];
         r1 += (uint32_t)__popc(m);
     }
 }
@@ -243,18 +372,71 @@ template <typename OutT>
 __global__ void __launch_bounds__(kThreads) k_wt_decode(WtDecArgs a) {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= a.total) return;
-    uint64_t lo = 0, hi = a.nsel - 1;  // largest s with out_off[s] <= e (skips empty lists)
-    while (lo < hi) {
-        uint64_t mid = lo + (hi - lo + 1) / 2;
-        if (__ldg(a.out_off + mid) <= e)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
+    const uint64_t lo = find_owner(a.out_off, a.nsel, e);
     uint64_t L = a.sel ? __ldg(a.sel + lo) : lo;
     uint64_t id = wt_select(a.v, (uint32_t)L, e - __ldg(a.out_off + lo));
     if (id == ~0ull) atomicOr(a.status, kWtStCorrupt);
     reinterpret_cast<OutT*>(a.out)[e] = (OutT)id;
+}
+
+// ---- get_ids of (nearly) everything as `levels` streaming passes: the build's stable partition replayed on a
+// payload (the id itself), the bit of every element read back from the level's bit vector. After the last level
+// payload[start[c] + k] is id number k of list c.
+template <bool kIota>
+__global__ void __launch_bounds__(kThreads) k_wt_replay(const uint32_t* __restrict__ in, uint64_t n, uint64_t nblk,
+                                                        const uint64_t* __restrict__ bits, const uint32_t* __restrict__ rank,
+                                                        uint32_t* __restrict__ out) {
+    const uint64_t blk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (blk >= nblk) return;
+    const uint64_t base = blk << kWtBlockLog;
+    const uint64_t z = n - __ldg(rank + nblk);
+    uint64_t r1 = __ldg(rank + blk);
+    const uint32_t word = lane < 16 ? __ldg(reinterpret_cast<const uint32_t*>(bits) + blk * 16 + lane) : 0u;
+    uint32_t v[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t i = base + (uint64_t)t * 32 + lane;
+        v[t] = kIota ? (uint32_t)i : (i < n ? __ldg(in + i) : 0u);
+    }
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t i = base + (uint64_t)t * 32 + lane;
+        uint32_t m = __shfl_sync(kFull, word, t);  // bits past n are zero: they were built from zero symbols
+        uint32_t b = (m >> lane) & 1u;
+        uint64_t ones_before = r1 + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (i < n) out[wt_partition_dest(i, b, z, ones_before)] = v[t];
+        r1 += (uint32_t)__popc(m);
+    }
+}
+
+struct WtEmitArgs {
+    const uint32_t* payload;
+    const uint32_t* start;
+    const uint64_t* sel;      // selected list numbers (NULL = all lists in order)
+    const uint64_t* out_off;  // nsel + 1 offsets of the output
+    uint64_t nsel, total;
+    void* out;
+};
+
+// one warp per tile of 512 output ids
+template <typename OutT>
+__global__ void __launch_bounds__(kThreads) k_wt_emit(WtEmitArgs a) {
+    const uint64_t tile = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t base = tile << 9;
+    if (base >= a.total) return;
+    uint32_t own[16];
+    tile_owners(a.out_off, a.nsel, base, a.total - 1, lane, own);
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t e = base + (uint64_t)t * 32 + lane;
+        if (e < a.total) {
+            uint64_t L = a.sel ? __ldg(a.sel + own[t]) : own[t];
+            uint64_t src = (uint64_t)__ldg(a.start + L) + (e - __ldg(a.out_off + own[t]));
+            reinterpret_cast<OutT*>(a.out)[e] = (OutT)__ldg(a.payload + src);
+        }
+    }
 }
 
 }  // namespace
@@ -319,19 +501,47 @@ int wt_build(idc_ctx* c, idc_wt_blob* b, const IdT* ids_dev) {
     const uint64_t E = sh.nblk + 1;
     const uint32_t P = (uint32_t)((E + kScanTile - 1) / kScanTile);
     const uint64_t Epad = (E + 31) & ~uint64_t(31);
-    IDC_TRY(c->scratch.reserve((Epad + P + 64) * sizeof(uint32_t)));
+    // sequences beyond L2 are filled through id-range buckets (IDC_WT_FILL=direct|bucket, IDC_WT_BUCKET_LOG override)
+    bool bucketed = n >= (1ull << 25);
+    uint32_t bucket_log = 23;  // 2^23 ids = a 32 MB window of the sequence
+    if (const char* e = getenv("IDC_WT_FILL")) bucketed = strcmp(e, "bucket") == 0 ? true : strcmp(e, "direct") == 0 ? false : bucketed;
+    if (const char* e = getenv("IDC_WT_BUCKET_LOG")) bucket_log = (uint32_t)std::min(31, std::max(4, atoi(e)));
+    while (((n - 1) >> bucket_log) + 1 > kMaxBuckets) bucket_log++;
+    const uint32_t nbuckets = (uint32_t)(((n - 1) >> bucket_log) + 1);
+    const uint64_t nb_pad = (nbuckets + 31) & ~uint64_t(31);
+    const uint64_t dir_words = (Epad + P + 64 + 63) & ~uint64_t(63);  // 32-bit words; keeps the 64-bit arrays aligned
+    IDC_TRY(c->scratch.reserve(dir_words * sizeof(uint32_t) + (bucketed ? (nb_pad + n) * 8 : 0)));
     uint32_t* local = c->scratch.as<uint32_t>();
     uint32_t* part = local + Epad;
+    unsigned long long* cursor = reinterpret_cast<unsigned long long*>(local + dir_words);
+    uint64_t* pairs = reinterpret_cast<uint64_t*>(cursor + nb_pad);
     IDC_TRY(c->status.reserve(64));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, s));
     IDC_CUDA(cudaMemsetAsync(seq, 0xff, n * sizeof(uint32_t), s));
-    {
+    if (bucketed) {
+        IDC_CUDA(cudaMemsetAsync(cursor, 0, nbuckets * 8, s));
+        {
+            LaunchScope ls(c, "k_wt_distribute");
+            k_wt_distribute<IdT><<<grid_for(sh.nblk * 32, kDistThreads), kDistThreads, 0, s>>>(
+                    ids_dev, b->d_list_off, (uint32_t)b->nlist, n, bucket_log, nbuckets, cursor, pairs, d_status);
+        }
+        {
+            LaunchScope ls(c, "k_wt_apply");
+            k_wt_apply<<<grid_for(n), kThreads, 0, s>>>(pairs, cursor, n, bucket_log, seq);
+        }
+    } else {
         LaunchScope ls(c, "k_wt_fill");
-        k_wt_fill<IdT><<<grid_for(n), kThreads, 0, s>>>(ids_dev, b->d_list_off, (uint32_t)b->nlist, n, seq, d_status);
+        k_wt_fill<IdT><<<grid_for(sh.nblk * 32), kThreads, 0, s>>>(ids_dev, b->d_list_off, (uint32_t)b->nlist, n, seq, d_status);
     }
     IDC_TRY(check_last_launch("k_wt_fill"));
     const uint32_t warp_grid = grid_for(sh.nblk * 32);
+    // Level 0 reads the 32-bit sequence (holes are 0xffffffff there); its partition already drops the bit it has
+    // consumed, so with <= 17 levels every later pass moves 16-bit symbols: half the traffic.
+    const bool narrow = sh.levels <= 17;
+    bool cur16 = false;
+    void* cur = seq;
+    void* nxt = next;
     for (uint32_t lev = 0; lev < sh.levels; lev++) {
         const uint32_t shift = sh.levels - 1 - lev;
         uint64_t* bits = b->d_bits + (uint64_t)lev * sh.words;
@@ -339,7 +549,10 @@ int wt_build(idc_ctx* c, idc_wt_blob* b, const IdT* ids_dev) {
         IDC_CUDA(cudaMemsetAsync(local + sh.nblk, 0, 4, s));  // entry nblk of the scan input: becomes the level's ones
         {
             LaunchScope ls(c, "k_wt_level_bits");
-            k_wt_level_bits<<<warp_grid, kThreads, 0, s>>>(seq, n, sh.nblk, shift, lev == 0 ? 1u : 0u, bits, local, d_status);
+            if (cur16)
+                k_wt_level_bits<uint16_t><<<warp_grid, kThreads, 0, s>>>((const uint16_t*)cur, n, sh.nblk, shift, 0u, bits, local, d_status);
+            else
+                k_wt_level_bits<uint32_t><<<warp_grid, kThreads, 0, s>>>((const uint32_t*)cur, n, sh.nblk, shift, lev == 0 ? 1u : 0u, bits, local, d_status);
         }
         {
             LaunchScope ls(c, "k_wt_scan");
@@ -357,8 +570,14 @@ int wt_build(idc_ctx* c, idc_wt_blob* b, const IdT* ids_dev) {
         }
         if (lev + 1 < sh.levels) {
             LaunchScope ls(c, "k_wt_level_scatter");
-            k_wt_level_scatter<<<warp_grid, kThreads, 0, s>>>(seq, n, sh.nblk, shift, rank, next);
-            std::swap(seq, next);
+            if (cur16)
+                k_wt_level_scatter<uint16_t, uint16_t><<<warp_grid, kThreads, 0, s>>>((const uint16_t*)cur, n, sh.nblk, shift, rank, (uint16_t*)nxt);
+            else if (narrow)
+                k_wt_level_scatter<uint32_t, uint16_t><<<warp_grid, kThreads, 0, s>>>((const uint32_t*)cur, n, sh.nblk, shift, rank, (uint16_t*)nxt);
+            else
+                k_wt_level_scatter<uint32_t, uint32_t><<<warp_grid, kThreads, 0, s>>>((const uint32_t*)cur, n, sh.nblk, shift, rank, (uint32_t*)nxt);
+            cur16 = narrow;
+            std::swap(cur, nxt);
         }
         IDC_TRY(check_last_launch("wavelet level"));
     }
@@ -565,8 +784,39 @@ int idc_wt_decode(idc_ctx* c, const idc_wt_blob* b, const uint64_t* list_nos, ui
     IDC_TRY(c->status.reserve(64));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
-    WtDecArgs a{b->view(), d_sel, d_off, nsel, total, out_dev, d_status};
-    {
+    // A large share of the index: replay the partitions on the ids themselves (streaming passes, cost independent
+    // of how many lists are asked for). Few lists: one select walk per id. IDC_WT_DECODE=select|replay forces a path.
+    bool replay = total >= b->total_ids / 8;
+    if (const char* e = getenv("IDC_WT_DECODE")) replay = strcmp(e, "replay") == 0 ? true : strcmp(e, "select") == 0 ? false : replay;
+    if (replay) {
+        const WtShape& sh = b->sh;
+        const uint64_t seq_elems = sh.nblk << kWtBlockLog;
+        IDC_TRY(c->ws.reserve(2 * seq_elems * sizeof(uint32_t)));
+        uint32_t* bufA = c->ws.as<uint32_t>();
+        uint32_t* bufB = bufA + seq_elems;
+        const uint32_t* in = nullptr;
+        uint32_t* out = bufA;
+        const uint32_t warp_grid = grid_for(sh.nblk * 32);
+        for (uint32_t lev = 0; lev < sh.levels; lev++) {
+            LaunchScope ls(c, "k_wt_replay");
+            const uint64_t* bits = b->d_bits + (uint64_t)lev * sh.words;
+            const uint32_t* rank = b->d_rank + (uint64_t)lev * sh.rank_stride;
+            if (lev == 0)
+                k_wt_replay<true><<<warp_grid, kThreads, 0, c->stream>>>(nullptr, sh.n, sh.nblk, bits, rank, out);
+            else
+                k_wt_replay<false><<<warp_grid, kThreads, 0, c->stream>>>(in, sh.n, sh.nblk, bits, rank, out);
+            in = out;
+            out = out == bufA ? bufB : bufA;
+        }
+        IDC_TRY(check_last_launch("k_wt_replay"));
+        WtEmitArgs a{in, b->d_start, d_sel, d_off, nsel, total, out_dev};
+        LaunchScope ls(c, "k_wt_emit");
+        if (id_bytes == 8)
+            k_wt_emit<int64_t><<<grid_for(((total + 511) >> 9) * 32), kThreads, 0, c->stream>>>(a);
+        else
+            k_wt_emit<int32_t><<<grid_for(((total + 511) >> 9) * 32), kThreads, 0, c->stream>>>(a);
+    } else {
+        WtDecArgs a{b->view(), d_sel, d_off, nsel, total, out_dev, d_status};
         LaunchScope ls(c, "k_wt_decode");
         if (id_bytes == 8)
             k_wt_decode<int64_t><<<grid_for(total), kThreads, 0, c->stream>>>(a);
