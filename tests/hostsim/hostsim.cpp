@@ -206,6 +206,59 @@ uint32_t sim_wt_access(uint64_t nlist, uint64_t n, const uint64_t* bits, const u
                        const uint32_t* sel0, const uint32_t* start, uint64_t i) {
     return wt_access(wt_view_of(nlist, n, bits, rank, sel1, sel0, start), i);
 }
+// k_wt_distribute + k_wt_apply CTA by CTA (8 tiles of 512 elements, per-CTA bucket counts, one cursor bump per
+// (CTA, bucket), bucket b owning the slots [b << bucket_log, ...) of the pair array). Returns the status bits
+// (1 hole / duplicate, 2 range, 4 unsorted); S is pre-filled with 0xffffffff like the device sequence.
+uint32_t sim_wt_fill_bucketed(uint64_t nlist, uint64_t n, const int64_t* ids, const uint64_t* list_off, uint32_t bucket_log,
+                              uint32_t* S) {
+    const uint64_t nbuckets = ((n - 1) >> bucket_log) + 1;
+    std::vector<uint64_t> cursor(nbuckets, 0), pairs(n, ~0ull);
+    uint32_t st = 0;
+    for (uint64_t i = 0; i < n; i++) S[i] = 0xffffffffu;
+    const uint64_t per_cta = 8 * 512;
+    for (uint64_t cta = 0; cta * per_cta < n; cta++) {
+        std::vector<uint32_t> cnt(nbuckets, 0);
+        std::vector<uint64_t> base(nbuckets, 0);
+        uint64_t e0 = cta * per_cta, e1 = std::min(n, e0 + per_cta);
+        std::vector<uint32_t> rank(e1 - e0), own(e1 - e0);
+        std::vector<uint64_t> id(e1 - e0);
+        for (uint64_t e = e0; e < e1; e++) {
+            uint64_t l = std::upper_bound(list_off, list_off + nlist + 1, e) - list_off - 1;  // largest l with off[l] <= e
+            own[e - e0] = (uint32_t)l;
+            uint64_t v = (uint64_t)ids[e];
+            bool bad = v >= n;
+            if (bad)
+                st |= 2u;
+            else if (e > list_off[l] && (uint64_t)ids[e - 1] >= v)
+                st |= 4u;
+            id[e - e0] = bad ? ~0ull : v;
+            if (!bad) rank[e - e0] = cnt[v >> bucket_log]++;
+        }
+        for (uint64_t b = 0; b < nbuckets; b++)
+            if (cnt[b]) {
+                base[b] = cursor[b];
+                cursor[b] += cnt[b];
+            }
+        for (uint64_t e = e0; e < e1; e++) {
+            uint64_t v = id[e - e0];
+            if (v == ~0ull) continue;
+            uint64_t b = v >> bucket_log, slot = base[b] + rank[e - e0];
+            uint64_t cap = std::min<uint64_t>(1ull << bucket_log, n - (b << bucket_log));
+            if (slot < cap)
+                pairs[(b << bucket_log) + slot] = (v << 32) | own[e - e0];
+            else
+                st |= 1u;
+        }
+    }
+    for (uint64_t i = 0; i < n; i++) {  // k_wt_apply
+        uint64_t b = i >> bucket_log;
+        if (i - (b << bucket_log) >= cursor[b]) continue;
+        S[pairs[i] >> 32] = (uint32_t)pairs[i];
+    }
+    for (uint64_t i = 0; i < n; i++)
+        if (S[i] == 0xffffffffu) st |= 1u;  // what level 0 of the build reports
+    return st;
+}
 // k_wt_replay + k_wt_emit lane by lane: the partitions replayed on the ids, bits read back from the structure
 void sim_wt_replay_all(uint64_t nlist, uint64_t n, const uint64_t* bits, const uint32_t* rank, const uint32_t* start,
                        const uint64_t* list_off, int64_t* out) {

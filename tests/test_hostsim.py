@@ -43,6 +43,8 @@ def sim():
     lib.sim_wt_select.argtypes = wt_arrays + [C.c_uint32, C.c_uint64]
     lib.sim_wt_access.restype = C.c_uint32
     lib.sim_wt_access.argtypes = wt_arrays + [C.c_uint64]
+    lib.sim_wt_fill_bucketed.restype = C.c_uint32
+    lib.sim_wt_fill_bucketed.argtypes = [C.c_uint64, C.c_uint64, i64p, u64p, C.c_uint32, u32p]
     lib.sim_wt_replay_all.restype = None
     lib.sim_wt_replay_all.argtypes = [C.c_uint64, C.c_uint64, u64p, u32p, u32p, u64p, i64p]
     lib.sim_wt_decode_all.restype = None
@@ -202,3 +204,22 @@ def test_wavelet_matrix_build_and_select(sim, nlist, n, skew):
     for c, k in [(0, 0), (nlist - 1, 0)]:
         if offsets[c + 1] > offsets[c]:
             assert sim.sim_wt_select(nlist, n, bits, rank, sel1, sel0, start, c, k) == int(ids[int(offsets[c]) + k])
+
+
+def test_wavelet_bucketed_fill(sim):
+    """k_wt_distribute / k_wt_apply, CTA by CTA: S[id] = list_no through id-range buckets equals the direct
+    definition (oracle.wt.sequence); the reference's asserts and holes / duplicates come back as status bits."""
+    from test_oracle_wt import make_lists
+
+    rng = np.random.default_rng(77)
+    for nlist, n, blog in [(50, 40_000, 5), (7, 10_000, 10), (300, 70_001, 9), (3, 5000, 23)]:
+        offsets, ids, _ = make_lists(rng, nlist, n)
+        S = np.zeros(n, np.uint32)
+        assert sim.sim_wt_fill_bucketed(nlist, n, ids, offsets, blog, S) == 0
+        assert np.array_equal(S, oracle.wt.sequence(offsets, ids))
+        for pos, val, bit in ((777, "prev", 4), (2000, n, 2), (3100, -5, 2), (4000, "dup", 1)):
+            bad = ids.copy()
+            bad[pos] = bad[pos - 1] if val == "prev" else (bad[5] if val == "dup" else val)
+            st = sim.sim_wt_fill_bucketed(nlist, n, bad, offsets, blog, S)
+            assert st & bit or st & 4, (nlist, n, pos, val, st)  # a duplicate may also break the order
+            assert st != 0
