@@ -146,3 +146,118 @@ def encode_sharded(offsets, ids, encode_fn: Callable, device, src: int = 0, grou
     mine, loc, local_ids = scatter_lists(offsets, ids, device, src=src, group=group)
     local = encode_fn(loc, local_ids)
     return gather_blobs(mine, local, nlist[0], dst=src, group=group)
+
+
+# ---------------------------------------------------------------- wavelet tree: sharding by id range
+# The wavelet-tree index is ONE structure over S[id] = list_no (custom_invlists_impl.cpp:346-397), so it cannot be
+# sharded by lists. It shards by ID RANGE: rank r indexes the ids [lo[r], lo[r+1]) (shifted to start at 0), i.e. the
+# slice S[lo[r] : lo[r+1]]. Ids are ascending inside a list, so list c's ids are the concatenation over ranks of its
+# local ids, and a (world x nlist) table of per-rank list counts routes get_single_id(c, k) to the one rank that
+# holds it. No collective inside the codec; NCCL moves the raw id blocks (scatter) and the answers (all-reduce /
+# gather) only.
+
+def wt_id_range_plan(offsets, ids, world: int, align: int = 512) -> dict:
+    """Split an index whose lists partition [0, n) into `world` id ranges of `chunk` ids (a multiple of `align`).
+    ids: numpy array or torch tensor (the plan is computed where the ids live: on the GPU for a device tensor).
+    -> lo[world+1], counts[world, nlist] (ids of list c held by rank r; numpy), order (torch: element indices
+    grouped by rank, list order and id order preserved)."""
+    import torch
+
+    offsets = np.asarray(offsets, dtype=np.int64)
+    ids_t = torch.as_tensor(ids).to(torch.int64)
+    nlist, n = offsets.size - 1, int(offsets[-1] - offsets[0])
+    chunk = max(-(-max(n, 1) // world), 1)
+    chunk = -(-chunk // align) * align
+    lo = np.minimum(np.arange(world + 1, dtype=np.int64) * chunk, n)
+    shard = torch.div(ids_t, chunk, rounding_mode="floor")
+    sizes = torch.as_tensor(np.diff(offsets), device=ids_t.device)
+    lists = torch.repeat_interleave(torch.arange(nlist, device=ids_t.device, dtype=torch.int64), sizes)
+    counts = torch.bincount(shard * nlist + lists, minlength=world * nlist).reshape(world, nlist).cpu().numpy()
+    order = torch.argsort(shard, stable=True)
+    return dict(lo=lo, counts=counts, order=order, chunk=chunk)
+
+
+class WtShardedIndex:
+    """Wavelet-tree index sharded by id range over the ranks of `group`.
+
+    encode_fn(local_offsets[nlist+1] u64, local_ids int64 tensor on `device`) -> an object with the capi.WtBlob
+    interface: .select(list_nos, offsets_in_list) -> int64 array, .decode() -> (ids, offsets). Rank `src` owns
+    (offsets, ids); the other ranks pass None."""
+
+    def __init__(self, offsets, ids, encode_fn: Callable, device, src: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        meta = [None]
+        plan = None
+        if self.rank == src:
+            plan = wt_id_range_plan(offsets, ids, self.world)
+            meta = [(np.asarray(offsets, dtype=np.int64) - int(offsets[0]), plan["lo"], plan["counts"])]
+        dist.broadcast_object_list(meta, src=src, group=group)
+        self.offsets, self.lo, self.counts = meta[0]
+        self.nlist = self.offsets.size - 1
+        # prefix[r, c] = ids of list c held by the ranks before r; prefix[world, c] = size of list c
+        self.prefix = np.zeros((self.world + 1, self.nlist), dtype=np.int64)
+        np.cumsum(self.counts, axis=0, out=self.prefix[1:])
+        n_mine = int(self.counts[self.rank].sum())
+        recv = torch.empty(n_mine, dtype=torch.int64, device=device)
+        ops, keep = [], []
+        if self.rank == src:
+            ids_t = torch.as_tensor(ids).to(torch.int64)[plan["order"]].to(device)
+            ends = np.cumsum(self.counts.sum(axis=1))
+            for r in range(self.world):
+                blk = ids_t[int(ends[r]) - int(self.counts[r].sum()): int(ends[r])] - int(self.lo[r])
+                if r == src:
+                    recv.copy_(blk)
+                elif blk.numel():
+                    keep.append(blk)
+                    ops.append(dist.P2POp(dist.isend, blk, r, group))
+        elif n_mine:
+            ops.append(dist.P2POp(dist.irecv, recv, src, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        self.local_offsets = np.zeros(self.nlist + 1, dtype=np.uint64)
+        self.local_offsets[1:] = np.cumsum(self.counts[self.rank])
+        self.local = encode_fn(self.local_offsets, recv) if n_mine else None
+
+    def select(self, list_nos, offsets_in_list) -> np.ndarray:
+        """get_single_id for the same (list, offset) pairs on every rank; -1 outside the index."""
+        import torch
+        import torch.distributed as dist
+
+        ln = np.asarray(list_nos, dtype=np.int64)
+        of = np.asarray(offsets_in_list, dtype=np.int64)
+        ok = (ln >= 0) & (ln < self.nlist) & (of >= 0)
+        lc = np.where(ok, ln, 0)
+        ok &= of < self.prefix[self.world, lc]
+        owner = (self.prefix[1:, lc] <= of[None, :]).sum(axis=0)  # ranks whose share of the list ends at or before k
+        mine = ok & (owner == self.rank)
+        out = np.full(ln.size, -1, dtype=np.int64)
+        if mine.any():
+            loc = self.local.select(lc[mine], of[mine] - self.prefix[self.rank, lc[mine]])
+            out[mine] = np.asarray(loc, dtype=np.int64) + int(self.lo[self.rank])
+        t = torch.as_tensor(out, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t.cpu().numpy()
+
+    def decode_all(self, dst: int = 0) -> Optional[np.ndarray]:
+        """get_ids of every list, in the global CSR order, on rank `dst` (None elsewhere)."""
+        import torch.distributed as dist
+
+        loc = np.zeros(0, dtype=np.int64)
+        if self.local is not None:
+            loc = np.asarray(self.local.decode()[0], dtype=np.int64) + int(self.lo[self.rank])
+        out = [None] * self.world if self.rank == dst else None
+        dist.gather_object(loc, out, dst=dst, group=self.group)
+        if self.rank != dst:
+            return None
+        res = np.empty(int(self.offsets[-1]), dtype=np.int64)
+        for r, blk in enumerate(out):
+            sizes = self.counts[r]
+            local_start = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+            dest = np.repeat(self.offsets[:-1] + self.prefix[r] - local_start, sizes) + np.arange(blk.size, dtype=np.int64)
+            res[dest] = blk
+        return res
