@@ -33,7 +33,9 @@ def test_every_entry_point_cites_the_reference():
     header = (ROOT / "include" / "idcodec.h").read_text()
     for anchor in ("codec.cpp:123-138", "codec.cpp:140-152", "custom_invlists_impl.cpp:147-194",
                    "custom_invlists_impl.cpp:210-219", "altid_impl.cpp:153-165", "elias_fano.hpp:22-57",
-                   "elias_fano.hpp:141-145", "custom_invlists_impl.cpp:292-311", "altid_impl.cpp:92-101"):
+                   "elias_fano.hpp:141-145", "custom_invlists_impl.cpp:292-311", "altid_impl.cpp:92-101",
+                   "custom_invlists_impl.cpp:346-397", "custom_invlists_impl.cpp:377-379",
+                   "custom_invlists_impl.cpp:381-392"):
         assert anchor in header, anchor
 
 

@@ -76,3 +76,34 @@ def test_rejects_what_the_reference_asserts():
     with pytest.raises(ValueError):
         oracle.wt.sequence(offsets, np.array([0, 1, 1, 3]))  # id owned twice -> another id owned by no list
     assert oracle.wt.sequence(offsets, np.array([0, 3, 1, 2])).tolist() == [0, 1, 1, 0]
+
+
+def test_property_random_partitions():
+    """hypothesis: any partition of [0, n) into ascending lists -> select(c, k) is the k-th id of list c, through the
+    wavelet walk and through the definition; access-by-rank consistency of the directories."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 1500), st.integers(0, 2**31 - 1))
+    def check(nlist, n, seed):
+        rng = np.random.default_rng(seed)
+        # skewed on purpose: most ids in few lists, long runs of equal symbols
+        lab = np.minimum((rng.pareto(0.8, size=n)).astype(np.int64), nlist - 1)
+        if seed & 1:
+            lab = np.sort(lab)
+        order = np.argsort(lab, kind="stable").astype(np.int64)
+        offsets = np.zeros(nlist + 1, np.uint64)
+        offsets[1:] = np.cumsum(np.bincount(lab, minlength=nlist))
+        S = oracle.wt.sequence(offsets, order)
+        wt = oracle.wt.build(nlist, S)
+        # rank directory: last entry of every level = ones of the level; entries ascending, steps <= 512
+        for lev in range(wt["levels"]):
+            r = wt["rank"][lev].astype(np.int64)
+            assert np.all(np.diff(r) >= 0) and np.all(np.diff(r) <= 512)
+        for c in rng.integers(0, nlist, size=6):
+            a, b = int(offsets[c]), int(offsets[c + 1])
+            if b > a:
+                k = int(rng.integers(0, b - a))
+                assert oracle.wt.select(wt, int(c), k) == int(order[a + k]) == oracle.wt.select_seq(S, int(c), k)
+
+    check()
