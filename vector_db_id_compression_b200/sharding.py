@@ -114,24 +114,34 @@ def gather_blobs(mine: np.ndarray, local: dict, nlist: int, dst: int = 0, group=
     dist.gather_object(payload, out, dst=dst, group=group)
     if rank != dst:
         return None
-    # global tables in list order
-    per_list = [None] * nlist
+    # global tables in list order, vectorised: every rank's units / words are scattered to their global positions
+    nunits_of = np.zeros(nlist, dtype=np.int64)
     for p in out:
-        uo = p["unit_offsets"]
-        for j, l in enumerate(p["lists"]):
-            u0, u1 = int(uo[j]), int(uo[j + 1])
-            w0, w1 = int(p["word_offsets"][u0]), int(p["word_offsets"][u1])
-            per_list[int(l)] = dict(unit_n=p["unit_n"][u0:u1], precision=p["precision"][u0:u1],
-                                    heads=p["heads"][u0:u1], nwords=np.diff(p["word_offsets"][u0: u1 + 1]),
-                                    words=p["words"][w0:w1])
+        nunits_of[p["lists"].astype(np.int64)] = np.diff(p["unit_offsets"].astype(np.int64))
     unit_offsets = np.zeros(nlist + 1, np.uint64)
-    unit_offsets[1:] = np.cumsum([x["unit_n"].size for x in per_list])
-    cat = lambda k, dt: (np.concatenate([x[k] for x in per_list]).astype(dt) if nlist else np.zeros(0, dt))
-    nwords = cat("nwords", np.uint64)
-    word_offsets = np.zeros(nwords.size + 1, np.uint64)
+    unit_offsets[1:] = np.cumsum(nunits_of)
+    nunits = int(unit_offsets[-1])
+    unit_n, precision = np.zeros(nunits, np.uint32), np.zeros(nunits, np.uint8)
+    heads, nwords = np.zeros(nunits, np.uint64), np.zeros(nunits, np.int64)
+    dest_units = []
+    for p in out:
+        lists = p["lists"].astype(np.int64)
+        uo = p["unit_offsets"].astype(np.int64)
+        nu = np.diff(uo)
+        du = np.repeat(unit_offsets[lists].astype(np.int64) - uo[:-1], nu) + np.arange(int(nu.sum()), dtype=np.int64)
+        dest_units.append(du)
+        unit_n[du], precision[du], heads[du] = p["unit_n"][: du.size], p["precision"][: du.size], p["heads"][: du.size]
+        nwords[du] = np.diff(p["word_offsets"].astype(np.int64))[: du.size]
+    word_offsets = np.zeros(nunits + 1, np.uint64)
     word_offsets[1:] = np.cumsum(nwords)
-    return dict(unit_offsets=unit_offsets, unit_n=cat("unit_n", np.uint32), precision=cat("precision", np.uint8),
-                heads=cat("heads", np.uint64), word_offsets=word_offsets, words=cat("words", np.uint32))
+    words = np.zeros(int(word_offsets[-1]), np.uint32)
+    for p, du in zip(out, dest_units):
+        wo = p["word_offsets"].astype(np.int64)[: du.size + 1]
+        nw = np.diff(wo)
+        dw = np.repeat(word_offsets[du].astype(np.int64) - wo[:-1], nw) + np.arange(int(nw.sum()), dtype=np.int64)
+        words[dw] = np.asarray(p["words"])[int(wo[0]): int(wo[0]) + dw.size] if dw.size else words[dw]
+    return dict(unit_offsets=unit_offsets, unit_n=unit_n, precision=precision, heads=heads,
+                word_offsets=word_offsets, words=words)
 
 
 def encode_sharded(offsets, ids, encode_fn: Callable, device, src: int = 0, group=None) -> Optional[dict]:
