@@ -89,7 +89,8 @@ static void check_graph(const char* name, const G& g, const std::vector<int32_t>
     std::printf("%-44s compressed ids %6zu B\n", name, (size_t)g.compressed_ids_size_in_bytes);
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const bool all = argc > 1 && std::string(argv[1]) == "--all";  // also the classes not yet run on a GPU
     try {
         std::mt19937 rng(4);
         ArrayIL il(8, 4);  // IVF8 over 1000 vectors, ids 0..999 in add order (ascending per list), list 5 left empty
@@ -127,6 +128,11 @@ int main() {
             }
             CHECK(threw, "WaveletTree: wt_type 1 must be rejected (not implemented)");
         }
+        if (all) {
+            CompressedIDInvertedListsPackedBits pb(il);
+            check_invlists("CompressedIDInvertedListsPackedBits", pb, il, true, true);
+            CHECK(pb.bits == 10, "PackedBits: bits %d for ntotal 1000", pb.bits);  // (1 << 10) >= 1001
+        }
         const int N = 200, K = 16;
         std::vector<int32_t> rows((size_t)N * K, -1);
         for (int i = 0; i < N; i++) {  // distinct neighbours != i, degree 3..16, -1 padded (altid_impl.cpp:110-117)
@@ -138,10 +144,20 @@ int main() {
             }
             std::copy(cand.begin(), cand.end(), rows.begin() + (size_t)i * K);
         }
+        if (all) {
+            std::vector<int32_t> data(rows);
+            faiss::nsg::Graph<int32_t> g(data.data(), N, K);
+            CompactBitNSGGraph cg(g);
+            CHECK(cg.bits == 8 && cg.stride == 16, "CompactBit: bits %d stride %zu", cg.bits, cg.stride);
+            struct Sized { const CompactBitNSGGraph& g; size_t compressed_ids_size_in_bytes;
+                           size_t get_neighbors(int i, int32_t* nb) const { return g.get_neighbors(i, nb); } };
+            check_graph("CompactBitNSGGraph", Sized{cg, cg.compressed_data.size()}, rows, N, K, false);
+        }
         {
             std::vector<int32_t> data(rows);
             faiss::nsg::Graph<int32_t> g(data.data(), N, K);
             EliasFanoNSGGraph eg(g);
+            CHECK(eg.overhead_in_bytes == 2 * (size_t)(N * 8 / 8.0), "EliasFanoNSGGraph: overhead %zu", eg.overhead_in_bytes);
             check_graph("EliasFanoNSGGraph", eg, rows, N, K, false);
         }
         {

@@ -1,7 +1,8 @@
 """The C++ host side end to end: tests/cpp/plugin_main.cpp drives the reference's plugin classes as defined by
 csrc/plugin/idc_faiss_plugin.h (on top of the C ABI, Faiss replaced by tests/faiss_shim.h) the way the reference's
 tests do (test_compressed_ivfs.py:26-90, test_altid.py:19-44). CPU: it compiles, links against libidcodec.so and
-fails loudly without a device. GPU: every check passes (first run on a B200: profiles/r1_plugin_cpp_b200.txt)."""
+fails loudly without a device. GPU: every check passes (first run on a B200: profiles/r1_plugin_cpp_b200.txt).
+Named zz so that it runs after the parity suites. `plugin_main --all` adds the packed-bits classes (not yet run on a GPU)."""
 import subprocess
 from pathlib import Path
 

@@ -81,7 +81,10 @@ class CompactBitNSGGraph(_CompressedGraph):
             self.bits += 1
         self.stride = (self.K * self.bits + 7) // 8
         vals = graph.data.astype(np.int64)
-        vals[vals == -1] = self.N
+        marker = vals == -1
+        ended = np.cumsum(marker, axis=1)       # >= 1 from the first -1 of a row on
+        vals[ended >= 1] = 0                    # nothing is written behind the end marker: the bytes stay zero
+        vals[marker & (ended == 1)] = self.N    # writer.write(N, bits); break;  (altid_impl.cpp:30-33)
         # one packed string per row, each padded to `stride` bytes
         per_row_bits = self.stride * 8
         flat = self.ctx.bits_pack(vals.ravel().astype(np.uint64), self.bits) if per_row_bits == self.K * self.bits else None

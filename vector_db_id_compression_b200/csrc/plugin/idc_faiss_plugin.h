@@ -10,6 +10,7 @@
 // members used here (tests/test_cabi_cpu.py::test_plugin_header_compiles).
 #pragma once
 
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -211,6 +212,54 @@ struct CompressedIDInvertedListsEliasFano : InvertedListsArrayCodes {
     }
 };
 
+/// Fixed-width ids (the baseline of every result table). custom_invlists_impl.h:37-53, .cpp:62-118.
+/// NOTE: compiled and linked (tests/test_cabi_cpu.py), exercised by `plugin_main --all`; not yet run on a GPU.
+struct CompressedIDInvertedListsPackedBits : InvertedListsArrayCodes {
+    int bits = 0;
+    std::vector<std::vector<uint8_t>> ids_all;
+    size_t compressed_ids_size_in_bytes = 0;
+    size_t codes_size_in_bytes = 0;
+    size_t overhead_in_bytes = 0;
+
+    explicit CompressedIDInvertedListsPackedBits(const faiss::InvertedLists& il) : InvertedListsArrayCodes(il) {
+        idc_plugin::Csr csr(il);
+        size_t ntotal = csr.ids.size();  // il.compute_ntotal(), :66
+        while ((1ull << bits) < ntotal + 1) bits++;  // :67
+        codes_all.resize(nlist);
+        ids_all.resize(nlist);
+        for (size_t l = 0; l < nlist; l++) {
+            size_t ls = il.list_size(l);
+            const faiss::idx_t* ids = csr.ids.data() + csr.offsets[l];
+            for (size_t i = 0; i < ls; i++)
+                if (ids[i] < 0 || (size_t)ids[i] >= ntotal)
+                    throw std::runtime_error("Error: 'ids_in[i] >= 0 && ids_in[i] < ntotal' failed");  // :87
+            ids_all[l].resize((ls * bits + 7) / 8);  // one BitstringWriter per list, :82-84
+            if (ls)
+                idc_plugin::check(idc_bits_pack(idc_plugin::context(), ls, ids, 8, IDC_MEM_HOST, bits, ids_all[l].data(),
+                                                ids_all[l].size(), IDC_MEM_HOST));
+            compressed_ids_size_in_bytes += ids_all[l].size();
+            take_codes(il, l, nullptr);
+            codes_size_in_bytes += codes_all[l].size();
+        }
+    }
+
+    const idx_t* get_ids(size_t list_no) const override {  // :96-106
+        size_t ls = list_size(list_no);
+        idx_t* the_ids = new idx_t[ls];
+        if (ls)
+            idc_plugin::check(idc_bits_unpack(idc_plugin::context(), ls, ids_all[list_no].data(), ids_all[list_no].size(),
+                                              IDC_MEM_HOST, bits, the_ids, 8, IDC_MEM_HOST));
+        return the_ids;
+    }
+    idx_t get_single_id(size_t list_no, size_t offset) const override {  // BitstringReader_get_bits, :35-58,109-114
+        const std::vector<uint8_t>& code = ids_all[list_no];
+        uint64_t v = 0;
+        for (size_t b = 0, pos = offset * bits; b < (size_t)bits; b++, pos++)
+            v |= (uint64_t)((code[pos >> 3] >> (pos & 7)) & 1u) << b;
+        return (idx_t)v;
+    }
+};
+
 /// Wavelet-tree ids. custom_invlists_impl.h:100-124, .cpp:346-397: one structure over S[id] = list_no,
 /// get_single_id(list_no, offset) = wt.select(offset + 1, list_no). wt_type 1 (rrr_vector<63>) throws: not implemented.
 struct CompressedIDInvertedListsWaveletTree : InvertedListsArrayCodes {
@@ -254,6 +303,45 @@ struct CompressedIDInvertedListsWaveletTree : InvertedListsArrayCodes {
     }
 };
 
+/// Fixed-width edges, N marks the end of a row. altid_impl.h:29-39, .cpp:20-51.
+/// NOTE: compiled and linked, exercised by `plugin_main --all`; not yet run on a GPU.
+struct CompactBitNSGGraph : faiss::nsg::Graph<int32_t> {
+    int bits = 0;
+    size_t stride = 0;
+    std::vector<uint8_t> compressed_data;
+    explicit CompactBitNSGGraph(const faiss::nsg::Graph<int32_t>& graph) : faiss::nsg::Graph<int32_t>(graph.data, graph.N, graph.K) {
+        while ((1 << bits) < N + 1) bits++;  // :22-23
+        stride = ((size_t)K * bits + 7) / 8;
+        compressed_data.assign((size_t)N * stride, 0);
+        std::vector<int32_t> vals((size_t)N * K, 0);  // the row up to and including its end marker; zeros behind it
+        for (size_t i = 0; i < (size_t)N; i++)
+            for (size_t j = 0; j < (size_t)K; j++) {
+                int32_t v = graph.data[i * K + j];
+                vals[i * K + j] = v == -1 ? N : v;
+                if (v == -1) break;
+            }
+        if (stride * 8 == (size_t)K * bits) {  // rows are byte-aligned: the whole graph is one packed string
+            idc_plugin::check(idc_bits_pack(idc_plugin::context(), (uint64_t)N * K, vals.data(), 4, IDC_MEM_HOST, bits,
+                                            compressed_data.data(), compressed_data.size(), IDC_MEM_HOST));
+        } else {  // one BitstringWriter per row (:27), each padded to `stride` bytes
+            for (size_t i = 0; i < (size_t)N; i++)
+                idc_plugin::check(idc_bits_pack(idc_plugin::context(), K, vals.data() + i * K, 4, IDC_MEM_HOST, bits,
+                                                compressed_data.data() + i * stride, stride, IDC_MEM_HOST));
+        }
+        data = nullptr;  // :38
+    }
+    size_t get_neighbors(int i, int32_t* neighbors) const override {  // :41-51
+        std::vector<int32_t> row(K);
+        idc_plugin::check(idc_bits_unpack(idc_plugin::context(), K, compressed_data.data() + (size_t)i * stride, stride,
+                                          IDC_MEM_HOST, bits, row.data(), 4, IDC_MEM_HOST));
+        for (int j = 0; j < K; j++) {
+            if (row[j] == N) return j;
+            neighbors[j] = row[j];
+        }
+        return K;
+    }
+};
+
 /// altid_impl.h:42-50, .cpp:53-101
 struct EliasFanoNSGGraph : faiss::nsg::Graph<int32_t> {
     idc_ef_blob* blob = nullptr;
@@ -264,6 +352,7 @@ struct EliasFanoNSGGraph : faiss::nsg::Graph<int32_t> {
         idc_ef_info info;
         idc_plugin::check(idc_ef_blob_info(blob, &info));
         compressed_ids_size_in_bytes = info.bits_total / 8;
+        overhead_in_bytes = 2 * (size_t)(N * std::ceil(std::log2((double)N)) / 8.0);  // :56-57 list sizes + max ids
         data = nullptr;  // :89
     }
     ~EliasFanoNSGGraph() override { idc_ef_blob_free(blob); }
@@ -289,6 +378,7 @@ struct ROCNSGGraph : faiss::nsg::Graph<int32_t> {
         idc_roc_info info;
         idc_plugin::check(idc_roc_blob_info(blob, &info));
         compressed_ids_size_in_bytes = info.ans_bytes;  // :148
+        overhead_in_bytes = (size_t)(N * std::ceil(std::log2((double)N)) / 8.0);  // :106
         num_outgoing_edges.resize(N);
         std::vector<uint8_t> prec(N);
         idc_plugin::check(idc_roc_blob_export(blob, nullptr, nullptr, num_outgoing_edges.data(), prec.data(), nullptr, nullptr, nullptr));
