@@ -43,7 +43,8 @@ class EliasFanoNSGGraph(_CompressedGraph):
     def __init__(self, graph: FinalNSGGraph, ctx: Optional[capi.Context] = None):
         super().__init__(graph, ctx)
         # size of each friend list + max id value, altid_impl.cpp:56-57
-        self.overhead_in_bytes = int(2 * (self.N * math.ceil(math.log2(self.N)) / 8.0)) if self.N > 1 else 0
+        # two `size_t += double` statements: each truncates (N = 100: 87 + 87, not 175)
+        self.overhead_in_bytes = 2 * int(self.N * math.ceil(math.log2(self.N)) / 8.0) if self.N > 1 else 0
         self.blob = self.ctx.ef_encode_rows(graph.data)
         self.compressed_ids_size_in_bytes = self.blob.bits_total // 8  # :86-88
 
