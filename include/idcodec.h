@@ -56,10 +56,15 @@ typedef struct idc_bits_blob idc_bits_blob;
 
 /* Bind to a CUDA device, create the stream the codec launches on and upload
  * the constant tables (mt19937(1234) words of codec.h:16-18,38; reciprocals
- * for the uniform pop/push of codec.cpp:21-63). */
+ * for the uniform pop/push of codec.cpp:21-63). No device-global state is
+ * touched unless the environment asks for it: IDC_L2_FETCH=32|64|128 sets
+ * cudaLimitMaxL2FetchGranularity for the lifetime of the context (the ROC
+ * kernels read isolated 32-byte sectors); idc_ctx_destroy restores it. */
 int idc_ctx_create(int device, idc_ctx** out);
 /* Same, but launch on an existing cudaStream_t (e.g. torch's current stream). */
 int idc_ctx_create_on_stream(int device, void* cuda_stream, idc_ctx** out);
+/* Fails with IDC_ERR_ARG (and leaves the context intact) while blobs created by it are still alive: a blob returns
+ * its arrays to the context's pool when it is freed. */
 int idc_ctx_destroy(idc_ctx* ctx);
 int idc_ctx_synchronize(idc_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py "gpu_launches") */
@@ -158,7 +163,8 @@ int idc_roc_blob_import(
         const uint32_t* words,
         idc_roc_blob** out);
 
-/* Sample order recorded with IDC_F_WANT_ORDER: order[offsets[l] + t] is the
+/* Sample order recorded with IDC_F_WANT_ORDER: order[(offsets[l] - offsets[0]) + t]
+ * (rebased to the first list, like every decode output) is the
  * position inside list l (input order) of the id emitted at step t, which is
  * also index t of the decoded list -- the permutation applied to codes at
  * custom_invlists_impl.cpp:189-193. */

@@ -77,8 +77,10 @@ class Context:
         self.device = device
 
     def close(self) -> None:
+        """Destroy the context. Raises (and keeps the context) while blobs created by it are alive: they hand their
+        device arrays back to the context's pool when they are freed (idc_ctx_destroy refuses, include/idcodec.h)."""
         if getattr(self, "_h", None):
-            self._l.idc_ctx_destroy(self._h)
+            _check(self._l.idc_ctx_destroy(self._h))
             self._h = None
 
     def __del__(self):

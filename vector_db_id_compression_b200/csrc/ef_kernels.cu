@@ -42,6 +42,7 @@ struct EfChunk {
 
 struct idc_ef_blob {
     idc_ctx* ctx = nullptr;
+    idc::CtxRef ref;  // declared right after ctx: destroyed last, after the arrays went back to the pool
     uint64_t nlist = 0, total_ids = 0, low_words = 0, high_words = 0, bits_total = 0, nsamples = 0;
     uint32_t row_stride = 0;
     uint32_t max_l = 0;
@@ -317,6 +318,8 @@ struct EfDecArgs {
     uint64_t ntiles;
     uint32_t row_stride;        // != 0: row mode
     uint32_t low_stage_words;   // shared-memory words per warp for staging lower-bits words
+    uint64_t nrows;             // row mode: rows of the blob (row numbers on the device are checked against it)
+    uint32_t* status;           // row mode: kStRange is OR-ed in when a row number is out of range
 };
 
 // One warp per chunk of 16 64-bit words (= 32 32-bit words, one per lane) of the upper-bits vector:
@@ -341,7 +344,20 @@ __global__ void __launch_bounds__(kDecThreads, 6) k_ef_decode(EfDecArgs a) {
     uint32_t* s_low = reinterpret_cast<uint32_t*>(s_warp + 2u * kDecTile);
     uint64_t di = warp;
     if (a.row_stride) {
-        if (a.row_nos) di = (uint64_t)(uint32_t)a.row_nos[warp];
+        if (a.row_nos) {
+            // row numbers may live on the device (e.g. -1 padded neighbour arrays): checked here, like k_roc_decode
+            const int64_t r = (int64_t)a.row_nos[warp];
+            if (r < 0 || r >= (int64_t)a.nrows) {
+                OutT* o = reinterpret_cast<OutT*>(a.out) + warp * a.row_stride;
+                for (uint32_t t = lane; t < a.row_stride; t += 32) o[t] = (OutT)-1;
+                if (lane == 0) {
+                    if (a.counts) a.counts[warp] = 0u;
+                    atomicOr(a.status, kStRange);
+                }
+                return;
+            }
+            di = (uint64_t)r;
+        }
     } else if (a.sel_desc) {
         di = a.sel_desc[warp];
     }
@@ -680,8 +696,11 @@ int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_sel_desc, 
     // stage up to 33 groups of max_l words per warp, capped so that 6 CTAs of 8 warps still fit an SM
     uint32_t stage_words = std::min<uint32_t>(33u * b->max_l + 1u, 768u);
     stage_words = (stage_words + 3u) & ~3u;
+    IDC_TRY(c->status.reserve(64));
+    uint32_t* d_status = c->status.as<uint32_t>();
+    if (row_stride) IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
     EfDecArgs a{b->d_dir, b->d_low, b->d_high, d_sel_desc, d_sel_out, d_row_nos, out_dev, counts_dev, ntiles, row_stride,
-                stage_words};
+                stage_words, b->nlist, d_status};
     const uint32_t wpb = kDecThreads / 32;
     const uint32_t grid = (uint32_t)((ntiles + wpb - 1) / wpb);
     const size_t smem = (size_t)wpb * (2u * kDecTile + 4u * stage_words);
@@ -695,7 +714,10 @@ int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_sel_desc, 
             k_ef_decode<int32_t><<<grid, kDecThreads, smem, c->stream>>>(a);
     }
     IDC_TRY(check_last_launch("k_ef_decode"));
+    uint32_t st = 0;
+    if (row_stride) IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
+    IDC_REQUIRE((st & kStRange) == 0, IDC_ERR_ARG, "ef_decode_rows: a row number is out of range (such rows were set to -1)");
     return IDC_OK;
 }
 
@@ -714,6 +736,7 @@ int idc_ef_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const voi
     c->begin_call();
     std::unique_ptr<idc_ef_blob> b(new idc_ef_blob());
     b->ctx = c;
+    b->ref.bind(c);
     b->nlist = nlist;
     b->list_offsets.resize(nlist + 1);
     std::vector<uint64_t> src(nlist);
@@ -739,7 +762,9 @@ int idc_ef_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const voi
 int idc_ef_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* data, int data_mem, uint32_t flags,
                        idc_ef_blob** out) {
     IDC_REQUIRE(c && out && (data || nrows == 0), IDC_ERR_ARG, "idc_ef_encode_rows: null argument");
-    IDC_REQUIRE(K >= 1 && K <= kMaxUnit, IDC_ERR_ARG, "K out of range");
+    // what idc_ef_decode_rows can read back: a row's upper-bits vector (<= 3 K + 2 bits) must fit one decoder chunk
+    IDC_REQUIRE(K >= 1 && K <= kDecTile && 3ull * K + 2 <= 64ull * kDecChunkWords, IDC_ERR_ARG,
+                "K = %u out of range: rows of up to %u entries are supported", K, (unsigned)((64u * kDecChunkWords - 2u) / 3u));
     IDC_REQUIRE(nrows < (1ull << 32), IDC_ERR_ARG, "too many rows");
     *out = nullptr;
     std::lock_guard<std::mutex> lock(c->mu);
@@ -747,6 +772,7 @@ int idc_ef_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* da
     c->begin_call();
     std::unique_ptr<idc_ef_blob> b(new idc_ef_blob());
     b->ctx = c;
+    b->ref.bind(c);
     b->nlist = nrows;
     b->row_stride = K;
     const int32_t* d_data = data;
@@ -831,6 +857,16 @@ int idc_ef_decode(idc_ctx* c, const idc_ef_blob* b, const uint64_t* list_nos, ui
     uint64_t total_out = 0, ntiles = 0;
     uint32_t* t_desc = nullptr;
     uint64_t* t_out = nullptr;
+    {  // argument errors surface before anything is allocated
+        uint64_t want = 0;
+        if (list_nos == nullptr) want = b->total_ids;
+        else
+            for (uint64_t i = 0; i < nsel; i++) {
+                IDC_REQUIRE(list_nos[i] < b->nlist, IDC_ERR_ARG, "list_no out of range");
+                want += b->list_offsets[list_nos[i] + 1] - b->list_offsets[list_nos[i]];
+            }
+        IDC_REQUIRE(want == 0 || ids_out != nullptr, IDC_ERR_ARG, "ids_out is NULL");
+    }
     if (list_nos == nullptr) {
         // decode everything: tile i is chunk descriptor i, no per-call planning at all
         ntiles = b->ndir;

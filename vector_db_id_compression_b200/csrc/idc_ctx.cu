@@ -175,13 +175,17 @@ int idc_ctx_create_on_stream(int device, void* cuda_stream, idc_ctx** out) {
     cudaDeviceProp prop;
     IDC_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    // The ROC kernels read isolated 32-byte sectors (tree nodes, bucket records) scattered over GBs: ask L2 not
-    // to promote such misses to 64/128-byte DRAM fetches (measured 3 sectors fetched per sector used otherwise).
-    // A hint only; IDC_L2_FETCH=32|64|128 overrides it for experiments.
-    {
-        size_t gran = 32;
-        if (const char* e = getenv("IDC_L2_FETCH")) gran = (size_t)atoi(e);
-        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    // The ROC kernels read isolated 32-byte sectors (tree nodes, bucket records) scattered over GBs: L2 can be asked
+    // not to promote such misses to 64/128-byte DRAM fetches (measured 3 sectors fetched per sector used otherwise).
+    // That limit is DEVICE-GLOBAL -- it changes the behaviour of every other kernel of the process (Faiss, torch) --
+    // so it is opt-in: IDC_L2_FETCH=32|64|128 sets it for the lifetime of the context, idc_ctx_destroy puts the
+    // previous value back. bench.py opts in and says so in its config.
+    if (const char* e = getenv("IDC_L2_FETCH")) {
+        const size_t gran = (size_t)atoi(e);
+        size_t before = 0;
+        if ((gran == 32 || gran == 64 || gran == 128) && cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity) == cudaSuccess &&
+            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) == cudaSuccess)
+            c->l2_fetch_saved = before;
         cudaGetLastError();
     }
 
@@ -216,8 +220,13 @@ int idc_ctx_create(int device, idc_ctx** out) { return idc_ctx_create_on_stream(
 
 int idc_ctx_destroy(idc_ctx* c) {
     if (!c) return IDC_OK;
+    // blobs give their arrays back to the context's pool when they are freed: the context must outlive them
+    IDC_REQUIRE(c->live_blobs.load() == 0, IDC_ERR_ARG,
+                "idc_ctx_destroy: %d blob(s) of this context are still alive; free them first (the context was left intact)",
+                c->live_blobs.load());
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->l2_fetch_saved) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, c->l2_fetch_saved);
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (auto s : c->aux) cudaStreamDestroy(s);
     for (auto e : c->aux_done) cudaEventDestroy(e);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -104,6 +105,8 @@ struct idc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    std::atomic<int> live_blobs{0};  // blobs created by this context and not freed yet (idc_ctx_destroy refuses while > 0)
+    size_t l2_fetch_saved = 0;       // cudaLimitMaxL2FetchGranularity before this context changed it (0: untouched)
     int sm_count = 148;
     uint64_t launches = 0;
     bool timing = false;
@@ -146,6 +149,18 @@ struct idc_ctx {
 };
 
 namespace idc {
+
+// member of every blob: keeps the owning context's live-blob count
+struct CtxRef {
+    idc_ctx* c = nullptr;
+    void bind(idc_ctx* ctx) {
+        c = ctx;
+        c->live_blobs++;
+    }
+    ~CtxRef() {
+        if (c) c->live_blobs--;
+    }
+};
 
 // RAII helper: times one kernel launch when ctx->timing is on, counts it always
 struct LaunchScope {

@@ -38,6 +38,7 @@ using namespace idc;
 // --------------------------------------------------------------------------
 struct idc_roc_blob {
     idc_ctx* ctx = nullptr;
+    idc::CtxRef ref;  // declared right after ctx: destroyed last, after the arrays went back to the pool
     uint64_t nlist = 0, nunits = 0, total_ids = 0, total_words = 0, ans_bytes = 0;
     uint32_t max_unit = IDC_MAX_UNIT_DEFAULT, row_stride = 0;
     uint32_t max_n = 0;  // largest unit
@@ -865,6 +866,7 @@ int idc_roc_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const vo
     c->begin_call();
     std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
     b->ctx = c;
+    b->ref.bind(c);
     std::vector<uint32_t> posbase;
     IDC_TRY(plan_units_csr(b.get(), nlist, offsets, max_unit, posbase));
     uint64_t first = offsets[0], elems = offsets[nlist];
@@ -893,6 +895,7 @@ int idc_roc_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* d
     c->begin_call();
     std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
     b->ctx = c;
+    b->ref.bind(c);
     HostTrace tr("roc_encode_rows");
     b->row_stride = K;
     b->nlist = nrows;
@@ -981,6 +984,7 @@ int idc_roc_blob_import(idc_ctx* c, uint64_t nlist, const uint32_t* unit_n, cons
     *out = nullptr;
     std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
     b->ctx = c;
+    b->ref.bind(c);
     b->nlist = b->nunits = nlist;
     b->unit_n.assign(unit_n, unit_n + nlist);
     b->list_offsets.resize(nlist + 1);
@@ -1038,8 +1042,11 @@ int idc_roc_blob_order(const idc_roc_blob* b, uint32_t* order, int order_mem) {
     IDC_REQUIRE(b && order, IDC_ERR_ARG, "null argument");
     IDC_REQUIRE(b->d_order != nullptr, IDC_ERR_ARG, "blob was encoded without IDC_F_WANT_ORDER");
     IDC_CUDA(cudaSetDevice(b->ctx->device));
+    // d_order is indexed like the caller's id array (absolute element offsets); the export is rebased to the
+    // first list, like every decode output: order[(offsets[l] - offsets[0]) + t]
+    const uint64_t first = b->row_stride ? 0 : b->list_offsets[0];
     uint64_t elems = b->row_stride ? b->nlist * b->row_stride : b->total_ids;
-    IDC_CUDA(cudaMemcpyAsync(order, b->d_order, elems * 4,
+    IDC_CUDA(cudaMemcpyAsync(order, b->d_order + first, elems * 4,
                              order_mem == IDC_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
                              b->ctx->stream));
     IDC_CUDA(cudaStreamSynchronize(b->ctx->stream));
@@ -1070,6 +1077,16 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
     uint32_t *t_unit = nullptr;
     uint64_t *t_out = nullptr, *t_ws = nullptr;
     std::vector<uint32_t> t_ns;
+    {  // argument errors surface before any plan buffer is allocated
+        uint64_t want = 0;
+        if (list_nos == nullptr) want = b->total_ids;
+        else
+            for (uint64_t i = 0; i < nsel; i++) {
+                IDC_REQUIRE(list_nos[i] < b->nlist, IDC_ERR_ARG, "list_no %llu out of range", (unsigned long long)list_nos[i]);
+                want += b->list_offsets[list_nos[i] + 1] - b->list_offsets[list_nos[i]];
+            }
+        IDC_REQUIRE(want == 0 || ids_out != nullptr, IDC_ERR_ARG, "ids_out is NULL");
+    }
     if (list_nos == nullptr) {
         if (!mb->plan_ready) {
             std::vector<uint32_t> units(b->nunits);

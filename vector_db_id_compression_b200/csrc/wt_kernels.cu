@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(kThreads) k_wt_emit(WtEmitArgs a) {
 
 struct idc_wt_blob {
     idc_ctx* ctx = nullptr;
+    idc::CtxRef ref;  // declared right after ctx: destroyed last, after the arrays went back to the pool
     uint64_t nlist = 0, total_ids = 0;
     int wt_type = 0;
     WtShape sh{};
@@ -605,6 +606,7 @@ int idc_wt_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const voi
     c->begin_call();
     std::unique_ptr<idc_wt_blob> b(new idc_wt_blob());
     b->ctx = c;
+    b->ref.bind(c);
     b->nlist = nlist;
     b->wt_type = wt_type;
     b->list_offsets.resize(nlist + 1);
