@@ -41,11 +41,15 @@ def parse_args():
     ap.add_argument("--zipf-s", type=float, default=1.0, help="list-length exponent; 0 = equal-length control")
     ap.add_argument("--max-unit", type=int, default=65536)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per reference step / baseline sample")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--parity-frac", type=float, default=0.25, help="share of the ids checked bit-exact against the CPU reference")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = --steps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ef", action="store_true")
     ap.add_argument("--no-wt", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1-C4 / control / s=0.5 sub-objects (N=1 only)")
+    ap.add_argument("--no-accessors", action="store_true", help="skip the per-call accessor leg (N=1 only)")
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
 
@@ -135,17 +139,10 @@ def make_workload(args, device, seed):
 
 def unit_table(offsets: np.ndarray, max_unit: int):
     """(start, n) of every ROC unit, in blob order (mirrors the library's list -> unit split)."""
-    starts, ns = [], []
-    for l in range(offsets.size - 1):
-        s, e = int(offsets[l]), int(offsets[l + 1])
-        if e == s:
-            starts.append(s)
-            ns.append(0)
-            continue
-        for a in range(s, e, max_unit):
-            starts.append(a)
-            ns.append(min(max_unit, e - a))
-    return np.asarray(starts, dtype=np.int64), np.asarray(ns, dtype=np.int64)
+    from vector_db_id_compression_b200.sharding import unit_table as ut
+
+    _, starts, ns = ut(np.asarray(offsets).astype(np.int64), max_unit)
+    return starts, ns
 
 
 def pick_sample_units(ns: np.ndarray, budget_ids: int, rng, always=()):
@@ -183,14 +180,31 @@ def cpu_roundtrip(codec, sample_ids: np.ndarray, sample_off: np.ndarray, prec: n
 
 def precision_rule_np(max_ids: np.ndarray) -> np.ndarray:
     # ceil(log2(m)) == bit_length(m - 1) for m >= 1 (custom_invlists_impl.cpp:163-164)
-    m = np.maximum(max_ids.astype(np.int64) - 1, 0)
+    m = np.maximum(max_ids.astype(np.int64) - 1, 0).astype(np.uint64)
     out = np.zeros(m.size, dtype=np.uint8)
-    nz = m > 0
-    out[nz] = np.floor(np.log2(m[nz].astype(np.float64))).astype(np.uint8) + 1
-    # exact fix-up for float rounding near powers of two
-    for i in np.nonzero(nz)[0]:
-        out[i] = int(m[i]).bit_length()
+    for _ in range(64):
+        nz = m > 0
+        if not nz.any():
+            break
+        out[nz] += 1
+        m[nz] >>= np.uint64(1)
     return out
+
+
+def gather_units(ids, out, starts, ns, units, dev):
+    """ids (and decoded ids) of the given units, concatenated; vectorised index arithmetic on the device."""
+    import torch
+
+    n_u = torch.as_tensor(ns[units], device=dev)
+    s_u = torch.as_tensor(starts[units], device=dev)
+    soff = np.zeros(units.size + 1, dtype=np.uint64)
+    soff[1:] = np.cumsum(ns[units])
+    total = int(soff[-1])
+    base = torch.repeat_interleave(s_u - torch.as_tensor(soff[:-1].astype(np.int64), device=dev), n_u)
+    idx = base + torch.arange(total, device=dev, dtype=torch.int64)
+    sid = ids[idx].cpu().numpy().astype(np.uint64)
+    dec = out[idx].cpu().numpy().astype(np.uint64) if out is not None else None
+    return sid, soff, dec
 
 
 # ------------------------------------------------------------------ reference arm
@@ -209,11 +223,8 @@ def run_reference(args):
     rng = np.random.default_rng(args.seed)
 
     def gather(units):
-        soff = np.zeros(units.size + 1, dtype=np.uint64)
-        soff[1:] = np.cumsum(ns[units])
-        idx = torch.cat([torch.arange(int(starts[u]), int(starts[u] + ns[u]), device=dev) for u in units])
-        sid = ids[idx].cpu().numpy().astype(np.uint64)
-        prec = precision_rule_np(np.array([sid[int(soff[i + 1]) - 1] for i in range(units.size)]))
+        sid, soff, _ = gather_units(ids, None, starts, ns, units, dev)
+        prec = precision_rule_np(sid[soff[1:].astype(np.int64) - 1])
         return sid, soff, prec
 
     # pilot to size the per-step sample
@@ -256,7 +267,9 @@ def workload_config(args, sizes):
                     f"ROC unit = <= {args.max_unit} consecutive ids of a list",
         "n_ids_per_gpu": int(args.n_ids), "nlist": args.nlist, "zipf_s": args.zipf_s, "max_unit": args.max_unit,
         "l2_policy": "inputs (8 B/id) and outputs exceed the 126 MB L2 by >50x; no explicit flush",
-        "parallelism": "lists sharded across GPUs, no data-path collective",
+        "l2_fetch_granularity": os.environ.get("IDC_L2_FETCH", "driver default") + " B (IDC_L2_FETCH: opt-in, device-global, restored on ctx destroy)",
+        "parallelism": "value / e2e: one workload per GPU (weak scaling, no data-path collective); "
+                       "sharded: ONE index owned by rank 0, NCCL scatter of id blocks + gather of blobs (strong scaling)",
     }
 
 
@@ -281,6 +294,9 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The ROC kernels read isolated 32-byte sectors: the bench opts into the 32-byte L2 fetch granularity (a
+    # device-global limit, so the library leaves it alone unless asked; restored when the context is destroyed).
+    os.environ.setdefault("IDC_L2_FETCH", "32")
     from vector_db_id_compression_b200.capi import Context
 
     sizes, offsets, ids = make_workload(args, dev, args.seed + 7919 * rank)
@@ -289,79 +305,37 @@ def run_b200(args):
     ctx.set_timing(True)
 
     # ---------------- device-resident timed region (value)
-    kern_ms = {}
-
-    def one_step(collect: bool):
-        blob = ctx.roc_encode(offsets, ids, sorted_ids=True, max_unit=args.max_unit)
-        if collect:
-            for k, v in ctx.last_kernel_breakdown():
-                kern_ms.setdefault(k, []).append(v)
-        out, _ = blob.decode(device=dev)
-        if collect:
-            for k, v in ctx.last_kernel_breakdown():
-                kern_ms.setdefault(k, []).append(v)
-        return blob, out
-
-    blob = out = None
-    for _ in range(args.warmup):
-        if blob is not None:
-            blob.free()
-        blob, out = one_step(False)
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    launches0 = ctx.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        if blob is not None:
-            blob.free()
-        del out
-        blob, out = one_step(True)
-    ev1.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-    launches = ctx.launch_count - launches0
-    ms = ev0.elapsed_time(ev1)
-    t_dev = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    ms_max = float(t_dev.item())
+    t_leg = time.perf_counter()
+    timed = time_roc(args, ctx, offsets, ids, dev, args.steps, args.warmup, world, barrier, sample_clocks=local)
+    blob, out = timed["blob"], timed["out"]
+    ms_max = timed["ms_total"]
     value = n_ids * world * args.steps / (ms_max * 1e-3)
+    avg = timed["kernel_ms"]
+    legs = {"value": time.perf_counter() - t_leg}
 
-    # ---------------- parity: sampled units (+ the longest) against the CPU oracle; also the cpu_baseline
+    # ---------------- parity: sampled units (+ the longest) against the CPU reference; also the cpu_baseline
     info = dict(nunits=blob.nunits, ans_bytes=blob.ans_bytes, total_words=blob.total_words)
     parity = cpu_base = None
+    t_leg = time.perf_counter()
     if rank == 0 and not args.no_cpu_baseline:
-        parity, cpu_base = parity_and_cpu_baseline(args, blob, out, offsets, ids, dev)
+        parity, cpu_base = roc_parity(args, blob, out, offsets, ids, dev, frac=args.parity_frac, always_longest=32,
+                                      cpu_seconds=max(args.cpu_seconds, 40.0), one_thread=True)
     elif rank == 0:
         parity = {"checked": False}
+    legs["parity"] = time.perf_counter() - t_leg
 
     # ---------------- roofline of the dominant kernel (algorithmic bytes / event time)
     peak, peak_src = measured_peak_gbs()
-    avg = {k: float(np.mean(v)) for k, v in kern_ms.items()}
-    enc_bytes = 8.0 * n_ids + blob.ans_bytes          # read int64 ids, write streams
-    dec_bytes = blob.ans_bytes + 8.0 * n_ids          # read streams, write int64 ids
-    dom = max(("k_roc_encode", "k_roc_decode"), key=lambda k: avg.get(k, 0.0))
-    dom_bytes = enc_bytes if dom == "k_roc_encode" else dec_bytes
-    achieved = dom_bytes / (avg[dom] * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic(dom, n_ids, args.zipf_s)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": avg[dom],
-                "other": {k: {"ms": avg[k]} for k in avg if k != dom}}
-    for k, b in (("k_roc_encode", enc_bytes), ("k_roc_decode", dec_bytes)):
-        if k in avg and k != dom:
-            roofline["other"][k].update(achieved=b / (avg[k] * 1e-3) / 1e9, frac=b / (avg[k] * 1e-3) / 1e9 / peak)
+    roofline = roc_roofline(avg, n_ids, blob.ans_bytes, peak, peak_src, args)
     blob.free()
     del out
 
     # ---------------- Elias-Fano (the HBM-bound codec) on the same lists
     ef = None
     if not args.no_ef:
-        ef = ef_section(args, ctx, offsets, ids, dev, peak)
+        t_leg = time.perf_counter()
+        ef = ef_section(args, ctx, offsets, ids, dev, peak, cpu=(rank == 0 and not args.no_cpu_baseline))
+        legs["ef"] = time.perf_counter() - t_leg
 
     # ---------------- end to end through the C ABI with host buffers
     e2e = None
@@ -369,6 +343,7 @@ def run_b200(args):
         # every rank pins 16 GB of host memory for this leg; if the box cannot give that to all ranks the leg is
         # reported as failed (on every rank alike, so that the collectives inside stay matched) instead of taking
         # the device-resident numbers down with it
+        t_leg = time.perf_counter()
         ok_local = 1
         host_bufs = None
         try:
@@ -383,14 +358,46 @@ def run_b200(args):
             e2e = e2e_section(args, ctx, offsets, ids, world, dev, barrier, host_bufs)
         else:
             e2e = {"value": None, "unit": "ids/s", "error": "pinned host memory for the e2e leg not available on every rank"}
+        del host_bufs
+        legs["e2e"] = time.perf_counter() - t_leg
 
-    # ---------------- wavelet tree (the third id index of the plugin surface) on the same lists (last: a failure here cannot touch the legs above)
+    # ---------------- the north-star multi-GPU path: ONE index owned by rank 0, NCCL scatter / encode / gather
+    sharded = None
+    if not args.no_sharded:
+        t_leg = time.perf_counter()
+        try:
+            sharded = sharded_section(args, ctx, offsets, ids, world, rank, dev, barrier)
+        except Exception as ex:  # noqa: BLE001
+            if world > 1:
+                raise  # a rank that left the collectives would hang the others: fail loudly instead
+            sharded = {"error": str(ex)}
+        legs["sharded"] = time.perf_counter() - t_leg
+
+    # ---------------- wavelet tree (the third id index of the plugin surface) on the same lists
     wt = None
     if not args.no_wt:
+        t_leg = time.perf_counter()
         try:
             wt = wt_section(args, ctx, offsets, ids, sizes, dev, peak)
         except Exception as ex:  # noqa: BLE001 -- never takes the headline numbers down with it
             wt = {"error": str(ex)}
+        legs["wt"] = time.perf_counter() - t_leg
+    del ids
+    torch.cuda.empty_cache()
+
+    # ---------------- the other configurations of BASELINE.json, the control and s = 0.5 (one GPU, rank 0)
+    configs = accessors = None
+    if world == 1 and not args.no_configs:
+        t_leg = time.perf_counter()
+        configs = configs_section(args, ctx, dev, peak)
+        legs["configs"] = time.perf_counter() - t_leg
+    if world == 1 and not args.no_accessors:
+        t_leg = time.perf_counter()
+        try:
+            accessors = accessors_section(args)
+        except Exception as ex:  # noqa: BLE001
+            accessors = {"error": str(ex)}
+        legs["accessors"] = time.perf_counter() - t_leg
 
     if rank == 0:
         line = {
@@ -398,97 +405,179 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": workload_config(args, sizes),
-            "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "parity": parity,
+            "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "gpu_launches": int(timed["launches"]),
+            "clocks": timed["clocks"], "parity": parity,
             "roc": {"encode_ids_per_s": n_ids / (sum(avg.get(k, 0) for k in ("k_unit_meta", "k_enc_records", "k_roc_encode", "k_roc_compact")) * 1e-3),
                     "decode_ids_per_s": n_ids / (sum(avg.get(k, 0) for k in ("memset_ws", "k_roc_decode")) * 1e-3),
                     "bits_per_id": 8.0 * info["ans_bytes"] / n_ids, "units": info["nunits"],
-                    "wall_ms_per_step": 1e3 * t_wall / args.steps},
-            "ef": ef, "wt": wt,
+                    "wall_ms_per_step": 1e3 * timed["wall_s"] / args.steps},
+            "ef": ef, "wt": wt, "sharded": sharded, "configs": configs, "accessors": accessors,
+            "leg_seconds": {k: round(v, 2) for k, v in legs.items()},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def parity_and_cpu_baseline(args, blob, out, offsets, ids, dev):
-    """Bit-exact check of a sample of units against the CPU codec, which is timed on the way (cpu_baseline)."""
+def time_roc(args, ctx, offsets, ids, dev, steps, warmup, world, barrier, sample_clocks=None, max_unit=None):
+    """W warm-up + K timed steps of ROC encode-everything + decode-everything with the ids resident in HBM; CUDA
+    events on the codec's stream, max over ranks. Returns the last blob / output for the parity check."""
     import torch
+    import torch.distributed as dist
 
+    mu = max_unit or args.max_unit
+    kern_ms = {}
+
+    def one_step(collect: bool):
+        blob = ctx.roc_encode(offsets, ids, sorted_ids=True, max_unit=mu)
+        if collect:
+            for k, v in ctx.last_kernel_breakdown():
+                kern_ms.setdefault(k, []).append(v)
+        out, _ = blob.decode(device=dev)
+        if collect:
+            for k, v in ctx.last_kernel_breakdown():
+                kern_ms.setdefault(k, []).append(v)
+        return blob, out
+
+    blob = out = None
+    for _ in range(warmup):
+        if blob is not None:
+            blob.free()
+        blob, out = one_step(False)
+    sampler = ClockSampler(sample_clocks) if sample_clocks is not None else None
+    barrier()
+    if sampler:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(steps):
+        if blob is not None:
+            blob.free()
+        del out
+        blob, out = one_step(True)
+    ev1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    ms = ev0.elapsed_time(ev1)
+    t_dev = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    return {"blob": blob, "out": out, "ms_total": float(t_dev.item()), "wall_s": t_wall, "clocks": clocks,
+            "launches": ctx.launch_count - launches0, "kernel_ms": {k: float(np.mean(v)) for k, v in kern_ms.items()}}
+
+
+def roc_roofline(avg, n_ids, ans_bytes, peak, peak_src, args, traffic_ok=True):
+    enc_bytes = 8.0 * n_ids + ans_bytes          # read int64 ids, write streams
+    dec_bytes = ans_bytes + 8.0 * n_ids          # read streams, write int64 ids
+    dom = max(("k_roc_encode", "k_roc_decode"), key=lambda k: avg.get(k, 0.0))
+    dom_bytes = enc_bytes if dom == "k_roc_encode" else dec_bytes
+    achieved = dom_bytes / (avg[dom] * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(dom, n_ids, args.zipf_s) if traffic_ok else (None, None)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": avg[dom],
+                "other": {k: {"ms": avg[k]} for k in avg if k != dom}}
+    for k, b in (("k_roc_encode", enc_bytes), ("k_roc_decode", dec_bytes)):
+        if k in avg and k != dom:
+            roofline["other"][k].update(achieved=b / (avg[k] * 1e-3) / 1e9, frac=b / (avg[k] * 1e-3) / 1e9 / peak)
+    return roofline
+
+
+def roc_parity(args, blob, out, offsets, ids, dev, frac, always_longest=0, cpu_seconds=40.0, one_thread=False, max_unit=None):
+    """Bit-exact check of `frac` of the ids (whole units, uniform random + the longest) against the CPU codec:
+    (head, words) of every checked unit byte-equal, precision per the reference rule, decoded array equal INCLUDING
+    order. The CPU codec is timed on the way (cpu_baseline)."""
     codec, kind = cpu_codec()
     threads = os.cpu_count() or 1
     ex = blob.export()
-    starts, ns = unit_table(offsets, args.max_unit)
+    starts, ns = unit_table(offsets, max_unit or args.max_unit)
     assert ns.size == blob.nunits
     rng = np.random.default_rng(99)
-    longest = np.argsort(-ns, kind="stable")[:32]
-
-    def gather(units):
-        soff = np.zeros(units.size + 1, dtype=np.uint64)
-        soff[1:] = np.cumsum(ns[units])
-        idx = torch.cat([torch.arange(int(starts[u]), int(starts[u] + ns[u]), device=dev) for u in units])
-        sid = ids[idx].cpu().numpy().astype(np.uint64)
-        dec = out[idx].cpu().numpy().astype(np.uint64)
-        return sid, soff, dec
-
-    # pilot -> budget
-    pilot = pick_sample_units(ns, max(200_000, 2 * int(ns.max())), rng)
-    sid, soff, _ = gather(pilot)
-    prec = ex["precision"][pilot].astype(np.uint8)
-    te, td, _ = cpu_roundtrip(codec, sid, soff, prec, threads)
-    rate = sid.size / (te + td)
-    budget = int(max(0.01 * ids.numel(), rate * args.cpu_seconds))
-    units = pick_sample_units(ns, budget, rng, always=[int(u) for u in longest])
-    sid, soff, gdec = gather(units)
+    n_total = int(ns.sum())
+    longest = np.argsort(-ns, kind="stable")[:always_longest]
+    if frac >= 1.0:
+        units = np.nonzero(ns > 0)[0]
+    else:
+        # pilot -> what the CPU can do in cpu_seconds caps the sample
+        pilot = pick_sample_units(ns, max(200_000, 2 * int(ns.max())), rng)
+        sid, soff, _ = gather_units(ids, None, starts, ns, pilot, dev)
+        te, td, _ = cpu_roundtrip(codec, sid, soff, ex["precision"][pilot].astype(np.uint8), threads)
+        rate = sid.size / (te + td)
+        budget = int(min(frac * n_total, max(0.01 * n_total, rate * cpu_seconds)))
+        units = pick_sample_units(ns, budget, rng, always=[int(u) for u in longest])
+    sid, soff, gdec = gather_units(ids, out, starts, ns, units, dev)
     prec = ex["precision"][units].astype(np.uint8)
     te, td, (heads, nwords, woff, words, cdec) = cpu_roundtrip(codec, sid, soff, prec, threads)
-    bad = 0
-    for i, u in enumerate(units):
-        w0, w1 = int(ex["word_offsets"][u]), int(ex["word_offsets"][u + 1])
-        cw = words[int(woff[i]): int(woff[i]) + int(nwords[i])]
-        a, b = int(soff[i]), int(soff[i + 1])
-        ok = (int(ex["heads"][u]) == int(heads[i]) and w1 - w0 == cw.size and np.array_equal(ex["words"][w0:w1], cw)
-              and np.array_equal(gdec[a:b], cdec[a:b]))
-        mx = int(sid[b - 1])
-        ok = ok and int(prec[i]) == (mx - 1).bit_length()
-        bad += 0 if ok else 1
+    # vectorised comparison: heads, word counts, precisions per unit; words and decoded ids as flat arrays
+    wo = ex["word_offsets"].astype(np.int64)
+    g_nw = (wo[units + 1] - wo[units])
+    c_nw = np.asarray(nwords[: units.size]).astype(np.int64)
+    unit_ok = (ex["heads"][units] == np.asarray(heads[: units.size])) & (g_nw == c_nw)
+    last = sid[soff[1:].astype(np.int64) - 1]
+    unit_ok &= prec == precision_rule_np(last)
+    both = np.nonzero(g_nw == c_nw)[0]
+    if both.size:
+        n_w = g_nw[both]
+        tot = int(n_w.sum())
+        rel = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(n_w) - n_w, n_w)
+        gw = ex["words"][np.repeat(wo[units[both]], n_w) + rel]
+        cw = words[np.repeat(np.asarray(woff[:-1]).astype(np.int64)[both], n_w) + rel]
+        neq = gw != cw
+        if neq.any():
+            unit_ok[both[np.unique(np.repeat(np.arange(both.size), n_w)[neq])]] = False
+    dneq = gdec != cdec[: gdec.size]
+    if dneq.any():
+        unit_ok[np.unique(np.repeat(np.arange(units.size), ns[units])[dneq])] = False
+    bad = int((~unit_ok).sum())
     parity = {"checked": True, "units_checked": int(units.size), "ids_checked": int(sid.size),
-              "fraction_of_ids": sid.size / ids.numel(), "includes_32_longest_units": True, "mismatching_units": bad,
-              "bit_exact": bad == 0, "against": kind}
+              "fraction_of_ids": sid.size / max(n_total, 1), "includes_longest_units": int(always_longest),
+              "mismatching_units": bad, "bit_exact": bad == 0, "against": kind,
+              "what": "(head, words) byte-equal, precision rule, decoded ids equal including order"}
     cpu_base = {"value": sid.size / (te + td), "unit": "ids/s", "cores": threads, "kind": kind,
-                "sample": f"{units.size} of {ns.size} ROC units ({sid.size} ids, uniform random units + the 32 longest), "
+                "sample": f"{units.size} of {ns.size} ROC units ({sid.size} ids, uniform random units"
+                          f"{' + the %d longest' % always_longest if always_longest else ''}), "
                           f"encode+decode once with {threads} OpenMP threads, schedule(dynamic)",
                 "encode_ids_per_s": sid.size / te, "decode_ids_per_s": sid.size / td, "seconds": te + td}
+    if one_thread:
+        small = pick_sample_units(ns, 1_500_000, np.random.default_rng(7))
+        s1, o1, _ = gather_units(ids, None, starts, ns, small, dev)
+        t1e, t1d, _ = cpu_roundtrip(codec, s1, o1, ex["precision"][small].astype(np.uint8), 1)
+        cpu_base["one_thread"] = {"value": s1.size / (t1e + t1d), "unit": "ids/s", "cores": 1, "ids": int(s1.size),
+                                  "encode_ids_per_s": s1.size / t1e, "decode_ids_per_s": s1.size / t1d}
     if bad:
         print(f"bench.py: PARITY FAILURE on {bad} units", file=sys.stderr)
     return parity, cpu_base
 
 
-def ef_section(args, ctx, offsets, ids, dev, peak):
+def ef_section(args, ctx, offsets, ids, dev, peak, cpu=False, steps=None, warmup=None):
     import torch
 
     n_ids = int(ids.numel())
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
     enc_ms, dec_ms, meta_ms = [], [], []
     eb = None
-    for it in range(args.warmup + args.steps):
+    for it in range(warmup + steps):
         if eb is not None:
             eb.free()
         eb = ctx.ef_encode(offsets, ids, sorted_ids=True)
         be = dict(ctx.last_kernel_breakdown())
         out, _ = eb.decode(device=dev)
         bd = dict(ctx.last_kernel_breakdown())
-        if it >= args.warmup:
+        if it >= warmup:
             enc_ms.append(be["k_ef_encode"])
             meta_ms.append(be.get("k_unit_meta", 0.0))
             dec_ms.append(bd["k_ef_decode"])
     exact = bool(torch.equal(out, ids))
     comp = eb.bits_total / 8.0
-    eb.free()
     del out
     e, d = float(np.mean(enc_ms)), float(np.mean(dec_ms))
     pm = float(np.mean(meta_ms))
-    return {
-        "bit_exact_roundtrip": exact, "bits_per_id": 8.0 * comp / n_ids,
+    res = {
+        "bit_exact_roundtrip": exact, "bits_per_id": 8.0 * comp / max(n_ids, 1),
         # prep = the metadata kernel in front of k_ef_encode (list ends for ascending input: the order / width check
         # of the ids happens inside k_ef_encode); frac_with_prep charges it to the encode
         "encode": {"kernel_ms": e, "prep_ms": pm, "ids_per_s": n_ids / (e * 1e-3),
@@ -497,6 +586,55 @@ def ef_section(args, ctx, offsets, ids, dev, peak):
         "decode": {"kernel_ms": d, "ids_per_s": n_ids / (d * 1e-3),
                    "achieved_GBs": (8.0 * n_ids + comp) / (d * 1e-3) / 1e9, "frac": (8.0 * n_ids + comp) / (d * 1e-3) / 1e9 / peak},
     }
+    if cpu:
+        res["cpu_baseline"], res["words_vs_restatement"] = ef_cpu_baseline(eb, offsets, ids, dev)
+    eb.free()
+    return res
+
+
+def ef_cpu_baseline(eb, offsets, ids, dev, budget_ids=60_000_000):
+    """The Elias-Fano restatement (oracle/ef_oracle.c: the reference class needs ot/succinct, absent) on a sample of
+    whole lists: OpenMP over lists like custom_invlists_impl.cpp:234 and one thread; its words are compared with the
+    GPU blob's on the way."""
+    import oracle
+
+    threads = os.cpu_count() or 1
+    off = np.asarray(offsets).astype(np.int64)
+    sizes = np.diff(off)
+    rng = np.random.default_rng(5)
+    # whole lists, none longer than a quarter of the budget (one 8.6e7-id list would be the whole sample)
+    cand = np.where(sizes <= budget_ids // 4, sizes, 0)
+    lists = pick_sample_units(cand, min(budget_ids, int(cand.sum())), rng)
+    sid, soff, _ = gather_units(ids, None, off[:-1], sizes, lists, dev)
+    t0 = time.perf_counter()
+    enc = oracle.ef.encode_lists(soff, sid, nthreads=threads)
+    t1 = time.perf_counter()
+    dec = oracle.ef.decode_lists(soff, enc, nthreads=threads)
+    t2 = time.perf_counter()
+    small = lists[: max(1, lists.size // 16)]
+    s1, o1, _ = gather_units(ids, None, off[:-1], sizes, small, dev)
+    t3 = time.perf_counter()
+    e1 = oracle.ef.encode_lists(o1, s1, nthreads=1)
+    t4 = time.perf_counter()
+    oracle.ef.decode_lists(o1, e1, nthreads=1)
+    t5 = time.perf_counter()
+    # bit level: the blob's words of the sampled lists against the restatement's
+    ex = eb.export()
+    ok = bool(np.array_equal(dec, sid)) and bool(np.array_equal(ex["l"][lists], enc["l"][: lists.size]))
+    for name in ("low", "high"):
+        go = ex[name + "_offsets"].astype(np.int64)
+        n_w = np.diff(enc[name + "_off"].astype(np.int64))
+        ok = ok and bool(np.array_equal(go[lists + 1] - go[lists], n_w))
+        if not ok:
+            break
+        tot = int(n_w.sum())
+        rel = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(n_w) - n_w, n_w)
+        ok = ok and bool(np.array_equal(ex[name][np.repeat(go[lists], n_w) + rel], enc[name][:tot]))
+    base = {"value": sid.size / (t2 - t0), "unit": "ids/s", "cores": threads, "kind": "port",
+            "sample": f"{lists.size} whole lists ({sid.size} ids), OpenMP over lists, {threads} threads",
+            "encode_ids_per_s": sid.size / (t1 - t0), "decode_ids_per_s": sid.size / (t2 - t1),
+            "one_thread": {"encode_ids_per_s": s1.size / (t4 - t3), "decode_ids_per_s": s1.size / (t5 - t4), "ids": int(s1.size)}}
+    return base, {"lists": int(lists.size), "ids": int(sid.size), "bit_equal": ok}
 
 
 def wt_section(args, ctx, offsets, ids, sizes, dev, peak):
@@ -565,6 +703,7 @@ def e2e_section(args, ctx, offsets, ids, world, dev, barrier, host_bufs):
     import torch.distributed as dist
 
     n_ids = int(ids.numel())
+    steps = args.e2e_steps or args.steps
     host_in, host_out = host_bufs
     hin, hout = host_in.numpy(), host_out.numpy()
     from vector_db_id_compression_b200 import capi
@@ -581,19 +720,371 @@ def e2e_section(args, ctx, offsets, ids, world, dev, barrier, host_bufs):
     step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
+    for _ in range(steps):
         step()
     barrier()
-    t = time.perf_counter() - t0
-    tt = torch.tensor([t], device=dev, dtype=torch.float64)
+    t_local = time.perf_counter() - t0
+    tt = torch.tensor([t_local], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t = float(tt.item())
-    ok = bool(torch.equal(torch.sort(host_out[: int(offsets[1])])[0], host_in[: int(offsets[1])]))
-    return {"value": n_ids * world * args.e2e_steps / t, "unit": "ids/s", "h2d_bytes_per_step": 8 * n_ids,
-            "d2h_bytes_per_step": 8 * n_ids, "steps": args.e2e_steps, "ms_per_step": 1e3 * t / args.e2e_steps,
-            "first_list_roundtrip_ok": ok,
+    # the whole round trip: every decoded list, sorted, equals its input list (a checksum of the sorted output per
+    # list would hide nothing more: the comparison runs on the GPU over all ids of this rank)
+    back = host_out.to(dev, non_blocking=False)
+    lab = torch.repeat_interleave(torch.arange(offsets.size - 1, device=dev, dtype=torch.int64),
+                                  torch.as_tensor(np.diff(offsets.astype(np.int64)), device=dev))
+    key, _ = torch.sort(back + (lab << 32))
+    ok = bool(torch.equal(key - (lab << 32), ids))
+    del back, lab, key
+    # per-rank PCIe rates: 8 B/id up during the encode, 8 B/id down during the decode, overlapped with the kernels
+    gbs = 16.0 * n_ids / t_local / 1e9 * steps
+    rates = [gbs]
+    if world > 1:
+        allr = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allr, torch.tensor([gbs], device=dev, dtype=torch.float64))
+        rates = [float(x.item()) for x in allr]
+    return {"value": n_ids * world * steps / t, "unit": "ids/s", "h2d_bytes_per_step": 8 * n_ids,
+            "d2h_bytes_per_step": 8 * n_ids, "steps": steps, "ms_per_step": 1e3 * t / steps,
+            "roundtrip_all_lists_ok": ok, "pcie_GBs_per_rank": [round(r, 2) for r in rates],
             "path": "idc_roc_encode(IDC_MEM_HOST, pinned) -> idc_roc_decode(IDC_MEM_HOST, pinned)"}
+
+
+# ------------------------------------------------------------------ sharded (rank 0 owns the index)
+
+def sharded_section(args, ctx, offsets, ids, world, rank, dev, barrier):
+    """BASELINE.json C5 / C4 as the north star states them: ONE index owned by rank 0; NCCL over NVLink scatters the
+    raw id blocks and gathers the compressed blobs, every rank encodes (and decodes) its share. Device buffers end to
+    end. Reported next to the 1-GPU encode of the same index measured in the same run on rank 0."""
+    import torch
+    import torch.distributed as dist
+
+    from vector_db_id_compression_b200 import sharding, workloads as W
+
+    codec = sharding.RocCudaCodec(ctx, args.max_unit)
+    res = {"n_ranks": world, "what": "rank 0 owns the index: tensor broadcast of the offsets, contiguous-unit-range "
+           "plan, ncclSend/Recv of id slices, per-rank idc_roc_encode, gather-v of device payloads, idc_roc_blob_assemble"}
+
+    def maxr(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run(name, off, idt, reps):
+        n = int(off[-1] - off[0]) if rank == 0 else 0
+        nt = torch.tensor([n], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.broadcast(nt, src=0)
+        n = int(nt.item())
+        # -- whole step, CUDA events on the current stream (NCCL waits are stream-ordered), max over ranks
+        step_ms, whole, local_blob, plan = [], None, None, None
+        for it in range(1 + reps):
+            if whole is not None:
+                whole.free()
+            if local_blob is not None:
+                local_blob.free()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            whole, local_blob, plan = sharding.encode_sharded(off, idt, codec, dev)
+            e1.record()
+            torch.cuda.synchronize()
+            if it:
+                step_ms.append(maxr(e0.elapsed_time(e1)))
+        # -- phases (each closed by a device sync; max over ranks per phase)
+        marks = []
+
+        def tick(nm):
+            torch.cuda.synchronize()
+            marks.append((nm, time.perf_counter()))
+
+        if whole is not None:
+            whole.free()
+        local_blob.free()
+        barrier()
+        t0 = time.perf_counter()
+        whole, local_blob, plan = sharding.encode_sharded(off, idt, codec, dev, timer=tick)
+        phases, prev = {}, t0
+        for nm, t in marks:
+            phases[nm] = maxr(1e3 * (t - prev))
+            prev = t
+        # -- ids already resident per rank (no scatter)
+        mine = sharding.scatter_id_blocks(plan, idt, dev) if world > 1 else idt[int(plan["ecut"][0]): int(plan["ecut"][1])]
+        res_ms = []
+        for it in range(1 + reps):
+            if whole is not None:
+                whole.free()
+            local_blob.free()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            whole, local_blob, plan = sharding.encode_sharded(off, idt, codec, dev, resident_ids=mine)
+            e1.record()
+            torch.cuda.synchronize()
+            if it:
+                res_ms.append(maxr(e0.elapsed_time(e1)))
+        # -- every rank decodes its own units; round trip against its id block
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dec, _ = local_blob.decode(device=dev)
+        e1.record()
+        torch.cuda.synchronize()
+        dec_ms = maxr(e0.elapsed_time(e1))
+        lo = plan["local_offsets"][rank if world > 1 else 0].astype(np.int64)
+        lab = torch.repeat_interleave(torch.arange(lo.size - 1, device=dev, dtype=torch.int64), torch.as_tensor(np.diff(lo), device=dev))
+        srt, _ = torch.sort(dec[: mine.numel()] + (lab << 32))
+        rt_ok = torch.tensor([1 if bool(torch.equal(srt - (lab << 32), mine)) else 0], device=dev, dtype=torch.int32)
+        if world > 1:
+            dist.all_reduce(rt_ok, op=dist.ReduceOp.MIN)
+        del dec, lab, srt
+        out = {"n_ids": n, "step_ms": float(np.mean(step_ms)), "phases_ms": {k: round(v, 3) for k, v in phases.items()},
+               "resident_step_ms": float(np.mean(res_ms)), "decode_ms": dec_ms, "roundtrip_ok": bool(rt_ok.item()),
+               "ids_per_s_encode": n / (np.mean(step_ms) * 1e-3), "ids_per_s_encode_decode": n / ((np.mean(step_ms) + dec_ms) * 1e-3)}
+        # -- rank 0: the same index on ONE GPU, same run; assembled blob byte-identical?
+        if rank == 0:
+            one_ms = []
+            single = None
+            for it in range(1 + reps):
+                if single is not None:
+                    single.free()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                single = ctx.roc_encode(off, idt, sorted_ids=True, max_unit=args.max_unit)
+                e1.record()
+                torch.cuda.synchronize()
+                if it:
+                    one_ms.append(e0.elapsed_time(e1))
+            a, b = whole.export_payload(device=dev), single.export_payload(device=dev)
+            same = all(bool(torch.equal(a[k], b[k])) for k in a) and whole.ans_bytes == single.ans_bytes
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            d1, _ = single.decode(device=dev)
+            e1.record()
+            torch.cuda.synchronize()
+            one_dec = e0.elapsed_time(e1)
+            del d1, a, b
+            t1 = float(np.mean(one_ms))
+            out.update(byte_identical_to_one_gpu=bool(same), one_gpu_encode_ms=t1, one_gpu_decode_ms=one_dec,
+                       blob_bytes=int(single.ans_bytes),
+                       strong_efficiency=t1 / (world * out["step_ms"]),
+                       strong_efficiency_resident=t1 / (world * out["resident_step_ms"]),
+                       strong_efficiency_encode_decode=(t1 + one_dec) / (world * (out["step_ms"] + dec_ms)))
+            if world > 1:
+                sent = 8.0 * n * (world - 1) / world
+                out["scatter_GBs"] = sent / (phases["scatter"] * 1e-3) / 1e9 if phases.get("scatter") else None
+                out["gather_GBs"] = single.ans_bytes * (world - 1) / world / (phases["gather"] * 1e-3) / 1e9 if phases.get("gather") else None
+                enc_share = phases.get("encode", 0.0) / max(sum(phases.values()), 1e-9)
+                out["limiter"] = ("codec kernels: the serial chains of the longest units (up to max_unit steps of ~1.5 us) do not get "
+                                  "shorter when the units are spread over more GPUs" if enc_share > 0.6 else
+                                  "rank 0's NVLink egress (scatter) / ingress (gather) and host-side planning")
+            single.free()
+        if world > 1:
+            barrier()
+        whole and whole.free()
+        local_blob.free()
+        del mine
+        return out
+
+    res["c5"] = run("c5", offsets if rank == 0 else None, ids if rank == 0 else None, reps=2)
+    c4_off = c4_ids = None
+    if rank == 0:
+        c4_off, c4_ids = W.uniform_label_lists(10_000_000, 65536, 5, dev)
+    res["c4"] = run("c4", c4_off, c4_ids, reps=3)
+    return res
+
+
+# ------------------------------------------------------------------ the other configurations (N = 1)
+
+def configs_section(args, ctx, dev, peak):
+    """BASELINE.json configs[0..3], the equal-length control and Zipf s = 0.5 of SURVEY 8(d): value, parity against
+    the CPU reference (all lists for C1-C4), roofline fraction of the slower ROC kernel. Each leg is independent."""
+    import torch
+
+    from vector_db_id_compression_b200 import workloads as W
+
+    res = {}
+
+    def guard(name, fn):
+        t0 = time.perf_counter()
+        try:
+            res[name] = fn()
+        except Exception as ex:  # noqa: BLE001
+            res[name] = {"error": f"{type(ex).__name__}: {ex}"}
+        res[name]["seconds"] = round(time.perf_counter() - t0, 2)
+        torch.cuda.empty_cache()
+
+    def ivf(n, nlist, seed, frac, zipf=None, steps=5):
+        if zipf is None:
+            off, idt = W.uniform_label_lists(n, nlist, seed, dev)
+        else:
+            off, idt = W.random_partition_lists(n, W.zipf_sizes(n, nlist, zipf), seed, dev)
+        t = time_roc(args, ctx, off, idt, dev, steps, 3, 1, torch.cuda.synchronize)
+        par, cpu = roc_parity(args, t["blob"], t["out"], off, idt, dev, frac=frac, always_longest=8 if frac < 1 else 0,
+                              cpu_seconds=6.0)
+        roof = roc_roofline(t["kernel_ms"], n, t["blob"].ans_bytes, peak, "", args, traffic_ok=False)
+        bits = 8.0 * t["blob"].ans_bytes / n
+        t["blob"].free()
+        efr = ef_section(args, ctx, off, idt, dev, peak, cpu=False, steps=3, warmup=2)
+        return {"n_ids": n, "nlist": nlist, "value": n * steps / (t["ms_total"] * 1e-3), "unit": "ids/s",
+                "ms_per_step": t["ms_total"] / steps, "kernel_ms": {k: round(v, 4) for k, v in t["kernel_ms"].items()},
+                "roofline": {"kernel": roof["kernel"], "frac": roof["frac"], "achieved": roof["achieved"]},
+                "bits_per_id": bits, "parity": par, "cpu_baseline": {k: cpu[k] for k in ("value", "cores", "kind")},
+                "ef": {"encode_frac": efr["encode"]["frac"], "decode_frac": efr["decode"]["frac"],
+                       "encode_ms": efr["encode"]["kernel_ms"], "decode_ms": efr["decode"]["kernel_ms"],
+                       "roundtrip": efr["bit_exact_roundtrip"]}}
+
+    guard("c1", lambda: config_c1(ctx, dev))
+    guard("c2", lambda: ivf(1_000_000, 1024, 2, 1.0))
+    guard("c3", lambda: config_c3(args, ctx, dev, peak))
+    guard("c4", lambda: ivf(10_000_000, 65536, 5, 1.0))
+    n5 = int(args.n_ids)
+    guard("control", lambda: ivf(n5, args.nlist, 6, 0.01, zipf=0.0, steps=3))
+    guard("s05", lambda: ivf(n5, args.nlist, 7, 0.01, zipf=0.5, steps=3))
+    return res
+
+
+def config_c1(ctx, dev):
+    """configs[0]: IVF256,Flat on 100 k vectors of d = 64 (256-byte codes) through the plugin classes (the host-side
+    mirror of custom_invlists): per list decoded id set, code <-> id pairing, ROC streams against the CPU reference,
+    Elias-Fano in id order (test_compressed_ivfs.py:26-90)."""
+    from vector_db_id_compression_b200 import custom_invlists as ci
+
+    codec, kind = cpu_codec()
+    rng = np.random.default_rng(1)
+    nb, nlist, cs = 100_000, 256, 256
+    assign = rng.integers(0, nlist, size=nb)
+    codes = rng.integers(0, 256, size=(nb, cs), dtype=np.uint8)
+    il = ci.InvertedLists(nlist, cs)
+    order = np.argsort(assign, kind="stable")
+    bounds = np.searchsorted(assign[order], np.arange(nlist + 1))
+    for l in range(nlist):
+        idl = order[bounds[l]: bounds[l + 1]]
+        il.add_entries(l, idl, codes[idl])
+    t0 = time.perf_counter()
+    roc = ci.CompressedIDInvertedListsFenwickTree(il, ctx)
+    t1 = time.perf_counter()
+    ef = ci.CompressedIDInvertedListsEliasFano(il, ctx)
+    t2 = time.perf_counter()
+    roc.prefetch(range(nlist))
+    ef.prefetch(range(nlist))
+    t3 = time.perf_counter()
+    ex = roc.blob.export()
+    off, idc = il.csr()
+    prec = ex["precision"].astype(np.uint8)
+    heads, nwords, woff, words = codec.encode_lists(off, idc.astype(np.uint64), prec, nthreads=0)
+    cdec = codec.decode_lists(off, prec, woff, nwords, heads, words, nthreads=0)
+    bad = 0
+    for l in range(nlist):
+        a, b = int(off[l]), int(off[l + 1])
+        got = roc.get_ids(l)
+        w0, w1 = int(ex["word_offsets"][l]), int(ex["word_offsets"][l + 1])
+        cw = words[int(woff[l]): int(woff[l]) + int(nwords[l])]
+        ok = (np.array_equal(np.sort(got), idc[a:b]) and np.array_equal(got.astype(np.uint64), cdec[a:b])
+              and int(ex["heads"][l]) == int(heads[l]) and np.array_equal(ex["words"][w0:w1], cw)
+              and np.array_equal(roc.get_codes(l), codes[got])            # code j belongs to id j
+              and np.array_equal(ef.get_ids(l), idc[a:b]) and np.array_equal(ef.get_codes(l), codes[idc[a:b]]))
+        bad += 0 if ok else 1
+    return {"n_ids": nb, "nlist": nlist, "code_size": cs, "lists_checked": nlist, "mismatching_lists": bad,
+            "bit_exact": bad == 0, "against": kind,
+            "what": "plugin classes: ROC (head, words) and decode order vs the reference, id sets, code <-> id pairing, EF in id order",
+            "roc_ctor_ms": 1e3 * (t1 - t0), "ef_ctor_ms": 1e3 * (t2 - t1), "decode_all_ms": 1e3 * (t3 - t2),
+            "roc_bits_per_id": 8.0 * roc.compressed_ids_size_in_bytes / nb, "ef_bits_per_id": 8.0 * ef.compressed_ids_size_in_bytes / nb}
+
+
+def config_c3(args, ctx, dev, peak):
+    """configs[2]: NSG-like adjacency, 1 M rows x K = 64, int32: row encode, decode of all rows, 10^7 random rows
+    (device-resident row numbers), for Elias-Fano and ROC; ROC streams of ALL rows against the CPU reference."""
+    import torch
+
+    from vector_db_id_compression_b200 import workloads as W
+
+    N, K = 1_000_000, 64
+    data, _ = W.nsg_like_graph(N, K, 3, dev)
+    deg = (data >= 0).sum(1)
+    edges = int(deg.sum())
+    sel = torch.randint(0, N, (10_000_000,), generator=torch.Generator(device=dev).manual_seed(4), device=dev, dtype=torch.int32)
+    big = torch.full_like(data, 2**31 - 1)
+    srt = torch.sort(torch.where(data >= 0, data, big), dim=1)[0]
+
+    def timed(fn, reps=3):
+        best, r = 1e9, None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            r = fn()
+            ctx.synchronize()
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t)
+        return r, best
+
+    out = {"rows": N, "K": K, "edges": edges}
+    for name, enc in (("ef", ctx.ef_encode_rows), ("roc", ctx.roc_encode_rows)):
+        blob, te = timed(lambda: enc(data), reps=3)
+        (nb, cnt), td = timed(lambda: blob.decode_rows(device=dev))
+        kms = ctx.last_kernel_ms()
+        (nb2, cnt2), tr = timed(lambda: blob.decode_rows(sel, device=dev), reps=2)
+        got = torch.sort(torch.where(nb >= 0, nb, big), dim=1)[0]
+        ok = bool(torch.equal(got, srt)) and bool(torch.equal(cnt.long(), deg)) and bool(torch.equal(nb2, nb[sel.long()]))
+        size = blob.bits_total / 8 if name == "ef" else blob.ans_bytes
+        alg = size + 4.0 * edges
+        r = {"bits_per_edge": 8 * size / edges, "encode_ms": 1e3 * te, "encode_edges_per_s": edges / te,
+             "decode_all_ms": 1e3 * td, "decode_all_kernel_ms": kms, "decode_edges_per_s": edges / td,
+             "decode_frac": alg / (kms * 1e-3) / 1e9 / peak if kms else None,
+             "random_rows": int(sel.numel()), "random_ms": 1e3 * tr, "random_rows_per_s": sel.numel() / tr, "roundtrip_ok": ok}
+        if name == "roc":
+            # all rows against the reference: (head, words) per row and the decode order
+            codec, kind = cpu_codec()
+            ex = blob.export()
+            degh = deg.cpu().numpy().astype(np.int64)
+            off = np.zeros(N + 1, np.uint64)
+            off[1:] = np.cumsum(degh)
+            flat = data[data >= 0].cpu().numpy().astype(np.uint64)  # row-major: row i's ids in input order
+            prec = ex["precision"].astype(np.uint8)
+            heads, nwords, woff, words = codec.encode_lists(off, flat, prec, nthreads=0)
+            cdec = codec.decode_lists(off, prec, woff, nwords, heads, words, nthreads=0)
+            wo = ex["word_offsets"].astype(np.int64)
+            nw = np.asarray(nwords[:N]).astype(np.int64)
+            same = bool(np.array_equal(ex["heads"], np.asarray(heads[:N]))) and bool(np.array_equal(np.diff(wo), nw))
+            if same:
+                rel = np.arange(int(nw.sum()), dtype=np.int64) - np.repeat(np.cumsum(nw) - nw, nw)
+                same = bool(np.array_equal(ex["words"], words[np.repeat(np.asarray(woff[:-1]).astype(np.int64), nw) + rel]))
+            gflat = nb[nb >= 0].cpu().numpy().astype(np.uint64)
+            same = same and bool(np.array_equal(gflat, cdec))
+            r["parity"] = {"rows_checked": N, "bit_exact": same, "against": kind,
+                           "what": "(head, words) of every row and the decoded order"}
+        else:
+            r["parity"] = {"rows_checked": N, "value_exact": ok, "what": "decoded rows = sorted input rows (all rows)"}
+        out[name] = r
+        blob.free()
+    return out
+
+
+# ------------------------------------------------------------------ per-call accessors (N = 1)
+
+def accessors_section(args):
+    """The path the reference's drivers time: per-call get_neighbors / get_ids / deferred translation through the C++
+    adapter (tools/accessor_bench.cpp, built by build()), with the CPU reference's per-row / per-list decode beside it."""
+    exe = ROOT / "tools" / "accessor_bench"
+    if not exe.exists():
+        return {"error": "tools/accessor_bench not built (run __graft_entry__.build())"}
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    if r.returncode != 0:
+        return {"error": f"accessor_bench exit {r.returncode}: {r.stderr[-400:]}"}
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    # CPU reference for the same shapes: single-thread per-row decode of K = 64 rows, per-list decode of ~977-id lists
+    codec, kind = cpu_codec()
+    rng = np.random.default_rng(3)
+    for name, n, count, bits in (("row_K64", 64, 20000, 20), ("list_977", 977, 2000, 20)):
+        off = np.arange(count + 1, dtype=np.uint64) * n
+        ids = np.concatenate([np.sort(rng.choice(1 << bits, size=n, replace=False)) for _ in range(count)]).astype(np.uint64)
+        prec = np.full(count, bits, np.uint8)
+        heads, nwords, woff, words = codec.encode_lists(off, ids, prec, nthreads=1)
+        t0 = time.perf_counter()
+        codec.decode_lists(off, prec, woff, nwords, heads, words, nthreads=1)
+        dt = time.perf_counter() - t0
+        res.setdefault("cpu_reference", {})[name] = {"us_per_call": 1e6 * dt / count, "kind": kind, "threads": 1}
+    return res
 
 
 if __name__ == "__main__":

@@ -163,6 +163,42 @@ int idc_roc_blob_import(
         const uint32_t* words,
         idc_roc_blob** out);
 
+/* The wire form of a blob: what a gather over NCCL (or a file) carries. Per unit, in unit order: precision,
+ * head, number of stream words, the decoder's id-range hints [lo, hi] (min / max id of the unit: they only steer
+ * the decoder's speed, never its result); then all stream words back to back. `mem` says where the destination
+ * buffers live (IDC_MEM_HOST or IDC_MEM_DEVICE: device -> device copies, nothing touches the host). Any pointer
+ * may be NULL. Sizes: nunits entries each (idc_roc_blob_info), words: total_words. */
+int idc_roc_blob_export_payload(
+        const idc_roc_blob* blob,
+        int mem,
+        uint8_t* unit_precision,
+        uint64_t* unit_heads,
+        uint32_t* unit_nwords,
+        uint32_t* unit_lo,
+        uint32_t* unit_hi,
+        uint32_t* words);
+
+/* The inverse: build a blob over nlist lists (list_offsets: HOST CSR of the id counts; lists longer than max_unit
+ * are split into units exactly as idc_roc_encode splits them) from per-unit payload arrays in unit order, HOST or
+ * DEVICE per `mem`. Used on the rank that owns an index to re-assemble the blobs its peers encoded (the units of
+ * consecutive ranks concatenate to the units of the whole index), and by the file loader. unit_lo / unit_hi may
+ * be NULL (hints derived from the precision). The result is indistinguishable from the blob idc_roc_encode
+ * returns for the whole index. */
+int idc_roc_blob_assemble(
+        idc_ctx* ctx,
+        uint64_t nlist,
+        const uint64_t* list_offsets,
+        uint32_t max_unit,
+        int mem,
+        const uint8_t* unit_precision,
+        const uint64_t* unit_heads,
+        const uint32_t* unit_nwords,
+        const uint32_t* unit_lo,
+        const uint32_t* unit_hi,
+        const uint32_t* words,
+        uint64_t total_words,
+        idc_roc_blob** out);
+
 /* Sample order recorded with IDC_F_WANT_ORDER: order[(offsets[l] - offsets[0]) + t]
  * (rebased to the first list, like every decode output) is the
  * position inside list l (input order) of the id emitted at step t, which is

@@ -320,6 +320,60 @@ class EfCodec:
         lib.oracle_ef_select.restype = C.c_uint64
         lib.oracle_ef_select.argtypes = [C.c_uint64, C.c_uint32, _u64p, _u64p]
 
+        lib.oracle_ef_encode_lists_mt.restype = C.c_int
+        lib.oracle_ef_encode_lists_mt.argtypes = [C.c_uint64, _u64p, _u64p, _u64p, _u64p, _u64p, _u64p, _u64p, C.c_int]
+        lib.oracle_ef_decode_lists_mt.restype = None
+        lib.oracle_ef_decode_lists_mt.argtypes = [C.c_uint64, _u64p, _u8p, _u64p, _u64p, _u64p, _u64p, _u64p, C.c_int]
+
+    def shapes(self, offsets, ids):
+        """Per list of an ascending CSR: universe (= last id, custom_invlists_impl.cpp:262), l, word offsets of the
+        two bit vectors (elias_fano.hpp:28-29). Vectorised."""
+        offsets = np.asarray(offsets).astype(np.int64)
+        ids = _as_u64(ids)
+        m = np.diff(offsets)
+        nz = m > 0
+        uni = np.zeros(m.size, dtype=np.uint64)
+        uni[nz] = ids[offsets[1:][nz] - 1]
+        q = np.zeros(m.size, dtype=np.uint64)
+        q[nz] = uni[nz] // m[nz].astype(np.uint64)
+        l = np.zeros(m.size, dtype=np.uint8)
+        qq = q.copy()
+        for _ in range(64):  # msb(q), 0 for q == 0
+            big = qq > 1
+            if not big.any():
+                break
+            l[big] += 1
+            qq[big] >>= np.uint64(1)
+        low_bits = m.astype(np.uint64) * l.astype(np.uint64)
+        high_bits = np.where(nz, m.astype(np.uint64) + 1 + (uni >> l.astype(np.uint64)) + 1, 0).astype(np.uint64)
+        low_off = np.zeros(m.size + 1, dtype=np.uint64)
+        high_off = np.zeros(m.size + 1, dtype=np.uint64)
+        np.cumsum((low_bits + 63) // 64, out=low_off[1:])
+        np.cumsum((high_bits + 63) // 64, out=high_off[1:])
+        return dict(universe=uni, l=l, low_off=low_off, high_off=high_off, bits_total=int(low_bits.sum() + high_bits.sum()))
+
+    def encode_lists(self, offsets, ids, nthreads: int = 0):
+        """All lists of an ascending CSR, OpenMP over lists. -> shapes() + low / high word arrays."""
+        sh = self.shapes(offsets, ids)
+        off = _as_u64(offsets)
+        ids = _as_u64(ids)
+        low = np.zeros(max(int(sh["low_off"][-1]), 1), dtype=np.uint64)
+        high = np.zeros(max(int(sh["high_off"][-1]), 1), dtype=np.uint64)
+        rc = self.lib.oracle_ef_encode_lists_mt(off.size - 1, off, ids if ids.size else np.zeros(1, np.uint64),
+                                                sh["universe"] if off.size > 1 else np.zeros(1, np.uint64),
+                                                sh["low_off"], sh["high_off"], low, high, int(nthreads))
+        if rc != 0:
+            raise ValueError("ids must be ascending")
+        return dict(sh, low=low, high=high)
+
+    def decode_lists(self, offsets, enc, nthreads: int = 0) -> np.ndarray:
+        off = _as_u64(offsets)
+        out = np.zeros(max(int(off[-1]), 1), dtype=np.uint64)
+        l = enc["l"] if enc["l"].size else np.zeros(1, np.uint8)
+        self.lib.oracle_ef_decode_lists_mt(off.size - 1, off, l, enc["low_off"], enc["high_off"], enc["low"], enc["high"],
+                                           out, int(nthreads))
+        return out[: int(off[-1])]
+
     def params(self, universe: int, m: int):
         """-> (l, low_bits, high_bits)"""
         l = C.c_uint32(0)

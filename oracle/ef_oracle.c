@@ -148,3 +148,52 @@ void oracle_ef_decode_lists(
             oracle_ef_decode(m, l[k], low + low_off[k], high + high_off[k], out + offsets[k]);
     }
 }
+
+/* The same loops over lists with OpenMP (what the reference's plugin constructor does:
+ * `#pragma omp parallel for` over list_no, custom_invlists_impl.cpp:234) -- bench.py's Elias-Fano cpu_baseline.
+ * nthreads <= 0: all host threads. */
+#include <omp.h>
+
+int oracle_ef_encode_lists_mt(
+        uint64_t nlist,
+        const uint64_t* offsets,
+        const uint64_t* ids,
+        const uint64_t* universe,
+        const uint64_t* low_off,
+        const uint64_t* high_off,
+        uint64_t* low,
+        uint64_t* high,
+        int nthreads) {
+    int bad = 0;
+    if (nthreads <= 0)
+        nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads) reduction(| : bad)
+    for (int64_t k = 0; k < (int64_t)nlist; k++) {
+        uint64_t m = offsets[k + 1] - offsets[k];
+        if (!m)
+            continue;
+        if (oracle_ef_encode(universe[k], m, ids + offsets[k], low + low_off[k], high + high_off[k]))
+            bad |= 1;
+    }
+    return bad ? -1 : 0;
+}
+
+void oracle_ef_decode_lists_mt(
+        uint64_t nlist,
+        const uint64_t* offsets,
+        const uint8_t* l,
+        const uint64_t* low_off,
+        const uint64_t* high_off,
+        const uint64_t* low,
+        const uint64_t* high,
+        uint64_t* out,
+        int nthreads) {
+    if (nthreads <= 0)
+        nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+    for (int64_t k = 0; k < (int64_t)nlist; k++) {
+        uint64_t m = offsets[k + 1] - offsets[k];
+        if (m)
+            oracle_ef_decode(m, l[k], low + low_off[k], high + high_off[k], out + offsets[k]);
+    }
+}

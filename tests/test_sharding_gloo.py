@@ -1,6 +1,7 @@
-"""CPU, world_size 2, gloo: the N>1 path -- LPT partition, scatter of raw id blocks, per-rank encode,
-gather of blobs -- re-assembled result must equal the single-process result byte for byte. The codec is
-injected (the oracle here; the CUDA codec on a GPU box: tests/test_gpu_parity.py::test_sharded_matches_single)."""
+"""CPU, world_size 2 and 3, gloo: the N>1 path of the ROC codec -- tensor broadcast of the offsets, the
+contiguous-unit-range plan, scatter of raw id blocks, per-rank encode, gather-v of the payload tensors, assembly --
+must give, on the owner, exactly the payload a single process produces for the whole index. The codec is injected
+(the oracle here; the CUDA codec on a GPU box: tests/test_gpu_sharded.py, which needs >= 2 GPUs)."""
 import os
 import socket
 import sys
@@ -13,6 +14,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = Path(__file__).resolve().parents[1]
+MAX_UNIT = 1000
 
 
 def _free_port():
@@ -26,39 +28,54 @@ def _free_port():
 def make_index(seed=0, nlist=37):
     rng = np.random.default_rng(seed)
     sizes = rng.integers(0, 400, size=nlist)
+    sizes[0] = 0
     sizes[5] = 0
-    sizes[11] = 3000
+    sizes[11] = 3000   # three units, straddles a rank boundary
+    sizes[12] = 2500
     offsets = np.zeros(nlist + 1, np.uint64)
     offsets[1:] = np.cumsum(sizes)
     ids = np.concatenate([np.sort(rng.choice(1 << 20, size=int(s), replace=False)) for s in sizes]).astype(np.int64)
     return offsets, ids
 
 
-def oracle_encode_fn(max_unit):
-    sys.path.insert(0, str(ROOT))
-    import oracle
+class OracleCodec:
+    """Same interface as sharding.RocCudaCodec, backed by the CPU oracle (test infrastructure)."""
 
-    def fn(loc, local_ids):
-        loc = np.asarray(loc, dtype=np.int64)
+    max_unit = MAX_UNIT
+
+    def __init__(self):
+        sys.path.insert(0, str(ROOT))
+        import oracle
+
+        self.oracle = oracle
+
+    def encode(self, local_offsets, local_ids):
+        from vector_db_id_compression_b200.sharding import unit_table
+
         ids = local_ids.cpu().numpy().astype(np.uint64)
-        unit_offsets, unit_n, prec, heads, words, woff = [0], [], [], [], [], [0]
-        for l in range(loc.size - 1):
-            s, e = int(loc[l]), int(loc[l + 1])
-            if e == s:
-                unit_n.append(0), prec.append(0), heads.append(1 << 31), woff.append(woff[-1])
-            for a in range(s, e, max_unit):
-                seg = ids[a: min(e, a + max_unit)]
-                p = oracle.port.precision_rule(int(seg.max()))
-                h, w = oracle.port.encode(seg, p)
-                unit_n.append(seg.size), prec.append(p), heads.append(h), words.append(w)
-                woff.append(woff[-1] + w.size)
-            unit_offsets.append(len(unit_n))
-        return dict(unit_offsets=np.asarray(unit_offsets, np.uint64), unit_n=np.asarray(unit_n, np.uint32),
-                    precision=np.asarray(prec, np.uint8), heads=np.asarray(heads, np.uint64),
-                    word_offsets=np.asarray(woff, np.uint64),
-                    words=np.concatenate(words) if words else np.zeros(0, np.uint32))
+        _, start, n = unit_table(np.asarray(local_offsets, dtype=np.int64), self.max_unit)
+        if np.asarray(local_offsets).size == 1:
+            start, n = start[:0], n[:0]
+        prec, heads, nwords, lo, hi, words = [], [], [], [], [], []
+        for s, m in zip(start.tolist(), n.tolist()):
+            if m == 0:
+                prec.append(0), heads.append(1 << 31), nwords.append(0), lo.append(0), hi.append(0)
+                continue
+            seg = ids[s: s + m]
+            p = self.oracle.port.precision_rule(int(seg.max()))
+            h, w = self.oracle.port.encode(seg, p)
+            prec.append(p), heads.append(h), nwords.append(w.size), lo.append(int(seg.min())), hi.append(int(seg.max()))
+            words.append(w)
+        return dict(precision=np.asarray(prec, np.uint8), heads=np.asarray(heads, np.uint64).view(np.int64),
+                    nwords=np.asarray(nwords, np.uint32).view(np.int32), lo=np.asarray(lo, np.uint32).view(np.int32),
+                    hi=np.asarray(hi, np.uint32).view(np.int32),
+                    words=(np.concatenate(words) if words else np.zeros(0, np.uint32)).view(np.int32))
 
-    return fn
+    def payload(self, blob, device):
+        return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in blob.items()}
+
+    def assemble(self, offsets, payload):
+        return {k: v.numpy() for k, v in payload.items()}
 
 
 def _worker(rank, world, port, q):
@@ -68,38 +85,49 @@ def _worker(rank, world, port, q):
     from vector_db_id_compression_b200 import sharding
 
     offsets, ids = make_index() if rank == 0 else (None, None)
-    res = sharding.encode_sharded(offsets, ids, oracle_encode_fn(1000), torch.device("cpu"))
+    phases = []
+    whole, local, plan = sharding.encode_sharded(offsets, ids, OracleCodec(), torch.device("cpu"), timer=phases.append)
+    assert phases == ["plan", "scatter", "encode", "gather", "assemble"]
     if rank == 0:
-        q.put({k: v.tolist() for k, v in res.items()})
+        q.put({k: v.tolist() for k, v in whole.items()})
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_lpt_partition_balances_and_covers():
-    from vector_db_id_compression_b200.sharding import lpt_partition
+def test_unit_range_plan_covers_and_balances():
+    from vector_db_id_compression_b200.sharding import unit_range_plan, unit_table
 
     rng = np.random.default_rng(0)
-    costs = np.concatenate([rng.integers(1, 100, size=5000), [65536] * 37]).astype(float)
-    parts = lpt_partition(costs, 8)
-    allidx = np.sort(np.concatenate(parts))
-    assert np.array_equal(allidx, np.arange(costs.size))
-    loads = np.array([costs[p].sum() for p in parts])
-    assert loads.max() / loads.mean() < 1.03
+    sizes = np.concatenate([[0, 5, 2500, 0, 1000, 999, 1001, 3000, 70000], rng.integers(0, 400, size=300)])
+    off = np.zeros(sizes.size + 1, np.int64)
+    off[1:] = np.cumsum(sizes)
+    for world in (1, 2, 3, 8):
+        plan = unit_range_plan(off, 1000, world)
+        assert plan["ucut"][0] == 0 and plan["ucut"][-1] == plan["nunits"] and plan["ecut"][-1] == off[-1]
+        # every rank's own list -> unit split reproduces the global one
+        want = unit_table(off, 1000)[2]
+        got = np.concatenate([unit_table(l.astype(np.int64), 1000)[2] if l.size > 1 else np.zeros(0, np.int64)
+                              for l in plan["local_offsets"]])
+        assert np.array_equal(want, got)
+        loads = np.diff(plan["ecut"])
+        assert loads.max() - loads.min() <= 2 * 1000, loads   # within one unit of the ideal cut on either side
+        for r in range(world):
+            assert int(plan["local_offsets"][r][-1]) == loads[r]
 
 
-def test_sharded_encode_equals_single_process():
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_encode_equals_single_process(world):
     port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = q.get(timeout=120)
+    got = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     offsets, ids = make_index()
-    want = oracle_encode_fn(1000)(offsets, torch.from_numpy(ids))
+    want = OracleCodec().encode(offsets, torch.from_numpy(ids))
     for k in want:
-        assert np.array_equal(np.asarray(got[k]), want[k]), k
+        assert np.array_equal(np.asarray(got[k], dtype=want[k].dtype), want[k]), k

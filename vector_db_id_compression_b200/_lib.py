@@ -46,6 +46,8 @@ SYMBOLS = {
     "idc_roc_blob_info": (C.c_int, [vp, C.POINTER(RocInfo)]),
     "idc_roc_blob_export": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "idc_roc_blob_import": (C.c_int, [vp, u64, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+    "idc_roc_blob_export_payload": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp]),
+    "idc_roc_blob_assemble": (C.c_int, [vp, u64, vp, u32, C.c_int, vp, vp, vp, vp, vp, vp, u64, C.POINTER(vp)]),
     "idc_roc_blob_order": (C.c_int, [vp, vp, C.c_int]),
     "idc_roc_blob_free": (C.c_int, [vp]),
     "idc_roc_decode": (C.c_int, [vp, vp, vp, u64, vp, C.c_int, C.c_int, vp]),

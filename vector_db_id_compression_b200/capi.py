@@ -144,6 +144,29 @@ class Context:
                                            heads.ctypes.data, word_offsets.ctypes.data, words.ctypes.data, C.byref(h)))
         return RocBlob(self, h)
 
+    def roc_assemble(self, list_offsets, payload: dict, *, max_unit: int = 65536) -> "RocBlob":
+        """idc_roc_blob_assemble: a blob over the lists of `list_offsets` from per-unit payload arrays in unit order
+        (numpy, or torch tensors on the host or on this context's device; all six from the same place)."""
+        off = _host_u64(list_offsets)
+        arrs, mems = [], set()
+        for k in RocBlob.PAYLOAD_KEYS:
+            a = payload.get(k)
+            if a is None:
+                arrs.append(None)
+                continue
+            if not _is_torch(a):
+                a = np.ascontiguousarray(a)
+            ptr, mem = _ptr(a)
+            arrs.append((a, ptr))
+            mems.add(mem)
+        assert len(mems) <= 1, "payload arrays must all live in the same memory"
+        mem = mems.pop() if mems else MEM_HOST
+        nwords_total = int(payload["words"].shape[0]) if payload.get("words") is not None else 0
+        h = C.c_void_p()
+        _check(self._l.idc_roc_blob_assemble(self._h, off.size - 1, off.ctypes.data, max_unit, mem,
+                                             *((a[1] if a is not None else None) for a in arrs), nwords_total, C.byref(h)))
+        return RocBlob(self, h)
+
     # ------------------------------------------------------------- EF -----
     def ef_encode(self, offsets, ids, *, sorted_ids: bool = False) -> "EfBlob":
         offsets = _host_u64(offsets)
@@ -257,6 +280,33 @@ class RocBlob:
         for k in ("unit_n", "precision", "heads"):
             d[k] = d[k][: i.nunits]
         d["words"] = d["words"][: i.total_words]
+        return d
+
+    PAYLOAD_KEYS = ("precision", "heads", "nwords", "lo", "hi", "words")
+
+    def export_payload(self, device=None) -> dict:
+        """The wire form of the blob (idc_roc_blob_export_payload): per-unit precision / head / word count / id-range
+        hints plus all stream words, as torch tensors on `device` (device -> device copies, nothing touches the
+        host) or, with device=None, as numpy arrays. Unsigned arrays travel as same-width signed torch dtypes."""
+        i = self.info
+        nu, nw = int(i.nunits), int(i.total_words)
+        if device is not None:
+            import torch
+
+            mk = lambda n, dt: torch.empty(max(n, 1), dtype=dt, device=device)
+            d = dict(precision=mk(nu, torch.uint8), heads=mk(nu, torch.int64), nwords=mk(nu, torch.int32),
+                     lo=mk(nu, torch.int32), hi=mk(nu, torch.int32), words=mk(nw, torch.int32))
+            ptr = lambda t: t.data_ptr()
+            mem = MEM_DEVICE if torch.device(device).type == "cuda" else MEM_HOST
+        else:
+            mk = lambda n, dt: np.empty(max(n, 1), dtype=dt)
+            d = dict(precision=mk(nu, np.uint8), heads=mk(nu, np.uint64), nwords=mk(nu, np.uint32),
+                     lo=mk(nu, np.uint32), hi=mk(nu, np.uint32), words=mk(nw, np.uint32))
+            ptr = lambda a: a.ctypes.data
+            mem = MEM_HOST
+        _check(self._l.idc_roc_blob_export_payload(self._h, mem, *(ptr(d[k]) for k in self.PAYLOAD_KEYS)))
+        for k in self.PAYLOAD_KEYS:
+            d[k] = d[k][: (nw if k == "words" else nu)]
         return d
 
     def order(self, device=None):

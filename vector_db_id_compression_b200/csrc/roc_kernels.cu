@@ -205,6 +205,12 @@ __global__ void __launch_bounds__(kThreads) k_roc_compact(const uint32_t* scratc
     for (uint32_t i = lane; i < cnt; i += 32) words[d0 + i] = __ldcs(src + i);
 }
 
+// nwords[u] = word_off[u + 1] - word_off[u]
+__global__ void __launch_bounds__(kThreads) k_unit_nwords(const uint64_t* word_off, uint32_t* nwords, uint64_t nunits) {
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < nunits) nwords[u] = (uint32_t)(word_off[u + 1] - word_off[u]);
+}
+
 // ids_out[i] = labels[i] < 0 ? labels[i] : decoded[src[i]]
 __global__ void __launch_bounds__(kThreads) k_translate_gather(const int64_t* labels, const uint64_t* src,
                                                                const int64_t* decoded, int64_t* out, uint64_t n) {
@@ -1032,6 +1038,110 @@ int idc_roc_blob_import(idc_ctx* c, uint64_t nlist, const uint32_t* unit_n, cons
     IDC_CUDA(cudaMemcpyAsync(b->d_word_off, woff.data(), (nlist + 1) * 8, cudaMemcpyHostToDevice, s));
     if (b->total_words)
         IDC_CUDA(cudaMemcpyAsync(b->d_words, words + word_offsets[0], b->total_words * 4, cudaMemcpyHostToDevice, s));
+    IDC_CUDA(cudaStreamSynchronize(s));
+    b->device_bytes = acct;
+    *out = b.release();
+    return IDC_OK;
+}
+
+int idc_roc_blob_export_payload(const idc_roc_blob* b, int mem, uint8_t* unit_precision, uint64_t* unit_heads,
+                                uint32_t* unit_nwords, uint32_t* unit_lo, uint32_t* unit_hi, uint32_t* words) {
+    IDC_REQUIRE(b, IDC_ERR_ARG, "null blob");
+    IDC_REQUIRE(mem == IDC_MEM_HOST || mem == IDC_MEM_DEVICE, IDC_ERR_ARG, "mem must be IDC_MEM_HOST or IDC_MEM_DEVICE");
+    idc_ctx* c = b->ctx;
+    std::lock_guard<std::mutex> lock(c->mu);
+    IDC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const cudaMemcpyKind kind = mem == IDC_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    const uint64_t nu = b->nunits;
+    if (unit_precision && nu) IDC_CUDA(cudaMemcpyAsync(unit_precision, b->d_unit_prec, nu, kind, s));
+    if (unit_heads && nu) IDC_CUDA(cudaMemcpyAsync(unit_heads, b->d_unit_head, nu * 8, kind, s));
+    if (unit_lo && nu) IDC_CUDA(cudaMemcpyAsync(unit_lo, b->d_unit_lo, nu * 4, kind, s));
+    if (unit_hi && nu) IDC_CUDA(cudaMemcpyAsync(unit_hi, b->d_unit_hi, nu * 4, kind, s));
+    if (unit_nwords && nu) {
+        uint32_t* d_nw = unit_nwords;
+        if (mem == IDC_MEM_HOST) {
+            IDC_TRY(c->meta.reserve(nu * 4 + 256));
+            d_nw = c->meta.as<uint32_t>();
+        }
+        k_unit_nwords<<<grid_for(nu), kThreads, 0, s>>>(b->d_word_off, d_nw, nu);
+        c->launches++;
+        IDC_TRY(check_last_launch("k_unit_nwords"));
+        if (mem == IDC_MEM_HOST) IDC_CUDA(cudaMemcpyAsync(unit_nwords, d_nw, nu * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (words && b->total_words) IDC_CUDA(cudaMemcpyAsync(words, b->d_words, b->total_words * 4, kind, s));
+    IDC_CUDA(cudaStreamSynchronize(s));
+    return IDC_OK;
+}
+
+int idc_roc_blob_assemble(idc_ctx* c, uint64_t nlist, const uint64_t* list_offsets, uint32_t max_unit, int mem,
+                          const uint8_t* unit_precision, const uint64_t* unit_heads, const uint32_t* unit_nwords,
+                          const uint32_t* unit_lo, const uint32_t* unit_hi, const uint32_t* words, uint64_t total_words,
+                          idc_roc_blob** out) {
+    IDC_REQUIRE(c && out && list_offsets, IDC_ERR_ARG, "idc_roc_blob_assemble: null argument");
+    IDC_REQUIRE(mem == IDC_MEM_HOST || mem == IDC_MEM_DEVICE, IDC_ERR_ARG, "mem must be IDC_MEM_HOST or IDC_MEM_DEVICE");
+    if (max_unit == 0) max_unit = IDC_MAX_UNIT_DEFAULT;
+    IDC_REQUIRE(max_unit <= kMaxUnit, IDC_ERR_ARG, "max_unit %u > 65536", max_unit);
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    std::unique_ptr<idc_roc_blob> b(new idc_roc_blob());
+    b->ctx = c;
+    b->ref.bind(c);
+    std::vector<uint32_t> posbase;
+    IDC_TRY(plan_units_csr(b.get(), nlist, list_offsets, max_unit, posbase));  // the very split idc_roc_encode makes
+    const uint64_t nu = b->nunits;
+    IDC_REQUIRE(nu == 0 || (unit_precision && unit_heads && unit_nwords), IDC_ERR_ARG, "idc_roc_blob_assemble: null unit array");
+    IDC_REQUIRE(total_words == 0 || words, IDC_ERR_ARG, "idc_roc_blob_assemble: words is NULL");
+    for (uint64_t u = 0; u < nu; u++) b->max_n = std::max(b->max_n, b->unit_n[u]);
+    uint64_t acct = 0;
+    IDC_TRY(dev_alloc(c, &b->d_unit_n, nu, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_prec, nu, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_head, nu, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_word_off, nu + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_lo, nu, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_hi, nu, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_words, total_words, &acct));
+    cudaStream_t s = c->stream;
+    const cudaMemcpyKind kind = mem == IDC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    IDC_TRY(upload(c, b->d_unit_n, b->unit_n));
+    std::vector<uint32_t> nw(nu);
+    std::vector<uint8_t> prec(nu);
+    if (nu) {
+        IDC_CUDA(cudaMemcpyAsync(b->d_unit_prec, unit_precision, nu, kind, s));
+        IDC_CUDA(cudaMemcpyAsync(b->d_unit_head, unit_heads, nu * 8, kind, s));
+        // word counts and precisions are metadata: a host copy feeds the offsets and the checks below
+        IDC_CUDA(cudaMemcpyAsync(nw.data(), unit_nwords, nu * 4, mem == IDC_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost, s));
+        IDC_CUDA(cudaMemcpyAsync(prec.data(), unit_precision, nu, mem == IDC_MEM_HOST ? cudaMemcpyHostToHost : cudaMemcpyDeviceToHost, s));
+    }
+    if (total_words) IDC_CUDA(cudaMemcpyAsync(b->d_words, words, total_words * 4, kind, s));
+    IDC_CUDA(cudaStreamSynchronize(s));
+    std::vector<uint64_t> woff(nu + 1, 0);
+    uint64_t ans = 0;
+    for (uint64_t u = 0; u < nu; u++) {
+        IDC_REQUIRE(prec[u] <= 32, IDC_ERR_DOMAIN, "unit %llu: precision %u > 32 not supported on device", (unsigned long long)u, prec[u]);
+        if (b->unit_n[u] == 0) nw[u] = 0;
+        woff[u + 1] = woff[u] + nw[u];
+        if (b->unit_n[u]) ans += 8 + 4ull * nw[u];
+    }
+    IDC_REQUIRE(woff[nu] == total_words, IDC_ERR_ARG, "idc_roc_blob_assemble: unit word counts sum to %llu, total_words is %llu",
+                (unsigned long long)woff[nu], (unsigned long long)total_words);
+    b->total_words = total_words;
+    b->ans_bytes = ans;
+    IDC_TRY(upload(c, b->d_word_off, woff));
+    if (nu) {
+        if (unit_lo && unit_hi) {
+            IDC_CUDA(cudaMemcpyAsync(b->d_unit_lo, unit_lo, nu * 4, kind, s));
+            IDC_CUDA(cudaMemcpyAsync(b->d_unit_hi, unit_hi, nu * 4, kind, s));
+        } else {  // no hints: every id below 2^precision (only the decoder's speed depends on them)
+            std::vector<uint32_t> lo(nu, 0), hi(nu);
+            for (uint64_t u = 0; u < nu; u++) hi[u] = prec[u] >= 32 ? 0xffffffffu : ((1u << prec[u]) - 1u);
+            IDC_TRY(upload(c, b->d_unit_lo, lo));
+            IDC_TRY(upload(c, b->d_unit_hi, hi));
+            IDC_CUDA(cudaStreamSynchronize(s));
+        }
+    }
     IDC_CUDA(cudaStreamSynchronize(s));
     b->device_bytes = acct;
     *out = b.release();

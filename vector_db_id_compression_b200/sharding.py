@@ -3,8 +3,8 @@
 Lists are independent coding units (custom_invlists_impl.h:59,76; altid_impl.h:43,58), so the codec needs
 no collective: one process per GPU, each encodes / decodes its own lists. NCCL (over NVLink 5 / NVSwitch) is
 used only to move data when a single rank owns the index: scatter-v of raw id blocks, gather-v of the
-compressed blobs. All functions work on any torch.distributed backend (tests run them on gloo / CPU with an
-injected codec; production passes a capi.Context-based codec on nccl / CUDA).
+compressed blobs -- device buffers end to end, no pickled objects. All functions work on any torch.distributed
+backend (tests run them on gloo / CPU with an injected codec; production passes RocCudaCodec on nccl / CUDA).
 """
 from __future__ import annotations
 
@@ -13,149 +13,196 @@ from typing import Callable, Optional
 import numpy as np
 
 
-def roc_cost(n: np.ndarray) -> np.ndarray:
-    """Serial steps dominate ROC: cost ~ n (each step is a fixed-latency chain); EF cost ~ n as well."""
-    return np.asarray(n, dtype=np.float64)
+# ---------------------------------------------------------------- ROC: sharding by contiguous unit ranges
+# A ROC *unit* (a list of <= max_unit ids, or one max_unit-run of a longer list) is an independent stream. The units
+# of an index, in list order, are cut into `world` contiguous ranges of near-equal id count; rank r gets the ids of
+# its range -- ONE contiguous slice of the owner's id array, so the scatter is a plain send of slices, no gather
+# kernel, no copy -- encodes them, and the owner concatenates the per-rank payloads (idc_roc_blob_export_payload) in
+# rank order: that IS the blob of the whole index (idc_roc_blob_assemble). A list longer than max_unit may straddle
+# two ranks; both pieces start at a unit boundary, so each rank's own list -> unit split reproduces the global one.
+#
+# Nothing in the data path is pickled: the plan is a pure function of (offsets, max_unit, world) that every rank
+# evaluates after ONE tensor broadcast of the offsets; ids, payload arrays and sizes travel as tensors (NCCL
+# send / recv / all_gather over NVLink on CUDA tensors, gloo on CPU tensors in the tests).
 
-
-def lpt_partition(costs: np.ndarray, nparts: int) -> list[np.ndarray]:
-    """Longest-processing-time-first greedy partition. Returns, per part, the item indices (ascending)."""
-    costs = np.asarray(costs, dtype=np.float64)
-    order = np.argsort(-costs, kind="stable")
-    loads = np.zeros(nparts)
-    parts: list[list[int]] = [[] for _ in range(nparts)]
-    # large items individually, the long tail in round-robin blocks (keeps this O(n log n) in numpy terms)
-    head = min(order.size, 64 * nparts)
-    for i in order[:head]:
-        p = int(np.argmin(loads))
-        parts[p].append(int(i))
-        loads[p] += costs[i]
-    tail = order[head:]
-    if tail.size:
-        # water-filling: every part is topped up to the common target with a run of consecutive tail items
-        tc = costs[tail]
-        need = np.maximum(costs.sum() / nparts - loads, 0.0)
-        need = need / need.sum() * tc.sum() if need.sum() > 0 else np.full(nparts, tc.sum() / nparts)
-        cuts = np.searchsorted(np.cumsum(tc), np.cumsum(need)[:-1], side="left")
-        for p, seg in enumerate(np.split(tail, cuts)):
-            parts[p].extend(int(x) for x in seg)
-            loads[p] += costs[seg].sum()
-    return [np.sort(np.asarray(p, dtype=np.int64)) for p in parts]
-
-
-def shard_csr(offsets: np.ndarray, lists: np.ndarray):
-    """Sub-CSR of the given lists: (local offsets, gather index ranges)."""
+def unit_table(offsets: np.ndarray, max_unit: int):
+    """(list, start element, n) of every unit in blob order -- the split plan_units_csr (roc_kernels.cu) makes;
+    an empty list owns one empty unit."""
     offsets = np.asarray(offsets, dtype=np.int64)
-    sizes = offsets[lists + 1] - offsets[lists]
-    loc = np.zeros(lists.size + 1, dtype=np.uint64)
-    loc[1:] = np.cumsum(sizes)
-    return loc, sizes
+    sizes = np.diff(offsets)
+    per_list = np.maximum(1, -(-sizes // max_unit))
+    first = np.zeros(sizes.size + 1, dtype=np.int64)
+    np.cumsum(per_list, out=first[1:])
+    unit_list = np.repeat(np.arange(sizes.size, dtype=np.int64), per_list)
+    seg = np.arange(int(first[-1]), dtype=np.int64) - first[unit_list]
+    start = offsets[unit_list] + seg * max_unit
+    n = np.clip(sizes[unit_list] - seg * max_unit, 0, max_unit)
+    return unit_list, start, n
 
 
-def _gather_index(goff: np.ndarray, lists: np.ndarray) -> np.ndarray:
-    """Element indices of the given lists, concatenated in the given order (vectorised: no per-list loop)."""
-    if lists.size == 0:
-        return np.zeros(0, np.int64)
-    starts = goff[lists].astype(np.int64)
-    sizes = (goff[lists + 1] - goff[lists]).astype(np.int64)
-    out_start = np.concatenate([[0], np.cumsum(sizes)[:-1]])
-    return np.repeat(starts - out_start, sizes) + np.arange(int(sizes.sum()), dtype=np.int64)
+def unit_range_plan(offsets: np.ndarray, max_unit: int, world: int) -> dict:
+    """Contiguous unit ranges of near-equal id count. -> ucut[world+1] (unit ranges), ecut[world+1] (element ranges
+    into the owner's id array), local_offsets[r] (the CSR rank r encodes, relative to ecut[r])."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    unit_list, start, n = unit_table(offsets, max_unit)
+    nunits = n.size
+    cum = np.cumsum(n)
+    total = int(cum[-1]) if nunits else 0
+    targets = (np.arange(1, world, dtype=np.float64) * total / world)
+    ucut = np.concatenate([[0], np.searchsorted(cum, targets, side="left") + (1 if nunits else 0), [nunits]]).astype(np.int64)
+    ucut = np.minimum(np.maximum.accumulate(ucut), nunits)
+    ends = start + n
+    ecut = np.zeros(world + 1, dtype=np.int64)
+    ecut[0] = offsets[0]
+    for r in range(world):
+        ecut[r + 1] = ends[ucut[r + 1] - 1] if ucut[r + 1] > ucut[r] else ecut[r]
+    local = []
+    for r in range(world):
+        u0, u1 = int(ucut[r]), int(ucut[r + 1])
+        if u1 == u0:
+            local.append(np.zeros(1, dtype=np.uint64))
+            continue
+        ul = unit_list[u0:u1]
+        grp = np.concatenate([[0], np.nonzero(np.diff(ul))[0] + 1])   # first unit of every (piece of a) list
+        sizes = np.add.reduceat(n[u0:u1], grp)
+        lo = np.zeros(sizes.size + 1, dtype=np.uint64)
+        lo[1:] = np.cumsum(sizes)
+        local.append(lo)
+    return dict(ucut=ucut, ecut=ecut, local_offsets=local, nunits=nunits, total=total)
 
 
-def scatter_lists(offsets, ids, device, src: int = 0, group=None):
-    """Rank `src` owns (offsets, ids); every rank gets (its list numbers, local offsets, its ids on `device`).
+def _rank_world(group=None):
+    """(rank, world) of the process group; (0, 1) when torch.distributed is not initialised (one GPU, no launcher)."""
+    import torch.distributed as dist
 
-    Plan = LPT over list lengths, broadcast as an object; raw id blocks move with batched send/recv
-    (ncclSend/ncclRecv under nccl) -- one message per destination rank."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def broadcast_offsets(offsets, max_unit: int, device, src: int = 0, group=None):
+    """The owner's CSR offsets (and max_unit) to every rank, as tensors."""
     import torch
     import torch.distributed as dist
 
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    plan = [None]
+    rank, world = _rank_world(group)
+    if world == 1:
+        return np.asarray(offsets).astype(np.int64), int(max_unit)
+    head = torch.zeros(2, dtype=torch.int64, device=device)
     if rank == src:
-        offsets = np.asarray(offsets, dtype=np.int64)
-        sizes = np.diff(offsets)
-        plan = [(lpt_partition(roc_cost(sizes), world), offsets)]
-    dist.broadcast_object_list(plan, src=src, group=group)
-    parts, goff = plan[0]
-    mine = parts[rank]
-    loc, sizes = shard_csr(goff, mine)
-    n_mine = int(loc[-1])
-    recv = torch.empty(n_mine, dtype=torch.int64, device=device)
+        off_np = np.asarray(offsets).astype(np.int64)
+        head = torch.tensor([off_np.size, int(max_unit)], dtype=torch.int64, device=device)
+    dist.broadcast(head, src=src, group=group)
+    n, mu = int(head[0]), int(head[1])
+    t = torch.as_tensor(off_np, device=device) if rank == src else torch.empty(n, dtype=torch.int64, device=device)
+    dist.broadcast(t, src=src, group=group)
+    return t.cpu().numpy(), mu
+
+
+def scatter_id_blocks(plan: dict, ids, device, src: int = 0, group=None):
+    """Rank r receives ids[ecut[r] : ecut[r+1]] of the owner's array (the owner's own block is a view of it)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = _rank_world(group)
+    ecut = plan["ecut"]
+    n_mine = int(ecut[rank + 1] - ecut[rank])
     ops = []
     if rank == src:
-        ids_t = torch.as_tensor(ids, dtype=torch.int64, device=device)
-        blocks = []
+        ids_t = ids if isinstance(ids, torch.Tensor) else torch.as_tensor(np.asarray(ids, dtype=np.int64))
+        ids_t = ids_t.to(device)
+        mine = ids_t[int(ecut[rank]): int(ecut[rank + 1])]
         for r in range(world):
-            lists = parts[r]
-            idx = _gather_index(goff, lists)
-            blk = ids_t[torch.as_tensor(idx, device=device)] if idx.size else torch.empty(0, dtype=torch.int64, device=device)
-            if r == src:
-                recv.copy_(blk)
-            elif blk.numel():
-                blocks.append(blk)
-                ops.append(dist.P2POp(dist.isend, blk, r, group))
-    elif n_mine:
-        ops.append(dist.P2POp(dist.irecv, recv, src, group))
+            if r != src and ecut[r + 1] > ecut[r]:
+                ops.append(dist.P2POp(dist.isend, ids_t[int(ecut[r]): int(ecut[r + 1])], r, group))
+    else:
+        mine = torch.empty(n_mine, dtype=torch.int64, device=device)
+        if n_mine:
+            ops.append(dist.P2POp(dist.irecv, mine, src, group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    return mine, loc, recv
+    return mine
 
 
-def gather_blobs(mine: np.ndarray, local: dict, nlist: int, dst: int = 0, group=None) -> Optional[dict]:
-    """Re-assemble per-rank ROC exports (capi.RocBlob.export() dicts over the rank's lists) in global list
-    order on rank `dst`. Sizes travel with all_gather_object, payload arrays with gather_object (gather-v)."""
+PAYLOAD_KEYS = ("precision", "heads", "nwords", "lo", "hi", "words")
+
+
+def gather_payloads(plan: dict, payload: dict, device, dst: int = 0, group=None) -> Optional[dict]:
+    """gather-v of the per-rank payload tensors into pre-sized arrays on `dst`, in rank (= unit) order."""
+    import torch
     import torch.distributed as dist
 
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    payload = dict(lists=np.asarray(mine), **{k: np.asarray(v) for k, v in local.items()})
-    out = [None] * world if rank == dst else None
-    dist.gather_object(payload, out, dst=dst, group=group)
-    if rank != dst:
-        return None
-    # global tables in list order, vectorised: every rank's units / words are scattered to their global positions
-    nunits_of = np.zeros(nlist, dtype=np.int64)
-    for p in out:
-        nunits_of[p["lists"].astype(np.int64)] = np.diff(p["unit_offsets"].astype(np.int64))
-    unit_offsets = np.zeros(nlist + 1, np.uint64)
-    unit_offsets[1:] = np.cumsum(nunits_of)
-    nunits = int(unit_offsets[-1])
-    unit_n, precision = np.zeros(nunits, np.uint32), np.zeros(nunits, np.uint8)
-    heads, nwords = np.zeros(nunits, np.uint64), np.zeros(nunits, np.int64)
-    dest_units = []
-    for p in out:
-        lists = p["lists"].astype(np.int64)
-        uo = p["unit_offsets"].astype(np.int64)
-        nu = np.diff(uo)
-        du = np.repeat(unit_offsets[lists].astype(np.int64) - uo[:-1], nu) + np.arange(int(nu.sum()), dtype=np.int64)
-        dest_units.append(du)
-        unit_n[du], precision[du], heads[du] = p["unit_n"][: du.size], p["precision"][: du.size], p["heads"][: du.size]
-        nwords[du] = np.diff(p["word_offsets"].astype(np.int64))[: du.size]
-    word_offsets = np.zeros(nunits + 1, np.uint64)
-    word_offsets[1:] = np.cumsum(nwords)
-    words = np.zeros(int(word_offsets[-1]), np.uint32)
-    for p, du in zip(out, dest_units):
-        wo = p["word_offsets"].astype(np.int64)[: du.size + 1]
-        nw = np.diff(wo)
-        dw = np.repeat(word_offsets[du].astype(np.int64) - wo[:-1], nw) + np.arange(int(nw.sum()), dtype=np.int64)
-        words[dw] = np.asarray(p["words"])[int(wo[0]): int(wo[0]) + dw.size] if dw.size else words[dw]
-    return dict(unit_offsets=unit_offsets, unit_n=unit_n, precision=precision, heads=heads,
-                word_offsets=word_offsets, words=words)
+    rank, world = _rank_world(group)
+    if world == 1:
+        return payload
+    ucut = plan["ucut"]
+    nw_mine = torch.tensor([int(payload["words"].shape[0])], dtype=torch.int64, device=device)
+    nw_all = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(nw_all, nw_mine, group=group)  # blob sizes, as tensors
+    nw = np.array([int(t.item()) for t in nw_all], dtype=np.int64)
+    wcut = np.concatenate([[0], np.cumsum(nw)])
+    ops, out = [], None
+    if rank == dst:
+        out = {k: torch.empty(int(wcut[-1]) if k == "words" else plan["nunits"], dtype=payload[k].dtype, device=device)
+               for k in PAYLOAD_KEYS}
+        for r in range(world):
+            for k in PAYLOAD_KEYS:
+                a, b = (int(wcut[r]), int(wcut[r + 1])) if k == "words" else (int(ucut[r]), int(ucut[r + 1]))
+                if b == a:
+                    continue
+                if r == dst:
+                    out[k][a:b].copy_(payload[k])
+                else:
+                    ops.append(dist.P2POp(dist.irecv, out[k][a:b], r, group))
+    else:
+        for k in PAYLOAD_KEYS:
+            if payload[k].numel():
+                ops.append(dist.P2POp(dist.isend, payload[k].contiguous(), dst, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out
 
 
-def encode_sharded(offsets, ids, encode_fn: Callable, device, src: int = 0, group=None) -> Optional[dict]:
-    """scatter -> per-rank encode -> gather. encode_fn(local_offsets, local_ids) must return a
-    RocBlob.export()-style dict. Returns the global blob tables on rank `src`, None elsewhere."""
-    import torch.distributed as dist
+class RocCudaCodec:
+    """The production codec of the sharded path: capi.Context on this rank's GPU."""
 
-    nlist = [None]
-    if dist.get_rank(group) == src:
-        nlist = [int(np.asarray(offsets).size - 1)]
-    dist.broadcast_object_list(nlist, src=src, group=group)
-    mine, loc, local_ids = scatter_lists(offsets, ids, device, src=src, group=group)
-    local = encode_fn(loc, local_ids)
-    return gather_blobs(mine, local, nlist[0], dst=src, group=group)
+    def __init__(self, ctx, max_unit: int = 65536):
+        self.ctx, self.max_unit = ctx, max_unit
+
+    def encode(self, local_offsets, local_ids):
+        return self.ctx.roc_encode(local_offsets, local_ids, sorted_ids=True, max_unit=self.max_unit)
+
+    def payload(self, blob, device):
+        return blob.export_payload(device=device)
+
+    def assemble(self, offsets, payload):
+        return self.ctx.roc_assemble(offsets, payload, max_unit=self.max_unit)
+
+
+def encode_sharded(offsets, ids, codec, device, src: int = 0, group=None, timer=None, resident_ids=None):
+    """broadcast offsets -> plan -> scatter id blocks -> per-rank encode -> gather payloads -> assemble on `src`.
+
+    codec: .encode(local_offsets, local_ids) -> blob, .payload(blob, device) -> dict of tensors (PAYLOAD_KEYS),
+    .assemble(offsets, payload) -> the whole index's blob. Returns (assembled blob on `src` else None, this rank's
+    local blob, plan). timer(name) is called after each phase (bench.py times the phases with it).
+    resident_ids: this rank's block is already on the device (skips the scatter)."""
+    rank, world = _rank_world(group)
+    tick = timer or (lambda name: None)
+    goff, max_unit = broadcast_offsets(offsets, getattr(codec, "max_unit", 65536), device, src=src, group=group)
+    plan = unit_range_plan(goff, max_unit, world)
+    tick("plan")
+    mine = resident_ids if resident_ids is not None else scatter_id_blocks(plan, ids, device, src=src, group=group)
+    tick("scatter")
+    blob = codec.encode(plan["local_offsets"][rank], mine)
+    tick("encode")
+    payload = codec.payload(blob, device)
+    gathered = gather_payloads(plan, payload, device, dst=src, group=group)
+    tick("gather")
+    whole = codec.assemble(goff, gathered) if rank == src else None
+    tick("assemble")
+    return whole, blob, plan
 
 
 # ---------------------------------------------------------------- wavelet tree: sharding by id range
