@@ -86,6 +86,14 @@ struct idc_ef_blob {
 
 namespace {
 
+// Tile descriptor of the encoder, 16 bytes: where the tile's ids are (element offset into the id array), which list
+// it belongs to, its number inside the list and how many ids it holds. One load tells a warp what to fetch.
+struct EfTile {
+    uint64_t src;      // element offset of the tile's first id
+    uint32_t list;
+    uint32_t idx_cnt;  // tile number inside the list << 10 | (ids in the tile - 1)
+};
+
 struct EfEncArgs {
     const void* ids;
     const uint64_t* list_src;   // element offset of each list in ids
@@ -100,9 +108,10 @@ struct EfEncArgs {
     uint32_t* samples;
     const uint64_t* dir_off;
     EfChunk* dir;
-    const uint32_t* tile_list;
-    const uint32_t* tile_idx;
+    const EfTile* tiles;        // one descriptor per tile of 1024 ids (k_ef_tile_desc)
+    const uint32_t* tile_base;  // first tile of each list
     uint32_t ntiles;
+    uint32_t nlist;
     uint32_t check_input;       // ascending input taken on trust so far: verify order and width while encoding
     uint32_t* status;
 };
@@ -150,149 +159,260 @@ __device__ __noinline__ void ef_emit_chunk(const EfEncArgs& a, uint32_t L, uint3
     a.dir[a.dir_off[L] + C] = d;
 }
 
+// ---- bulk asynchronous copies (the TMA unit's 1-D form, cp.async.bulk: ONE instruction moves a whole tile from
+// global to shared memory, completion is signalled on an mbarrier; SASS: UBLKCP + SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// src and dst 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "EF_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra EF_DONE;\n"
+        "bra EF_WAIT;\n"
+        "EF_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// per-tile descriptors from the per-list tile counts: one warp per list
+__global__ void __launch_bounds__(kThreads) k_ef_tile_desc(const uint64_t* list_src, const uint64_t* list_off, const uint32_t* tile_base,
+                                                           uint32_t nlist, EfTile* tiles) {
+    const uint32_t L = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (L >= nlist) return;
+    const uint64_t m = list_off[L + 1] - list_off[L], src = list_src[L];
+    const uint32_t nt = tile_base[L + 1] - tile_base[L];
+    EfTile* out = tiles + tile_base[L];
+    for (uint32_t t = lane; t < nt; t += 32) {
+        const uint64_t i0 = (uint64_t)t * kEncTileIds;
+        const uint32_t cnt = (uint32_t)(m - i0 < kEncTileIds ? m - i0 : kEncTileIds);
+        out[t] = EfTile{src + i0, L, (t << 10) | (cnt - 1u)};
+    }
+}
+
+constexpr int kEncWarps = 4;  // warps per CTA of k_ef_encode
+
+// shared memory of one warp: the raw tile as it lies in global memory (bulk-copy target, + 16 bytes of alignment
+// slack), the transposed 32-bit tile, the upper-bits window, the mbarrier
 template <typename IdT>
-__global__ void __launch_bounds__(kThreads, 4) k_ef_encode(EfEncArgs a) {
-    __shared__ uint32_t tile_sm[kThreads / 32][kEncTileIds + 32];
-    __shared__ uint32_t win_sm[kThreads / 32][kEncWinWords];
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= a.ntiles) return;
-    const uint32_t L = a.tile_list[warp];
-    const uint64_t m = a.list_off[L + 1] - a.list_off[L];
-    if (m == 0) return;
-    const IdT* ids = reinterpret_cast<const IdT*>(a.ids) + a.list_src[L];
-    const uint32_t l = a.l[L];
-    const uint64_t hw = a.high_off[L + 1] - a.high_off[L];
-    const uint64_t i0 = (uint64_t)a.tile_idx[warp] * kEncTileIds;
-    const uint32_t cnt = (uint32_t)(m - i0 < kEncTileIds ? m - i0 : kEncTileIds);
-    const bool last_tile = i0 + cnt == m;
-    uint32_t* low32 = reinterpret_cast<uint32_t*>(a.low + a.low_off[L]) + (i0 * l) / 32;
-    uint32_t* high32 = reinterpret_cast<uint32_t*>(a.high + a.high_off[L]);
-    uint32_t* ts = tile_sm[threadIdx.x >> 5];
-    uint32_t* win = win_sm[threadIdx.x >> 5];
-    // ---- coalesced rows -> shared memory (element e at e + e / 32: both access patterns are conflict-free)
-    uint32_t bad = 0;
-    {
-        uint32_t row[32];
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            const uint64_t id = (uint32_t)r * 32u + lane < cnt ? load_id(ids + i0 + (uint32_t)r * 32u + lane) : 0ull;
-            if (sizeof(IdT) == 8 && (id >> 32)) bad |= kStWide;
-            row[r] = (uint32_t)id;
-        }
-#pragma unroll
-        for (int r = 0; r < 32; r++) ts[33u * (uint32_t)r + lane] = row[r];
-    }
-    // the one before this tile's first one (-1: none)
-    const uint64_t id_prev_tile = i0 ? load_id(ids + i0 - 1) : 0ull;
-    const int64_t hp_prev_tile = i0 ? (int64_t)((id_prev_tile >> l) + i0 - 1) : -1;
+struct EfEncSmem {
+    alignas(16) uint8_t raw[kEncTileIds * sizeof(IdT) + 16];
+    uint32_t ts[kEncTileIds + 32];
+    uint32_t win[kEncWinWords];
+    alignas(8) uint64_t bar;
+};
+
+// PERSISTENT warps, one tile of 1024 consecutive ids of a list at a time. The tile is fetched by ONE bulk
+// asynchronous copy (cp.async.bulk, completion on the warp's mbarrier) that is issued a whole tile ahead: while a
+// warp packs tile k, the copy engine lands tile k + 1 in its raw buffer -- the global-memory latency is off the
+// warp's critical path, no register tile of in-flight loads is needed (v3: 128 registers, 25 % occupancy,
+// latency-bound at 44 % of the HBM roofline). Every id is read exactly once. The raw tile is then moved to the
+// padded 32-bit tile (conflict-free in both directions) so that lane j holds the 32 CONSECUTIVE ids
+// 32 j .. 32 j + 31; everything after that is lane-local:
+//   lower bits: a lane's 32 fields are exactly l consecutive 32-bit words (1024 l bits per tile = a whole number of
+//               64-bit words, so tiles own their lower-bits words): packed through a 64-bit accumulator, staged in
+//               shared memory, stored coalesced.
+//   upper bits: a lane's ones are strictly increasing and ~96 bits apart from the next lane's, so setting them in
+//               an 8192-bit shared-memory window is an atomicOr without conflicts. Words strictly between the tile's
+//               first and last one belong to the tile alone (plain stores); its first and last word may be shared
+//               with the neighbouring tiles (atomicOr on the pre-zeroed array).
+//   chunk descriptors for the decoder: id e announces the chunk boundaries between the previous id's one and its
+//               own (ids before such a boundary = e); the list's last tile adds the trailing ones.
+template <typename IdT>
+__global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(EfEncArgs a) {
+    extern __shared__ __align__(128) uint8_t ef_enc_smem[];
+    EfEncSmem<IdT>* sm = reinterpret_cast<EfEncSmem<IdT>*>(ef_enc_smem) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * kEncWarps;
+    uint32_t tile = blockIdx.x * kEncWarps + (threadIdx.x >> 5);
+    uint32_t* ts = sm->ts;
+    uint32_t* win = sm->win;
+    if (lane == 0) mbar_init(&sm->bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    uint32_t v[32];  // lane-major: v[r] = id of element 32 * lane + r
-#pragma unroll
-    for (int r = 0; r < 32; r++) v[r] = ts[33u * lane + (uint32_t)r];
-    if (a.check_input) {
-        // ascending? inside the lane, across lanes, across the tile's start (ids past the list's end were loaded as 0)
-#pragma unroll
-        for (int r = 0; r + 1 < 32; r++)
-            if (32u * lane + (uint32_t)r + 1u < cnt && v[r + 1] < v[r]) bad |= kStUnsorted;
-        const uint32_t next_first = __shfl_down_sync(0xffffffffu, v[0], 1);
-        if (lane < 31u && 32u * (lane + 1u) < cnt && next_first < v[31]) bad |= kStUnsorted;
-        if (lane == 0 && i0 && (uint64_t)v[0] < id_prev_tile) bad |= kStUnsorted;
-        // The list's shapes were derived from its LAST id. If this tile is ascending its largest position is its
-        // last one; should that lie outside the list's bit vector (only possible when the list as a whole is not
-        // ascending), or the tile itself be out of order, nothing of it is written: the call fails anyway.
-        const uint64_t last_pos = (uint64_t)(ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0 + cnt - 1u;
-        if (last_pos >= hw * 64) bad |= kStUnsorted;
-        if (bad) atomicOr(a.status, bad);
-        if (__any_sync(0xffffffffu, (bad & kStUnsorted) != 0)) return;
+    // fetch of a tile: the copy starts at the 16-byte boundary at or below the tile's first id; `skew` = bytes to skip
+    auto fetch = [&](const EfTile& d) -> uint32_t {
+        const uintptr_t p = reinterpret_cast<uintptr_t>(reinterpret_cast<const IdT*>(a.ids) + d.src);
+        const uint32_t skew = (uint32_t)(p & 15u);
+        const uint32_t bytes = (skew + ((d.idx_cnt & 1023u) + 1u) * (uint32_t)sizeof(IdT) + 15u) & ~15u;
+        if (lane == 0) {
+            mbar_expect_tx(&sm->bar, bytes);
+            bulk_g2s(sm->raw, reinterpret_cast<const void*>(p - skew), bytes, &sm->bar);
+        }
+        return skew;
+    };
+    EfTile cur{0, 0, 0}, nxt{0, 0, 0};
+    uint32_t skew = 0, parity = 0;
+    if (tile < a.ntiles) {
+        cur = a.tiles[tile];
+        skew = fetch(cur);
     }
-    // positions in the high bit vector fit 32 bits (ef_build rejects lists whose vector is longer)
-    const uint32_t i0w = (uint32_t)i0;
-    const uint32_t hpF = (ts[0] >> l) + i0w;
-    const uint32_t hpL = (ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0w + cnt - 1u;
-    // ---- chunk descriptors (a chunk = kDecChunkWords 64-bit words = 1024 bits of the high vector). Id e announces
-    // the chunks C with prev < 1024 C <= hp(e), prev = the one before it: it is the first id at or past their first
-    // bit, so `ids before the chunk` = e. A straight-line pass marks the announcing ids (a few per tile); the
-    // descriptors are written in a rolled loop that re-reads those ids from shared memory (still intact here).
-    {
-        const uint32_t my_last = (v[31] >> l) + i0w + 32u * lane + 31u;
-        int64_t prev = (int64_t)__shfl_up_sync(0xffffffffu, my_last, 1);
-        if (lane == 0) prev = hp_prev_tile;
-        uint32_t c_lo = prev < 0 ? 0u : (uint32_t)(prev >> 10) + 1u;  // first chunk not announced yet
-        uint32_t bm = 0;
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            const uint32_t e = 32u * lane + (uint32_t)r;
-            const uint32_t c_hi = ((v[r] >> l) + i0w + e) >> 10;
-            if (e < cnt) {
-                bm |= c_hi >= c_lo ? 1u << r : 0u;
-                c_lo = c_hi + 1u;
+    if (tile + nwarps < a.ntiles) nxt = a.tiles[tile + nwarps];
+    for (; tile < a.ntiles; tile += nwarps) {
+        const uint32_t L = cur.list;
+        const uint64_t m = a.list_off[L + 1] - a.list_off[L];
+        const IdT* ids = reinterpret_cast<const IdT*>(a.ids) + a.list_src[L];
+        const uint32_t l = a.l[L];
+        const uint64_t hw = a.high_off[L + 1] - a.high_off[L];
+        const uint64_t i0 = (uint64_t)(cur.idx_cnt >> 10) * kEncTileIds;
+        const uint32_t cnt = (cur.idx_cnt & 1023u) + 1u;
+        const bool last_tile = i0 + cnt == m;
+        uint32_t* low32 = reinterpret_cast<uint32_t*>(a.low + a.low_off[L]) + (i0 * l) / 32;
+        uint32_t* high32 = reinterpret_cast<uint32_t*>(a.high + a.high_off[L]);
+        // the one before this tile's first one (-1: none)
+        const uint64_t id_prev_tile = i0 ? load_id(ids + i0 - 1) : 0ull;
+        // ---- the tile has landed: raw rows -> padded 32-bit tile (element e at e + e / 32)
+        mbar_wait(&sm->bar, parity);
+        parity ^= 1u;
+        uint32_t bad = 0;
+        {
+            const IdT* raw = reinterpret_cast<const IdT*>(sm->raw + skew);
+#pragma unroll 8
+            for (int r = 0; r < 32; r++) {
+                const uint32_t e = (uint32_t)r * 32u + lane;
+                uint64_t id = 0;
+                if (e < cnt) id = sizeof(IdT) == 8 ? (uint64_t)raw[e] : (uint64_t)(uint32_t)raw[e];
+                if (sizeof(IdT) == 8 && (id >> 32)) bad |= kStWide;
+                ts[33u * (uint32_t)r + lane] = (uint32_t)id;
             }
         }
-        while (bm) {
-            const uint32_t r = (uint32_t)__ffs((int)bm) - 1u;
-            bm &= bm - 1u;
-            const uint32_t e = 32u * lane + r;
-            const uint32_t c_hi = ((ts[33u * lane + r] >> l) + i0w + e) >> 10;
-            const int64_t pp = r ? (int64_t)((ts[33u * lane + r - 1u] >> l) + i0w + e - 1u) : prev;
-            for (uint32_t C = pp < 0 ? 0u : (uint32_t)(pp >> 10) + 1u; C <= c_hi; C++) ef_emit_chunk(a, L, l, m, hw, C, i0 + e);
-        }
-        if (last_tile) {
-            const uint64_t nchunks = (hw + kDecChunkWords - 1) / kDecChunkWords;
-            for (uint64_t C = (uint64_t)(hpL >> 10) + 1 + lane; C < nchunks; C += 32) ef_emit_chunk(a, L, l, m, hw, C, m);
-        }
-    }
-    __syncwarp();
-    // ---- lower bits
-    if (l) {
-        const uint32_t nlw = ((cnt * l + 63u) / 64u) * 2u;  // 32-bit words, a whole number of 64-bit words
-        const uint32_t fmask = (1u << l) - 1u;             // l <= 31 for ids < 2^32
-        uint64_t acc = 0;
-        uint32_t fill = 0, wq = lane * l;
+        __syncwarp();  // every lane is done with the raw buffer: the next tile may land in it
+        const uint32_t tn = tile + nwarps;
+        uint32_t skew_next = 0;
+        if (tn < a.ntiles) skew_next = fetch(nxt);
+        const EfTile after = tn + nwarps < a.ntiles ? a.tiles[tn + nwarps] : EfTile{0, 0, 0};
+        const int64_t hp_prev_tile = i0 ? (int64_t)((id_prev_tile >> l) + i0 - 1) : -1;
+        uint32_t v[32];  // lane-major: v[r] = id of element 32 * lane + r
 #pragma unroll
-        for (int r = 0; r < 32; r++) {
-            acc |= (uint64_t)(v[r] & fmask) << fill;  // ids past the end of the list were loaded as 0
-            fill += l;
-            if (fill >= 32u) {
-                ts[wq++] = (uint32_t)acc;
-                acc >>= 32;
-                fill -= 32u;
+        for (int r = 0; r < 32; r++) v[r] = ts[33u * lane + (uint32_t)r];
+        bool skip = false;
+        if (a.check_input) {
+            // ascending? inside the lane, across lanes, across the tile's start (ids past the list's end were loaded as 0)
+#pragma unroll
+            for (int r = 0; r + 1 < 32; r++)
+                if (32u * lane + (uint32_t)r + 1u < cnt && v[r + 1] < v[r]) bad |= kStUnsorted;
+            const uint32_t next_first = __shfl_down_sync(0xffffffffu, v[0], 1);
+            if (lane < 31u && 32u * (lane + 1u) < cnt && next_first < v[31]) bad |= kStUnsorted;
+            if (lane == 0 && i0 && (uint64_t)v[0] < id_prev_tile) bad |= kStUnsorted;
+            // The list's shapes were derived from its LAST id. If this tile is ascending its largest position is its
+            // last one; should that lie outside the list's bit vector (only possible when the list as a whole is not
+            // ascending), or the tile itself be out of order, nothing of it is written: the call fails anyway.
+            const uint64_t last_pos = (uint64_t)(ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0 + cnt - 1u;
+            if (last_pos >= hw * 64) bad |= kStUnsorted;
+            if (bad) atomicOr(a.status, bad);
+            skip = __any_sync(0xffffffffu, (bad & kStUnsorted) != 0);
+        } else if (bad) {
+            atomicOr(a.status, bad);
+        }
+        if (!skip) {
+            // positions in the high bit vector fit 32 bits (ef_build rejects lists whose vector is longer)
+            const uint32_t i0w = (uint32_t)i0;
+            const uint32_t hpF = (ts[0] >> l) + i0w;
+            const uint32_t hpL = (ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0w + cnt - 1u;
+            // ---- chunk descriptors (a chunk = kDecChunkWords 64-bit words = 1024 bits of the high vector). Id e
+            // announces the chunks C with prev < 1024 C <= hp(e), prev = the one before it: it is the first id at or
+            // past their first bit, so `ids before the chunk` = e. A straight-line pass marks the announcing ids (a
+            // few per tile); the descriptors are written in a rolled loop that re-reads those ids from shared memory.
+            {
+                const uint32_t my_last = (v[31] >> l) + i0w + 32u * lane + 31u;
+                int64_t prev = (int64_t)__shfl_up_sync(0xffffffffu, my_last, 1);
+                if (lane == 0) prev = hp_prev_tile;
+                uint32_t c_lo = prev < 0 ? 0u : (uint32_t)(prev >> 10) + 1u;  // first chunk not announced yet
+                uint32_t bm = 0;
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    const uint32_t e = 32u * lane + (uint32_t)r;
+                    const uint32_t c_hi = ((v[r] >> l) + i0w + e) >> 10;
+                    if (e < cnt) {
+                        bm |= c_hi >= c_lo ? 1u << r : 0u;
+                        c_lo = c_hi + 1u;
+                    }
+                }
+                while (bm) {
+                    const uint32_t r = (uint32_t)__ffs((int)bm) - 1u;
+                    bm &= bm - 1u;
+                    const uint32_t e = 32u * lane + r;
+                    const uint32_t c_hi = ((ts[33u * lane + r] >> l) + i0w + e) >> 10;
+                    const int64_t pp = r ? (int64_t)((ts[33u * lane + r - 1u] >> l) + i0w + e - 1u) : prev;
+                    for (uint32_t C = pp < 0 ? 0u : (uint32_t)(pp >> 10) + 1u; C <= c_hi; C++) ef_emit_chunk(a, L, l, m, hw, C, i0 + e);
+                }
+                if (last_tile) {
+                    const uint64_t nchunks = (hw + kDecChunkWords - 1) / kDecChunkWords;
+                    for (uint64_t C = (uint64_t)(hpL >> 10) + 1 + lane; C < nchunks; C += 32) ef_emit_chunk(a, L, l, m, hw, C, m);
+                }
+            }
+            __syncwarp();
+            // ---- lower bits
+            if (l) {
+                const uint32_t nlw = ((cnt * l + 63u) / 64u) * 2u;  // 32-bit words, a whole number of 64-bit words
+                const uint32_t fmask = (1u << l) - 1u;             // l <= 31 for ids < 2^32
+                uint64_t acc = 0;
+                uint32_t fill = 0, wq = lane * l;
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    acc |= (uint64_t)(v[r] & fmask) << fill;  // ids past the end of the list were loaded as 0
+                    fill += l;
+                    if (fill >= 32u) {
+                        ts[wq++] = (uint32_t)acc;
+                        acc >>= 32;
+                        fill -= 32u;
+                    }
+                }
+                __syncwarp();
+                for (uint32_t q = lane; q < nlw; q += 32) low32[q] = ts[q];
+            }
+            // ---- upper bits
+            const uint32_t gF = hpF >> 5, gL = hpL >> 5;  // the tile's first / last 32-bit word of the high vector
+            if (lane % 8u == 0u && 32u * lane < cnt)
+                (a.samples + a.samp_off[L])[(i0 + 32u * lane) >> kEfSampleLog] = (v[0] >> l) + i0w + 32u * lane;
+            uint32_t wb = hpF & ~31u;  // window base (a bit position)
+            for (;;) {
+                for (uint32_t q = lane; q < kEncWinWords; q += 32) win[q] = 0u;
+                __syncwarp();
+                const bool more = hpL - wb >= 32u * kEncWinWords;  // warp-uniform: some ones lie past this window
+                uint32_t next = 0xffffffffu;
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    const uint32_t e = 32u * lane + (uint32_t)r;
+                    const uint32_t hp = (v[r] >> l) + i0w + e;
+                    const uint32_t rel = hp - wb;  // wraps (huge) for positions below the window: handled in an earlier pass
+                    if (e < cnt && rel < 32u * kEncWinWords) atomicOr(win + (rel >> 5), 1u << (hp & 31u));
+                    if (more && e < cnt && hp >= wb && rel >= 32u * kEncWinWords && hp < next) next = hp;
+                }
+                __syncwarp();
+                for (uint32_t q = lane; q < kEncWinWords; q += 32) {
+                    const uint32_t g = (wb >> 5) + q;
+                    if (g < gF || g > gL) continue;
+                    const uint32_t val = win[q];
+                    if (g == gF || g == gL) {
+                        if (val) atomicOr(high32 + g, val);
+                    } else {
+                        high32[g] = val;
+                    }
+                }
+                if (!more) break;
+                next = __reduce_min_sync(0xffffffffu, next);
+                wb = next & ~31u;
+                __syncwarp();
             }
         }
-        __syncwarp();
-        for (uint32_t q = lane; q < nlw; q += 32) low32[q] = ts[q];
-    }
-    // ---- upper bits
-    const uint32_t gF = hpF >> 5, gL = hpL >> 5;  // the tile's first / last 32-bit word of the high vector
-    if (lane % 8u == 0u && 32u * lane < cnt) (a.samples + a.samp_off[L])[(i0 + 32u * lane) >> kEfSampleLog] = (v[0] >> l) + i0w + 32u * lane;
-    uint32_t wb = hpF & ~31u;  // window base (a bit position)
-    for (;;) {
-        for (uint32_t q = lane; q < kEncWinWords; q += 32) win[q] = 0u;
-        __syncwarp();
-        const bool more = hpL - wb >= 32u * kEncWinWords;  // warp-uniform: some ones lie past this window
-        uint32_t next = 0xffffffffu;
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            const uint32_t e = 32u * lane + (uint32_t)r;
-            const uint32_t hp = (v[r] >> l) + i0w + e;
-            const uint32_t rel = hp - wb;  // wraps (huge) for positions below the window: handled in an earlier pass
-            if (e < cnt && rel < 32u * kEncWinWords) atomicOr(win + (rel >> 5), 1u << (hp & 31u));
-            if (more && e < cnt && hp >= wb && rel >= 32u * kEncWinWords && hp < next) next = hp;
-        }
-        __syncwarp();
-        for (uint32_t q = lane; q < kEncWinWords; q += 32) {
-            const uint32_t g = (wb >> 5) + q;
-            if (g < gF || g > gL) continue;
-            const uint32_t val = win[q];
-            if (g == gF || g == gL) {
-                if (val) atomicOr(high32 + g, val);
-            } else {
-                high32[g] = val;
-            }
-        }
-        if (!more) break;
-        next = __reduce_min_sync(0xffffffffu, next);
-        wb = next & ~31u;
-        __syncwarp();
+        __syncwarp();  // ts / win are rewritten by the next tile
+        cur = nxt;
+        nxt = after;
+        skew = skew_next;
     }
 }
 
@@ -570,9 +690,7 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     b->high_off.assign(nl + 1, 0);
     b->samp_off.assign(nl + 1, 0);
     b->dir_off.assign(nl + 1, 0);
-    std::vector<uint32_t> tile_list, tile_idx;
-    tile_list.reserve(nl + b->total_ids / kEncTileIds);
-    tile_idx.reserve(nl + b->total_ids / kEncTileIds);
+    std::vector<uint32_t> tile_base(nl + 1, 0);  // first encoder tile of each list; the per-tile table is built on the device
     uint64_t bits_total = 0;
     for (uint64_t i = 0; i < nl; i++) {
         EfShape s = ef_shape(hi[i], n32[i]);
@@ -587,10 +705,9 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
         b->samp_off[i + 1] = b->samp_off[i] + s.samples;
         b->dir_off[i + 1] = b->dir_off[i] + std::max<uint64_t>(1, (s.high_words + kDecChunkWords - 1) / kDecChunkWords);
         bits_total += s.low_bits + s.high_bits;
-        for (uint64_t t = 0; t * kEncTileIds < n32[i]; t++) {
-            tile_list.push_back((uint32_t)i);
-            tile_idx.push_back((uint32_t)t);
-        }
+        const uint64_t nt = tile_base[i] + ((uint64_t)n32[i] + kEncTileIds - 1) / kEncTileIds;
+        IDC_REQUIRE(nt < (1ull << 32), IDC_ERR_ARG, "too many encoder tiles");
+        tile_base[i + 1] = (uint32_t)nt;
     }
     tr.mark("shapes + tile tables");
     b->low_words = b->low_off[nl];
@@ -621,8 +738,9 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     // sort when needed (ids < 2^32 was checked by the metadata kernel)
     const void* enc_ids = ids_dev;
     int enc_id_bytes = id_bytes;
-    const uint64_t ntiles = tile_list.size();
-    size_t tile_bytes = ((ntiles * 4 + 255) & ~size_t(255)) * 2;
+    const uint64_t ntiles = tile_base[nl];
+    const size_t base_bytes = ((nl + 1) * 4 + 255) & ~size_t(255);
+    size_t tile_bytes = base_bytes + ((ntiles * sizeof(EfTile) + 255) & ~size_t(255));
     size_t ws_need = tile_bytes;
     size_t sorted_off = 0, sortidx_off = 0, big_off = 0, posbase_off = 0;
     uint32_t sort_grid = 0;
@@ -642,10 +760,9 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
         ws_need = big_off + (need_big ? (size_t)sort_grid * kMaxUnit * 8 : 0);
     }
     IDC_TRY(c->ws.reserve(ws_need + 256));
-    uint32_t* d_tile_list = c->ws.as<uint32_t>();
-    uint32_t* d_tile_idx = reinterpret_cast<uint32_t*>(c->ws.as<uint8_t>() + tile_bytes / 2);
-    IDC_TRY(upload(c, d_tile_list, tile_list));
-    IDC_TRY(upload(c, d_tile_idx, tile_idx));
+    uint32_t* d_tile_base = c->ws.as<uint32_t>();
+    EfTile* d_tiles = reinterpret_cast<EfTile*>(c->ws.as<uint8_t>() + base_bytes);
+    IDC_TRY(upload(c, d_tile_base, tile_base));
     if (!sorted_in && nl) {
         uint32_t* d_sorted = (uint32_t*)(c->ws.as<uint8_t>() + sorted_off);
         uint32_t* d_sort_idx = (uint32_t*)(c->ws.as<uint8_t>() + sortidx_off);
@@ -663,14 +780,33 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     // tiles OR their first / last upper-bits word into the array: it starts out zero
     IDC_CUDA(cudaMemsetAsync(b->d_high, 0, std::max<uint64_t>(b->high_words, 1) * 8, c->stream));
     if (ntiles) {
+        {
+            LaunchScope ls(c, "k_ef_tile_desc");
+            k_ef_tile_desc<<<grid_for(nl * 32), kThreads, 0, c->stream>>>(d_src, b->d_list_off, d_tile_base, (uint32_t)nl, d_tiles);
+        }
+        IDC_TRY(check_last_launch("k_ef_tile_desc"));
         EfEncArgs e{enc_ids, d_src, b->d_list_off, b->d_l, d_hi, b->d_low_off, b->d_high_off, b->d_samp_off,
-                    b->d_low, b->d_high, b->d_samples, b->d_dir_off, b->d_dir, d_tile_list, d_tile_idx, (uint32_t)ntiles,
-                    sorted_in ? 1u : 0u, d_status};
+                    b->d_low, b->d_high, b->d_samples, b->d_dir_off, b->d_dir, d_tiles, d_tile_base, (uint32_t)ntiles,
+                    (uint32_t)nl, sorted_in ? 1u : 0u, d_status};
+        // persistent warps: as many CTAs as stay resident (shared memory: one raw tile + the 32-bit tile + the
+        // window per warp), each warp walks the tile list with the stride of the whole grid
+        const size_t smem = kEncWarps * (enc_id_bytes == 8 ? sizeof(EfEncSmem<int64_t>) : sizeof(EfEncSmem<uint32_t>));
+        int per_sm = 0;
+        if (enc_id_bytes == 8) {
+            IDC_CUDA(cudaFuncSetAttribute(k_ef_encode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            IDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ef_encode<int64_t>, kEncWarps * 32, smem));
+        } else {
+            IDC_CUDA(cudaFuncSetAttribute(k_ef_encode<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            IDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ef_encode<uint32_t>, kEncWarps * 32, smem));
+        }
+        if (const char* ev = getenv("IDC_EF_ENC_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(ev)));  // experiments
+        const uint64_t want = (ntiles + kEncWarps - 1) / kEncWarps;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)std::max(per_sm, 1) * c->sm_count);
         LaunchScope ls(c, "k_ef_encode");
         if (enc_id_bytes == 8)
-            k_ef_encode<int64_t><<<grid_for(ntiles * 32), kThreads, 0, c->stream>>>(e);
+            k_ef_encode<int64_t><<<grid, kEncWarps * 32, smem, c->stream>>>(e);
         else
-            k_ef_encode<uint32_t><<<grid_for(ntiles * 32), kThreads, 0, c->stream>>>(e);
+            k_ef_encode<uint32_t><<<grid, kEncWarps * 32, smem, c->stream>>>(e);
     }
     IDC_TRY(check_last_launch("k_ef_encode"));
     if (b->ndir) {
