@@ -86,32 +86,30 @@ struct idc_ef_blob {
 
 namespace {
 
-// Tile descriptor of the encoder, 16 bytes: where the tile's ids are (element offset into the id array), which list
-// it belongs to, its number inside the list and how many ids it holds. One load tells a warp what to fetch.
-struct EfTile {
-    uint64_t src;      // element offset of the tile's first id
-    uint32_t list;
-    uint32_t idx_cnt;  // tile number inside the list << 10 | (ids in the tile - 1)
+// Tile descriptor of the encoder, 64 bytes, written by k_ef_tile_desc: everything a warp needs to know about a tile of
+// 1024 consecutive ids and about the tile's list, so that the encode kernel does no dependent global loads at all.
+struct alignas(16) EfTile {
+    uint64_t src;       // element offset of the tile's first id
+    uint64_t low32;     // offset (32-bit words, from the start of the blob's lower-bits array) of the tile's first word
+    uint64_t high_off;  // offset (64-bit words) of the list's upper-bits vector
+    uint64_t out_base;  // element offset of the list's first id in a decode-everything output (chunk descriptors)
+    uint64_t dir_off;   // first chunk descriptor of the list
+    uint64_t samp;      // slot of the tile's first select sample
+    uint32_t m;         // ids of the list
+    uint32_t hw;        // 64-bit words of the list's upper-bits vector
+    uint32_t idx_cnt;   // tile number inside the list << 10 | (ids in the tile - 1)
+    uint32_t l;
 };
+static_assert(sizeof(EfTile) == 64, "EfTile is copied as four 16-byte pieces");
 
 struct EfEncArgs {
     const void* ids;
-    const uint64_t* list_src;   // element offset of each list in ids
-    const uint64_t* list_off;   // CSR (n = list_off[l+1] - list_off[l])
-    const uint8_t* l;
-    const uint32_t* list_hi;    // universe = max id
-    const uint64_t* low_off;
-    const uint64_t* high_off;
-    const uint64_t* samp_off;
     uint64_t* low;
     uint64_t* high;
     uint32_t* samples;
-    const uint64_t* dir_off;
     EfChunk* dir;
     const EfTile* tiles;        // one descriptor per tile of 1024 ids (k_ef_tile_desc)
-    const uint32_t* tile_base;  // first tile of each list
     uint32_t ntiles;
-    uint32_t nlist;
     uint32_t check_input;       // ascending input taken on trust so far: verify order and width while encoding
     uint32_t* status;
 };
@@ -131,32 +129,22 @@ __global__ void __launch_bounds__(kThreads) k_list_ends(const void* ids, const u
     hi[L] = (uint32_t)last;
 }
 
-// One warp per tile of 1024 consecutive ids of a list. Every id is read exactly once (32 coalesced rows, all
-// requested before the first is used) and transposed through shared memory so that lane j holds the 32
-// CONSECUTIVE ids 32 j .. 32 j + 31 of the tile; everything after that is lane-local:
-//   lower bits: a lane's 32 fields are exactly l consecutive 32-bit words (1024 l bits per tile = a whole number of
-//               64-bit words, so tiles own their lower-bits words): packed through a 64-bit accumulator, staged in
-//               shared memory, stored coalesced.
-//   upper bits: a lane's ones are strictly increasing and ~96 bits apart from the next lane's, so setting them in
-//               an 8192-bit shared-memory window is an atomicOr without conflicts. Words strictly between the tile's
-//               first and last one belong to the tile alone (plain stores); its first and last word may be shared
-//               with the neighbouring tiles (atomicOr on the pre-zeroed array).
-//   chunk descriptors for the decoder: id e announces the chunk boundaries between the previous id's one and its
-//               own (ids before such a boundary = e); the list's last tile adds the trailing ones.
-__device__ __noinline__ void ef_emit_chunk(const EfEncArgs& a, uint32_t L, uint32_t l, uint64_t m, uint64_t hw,
-                                              uint64_t C, uint64_t before) {
-    const uint64_t W = C * kDecChunkWords;
+// Chunk descriptor C of the tile's list (a chunk = kDecChunkWords 64-bit words = 1024 bits of the upper-bits vector);
+// `before` = ids of the list in front of the chunk's first bit.
+__device__ __forceinline__ void ef_emit_chunk(const EfEncArgs& a, const EfTile& t, uint64_t C, uint64_t before) {
+    const uint64_t W = C * kDecChunkWords, hw = t.hw;
     if (W >= hw) return;
     const bool last = W + kDecChunkWords >= hw;
-    const uint64_t cntc = last ? m - before : 0x7ffull;  // 0x7ff: k_ef_finish_chunks takes it from the next descriptor
+    const uint64_t cntc = last ? t.m - before : 0x7ffull;  // 0x7ff: k_ef_finish_chunks takes it from the next descriptor
     const uint64_t rest = hw - W;
     const uint64_t nw32 = 2 * (rest < kDecChunkWords ? rest : kDecChunkWords);
+    const uint64_t low_base = t.low32 - (uint64_t)(t.idx_cnt >> 10) * (kEncTileIds / 32) * t.l;  // the list's first lower-bits word
     EfChunk d;
-    d.a = (2 * (a.high_off[L] + W)) | (cntc << 40) | ((uint64_t)l << 51) | (nw32 << 56);
-    d.low32 = 2 * a.low_off[L] + (before >> 5) * l;
-    d.out_base = a.list_off[L];
+    d.a = (2 * (t.high_off + W)) | (cntc << 40) | ((uint64_t)t.l << 51) | (nw32 << 56);
+    d.low32 = low_base + (before >> 5) * t.l;
+    d.out_base = t.out_base;
     d.b = before | ((W * 64 - before) << 32);
-    a.dir[a.dir_off[L] + C] = d;
+    a.dir[t.dir_off + C] = d;
 }
 
 // ---- bulk asynchronous copies (the TMA unit's 1-D form, cp.async.bulk: ONE instruction moves a whole tile from
@@ -188,231 +176,434 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// per-tile descriptors from the per-list tile counts: one warp per list
-__global__ void __launch_bounds__(kThreads) k_ef_tile_desc(const uint64_t* list_src, const uint64_t* list_off, const uint32_t* tile_base,
-                                                           uint32_t nlist, EfTile* tiles) {
-    const uint32_t L = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (L >= nlist) return;
-    const uint64_t m = list_off[L + 1] - list_off[L], src = list_src[L];
-    const uint32_t nt = tile_base[L + 1] - tile_base[L];
-    EfTile* out = tiles + tile_base[L];
-    for (uint32_t t = lane; t < nt; t += 32) {
-        const uint64_t i0 = (uint64_t)t * kEncTileIds;
-        const uint32_t cnt = (uint32_t)(m - i0 < kEncTileIds ? m - i0 : kEncTileIds);
-        out[t] = EfTile{src + i0, L, (t << 10) | (cnt - 1u)};
+// per-tile descriptors from the per-list tables
+struct EfTileDescArgs {
+    const uint64_t* list_src;
+    const uint64_t* list_off;
+    const uint8_t* l;
+    const uint64_t* low_off;
+    const uint64_t* high_off;
+    const uint64_t* samp_off;
+    const uint64_t* dir_off;
+    const uint32_t* tile_base;
+    uint32_t nlist;
+    EfTile* tiles;
+};
+
+// one thread per tile; its list = the last one whose first tile is not past it (binary search over tile_base)
+__global__ void __launch_bounds__(kThreads) k_ef_tile_desc(EfTileDescArgs a, uint32_t ntiles) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ntiles) return;
+    uint32_t lo = 0, hi = a.nlist;  // tile_base[lo] <= g < tile_base[hi]
+    while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a.tile_base + mid) <= g)
+            lo = mid;
+        else
+            hi = mid;
     }
+    const uint32_t L = lo, t = g - a.tile_base[L], l = a.l[L];
+    const uint64_t o0 = a.list_off[L], m = a.list_off[L + 1] - o0;
+    const uint64_t h0 = a.high_off[L], hw = a.high_off[L + 1] - h0;
+    const uint64_t i0 = (uint64_t)t * kEncTileIds;
+    const uint32_t cnt = (uint32_t)(m - i0 < kEncTileIds ? m - i0 : kEncTileIds);
+    EfTile d;
+    d.src = a.list_src[L] + i0;
+    d.low32 = 2 * a.low_off[L] + (uint64_t)t * (kEncTileIds / 32) * l;
+    d.high_off = h0;
+    d.out_base = o0;
+    d.dir_off = a.dir_off[L];
+    d.samp = a.samp_off[L] + (i0 >> kEfSampleLog);
+    d.m = (uint32_t)m;
+    d.hw = (uint32_t)hw;  // < 2^26: the vector has < 2^32 bits
+    d.idx_cnt = (t << 10) | (cnt - 1u);
+    d.l = l;
+    a.tiles[g] = d;
 }
 
-constexpr int kEncWarps = 4;  // warps per CTA of k_ef_encode
+constexpr int kEncWarps = 4;          // warps per CTA of k_ef_encode
+constexpr uint32_t kEncSubIds = 128;  // ids per bulk copy: a tile arrives as 8 copies of 4 lane runs each
+constexpr int kEncMaxFastL = 22;      // widest lower-bits field a full tile can have (1024 ids below 2^32)
 
-// shared memory of one warp: the raw tile as it lies in global memory (bulk-copy target, + 16 bytes of alignment
-// slack), the transposed 32-bit tile, the upper-bits window, the mbarrier
+// shared memory of one warp. `raw` is the bulk-copy target: sub-block c (ids 128 c .. 128 c + 127 of the tile, as they
+// lie in global memory from the 16-byte boundary below the tile's first id) sits at 16 + c * kSubStride; the 16 bytes in
+// front of sub-block 0 receive the id before the tile (tiles after a list's first one fetch 16 bytes more). The stride
+// is the sub-block's size + 16 bytes, so the four 32-id runs of a sub-block go to the four quarter-warps and the eight
+// lanes of a quarter-warp (one run from every sub-block) read different banks. `desc` is a ring of tile descriptors,
+// filled two tiles ahead by cp.async: the persistent loop carries no prefetched state in registers.
 template <typename IdT>
 struct EfEncSmem {
-    alignas(16) uint8_t raw[kEncTileIds * sizeof(IdT) + 16];
-    uint32_t ts[kEncTileIds + 32];
+    static constexpr uint32_t kSubStride = kEncSubIds * sizeof(IdT) + 16;
+    alignas(16) uint8_t raw[16 + 8 * kSubStride];
+    alignas(16) EfTile desc[3];
+    uint32_t ts[kEncTileIds + 32];  // slow path: the transposed 32-bit tile; fast path: staging of the lower-bits words
     uint32_t win[kEncWinWords];
     alignas(8) uint64_t bar;
 };
 
-// PERSISTENT warps, one tile of 1024 consecutive ids of a list at a time. The tile is fetched by ONE bulk
-// asynchronous copy (cp.async.bulk, completion on the warp's mbarrier) that is issued a whole tile ahead: while a
-// warp packs tile k, the copy engine lands tile k + 1 in its raw buffer -- the global-memory latency is off the
-// warp's critical path, no register tile of in-flight loads is needed (v3: 128 registers, 25 % occupancy,
-// latency-bound at 44 % of the HBM roofline). Every id is read exactly once. The raw tile is then moved to the
-// padded 32-bit tile (conflict-free in both directions) so that lane j holds the 32 CONSECUTIVE ids
-// 32 j .. 32 j + 31; everything after that is lane-local:
-//   lower bits: a lane's 32 fields are exactly l consecutive 32-bit words (1024 l bits per tile = a whole number of
-//               64-bit words, so tiles own their lower-bits words): packed through a 64-bit accumulator, staged in
-//               shared memory, stored coalesced.
-//   upper bits: a lane's ones are strictly increasing and ~96 bits apart from the next lane's, so setting them in
-//               an 8192-bit shared-memory window is an atomicOr without conflicts. Words strictly between the tile's
+// Lower bits of one lane's run of 32 consecutive ids with a COMPILE-TIME field width: the 32 fields are exactly L
+// 32-bit words; every shift and word index is a constant (mask + shift-add per id, nothing data dependent). The words
+// are staged in shared memory (row stride L | 1: conflict-free) and leave as coalesced 128-byte stores.
+template <int L>
+__device__ __forceinline__ void ef_low_tile(const uint32_t (&v)[32], uint32_t* stage, uint32_t* low32, uint32_t run, uint32_t lane) {
+    if constexpr (L > 0) {
+        constexpr uint32_t kMask = (1u << L) - 1u, kRow = (uint32_t)L | 1u;
+        uint32_t w[L];
+#pragma unroll
+        for (int k = 0; k < L; k++) w[k] = 0u;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const uint32_t f = v[r] & kMask;
+            const int k = (r * L) >> 5, s = (r * L) & 31;
+            w[k] += f << s;  // disjoint bits: + is | (one shift-add)
+            if (s + L > 32) w[k + 1] = f >> (32 - s);
+        }
+        uint32_t* row = stage + run * kRow;
+#pragma unroll
+        for (int k = 0; k < L; k++) row[k] = w[k];
+        __syncwarp();
+        // (the lane number goes through an opaque move: otherwise the compiler hoists the 253 staging indices of all
+        // field widths out of the persistent tile loop and keeps them in local memory)
+        asm volatile("" : "+r"(lane));
+#pragma unroll
+        for (int k = 0; k < L; k++) {
+            const uint32_t q = 32u * (uint32_t)k + lane;
+            if constexpr ((L & 1) != 0) {
+                low32[q] = stage[q];
+            } else {
+                const uint32_t rr = q / (uint32_t)L;
+                low32[q] = stage[q + rr];
+            }
+        }
+    }
+}
+
+// SLOW path of k_ef_encode (partial tiles, upper bits wider than one window, input that is about to be refused): the
+// tile has been transposed into `ts` (element e at e + e / 32, ids past the end of the list as 0), lane j owns the run
+// of ids 32 j .. 32 j + 31. Out of line: it is rare and must not weigh on the fast path's register allocation.
+__device__ __noinline__ void ef_tile_slow(const EfEncArgs& a, uint32_t* ts, uint32_t* win, const EfTile* tp, uint64_t id_prev_tile,
+                                           uint32_t bad, uint32_t lane) {
+    const EfTile t = *tp;
+    const uint64_t m = t.m, hw = t.hw, i0 = (uint64_t)(t.idx_cnt >> 10) * kEncTileIds;
+    const uint32_t l = t.l, i0w = (uint32_t)i0, cnt = (t.idx_cnt & 1023u) + 1u;
+    const bool last_tile = i0 + cnt == m;
+    uint32_t* low32 = reinterpret_cast<uint32_t*>(a.low) + t.low32;
+    uint32_t* high32 = reinterpret_cast<uint32_t*>(a.high + t.high_off);
+    const int64_t hp_prev_tile = i0 ? (int64_t)((id_prev_tile >> l) + i0 - 1) : -1;  // the one before this tile's first one
+    uint32_t v[32];  // lane-major: v[r] = id of element 32 * lane + r
+#pragma unroll
+    for (int r = 0; r < 32; r++) v[r] = ts[33u * lane + (uint32_t)r];
+    if (a.check_input) {
+        // ascending? inside the lane, across lanes, across the tile's start (ids past the list's end were loaded as 0)
+#pragma unroll
+        for (int r = 0; r + 1 < 32; r++)
+            if (32u * lane + (uint32_t)r + 1u < cnt && v[r + 1] < v[r]) bad |= kStUnsorted;
+        const uint32_t next_first = __shfl_down_sync(0xffffffffu, v[0], 1);
+        if (lane < 31u && 32u * (lane + 1u) < cnt && next_first < v[31]) bad |= kStUnsorted;
+        if (lane == 0 && i0 && (uint64_t)v[0] < id_prev_tile) bad |= kStUnsorted;
+        // The list's shapes were derived from its LAST id. If this tile is ascending its largest position is its
+        // last one; should that lie outside the list's bit vector (only possible when the list as a whole is not
+        // ascending), or the tile itself be out of order, nothing of it is written: the call fails anyway.
+        const uint64_t last_pos = (uint64_t)(ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0 + cnt - 1u;
+        if (last_pos >= hw * 64) bad |= kStUnsorted;
+        if (bad) atomicOr(a.status, bad);
+        if (__any_sync(0xffffffffu, (bad & kStUnsorted) != 0)) return;
+    } else if (bad) {
+        atomicOr(a.status, bad);
+    }
+    const uint32_t hpF = (ts[0] >> l) + i0w;
+    const uint32_t hpL = (ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0w + cnt - 1u;
+    // ---- chunk descriptors: id e announces the chunks C with prev < 1024 C <= hp(e), prev = the one before it: it
+    // is the first id at or past their first bit, so `ids before the chunk` = e. A straight-line pass marks the
+    // announcing ids (a few per tile); the descriptors are written in a rolled loop that re-reads those ids.
+    {
+        const uint32_t my_last = (v[31] >> l) + i0w + 32u * lane + 31u;
+        int64_t prev = (int64_t)__shfl_up_sync(0xffffffffu, my_last, 1);
+        if (lane == 0) prev = hp_prev_tile;
+        uint32_t c_lo = prev < 0 ? 0u : (uint32_t)(prev >> 10) + 1u;  // first chunk not announced yet
+        uint32_t bm = 0;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const uint32_t e = 32u * lane + (uint32_t)r;
+            const uint32_t c_hi = ((v[r] >> l) + i0w + e) >> 10;
+            if (e < cnt) {
+                bm |= c_hi >= c_lo ? 1u << r : 0u;
+                c_lo = c_hi + 1u;
+            }
+        }
+        while (bm) {
+            const uint32_t r = (uint32_t)__ffs((int)bm) - 1u;
+            bm &= bm - 1u;
+            const uint32_t e = 32u * lane + r;
+            const uint32_t c_hi = ((ts[33u * lane + r] >> l) + i0w + e) >> 10;
+            const int64_t pp = r ? (int64_t)((ts[33u * lane + r - 1u] >> l) + i0w + e - 1u) : prev;
+            for (uint32_t C = pp < 0 ? 0u : (uint32_t)(pp >> 10) + 1u; C <= c_hi; C++) ef_emit_chunk(a, t, C, i0 + e);
+        }
+        if (last_tile) {
+            const uint64_t nchunks = (hw + kDecChunkWords - 1) / kDecChunkWords;
+            for (uint64_t C = (uint64_t)(hpL >> 10) + 1 + lane; C < nchunks; C += 32) ef_emit_chunk(a, t, C, m);
+        }
+    }
+    __syncwarp();
+    // ---- lower bits
+    if (l) {
+        const uint32_t nlw = ((cnt * l + 63u) / 64u) * 2u;  // 32-bit words, a whole number of 64-bit words
+        const uint32_t fmask = (1u << l) - 1u;             // l <= 31 for ids < 2^32
+        uint64_t acc = 0;
+        uint32_t fill = 0, wq = lane * l;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            acc |= (uint64_t)(v[r] & fmask) << fill;  // ids past the end of the list were loaded as 0
+            fill += l;
+            if (fill >= 32u) {
+                ts[wq++] = (uint32_t)acc;
+                acc >>= 32;
+                fill -= 32u;
+            }
+        }
+        __syncwarp();
+        for (uint32_t q = lane; q < nlw; q += 32) low32[q] = ts[q];
+    }
+    // ---- upper bits
+    const uint32_t gF = hpF >> 5, gL = hpL >> 5;  // the tile's first / last 32-bit word of the high vector
+    if (lane % 8u == 0u && 32u * lane < cnt) a.samples[t.samp + (lane >> 3)] = (v[0] >> l) + i0w + 32u * lane;
+    uint32_t wb = hpF & ~31u;  // window base (a bit position)
+    for (;;) {
+        for (uint32_t q = lane; q < kEncWinWords; q += 32) win[q] = 0u;
+        __syncwarp();
+        const bool more = hpL - wb >= 32u * kEncWinWords;  // warp-uniform: some ones lie past this window
+        uint32_t next = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const uint32_t e = 32u * lane + (uint32_t)r;
+            const uint32_t hp = (v[r] >> l) + i0w + e;
+            const uint32_t rel = hp - wb;  // wraps (huge) for positions below the window: handled in an earlier pass
+            if (e < cnt && rel < 32u * kEncWinWords) atomicOr(win + (rel >> 5), 1u << (hp & 31u));
+            if (more && e < cnt && hp >= wb && rel >= 32u * kEncWinWords && hp < next) next = hp;
+        }
+        __syncwarp();
+        for (uint32_t q = lane; q < kEncWinWords; q += 32) {
+            const uint32_t g = (wb >> 5) + q;
+            if (g < gF || g > gL) continue;
+            const uint32_t val = win[q];
+            if (g == gF || g == gL) {
+                if (val) atomicOr(high32 + g, val);
+            } else {
+                high32[g] = val;
+            }
+        }
+        if (!more) break;
+        next = __reduce_min_sync(0xffffffffu, next);
+        wb = next & ~31u;
+        __syncwarp();
+    }
+}
+
+// PERSISTENT warps, one tile of 1024 consecutive ids of a list at a time. A tile is fetched by bulk asynchronous
+// copies (cp.async.bulk = the TMA unit's 1-D form, completion on the warp's mbarrier) issued a whole tile ahead: while
+// a warp packs tile k, the copy engine lands tile k + 1 in its raw buffer -- the global-memory latency is off the
+// warp's critical path and no register tile of in-flight loads is needed. Every id is read exactly once. The tile
+// descriptors (64 bytes, everything about the tile and its list) arrive two tiles ahead in a shared-memory ring.
+// Lane j owns a run of 32 CONSECUTIVE ids; everything after the fetch is lane-local:
+//   lower bits: a run's 32 fields are exactly l consecutive 32-bit words (1024 l bits per tile = a whole number of
+//               64-bit words, so tiles own their lower-bits words), staged in shared memory, stored coalesced.
+//   upper bits: a run's ones are strictly increasing and ~96 bits apart from the next run's, so setting them in an
+//               8192-bit shared-memory window is an atomicOr without conflicts. Words strictly between the tile's
 //               first and last one belong to the tile alone (plain stores); its first and last word may be shared
 //               with the neighbouring tiles (atomicOr on the pre-zeroed array).
-//   chunk descriptors for the decoder: id e announces the chunk boundaries between the previous id's one and its
-//               own (ids before such a boundary = e); the list's last tile adds the trailing ones.
+//   chunk descriptors for the decoder: the first id at or past a chunk's first bit announces it (ids before the
+//               chunk = its number); the list's last tile adds the trailing ones.
+// FAST path (full tiles whose upper bits fit one window and whose runs cross at most one chunk boundary each -- all
+// but the last tile of a list): the run is read straight from the raw buffer into registers (lane 8 i + c owns run
+// 4 c + i, see EfEncSmem), the lower bits are packed with the field width as a template parameter, the upper bits
+// need one window pass without range checks, and a run that crosses a chunk boundary finds the announcing id by a
+// binary search over its part of the raw buffer.
+// SLOW path (everything else): ef_tile_slow, through a transposed 32-bit tile.
 template <typename IdT>
-__global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(EfEncArgs a) {
+__global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(const __grid_constant__ EfEncArgs a) {
     extern __shared__ __align__(128) uint8_t ef_enc_smem[];
-    EfEncSmem<IdT>* sm = reinterpret_cast<EfEncSmem<IdT>*>(ef_enc_smem) + (threadIdx.x >> 5);
-    const uint32_t lane = threadIdx.x & 31;
+    using Smem = EfEncSmem<IdT>;
+    Smem* sm = reinterpret_cast<Smem*>(ef_enc_smem) + (threadIdx.x >> 5);
+    uint32_t lane = threadIdx.x & 31;
     const uint32_t nwarps = gridDim.x * kEncWarps;
     uint32_t tile = blockIdx.x * kEncWarps + (threadIdx.x >> 5);
     uint32_t* ts = sm->ts;
     uint32_t* win = sm->win;
+    if (tile >= a.ntiles) return;
     if (lane == 0) mbar_init(&sm->bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    // fetch of a tile: the copy starts at the 16-byte boundary at or below the tile's first id; `skew` = bytes to skip
-    auto fetch = [&](const EfTile& d) -> uint32_t {
-        const uintptr_t p = reinterpret_cast<uintptr_t>(reinterpret_cast<const IdT*>(a.ids) + d.src);
-        const uint32_t skew = (uint32_t)(p & 15u);
-        const uint32_t bytes = (skew + ((d.idx_cnt & 1023u) + 1u) * (uint32_t)sizeof(IdT) + 15u) & ~15u;
-        if (lane == 0) {
-            mbar_expect_tx(&sm->bar, bytes);
-            bulk_g2s(sm->raw, reinterpret_cast<const void*>(p - skew), bytes, &sm->bar);
-        }
-        return skew;
+    // descriptor of tile t -> ring slot (asynchronous: lanes 0..3 move 16 bytes each)
+    auto fetch_desc = [&](uint32_t t, uint32_t slot) {
+        if (lane < 4u && t < a.ntiles)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(sm->desc + slot) + 16u * lane)),
+                         "l"(reinterpret_cast<const uint8_t*>(a.tiles + t) + 16u * lane)
+                         : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    EfTile cur{0, 0, 0}, nxt{0, 0, 0};
-    uint32_t skew = 0, parity = 0;
-    if (tile < a.ntiles) {
-        cur = a.tiles[tile];
-        skew = fetch(cur);
-    }
-    if (tile + nwarps < a.ntiles) nxt = a.tiles[tile + nwarps];
+    // fetch of a tile's ids: sub-block c starts at the 16-byte boundary at or below its first id, sub-block 0 of a
+    // tile that is not its list's first one 16 bytes earlier (the id before the tile)
+    auto fetch = [&](const EfTile& d) {
+        const uintptr_t p = reinterpret_cast<uintptr_t>(reinterpret_cast<const IdT*>(a.ids) + d.src);
+        const uint32_t skew = (uint32_t)(p & 15u), cnt = (d.idx_cnt & 1023u) + 1u;
+        const uint32_t first = lane * kEncSubIds;
+        const uint32_t nsub = first < cnt ? (cnt - first < kEncSubIds ? cnt - first : kEncSubIds) : 0u;  // lane c: ids of sub-block c
+        const uint32_t lead = (lane == 0u && (d.idx_cnt >> 10)) ? 16u : 0u;
+        const uint32_t bytes = nsub ? lead + ((skew + nsub * (uint32_t)sizeof(IdT) + 15u) & ~15u) : 0u;
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+        if (lane == 0) mbar_expect_tx(&sm->bar, total);
+        __syncwarp();
+        if (bytes)
+            bulk_g2s(sm->raw + 16u - lead + lane * Smem::kSubStride,
+                     reinterpret_cast<const void*>(p - skew - lead + (size_t)first * sizeof(IdT)), bytes, &sm->bar);
+    };
+    // prologue: descriptors of the first two tiles, ids of the first
+    fetch_desc(tile, 0);
+    fetch_desc(tile + nwarps, 1);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    fetch(sm->desc[0]);
+    const uint32_t run = ((lane & 7u) << 2) | (lane >> 3);  // fast path: the run of this lane
+    const uint32_t lane_next = (((run + 1u) & 3u) << 3) | (((run + 1u) & 31u) >> 2), lane_prev = (((run - 1u) & 3u) << 3) | (((run - 1u) & 31u) >> 2);
+    uint32_t parity = 0, slot = 0;
     for (; tile < a.ntiles; tile += nwarps) {
-        const uint32_t L = cur.list;
-        const uint64_t m = a.list_off[L + 1] - a.list_off[L];
-        const IdT* ids = reinterpret_cast<const IdT*>(a.ids) + a.list_src[L];
-        const uint32_t l = a.l[L];
-        const uint64_t hw = a.high_off[L + 1] - a.high_off[L];
-        const uint64_t i0 = (uint64_t)(cur.idx_cnt >> 10) * kEncTileIds;
-        const uint32_t cnt = (cur.idx_cnt & 1023u) + 1u;
-        const bool last_tile = i0 + cnt == m;
-        uint32_t* low32 = reinterpret_cast<uint32_t*>(a.low + a.low_off[L]) + (i0 * l) / 32;
-        uint32_t* high32 = reinterpret_cast<uint32_t*>(a.high + a.high_off[L]);
-        // the one before this tile's first one (-1: none)
-        const uint64_t id_prev_tile = i0 ? load_id(ids + i0 - 1) : 0ull;
-        // ---- the tile has landed: raw rows -> padded 32-bit tile (element e at e + e / 32)
+        const EfTile* tp = sm->desc + slot;
+        const uint32_t slot1 = slot == 2u ? 0u : slot + 1u, slot2 = slot1 == 2u ? 0u : slot1 + 1u;
+        const uint32_t l = tp->l, idx_cnt = tp->idx_cnt;
+        const uint64_t i0 = (uint64_t)(idx_cnt >> 10) * kEncTileIds;
+        const uint32_t cnt = (idx_cnt & 1023u) + 1u;
+        const uint32_t i0w = (uint32_t)i0;  // positions in the high bit vector fit 32 bits (ef_build rejects longer vectors)
+        const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(reinterpret_cast<const IdT*>(a.ids) + tp->src) & 15u);
+        const uint8_t* raw0 = sm->raw + 16u + skew;  // the tile's first id
+        // ---- the tile has landed
         mbar_wait(&sm->bar, parity);
         parity ^= 1u;
+        const uint64_t id_prev_tile = i0 ? (sizeof(IdT) == 8 ? (uint64_t) * (reinterpret_cast<const IdT*>(raw0) - 1)
+                                                             : (uint64_t)(uint32_t) * (reinterpret_cast<const IdT*>(raw0) - 1))
+                                         : 0ull;
+        uint32_t v[32];
+        uint32_t hpF = 0, hpL = 0, hp_first = 0, ann_c = 0, ann_before = 0xffffffffu;
+        const uint32_t hb = i0w + 32u * run;  // fast path: hp(r) = (v[r] >> l) + hb + r
+        bool fast = cnt == kEncTileIds && l <= (uint32_t)kEncMaxFastL;
+        if (fast) {
+            uint32_t wide = 0;
+            const IdT* rp = reinterpret_cast<const IdT*>(raw0 + (lane & 7u) * Smem::kSubStride) + (lane >> 3) * 32u;
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                if (sizeof(IdT) == 8) {
+                    const uint2 x = *reinterpret_cast<const uint2*>(rp + r);
+                    v[r] = x.x;
+                    wide |= x.y;
+                } else {
+                    v[r] = (uint32_t)rp[r];
+                }
+            }
+            hp_first = (v[0] >> l) + hb;
+            const uint32_t hp_last = (v[31] >> l) + hb + 31u;
+            hpF = __shfl_sync(0xffffffffu, hp_first, 0);
+            hpL = __shfl_sync(0xffffffffu, hp_last, 31);
+            const uint32_t next_first = __shfl_sync(0xffffffffu, v[0], lane_next);
+            const uint32_t prev_last = __shfl_sync(0xffffffffu, hp_last, lane_prev);
+            bool no = wide != 0u;  // anything the slow path has to deal with (or refuse)
+            if (a.check_input) {
+                // ascending? inside the run, across runs, across the tile's start
+#pragma unroll
+                for (int r = 0; r + 1 < 32; r++) no |= v[r + 1] < v[r];
+                no |= run < 31u && next_first < v[31];
+                no |= run == 0u && i0 && (uint64_t)v[0] < id_prev_tile;
+                // The list's shapes were derived from its LAST id: an ascending tile's largest position is its last
+                // one; should that lie outside the list's bit vector the list as a whole is not ascending.
+                no |= (uint64_t)hpL >= (uint64_t)tp->hw * 64;
+            }
+            // chunks (1024 bits of the high vector) this run announces: prev < 1024 C <= hp(last id of the run)
+            const int64_t prev = run ? (int64_t)prev_last : (i0 ? (int64_t)((id_prev_tile >> l) + i0 - 1) : -1);
+            const uint32_t c_lo = prev < 0 ? 0u : (uint32_t)(prev >> 10) + 1u, c_hi = hp_last >> 10;
+            no |= c_hi > c_lo;                                  // two boundaries inside one run
+            no |= hpL - (hpF & ~31u) >= 32u * kEncWinWords;     // upper bits wider than the window
+            fast = !__any_sync(0xffffffffu, no);
+            if (fast && c_hi == c_lo) {
+                // ids of the run before the boundary: hp(r) < 1024 C  <=>  (id(r) >> l) + r < T; the keys ascend and
+                // the last one is not below T: binary search over the run in the raw buffer
+                const uint32_t T = (c_lo << 10) - hb;
+                uint32_t before = 0;
+#pragma unroll
+                for (uint32_t step = 16; step; step >>= 1) {
+                    const uint32_t r = before + step - 1u;
+                    if (((uint32_t)rp[r] >> l) + r < T) before += step;
+                }
+                ann_c = c_lo;
+                ann_before = 32u * run + before;
+            }
+        }
         uint32_t bad = 0;
-        {
-            const IdT* raw = reinterpret_cast<const IdT*>(sm->raw + skew);
-#pragma unroll 8
+        if (!fast) {
+            // ---- raw rows -> padded 32-bit tile (element e at e + e / 32)
+#pragma unroll 4
             for (int r = 0; r < 32; r++) {
                 const uint32_t e = (uint32_t)r * 32u + lane;
+                const IdT* ep = reinterpret_cast<const IdT*>(raw0 + (e >> 7) * Smem::kSubStride) + (e & (kEncSubIds - 1u));
                 uint64_t id = 0;
-                if (e < cnt) id = sizeof(IdT) == 8 ? (uint64_t)raw[e] : (uint64_t)(uint32_t)raw[e];
+                if (e < cnt) id = sizeof(IdT) == 8 ? (uint64_t)*ep : (uint64_t)(uint32_t)*ep;
                 if (sizeof(IdT) == 8 && (id >> 32)) bad |= kStWide;
                 ts[33u * (uint32_t)r + lane] = (uint32_t)id;
             }
         }
-        __syncwarp();  // every lane is done with the raw buffer: the next tile may land in it
-        const uint32_t tn = tile + nwarps;
-        uint32_t skew_next = 0;
-        if (tn < a.ntiles) skew_next = fetch(nxt);
-        const EfTile after = tn + nwarps < a.ntiles ? a.tiles[tn + nwarps] : EfTile{0, 0, 0};
-        const int64_t hp_prev_tile = i0 ? (int64_t)((id_prev_tile >> l) + i0 - 1) : -1;
-        uint32_t v[32];  // lane-major: v[r] = id of element 32 * lane + r
-#pragma unroll
-        for (int r = 0; r < 32; r++) v[r] = ts[33u * lane + (uint32_t)r];
-        bool skip = false;
-        if (a.check_input) {
-            // ascending? inside the lane, across lanes, across the tile's start (ids past the list's end were loaded as 0)
-#pragma unroll
-            for (int r = 0; r + 1 < 32; r++)
-                if (32u * lane + (uint32_t)r + 1u < cnt && v[r + 1] < v[r]) bad |= kStUnsorted;
-            const uint32_t next_first = __shfl_down_sync(0xffffffffu, v[0], 1);
-            if (lane < 31u && 32u * (lane + 1u) < cnt && next_first < v[31]) bad |= kStUnsorted;
-            if (lane == 0 && i0 && (uint64_t)v[0] < id_prev_tile) bad |= kStUnsorted;
-            // The list's shapes were derived from its LAST id. If this tile is ascending its largest position is its
-            // last one; should that lie outside the list's bit vector (only possible when the list as a whole is not
-            // ascending), or the tile itself be out of order, nothing of it is written: the call fails anyway.
-            const uint64_t last_pos = (uint64_t)(ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0 + cnt - 1u;
-            if (last_pos >= hw * 64) bad |= kStUnsorted;
-            if (bad) atomicOr(a.status, bad);
-            skip = __any_sync(0xffffffffu, (bad & kStUnsorted) != 0);
-        } else if (bad) {
-            atomicOr(a.status, bad);
-        }
-        if (!skip) {
-            // positions in the high bit vector fit 32 bits (ef_build rejects lists whose vector is longer)
-            const uint32_t i0w = (uint32_t)i0;
-            const uint32_t hpF = (ts[0] >> l) + i0w;
-            const uint32_t hpL = (ts[(cnt - 1u) + ((cnt - 1u) >> 5)] >> l) + i0w + cnt - 1u;
-            // ---- chunk descriptors (a chunk = kDecChunkWords 64-bit words = 1024 bits of the high vector). Id e
-            // announces the chunks C with prev < 1024 C <= hp(e), prev = the one before it: it is the first id at or
-            // past their first bit, so `ids before the chunk` = e. A straight-line pass marks the announcing ids (a
-            // few per tile); the descriptors are written in a rolled loop that re-reads those ids from shared memory.
+        // every lane is done with the raw buffer: the next tile (its descriptor has arrived) may land in it, and the
+        // descriptor after that sets out
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (tile + nwarps < a.ntiles) fetch(sm->desc[slot1]);
+        fetch_desc(tile + 2u * nwarps, slot2);
+        if (fast) {
+            uint32_t* low32 = reinterpret_cast<uint32_t*>(a.low) + tp->low32;
+            uint32_t* high32 = reinterpret_cast<uint32_t*>(a.high + tp->high_off);
+            // ---- upper bits: one window, based at the word of the tile's first one
+            const uint32_t wb = hpF & ~31u, nwin = ((hpL - wb) >> 5) + 1u;
+            for (uint32_t q = lane; q < nwin; q += 32) win[q] = 0u;
+            if ((run & 7u) == 0u) a.samples[tp->samp + (run >> 3)] = hp_first;
+            __syncwarp();
             {
-                const uint32_t my_last = (v[31] >> l) + i0w + 32u * lane + 31u;
-                int64_t prev = (int64_t)__shfl_up_sync(0xffffffffu, my_last, 1);
-                if (lane == 0) prev = hp_prev_tile;
-                uint32_t c_lo = prev < 0 ? 0u : (uint32_t)(prev >> 10) + 1u;  // first chunk not announced yet
-                uint32_t bm = 0;
+                const uint32_t hbw = hb - wb;
 #pragma unroll
                 for (int r = 0; r < 32; r++) {
-                    const uint32_t e = 32u * lane + (uint32_t)r;
-                    const uint32_t c_hi = ((v[r] >> l) + i0w + e) >> 10;
-                    if (e < cnt) {
-                        bm |= c_hi >= c_lo ? 1u << r : 0u;
-                        c_lo = c_hi + 1u;
-                    }
+                    const uint32_t rel = (v[r] >> l) + hbw + (uint32_t)r;
+                    atomicOr(win + (rel >> 5), 1u << (rel & 31u));
                 }
-                while (bm) {
-                    const uint32_t r = (uint32_t)__ffs((int)bm) - 1u;
-                    bm &= bm - 1u;
-                    const uint32_t e = 32u * lane + r;
-                    const uint32_t c_hi = ((ts[33u * lane + r] >> l) + i0w + e) >> 10;
-                    const int64_t pp = r ? (int64_t)((ts[33u * lane + r - 1u] >> l) + i0w + e - 1u) : prev;
-                    for (uint32_t C = pp < 0 ? 0u : (uint32_t)(pp >> 10) + 1u; C <= c_hi; C++) ef_emit_chunk(a, L, l, m, hw, C, i0 + e);
-                }
-                if (last_tile) {
-                    const uint64_t nchunks = (hw + kDecChunkWords - 1) / kDecChunkWords;
-                    for (uint64_t C = (uint64_t)(hpL >> 10) + 1 + lane; C < nchunks; C += 32) ef_emit_chunk(a, L, l, m, hw, C, m);
-                }
+            }
+            // ---- lower bits (the staging area is the slow path's tile)
+            switch (l) {
+#define IDC_EF_LOW_CASE(LL)                       \
+    case LL:                                      \
+        ef_low_tile<LL>(v, ts, low32, run, lane); \
+        break;
+                IDC_EF_LOW_CASE(1) IDC_EF_LOW_CASE(2) IDC_EF_LOW_CASE(3) IDC_EF_LOW_CASE(4) IDC_EF_LOW_CASE(5) IDC_EF_LOW_CASE(6)
+                IDC_EF_LOW_CASE(7) IDC_EF_LOW_CASE(8) IDC_EF_LOW_CASE(9) IDC_EF_LOW_CASE(10) IDC_EF_LOW_CASE(11) IDC_EF_LOW_CASE(12)
+                IDC_EF_LOW_CASE(13) IDC_EF_LOW_CASE(14) IDC_EF_LOW_CASE(15) IDC_EF_LOW_CASE(16) IDC_EF_LOW_CASE(17) IDC_EF_LOW_CASE(18)
+                IDC_EF_LOW_CASE(19) IDC_EF_LOW_CASE(20) IDC_EF_LOW_CASE(21) IDC_EF_LOW_CASE(22)
+#undef IDC_EF_LOW_CASE
+                default:
+                    break;
             }
             __syncwarp();
-            // ---- lower bits
-            if (l) {
-                const uint32_t nlw = ((cnt * l + 63u) / 64u) * 2u;  // 32-bit words, a whole number of 64-bit words
-                const uint32_t fmask = (1u << l) - 1u;             // l <= 31 for ids < 2^32
-                uint64_t acc = 0;
-                uint32_t fill = 0, wq = lane * l;
-#pragma unroll
-                for (int r = 0; r < 32; r++) {
-                    acc |= (uint64_t)(v[r] & fmask) << fill;  // ids past the end of the list were loaded as 0
-                    fill += l;
-                    if (fill >= 32u) {
-                        ts[wq++] = (uint32_t)acc;
-                        acc >>= 32;
-                        fill -= 32u;
-                    }
+            for (uint32_t q = lane; q < nwin; q += 32) {
+                const uint32_t val = win[q];
+                if (q == 0u || q == nwin - 1u) {
+                    if (val) atomicOr(high32 + (wb >> 5) + q, val);
+                } else {
+                    high32[(wb >> 5) + q] = val;
                 }
-                __syncwarp();
-                for (uint32_t q = lane; q < nlw; q += 32) low32[q] = ts[q];
             }
-            // ---- upper bits
-            const uint32_t gF = hpF >> 5, gL = hpL >> 5;  // the tile's first / last 32-bit word of the high vector
-            if (lane % 8u == 0u && 32u * lane < cnt)
-                (a.samples + a.samp_off[L])[(i0 + 32u * lane) >> kEfSampleLog] = (v[0] >> l) + i0w + 32u * lane;
-            uint32_t wb = hpF & ~31u;  // window base (a bit position)
-            for (;;) {
-                for (uint32_t q = lane; q < kEncWinWords; q += 32) win[q] = 0u;
-                __syncwarp();
-                const bool more = hpL - wb >= 32u * kEncWinWords;  // warp-uniform: some ones lie past this window
-                uint32_t next = 0xffffffffu;
-#pragma unroll
-                for (int r = 0; r < 32; r++) {
-                    const uint32_t e = 32u * lane + (uint32_t)r;
-                    const uint32_t hp = (v[r] >> l) + i0w + e;
-                    const uint32_t rel = hp - wb;  // wraps (huge) for positions below the window: handled in an earlier pass
-                    if (e < cnt && rel < 32u * kEncWinWords) atomicOr(win + (rel >> 5), 1u << (hp & 31u));
-                    if (more && e < cnt && hp >= wb && rel >= 32u * kEncWinWords && hp < next) next = hp;
-                }
-                __syncwarp();
-                for (uint32_t q = lane; q < kEncWinWords; q += 32) {
-                    const uint32_t g = (wb >> 5) + q;
-                    if (g < gF || g > gL) continue;
-                    const uint32_t val = win[q];
-                    if (g == gF || g == gL) {
-                        if (val) atomicOr(high32 + g, val);
-                    } else {
-                        high32[g] = val;
-                    }
-                }
-                if (!more) break;
-                next = __reduce_min_sync(0xffffffffu, next);
-                wb = next & ~31u;
-                __syncwarp();
+            // ---- chunk descriptors
+            if (ann_before != 0xffffffffu) ef_emit_chunk(a, *tp, ann_c, i0 + ann_before);
+            if (i0 + cnt == tp->m) {
+                const uint64_t nchunks = ((uint64_t)tp->hw + kDecChunkWords - 1) / kDecChunkWords;
+                for (uint64_t C = (uint64_t)(hpL >> 10) + 1 + lane; C < nchunks; C += 32) ef_emit_chunk(a, *tp, C, tp->m);
             }
+        } else {
+            ef_tile_slow(a, ts, win, tp, id_prev_tile, bad, lane);
         }
-        __syncwarp();  // ts / win are rewritten by the next tile
-        cur = nxt;
-        nxt = after;
-        skew = skew_next;
+        __syncwarp();  // ts / win / the descriptor slot are rewritten by the following tiles
+        slot = slot1;
     }
 }
 
@@ -442,26 +633,72 @@ struct EfDecArgs {
     uint32_t* status;           // row mode: kStRange is OR-ed in when a row number is out of range
 };
 
+constexpr uint32_t kDecHighStage = 36;  // staged upper-bits words per warp: 32 + the 16-byte alignment slack on both sides
+
+// Output pass of k_ef_decode with a COMPILE-TIME field width: groups of 32 consecutive id numbers; the L-bit lower
+// fields of a group are exactly L consecutive 32-bit words of the staged stream, lane j's field starts at bit j L of
+// them (two LDS + one funnel shift, all offsets immediates); upper part from shared memory, one coalesced store.
+template <int L, typename OutT>
+__device__ __forceinline__ void ef_dec_out(const uint32_t* s_low, const uint16_t* hi_part, OutT* out, uint32_t lane, uint32_t lead,
+                                           uint32_t count, uint32_t ngroups, uint32_t zeros) {
+    constexpr uint32_t kMask = L ? (0xffffffffu >> (32 - (L ? L : 1))) : 0u;
+    const uint32_t fs = (lane * (uint32_t)L) & 31u;
+    const uint32_t* sp = s_low + ((lane * (uint32_t)L) >> 5);
+    uint32_t j = lane - lead;  // id number inside the chunk (wraps for the lanes in front of the chunk's first id)
+    const uint16_t* hp = hi_part + (int32_t)j;
+    OutT* o = out + (int32_t)j;
+    auto one = [&](uint32_t u) {
+        if (j + 32u * u < count) {
+            uint32_t f = 0;
+            if constexpr (L > 0) f = __funnelshift_r(sp[u * L], sp[u * L + 1], fs) & kMask;
+            const uint32_t id = (((uint32_t)hp[32u * u] + zeros) << L) | f;  // ids < 2^32 on the device path
+            o[32u * u] = (OutT)id;
+        }
+    };
+    uint32_t g = 0;
+    for (; g + 4u <= ngroups; g += 4u) {
+        one(0);
+        one(1);
+        one(2);
+        one(3);
+        j += 128u;
+        hp += 128;
+        o += 128;
+        sp += 4 * L;
+    }
+    for (; g < ngroups; g++) {
+        one(0);
+        j += 32u;
+        hp += 32;
+        o += 32;
+        sp += L;
+    }
+}
+
 // One warp per chunk of 16 64-bit words (= 32 32-bit words, one per lane) of the upper-bits vector:
 //   1. one 32-byte descriptor (written by the encoder) tells the warp everything: where the chunk's words
 //      are, the id number it starts at, how many ids it holds, l, where they go;
-//   2. popcount + warp scan -> where each word's ids land;
-//   3. every lane peels the set bits of its word (highest first: FLO, clear, store) into shared memory as
-//      upper parts (position - id number);
-//   4. a coalesced pass over the chunk's ids: the l-bit lower fields of 32 consecutive ids are exactly l
-//      consecutive 32-bit words; the chunk's words were fetched into shared memory by cp.async while steps
-//      2-3 ran (LDGSTS), a field is two LDS + a funnel shift; ids leave as full 256-byte warp stores.
+//   2. the chunk's upper-bits words and the lower-bits words of its ids are STAGED in shared memory by two bulk
+//      asynchronous copies (cp.async.bulk, the TMA unit's 1-D form; one elected lane issues them, completion on
+//      the warp's mbarrier) instead of one 4-byte cp.async per lane and word;
+//   3. popcount + warp scan over the staged upper-bits words -> where each word's ids land;
+//   4. every lane peels the set bits of its word (highest first: FLO, clear, store; four per round) into shared
+//      memory as upper parts (position - id number);
+//   5. a coalesced pass over the chunk's ids with the field width as a template parameter (ef_dec_out); ids leave
+//      as full 256-byte warp stores.
 template <typename OutT>
 __global__ void __launch_bounds__(kDecThreads, 6) k_ef_decode(EfDecArgs a) {
-    // per warp: 1024 upper parts as u16 (position - id number inside the chunk <= 1023) + the chunk's lower-bits
-    // words, staged by cp.async while the upper bits are being scanned
+    // per warp: 1024 upper parts as u16 (position - id number inside the chunk <= 1023), the staged lower-bits
+    // words (+ 4: alignment slack), the staged upper-bits words, the mbarrier
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t)blockIdx.x * (kDecThreads / 32) + wib;
     if (warp >= a.ntiles) return;
-    uint8_t* s_warp = s_dyn + (size_t)wib * (2u * kDecTile + 4u * a.low_stage_words);
+    uint8_t* s_warp = s_dyn + (size_t)wib * (2u * kDecTile + 4u * (a.low_stage_words + 4u) + 4u * kDecHighStage + 16u);
     uint16_t* hi_part = reinterpret_cast<uint16_t*>(s_warp);
     uint32_t* s_low = reinterpret_cast<uint32_t*>(s_warp + 2u * kDecTile);
+    uint32_t* s_high = s_low + a.low_stage_words + 4u;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_high + kDecHighStage);
     uint64_t di = warp;
     if (a.row_stride) {
         if (a.row_nos) {
@@ -481,6 +718,7 @@ __global__ void __launch_bounds__(kDecThreads, 6) k_ef_decode(EfDecArgs a) {
     } else if (a.sel_desc) {
         di = a.sel_desc[warp];
     }
+    if (lane == 0) mbar_init(bar, 1);
     const uint4* dp = reinterpret_cast<const uint4*>(a.dir + di);
     const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
     const uint64_t da = (uint64_t)d0.x | ((uint64_t)d0.y << 32);
@@ -499,15 +737,21 @@ __global__ void __launch_bounds__(kDecThreads, 6) k_ef_decode(EfDecArgs a) {
         const uint32_t ngroups = (lead + count + 31u) >> 5;   // groups of 32 consecutive id numbers
         const uint32_t nlow = ngroups * l;                     // 32-bit lower-bits words covering them
         const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(a.low) + low32o;
-        const bool staged = nlow <= a.low_stage_words;
-        if (staged) {
-            uint32_t sdst = (uint32_t)__cvta_generic_to_shared(s_low);
-            for (uint32_t i = lane; i < nlow; i += 32)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst + 4u * i), "l"(lsrc + i));
-            asm volatile("cp.async.commit_group;");
-        }
         const uint32_t* h32 = reinterpret_cast<const uint32_t*>(a.high) + high32;
-        uint32_t w = lane < nw32 ? __ldg(h32 + lane) : 0u;
+        const bool staged = nlow <= a.low_stage_words;
+        // both sources are only 4- / 8-byte aligned: the copies start at the 16-byte boundary below them
+        const uint32_t lskew = (uint32_t)(reinterpret_cast<uintptr_t>(lsrc) & 15u), hskew = (uint32_t)(reinterpret_cast<uintptr_t>(h32) & 15u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t hbytes = (hskew + 4u * nw32 + 15u) & ~15u;
+            const uint32_t lbytes = (staged && nlow) ? (lskew + 4u * nlow + 15u) & ~15u : 0u;
+            mbar_expect_tx(bar, hbytes + lbytes);
+            bulk_g2s(s_high, reinterpret_cast<const uint8_t*>(h32) - hskew, hbytes, bar);
+            if (lbytes) bulk_g2s(s_low, reinterpret_cast<const uint8_t*>(lsrc) - lskew, lbytes, bar);
+        }
+        mbar_wait(bar, 0);
+        uint32_t w = lane < nw32 ? s_high[(hskew >> 2) + lane] : 0u;
         uint32_t sc = (uint32_t)__popc(w);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -520,28 +764,38 @@ __global__ void __launch_bounds__(kDecThreads, 6) k_ef_decode(EfDecArgs a) {
             uint16_t* p = hi_part + sc;   // one past this word's last id
             uint32_t v = 32u * lane - sc; // (bit base) - (id number): grows by one for every step back
             while (w) {
-                uint32_t b = 31u - (uint32_t)__clz((int)w);
-                w ^= 1u << b;
-                --p;
-                ++v;
-                *p = (uint16_t)(v + b);
+#pragma unroll
+                for (int u = 1; u <= 4; u++) {
+                    if (w) {
+                        const uint32_t b = 31u - (uint32_t)__clz((int)w);
+                        w ^= 1u << b;
+                        p[-u] = (uint16_t)(v + (uint32_t)u + b);
+                    }
+                }
+                p -= 4;
+                v += 4u;
             }
         }
-        if (staged) asm volatile("cp.async.wait_group 0;");
         __syncwarp();
-        const uint32_t fw = (lane * l) >> 5, fs = (lane * l) & 31u, fmask = l ? (0xffffffffu >> (32u - l)) : 0u;
-        const int32_t end = (int32_t)count;
-        int32_t j = (int32_t)lane - (int32_t)lead;
         if (staged) {
-            const uint32_t* sp = s_low + fw;
-            for (uint32_t g = 0; g < ngroups; g++, j += 32, sp += l) {
-                if (j >= 0 && j < end) {
-                    uint32_t f = l ? (__funnelshift_r(sp[0], sp[1], fs) & fmask) : 0u;
-                    uint64_t id = ((uint64_t)((uint32_t)hi_part[j] + zeros) << l) | f;
-                    out[j] = (OutT)id;
-                }
+            const uint32_t* sl = s_low + (lskew >> 2);
+            switch (l) {
+#define IDC_EF_DEC_CASE(LL)                                                           \
+    case LL:                                                                          \
+        ef_dec_out<LL, OutT>(sl, hi_part, out, lane, lead, count, ngroups, zeros);    \
+        break;
+                IDC_EF_DEC_CASE(0) IDC_EF_DEC_CASE(1) IDC_EF_DEC_CASE(2) IDC_EF_DEC_CASE(3) IDC_EF_DEC_CASE(4) IDC_EF_DEC_CASE(5)
+                IDC_EF_DEC_CASE(6) IDC_EF_DEC_CASE(7) IDC_EF_DEC_CASE(8) IDC_EF_DEC_CASE(9) IDC_EF_DEC_CASE(10) IDC_EF_DEC_CASE(11)
+                IDC_EF_DEC_CASE(12) IDC_EF_DEC_CASE(13) IDC_EF_DEC_CASE(14) IDC_EF_DEC_CASE(15) IDC_EF_DEC_CASE(16) IDC_EF_DEC_CASE(17)
+                IDC_EF_DEC_CASE(18) IDC_EF_DEC_CASE(19) IDC_EF_DEC_CASE(20) IDC_EF_DEC_CASE(21) IDC_EF_DEC_CASE(22) IDC_EF_DEC_CASE(23)
+                IDC_EF_DEC_CASE(24) IDC_EF_DEC_CASE(25) IDC_EF_DEC_CASE(26) IDC_EF_DEC_CASE(27) IDC_EF_DEC_CASE(28) IDC_EF_DEC_CASE(29)
+                IDC_EF_DEC_CASE(30) IDC_EF_DEC_CASE(31)
+#undef IDC_EF_DEC_CASE
             }
         } else {
+            const uint32_t fw = (lane * l) >> 5, fs = (lane * l) & 31u, fmask = l ? (0xffffffffu >> (32u - l)) : 0u;
+            const int32_t end = (int32_t)count;
+            int32_t j = (int32_t)lane - (int32_t)lead;
             const uint32_t* lp = lsrc + lane;
             for (uint32_t g = 0; g < ngroups; g++, j += 32, lp += l) {
                 uint32_t lwv = lane < l ? __ldg(lp) : 0u;
@@ -724,7 +978,7 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     IDC_TRY(dev_alloc(c, &b->d_dir_off, nl + 1, &acct));
     IDC_TRY(dev_alloc(c, &b->d_dir, b->ndir, &acct));
     IDC_TRY(dev_alloc(c, &b->d_low, b->low_words + 32, &acct));  // +256 B: the decoder's last group may read past the end
-    IDC_TRY(dev_alloc(c, &b->d_high, b->high_words, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_high, b->high_words + 2, &acct));  // + 16 B: the decoder stages whole 16-byte pieces
     IDC_TRY(dev_alloc(c, &b->d_samples, b->nsamples, &acct));
     IDC_TRY(upload(c, b->d_list_off, b->list_offsets));
     IDC_TRY(upload(c, b->d_l, b->l));
@@ -782,12 +1036,11 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
     if (ntiles) {
         {
             LaunchScope ls(c, "k_ef_tile_desc");
-            k_ef_tile_desc<<<grid_for(nl * 32), kThreads, 0, c->stream>>>(d_src, b->d_list_off, d_tile_base, (uint32_t)nl, d_tiles);
+            EfTileDescArgs t{d_src, b->d_list_off, b->d_l, b->d_low_off, b->d_high_off, b->d_samp_off, b->d_dir_off, d_tile_base, (uint32_t)nl, d_tiles};
+            k_ef_tile_desc<<<grid_for(ntiles), kThreads, 0, c->stream>>>(t, (uint32_t)ntiles);
         }
         IDC_TRY(check_last_launch("k_ef_tile_desc"));
-        EfEncArgs e{enc_ids, d_src, b->d_list_off, b->d_l, d_hi, b->d_low_off, b->d_high_off, b->d_samp_off,
-                    b->d_low, b->d_high, b->d_samples, b->d_dir_off, b->d_dir, d_tiles, d_tile_base, (uint32_t)ntiles,
-                    (uint32_t)nl, sorted_in ? 1u : 0u, d_status};
+        EfEncArgs e{enc_ids, b->d_low, b->d_high, b->d_samples, b->d_dir, d_tiles, (uint32_t)ntiles, sorted_in ? 1u : 0u, d_status};
         // persistent warps: as many CTAs as stay resident (shared memory: one raw tile + the 32-bit tile + the
         // window per warp), each warp walks the tile list with the stride of the whole grid
         const size_t smem = kEncWarps * (enc_id_bytes == 8 ? sizeof(EfEncSmem<int64_t>) : sizeof(EfEncSmem<uint32_t>));
@@ -839,7 +1092,7 @@ int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_sel_desc, 
                 stage_words, b->nlist, d_status};
     const uint32_t wpb = kDecThreads / 32;
     const uint32_t grid = (uint32_t)((ntiles + wpb - 1) / wpb);
-    const size_t smem = (size_t)wpb * (2u * kDecTile + 4u * stage_words);
+    const size_t smem = (size_t)wpb * (2u * kDecTile + 4u * (stage_words + 4u) + 4u * kDecHighStage + 16u);
     IDC_CUDA(cudaFuncSetAttribute(k_ef_decode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IDC_CUDA(cudaFuncSetAttribute(k_ef_decode<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
