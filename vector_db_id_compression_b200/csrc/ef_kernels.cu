@@ -633,6 +633,7 @@ struct EfDecArgs {
     uint32_t* status;           // row mode: kStRange is OR-ed in when a row number is out of range
 };
 
+constexpr uint32_t kDecStageCap = 384;  // staged lower-bits words per warp, at most
 constexpr uint32_t kDecHighStage = 36;  // staged upper-bits words per warp: 32 + the 16-byte alignment slack on both sides
 
 // Output pass of k_ef_decode with a COMPILE-TIME field width: groups of 32 consecutive id numbers; the L-bit lower
@@ -645,18 +646,16 @@ __device__ __forceinline__ void ef_dec_out(const uint32_t* s_low, const uint16_t
     const uint32_t fs = (lane * (uint32_t)L) & 31u;
     const uint32_t* sp = s_low + ((lane * (uint32_t)L) >> 5);
     uint32_t j = lane - lead;  // id number inside the chunk (wraps for the lanes in front of the chunk's first id)
-    const uint16_t* hp = hi_part + (int32_t)j;
-    OutT* o = out + (int32_t)j;
+    const uint16_t* hp = hi_part + (int32_t)j;  // (hi_part has 32 entries of slack in front and reads past the chunk's
+    OutT* o = out + (int32_t)j;                 //  ids stay inside the CTA's shared memory: only the store is predicated)
     auto one = [&](uint32_t u) {
-        if (j + 32u * u < count) {
-            uint32_t f = 0;
-            if constexpr (L > 0) f = __funnelshift_r(sp[u * L], sp[u * L + 1], fs) & kMask;
-            const uint32_t id = (((uint32_t)hp[32u * u] + zeros) << L) | f;  // ids < 2^32 on the device path
-            o[32u * u] = (OutT)id;
-        }
+        uint32_t f = 0;
+        if constexpr (L > 0) f = __funnelshift_r(sp[u * L], sp[u * L + 1], fs) & kMask;
+        const uint32_t id = (((uint32_t)hp[32u * u] + zeros) << L) | f;  // ids < 2^32 on the device path
+        if (j + 32u * u < count) o[32u * u] = (OutT)id;
     };
-    uint32_t g = 0;
-    for (; g + 4u <= ngroups; g += 4u) {
+    // four groups per round, the last round's surplus groups are predicated off like the lanes past the chunk's end
+    for (uint32_t g = 0; g < ngroups; g += 4u) {
         one(0);
         one(1);
         one(2);
@@ -666,37 +665,140 @@ __device__ __forceinline__ void ef_dec_out(const uint32_t* s_low, const uint16_t
         o += 128;
         sp += 4 * L;
     }
-    for (; g < ngroups; g++) {
-        one(0);
-        j += 32u;
-        hp += 32;
-        o += 32;
-        sp += L;
+}
+
+// ---- decoding one chunk of 16 64-bit words (= 32 32-bit words, one per lane) of the upper-bits vector
+struct EfDecChunk {  // the 32-byte descriptor, unpacked
+    uint64_t high32, low32o, out_base;
+    uint32_t count, l, nw32, r0, zeros;
+};
+
+__device__ __forceinline__ EfDecChunk ef_dec_unpack(uint4 d0, uint4 d1) {
+    EfDecChunk d;
+    const uint64_t da = (uint64_t)d0.x | ((uint64_t)d0.y << 32);
+    d.high32 = da & ((1ull << 40) - 1);
+    d.count = (uint32_t)(da >> 40) & 0x7ffu;
+    d.l = (uint32_t)(da >> 51) & 31u;
+    d.nw32 = (uint32_t)(da >> 56) & 63u;
+    d.low32o = (uint64_t)d0.z | ((uint64_t)d0.w << 32);
+    d.out_base = (uint64_t)d1.x | ((uint64_t)d1.y << 32);
+    d.r0 = d1.z;
+    d.zeros = d1.w;
+    return d;
+}
+
+// Staging of a chunk (one lane): its upper-bits words and the lower-bits words of its ids arrive in shared memory by two
+// bulk asynchronous copies (cp.async.bulk, the TMA unit's 1-D form), completion on the mbarrier. Both sources are only
+// 4- / 8-byte aligned: the copies start at the 16-byte boundary below them.
+__device__ __forceinline__ void ef_dec_stage(const EfDecArgs& a, const EfDecChunk& d, uint32_t* s_low, uint32_t* s_high, uint64_t* bar) {
+    const uint32_t lead = d.r0 & 31u, nlow = ((lead + d.count + 31u) >> 5) * d.l;
+    const uint8_t* lsrc = reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint32_t*>(a.low) + d.low32o);
+    const uint8_t* hsrc = reinterpret_cast<const uint8_t*>(reinterpret_cast<const uint32_t*>(a.high) + d.high32);
+    const uint32_t lskew = (uint32_t)(reinterpret_cast<uintptr_t>(lsrc) & 15u), hskew = (uint32_t)(reinterpret_cast<uintptr_t>(hsrc) & 15u);
+    const uint32_t hbytes = d.count ? (hskew + 4u * d.nw32 + 15u) & ~15u : 0u;
+    const uint32_t lbytes = (d.count && nlow && nlow <= a.low_stage_words) ? (lskew + 4u * nlow + 15u) & ~15u : 0u;
+    mbar_expect_tx(bar, hbytes + lbytes);  // (an empty chunk: the arrival alone completes the phase)
+    if (hbytes) bulk_g2s(s_high, hsrc - hskew, hbytes, bar);
+    if (lbytes) bulk_g2s(s_low, lsrc - lskew, lbytes, bar);
+}
+
+// The staged chunk -> ids:
+//   popcount + warp scan over the upper-bits words -> where each word's ids land;
+//   every lane peels the set bits of its word (highest first: FLO, clear, store; four per round) into shared memory
+//   as upper parts (position - id number);
+//   a coalesced pass over the chunk's ids with the field width as a template parameter (ef_dec_out); ids leave as
+//   full 256-byte warp stores.
+template <typename OutT>
+__device__ __forceinline__ void ef_dec_chunk(const EfDecArgs& a, const EfDecChunk& d, const uint32_t* s_low, const uint32_t* s_high,
+                                             uint16_t* hi_part, OutT* out, uint32_t lane) {
+    const uint32_t count = d.count, l = d.l, zeros = d.zeros;
+    const uint32_t lead = d.r0 & 31u;
+    const uint32_t ngroups = (lead + count + 31u) >> 5;   // groups of 32 consecutive id numbers
+    const uint32_t nlow = ngroups * l;                     // 32-bit lower-bits words covering them
+    const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(a.low) + d.low32o;
+    const uint32_t lskew = (uint32_t)(reinterpret_cast<uintptr_t>(lsrc) & 15u);
+    const uint32_t hskew = (uint32_t)(reinterpret_cast<uintptr_t>(reinterpret_cast<const uint32_t*>(a.high) + d.high32) & 15u);
+    uint32_t w = lane < d.nw32 ? s_high[(hskew >> 2) + lane] : 0u;
+    uint32_t sc = (uint32_t)__popc(w);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, sc, o);
+        if ((int)lane >= o) sc += v;
+    }
+    // The id with chunk-relative number j whose one sits at chunk bit P has upper part
+    //   (chunk_bit0 + P) - (r0 + j) = zeros + (P - j);  shared memory gets P - j, `zeros` is added on the way out.
+    {
+        uint16_t* p = hi_part + sc;   // one past this word's last id
+        uint32_t v = 32u * lane - sc; // (bit base) - (id number): grows by one for every step back
+        while (w) {
+            // four ones per round, straight-line: a lane that runs out of ones keeps w = 0 and skips the stores
+#pragma unroll
+            for (int u = 1; u <= 4; u++) {
+                const uint32_t b = 31u - (uint32_t)__clz((int)w);
+                const bool on = w != 0u;
+                w &= ~(1u << (b & 31u));
+                if (on) p[-u] = (uint16_t)(v + (uint32_t)u + b);
+            }
+            p -= 4;
+            v += 4u;
+        }
+    }
+    __syncwarp();
+    if (nlow <= a.low_stage_words) {
+        const uint32_t* sl = s_low + (lskew >> 2);
+        switch (l) {
+#define IDC_EF_DEC_CASE(LL)                                                        \
+    case LL:                                                                       \
+        ef_dec_out<LL, OutT>(sl, hi_part, out, lane, lead, count, ngroups, zeros); \
+        break;
+            IDC_EF_DEC_CASE(0) IDC_EF_DEC_CASE(1) IDC_EF_DEC_CASE(2) IDC_EF_DEC_CASE(3) IDC_EF_DEC_CASE(4) IDC_EF_DEC_CASE(5)
+            IDC_EF_DEC_CASE(6) IDC_EF_DEC_CASE(7) IDC_EF_DEC_CASE(8) IDC_EF_DEC_CASE(9) IDC_EF_DEC_CASE(10) IDC_EF_DEC_CASE(11)
+            IDC_EF_DEC_CASE(12) IDC_EF_DEC_CASE(13) IDC_EF_DEC_CASE(14) IDC_EF_DEC_CASE(15) IDC_EF_DEC_CASE(16) IDC_EF_DEC_CASE(17)
+            IDC_EF_DEC_CASE(18) IDC_EF_DEC_CASE(19) IDC_EF_DEC_CASE(20) IDC_EF_DEC_CASE(21) IDC_EF_DEC_CASE(22) IDC_EF_DEC_CASE(23)
+            IDC_EF_DEC_CASE(24) IDC_EF_DEC_CASE(25) IDC_EF_DEC_CASE(26) IDC_EF_DEC_CASE(27) IDC_EF_DEC_CASE(28) IDC_EF_DEC_CASE(29)
+            IDC_EF_DEC_CASE(30) IDC_EF_DEC_CASE(31)
+#undef IDC_EF_DEC_CASE
+        }
+    } else {
+        // more lower-bits words than the staging area holds (wide fields): straight from global memory
+        const uint32_t fw = (lane * l) >> 5, fs = (lane * l) & 31u, fmask = l ? (0xffffffffu >> (32u - l)) : 0u;
+        const int32_t end = (int32_t)count;
+        int32_t j = (int32_t)lane - (int32_t)lead;
+        const uint32_t* lp = lsrc + lane;
+        for (uint32_t g = 0; g < ngroups; g++, j += 32, lp += l) {
+            uint32_t lwv = lane < l ? __ldg(lp) : 0u;
+            uint32_t x0 = __shfl_sync(0xffffffffu, lwv, fw);
+            uint32_t x1 = __shfl_sync(0xffffffffu, lwv, (fw + 1) & 31);
+            uint32_t f = __funnelshift_r(x0, x1, fs) & fmask;
+            if (j >= 0 && j < end) {
+                uint64_t id = ((uint64_t)((uint32_t)hi_part[j] + zeros) << l) | f;
+                out[j] = (OutT)id;
+            }
+        }
     }
 }
 
-// One warp per chunk of 16 64-bit words (= 32 32-bit words, one per lane) of the upper-bits vector:
+// shared memory of one warp of the decoders: 1024 upper parts as u16 (position - id number inside the chunk <= 1023;
+// 32 entries of slack in front), then per stage: the lower-bits words (+ 4: alignment slack) and the upper-bits words,
+// then one mbarrier per stage
+__host__ __device__ inline uint32_t ef_dec_stage_bytes(uint32_t low_stage_words) { return 4u * (low_stage_words + 4u) + 4u * kDecHighStage; }
+__host__ __device__ inline uint32_t ef_dec_warp_bytes(uint32_t low_stage_words, uint32_t stages) {
+    return 64u + 2u * kDecTile + stages * ef_dec_stage_bytes(low_stage_words) + 16u;
+}
+
+// One warp per chunk; subsets of lists (sel_desc) and graph rows (row mode), one chunk staged per warp:
 //   1. one 32-byte descriptor (written by the encoder) tells the warp everything: where the chunk's words
 //      are, the id number it starts at, how many ids it holds, l, where they go;
-//   2. the chunk's upper-bits words and the lower-bits words of its ids are STAGED in shared memory by two bulk
-//      asynchronous copies (cp.async.bulk, the TMA unit's 1-D form; one elected lane issues them, completion on
-//      the warp's mbarrier) instead of one 4-byte cp.async per lane and word;
-//   3. popcount + warp scan over the staged upper-bits words -> where each word's ids land;
-//   4. every lane peels the set bits of its word (highest first: FLO, clear, store; four per round) into shared
-//      memory as upper parts (position - id number);
-//   5. a coalesced pass over the chunk's ids with the field width as a template parameter (ef_dec_out); ids leave
-//      as full 256-byte warp stores.
+//   2. ef_dec_stage, 3. ef_dec_chunk.
 template <typename OutT>
 __global__ void __launch_bounds__(kDecThreads, 6) k_ef_decode(EfDecArgs a) {
-    // per warp: 1024 upper parts as u16 (position - id number inside the chunk <= 1023), the staged lower-bits
-    // words (+ 4: alignment slack), the staged upper-bits words, the mbarrier
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t warp = (uint64_t)blockIdx.x * (kDecThreads / 32) + wib;
     if (warp >= a.ntiles) return;
-    uint8_t* s_warp = s_dyn + (size_t)wib * (2u * kDecTile + 4u * (a.low_stage_words + 4u) + 4u * kDecHighStage + 16u);
-    uint16_t* hi_part = reinterpret_cast<uint16_t*>(s_warp);
-    uint32_t* s_low = reinterpret_cast<uint32_t*>(s_warp + 2u * kDecTile);
+    uint8_t* s_warp = s_dyn + (size_t)wib * ef_dec_warp_bytes(a.low_stage_words, 1);
+    uint16_t* hi_part = reinterpret_cast<uint16_t*>(s_warp + 64u);
+    uint32_t* s_low = reinterpret_cast<uint32_t*>(s_warp + 64u + 2u * kDecTile);
     uint32_t* s_high = s_low + a.low_stage_words + 4u;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_high + kDecHighStage);
     uint64_t di = warp;
@@ -720,98 +822,22 @@ __global__ void __launch_bounds__(kDecThreads, 6) k_ef_decode(EfDecArgs a) {
     }
     if (lane == 0) mbar_init(bar, 1);
     const uint4* dp = reinterpret_cast<const uint4*>(a.dir + di);
-    const uint4 d0 = __ldg(dp), d1 = __ldg(dp + 1);
-    const uint64_t da = (uint64_t)d0.x | ((uint64_t)d0.y << 32);
-    const uint64_t high32 = da & ((1ull << 40) - 1);
-    const uint32_t count = (uint32_t)(da >> 40) & 0x7ffu, l = (uint32_t)(da >> 51) & 31u, nw32 = (uint32_t)(da >> 56) & 63u;
-    const uint64_t low32o = (uint64_t)d0.z | ((uint64_t)d0.w << 32);
-    const uint64_t out_base = (uint64_t)d1.x | ((uint64_t)d1.y << 32);
-    const uint32_t r0 = d1.z, zeros = d1.w;
+    const EfDecChunk d = ef_dec_unpack(__ldg(dp), __ldg(dp + 1));
     OutT* out;
     if (a.row_stride)
         out = reinterpret_cast<OutT*>(a.out) + warp * a.row_stride;
     else
-        out = reinterpret_cast<OutT*>(a.out) + (a.sel_out ? a.sel_out[warp] : out_base) + r0;
-    if (count) {
-        const uint32_t lead = r0 & 31u;
-        const uint32_t ngroups = (lead + count + 31u) >> 5;   // groups of 32 consecutive id numbers
-        const uint32_t nlow = ngroups * l;                     // 32-bit lower-bits words covering them
-        const uint32_t* lsrc = reinterpret_cast<const uint32_t*>(a.low) + low32o;
-        const uint32_t* h32 = reinterpret_cast<const uint32_t*>(a.high) + high32;
-        const bool staged = nlow <= a.low_stage_words;
-        // both sources are only 4- / 8-byte aligned: the copies start at the 16-byte boundary below them
-        const uint32_t lskew = (uint32_t)(reinterpret_cast<uintptr_t>(lsrc) & 15u), hskew = (uint32_t)(reinterpret_cast<uintptr_t>(h32) & 15u);
+        out = reinterpret_cast<OutT*>(a.out) + (a.sel_out ? a.sel_out[warp] : d.out_base) + d.r0;
+    if (d.count) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
-            const uint32_t hbytes = (hskew + 4u * nw32 + 15u) & ~15u;
-            const uint32_t lbytes = (staged && nlow) ? (lskew + 4u * nlow + 15u) & ~15u : 0u;
-            mbar_expect_tx(bar, hbytes + lbytes);
-            bulk_g2s(s_high, reinterpret_cast<const uint8_t*>(h32) - hskew, hbytes, bar);
-            if (lbytes) bulk_g2s(s_low, reinterpret_cast<const uint8_t*>(lsrc) - lskew, lbytes, bar);
-        }
+        if (lane == 0) ef_dec_stage(a, d, s_low, s_high, bar);
         mbar_wait(bar, 0);
-        uint32_t w = lane < nw32 ? s_high[(hskew >> 2) + lane] : 0u;
-        uint32_t sc = (uint32_t)__popc(w);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, sc, o);
-            if ((int)lane >= o) sc += v;
-        }
-        // The id with chunk-relative number j whose one sits at chunk bit P has upper part
-        //   (chunk_bit0 + P) - (r0 + j) = zeros + (P - j);  shared memory gets P - j, `zeros` is added on the way out.
-        {
-            uint16_t* p = hi_part + sc;   // one past this word's last id
-            uint32_t v = 32u * lane - sc; // (bit base) - (id number): grows by one for every step back
-            while (w) {
-#pragma unroll
-                for (int u = 1; u <= 4; u++) {
-                    if (w) {
-                        const uint32_t b = 31u - (uint32_t)__clz((int)w);
-                        w ^= 1u << b;
-                        p[-u] = (uint16_t)(v + (uint32_t)u + b);
-                    }
-                }
-                p -= 4;
-                v += 4u;
-            }
-        }
-        __syncwarp();
-        if (staged) {
-            const uint32_t* sl = s_low + (lskew >> 2);
-            switch (l) {
-#define IDC_EF_DEC_CASE(LL)                                                           \
-    case LL:                                                                          \
-        ef_dec_out<LL, OutT>(sl, hi_part, out, lane, lead, count, ngroups, zeros);    \
-        break;
-                IDC_EF_DEC_CASE(0) IDC_EF_DEC_CASE(1) IDC_EF_DEC_CASE(2) IDC_EF_DEC_CASE(3) IDC_EF_DEC_CASE(4) IDC_EF_DEC_CASE(5)
-                IDC_EF_DEC_CASE(6) IDC_EF_DEC_CASE(7) IDC_EF_DEC_CASE(8) IDC_EF_DEC_CASE(9) IDC_EF_DEC_CASE(10) IDC_EF_DEC_CASE(11)
-                IDC_EF_DEC_CASE(12) IDC_EF_DEC_CASE(13) IDC_EF_DEC_CASE(14) IDC_EF_DEC_CASE(15) IDC_EF_DEC_CASE(16) IDC_EF_DEC_CASE(17)
-                IDC_EF_DEC_CASE(18) IDC_EF_DEC_CASE(19) IDC_EF_DEC_CASE(20) IDC_EF_DEC_CASE(21) IDC_EF_DEC_CASE(22) IDC_EF_DEC_CASE(23)
-                IDC_EF_DEC_CASE(24) IDC_EF_DEC_CASE(25) IDC_EF_DEC_CASE(26) IDC_EF_DEC_CASE(27) IDC_EF_DEC_CASE(28) IDC_EF_DEC_CASE(29)
-                IDC_EF_DEC_CASE(30) IDC_EF_DEC_CASE(31)
-#undef IDC_EF_DEC_CASE
-            }
-        } else {
-            const uint32_t fw = (lane * l) >> 5, fs = (lane * l) & 31u, fmask = l ? (0xffffffffu >> (32u - l)) : 0u;
-            const int32_t end = (int32_t)count;
-            int32_t j = (int32_t)lane - (int32_t)lead;
-            const uint32_t* lp = lsrc + lane;
-            for (uint32_t g = 0; g < ngroups; g++, j += 32, lp += l) {
-                uint32_t lwv = lane < l ? __ldg(lp) : 0u;
-                uint32_t x0 = __shfl_sync(0xffffffffu, lwv, fw);
-                uint32_t x1 = __shfl_sync(0xffffffffu, lwv, (fw + 1) & 31);
-                uint32_t f = __funnelshift_r(x0, x1, fs) & fmask;
-                if (j >= 0 && j < end) {
-                    uint64_t id = ((uint64_t)((uint32_t)hi_part[j] + zeros) << l) | f;
-                    out[j] = (OutT)id;
-                }
-            }
-        }
+        ef_dec_chunk<OutT>(a, d, s_low, s_high, hi_part, out, lane);
     }
     if (a.row_stride) {
-        for (uint32_t t = count + lane; t < a.row_stride; t += 32) out[t] = (OutT)-1;
-        if (a.counts && lane == 0) a.counts[warp] = count;
+        for (uint32_t t = d.count + lane; t < a.row_stride; t += 32) out[t] = (OutT)-1;
+        if (a.counts && lane == 0) a.counts[warp] = d.count;
     }
 }
 
@@ -1082,8 +1108,10 @@ int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_sel_desc, 
                   const int32_t* d_row_nos, uint64_t ntiles, void* out_dev, int id_bytes, uint32_t* counts_dev,
                   uint32_t row_stride) {
     if (ntiles == 0) return IDC_OK;
-    // stage up to 33 groups of max_l words per warp, capped so that 6 CTAs of 8 warps still fit an SM
-    uint32_t stage_words = std::min<uint32_t>(33u * b->max_l + 1u, 768u);
+    // stage up to 33 groups of max_l words per warp, capped so that 6 CTAs of 8 warps still fit an SM (chunks that need
+    // more -- short lists with wide fields -- read their lower bits straight from global memory)
+    uint32_t stage_words = std::min<uint32_t>(33u * b->max_l + 1u, kDecStageCap);
+    if (const char* ev = getenv("IDC_EF_DEC_STAGE")) stage_words = std::min<uint32_t>(33u * b->max_l + 1u, (uint32_t)atoi(ev));  // experiments
     stage_words = (stage_words + 3u) & ~3u;
     IDC_TRY(c->status.reserve(64));
     uint32_t* d_status = c->status.as<uint32_t>();
@@ -1092,7 +1120,7 @@ int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_sel_desc, 
                 stage_words, b->nlist, d_status};
     const uint32_t wpb = kDecThreads / 32;
     const uint32_t grid = (uint32_t)((ntiles + wpb - 1) / wpb);
-    const size_t smem = (size_t)wpb * (2u * kDecTile + 4u * (stage_words + 4u) + 4u * kDecHighStage + 16u);
+    const size_t smem = (size_t)wpb * ef_dec_warp_bytes(stage_words, 1) + 512u;  // + 512: the output pass reads (and ignores) up to 3 groups past a chunk's words
     IDC_CUDA(cudaFuncSetAttribute(k_ef_decode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     IDC_CUDA(cudaFuncSetAttribute(k_ef_decode<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
