@@ -569,7 +569,7 @@ def ef_section(args, ctx, offsets, ids, dev, peak, cpu=False, steps=None, warmup
         bd = dict(ctx.last_kernel_breakdown())
         if it >= warmup:
             enc_ms.append(be["k_ef_encode"])
-            meta_ms.append(be.get("k_unit_meta", 0.0))
+            meta_ms.append(be.get("k_unit_meta", 0.0) + be.get("k_ef_tile_desc", 0.0) + be.get("k_ef_finish_chunks", 0.0))
             dec_ms.append(bd["k_ef_decode"])
     exact = bool(torch.equal(out, ids))
     comp = eb.bits_total / 8.0
@@ -578,8 +578,9 @@ def ef_section(args, ctx, offsets, ids, dev, peak, cpu=False, steps=None, warmup
     pm = float(np.mean(meta_ms))
     res = {
         "bit_exact_roundtrip": exact, "bits_per_id": 8.0 * comp / max(n_ids, 1),
-        # prep = the metadata kernel in front of k_ef_encode (list ends for ascending input: the order / width check
-        # of the ids happens inside k_ef_encode); frac_with_prep charges it to the encode
+        # prep = the small kernels around k_ef_encode (list ends for ascending input -- the order / width check of the
+        # ids happens inside k_ef_encode --, the tile descriptors, the chunk-count fix-up); frac_with_prep charges them
+        # to the encode
         "encode": {"kernel_ms": e, "prep_ms": pm, "ids_per_s": n_ids / (e * 1e-3),
                    "achieved_GBs": (8.0 * n_ids + comp) / (e * 1e-3) / 1e9, "frac": (8.0 * n_ids + comp) / (e * 1e-3) / 1e9 / peak,
                    "frac_with_prep": (8.0 * n_ids + comp) / ((e + pm) * 1e-3) / 1e9 / peak},
