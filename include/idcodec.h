@@ -208,6 +208,13 @@ int idc_roc_blob_order(const idc_roc_blob* blob, uint32_t* order, int order_mem)
 
 int idc_roc_blob_free(idc_roc_blob* blob);
 
+/* Flat file form of a blob (layout: csrc/idc_file.h): the list CSR and the wire payload of
+ * idc_roc_blob_export_payload. The reference keeps its ANS states in memory only (ans_states,
+ * custom_invlists_impl.h:59; altid_impl.h:58); an index built once is saved and loaded with these instead of being
+ * re-encoded. A loaded blob is indistinguishable from the saved one (row blobs included). */
+int idc_roc_blob_save(const idc_roc_blob* blob, const char* path);
+int idc_roc_blob_load(idc_ctx* ctx, const char* path, idc_roc_blob** out);
+
 /* Replaces decompress() (codec.cpp:140-152) /
  * CompressedIDInvertedListsFenwickTree::get_ids (custom_invlists_impl.cpp:210-219)
  * in bulk. list_nos (HOST, may be NULL = all lists in order) selects nsel lists;
@@ -309,6 +316,27 @@ int idc_ef_blob_export(
         uint64_t* low,
         uint64_t* high);
 
+/* The inverse of idc_ef_blob_export: list_offsets[nlist+1] (HOST CSR of the list lengths), universe[nlist] (HOST,
+ * max id of each list = the n passed to the elias_fano builder, custom_invlists_impl.cpp:262-263), the two bit vectors
+ * (HOST or DEVICE per `mem`; sizes and per-list offsets follow from (universe, length) as in elias_fano.hpp:28-29).
+ * row_stride != 0 makes it a row blob (idc_ef_decode_rows). The select samples and the decoder's chunk directory are
+ * rebuilt on the device; a bit vector that does not hold one set bit per id is refused (IDC_ERR_ARG). */
+int idc_ef_blob_import(
+        idc_ctx* ctx,
+        uint64_t nlist,
+        const uint64_t* list_offsets,
+        const uint64_t* universe,
+        uint32_t row_stride,
+        const uint64_t* low,
+        const uint64_t* high,
+        int mem,
+        idc_ef_blob** out);
+
+/* Flat file form (csrc/idc_file.h): the list CSR, the universes and the two bit vectors (ef_bitstreams,
+ * custom_invlists_impl.h:76; altid_impl.h:43). */
+int idc_ef_blob_save(const idc_ef_blob* blob, const char* path);
+int idc_ef_blob_load(idc_ctx* ctx, const char* path, idc_ef_blob** out);
+
 int idc_ef_blob_free(idc_ef_blob* blob);
 
 /* select_enumerator over whole lists: CompressedIDInvertedListsEliasFano::get_ids
@@ -400,6 +428,23 @@ int idc_wt_blob_export(
         uint32_t* sel1,
         uint32_t* sel0,
         uint32_t* start);
+
+/* The inverse of idc_wt_blob_export (arrays HOST or DEVICE per `mem`), and the flat file form of the index (the
+ * reference's `wt` member, custom_invlists_impl.h:104-105; csrc/idc_file.h). */
+int idc_wt_blob_import(
+        idc_ctx* ctx,
+        uint64_t nlist,
+        const uint64_t* list_offsets,
+        int wt_type,
+        const uint64_t* bits,
+        const uint32_t* rank,
+        const uint32_t* sel1,
+        const uint32_t* sel0,
+        const uint32_t* start,
+        int mem,
+        idc_wt_blob** out);
+int idc_wt_blob_save(const idc_wt_blob* blob, const char* path);
+int idc_wt_blob_load(idc_ctx* ctx, const char* path, idc_wt_blob** out);
 
 int idc_wt_blob_free(idc_wt_blob* blob);
 

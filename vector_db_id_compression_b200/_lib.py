@@ -50,6 +50,8 @@ SYMBOLS = {
     "idc_roc_blob_assemble": (C.c_int, [vp, u64, vp, u32, C.c_int, vp, vp, vp, vp, vp, vp, u64, C.POINTER(vp)]),
     "idc_roc_blob_order": (C.c_int, [vp, vp, C.c_int]),
     "idc_roc_blob_free": (C.c_int, [vp]),
+    "idc_roc_blob_save": (C.c_int, [vp, C.c_char_p]),
+    "idc_roc_blob_load": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     "idc_roc_decode": (C.c_int, [vp, vp, vp, u64, vp, C.c_int, C.c_int, vp]),
     "idc_roc_translate": (C.c_int, [vp, vp, vp, C.c_int, u64, vp, C.c_int]),
     "idc_roc_decode_rows": (C.c_int, [vp, vp, vp, C.c_int, u64, vp, vp, C.c_int]),
@@ -57,6 +59,9 @@ SYMBOLS = {
     "idc_ef_encode_rows": (C.c_int, [vp, u64, u32, vp, C.c_int, u32, C.POINTER(vp)]),
     "idc_ef_blob_info": (C.c_int, [vp, C.POINTER(EfInfo)]),
     "idc_ef_blob_export": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
+    "idc_ef_blob_import": (C.c_int, [vp, u64, vp, vp, u32, vp, vp, C.c_int, C.POINTER(vp)]),
+    "idc_ef_blob_save": (C.c_int, [vp, C.c_char_p]),
+    "idc_ef_blob_load": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     "idc_ef_blob_free": (C.c_int, [vp]),
     "idc_ef_decode": (C.c_int, [vp, vp, vp, u64, vp, C.c_int, C.c_int, vp]),
     "idc_ef_decode_rows": (C.c_int, [vp, vp, vp, C.c_int, u64, vp, vp, C.c_int]),
@@ -64,6 +69,9 @@ SYMBOLS = {
     "idc_wt_encode": (C.c_int, [vp, u64, vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "idc_wt_blob_info": (C.c_int, [vp, C.POINTER(WtInfo)]),
     "idc_wt_blob_export": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "idc_wt_blob_import": (C.c_int, [vp, u64, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]),
+    "idc_wt_blob_save": (C.c_int, [vp, C.c_char_p]),
+    "idc_wt_blob_load": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     "idc_wt_blob_free": (C.c_int, [vp]),
     "idc_wt_select": (C.c_int, [vp, vp, vp, vp, u64, C.c_int, vp, C.c_int]),
     "idc_wt_decode": (C.c_int, [vp, vp, vp, u64, vp, C.c_int, C.c_int, vp]),

@@ -167,7 +167,33 @@ class Context:
                                              *((a[1] if a is not None else None) for a in arrs), nwords_total, C.byref(h)))
         return RocBlob(self, h)
 
+    def roc_load(self, path) -> "RocBlob":
+        """idc_roc_blob_load: a blob from its flat file form (RocBlob.save)."""
+        h = C.c_void_p()
+        _check(self._l.idc_roc_blob_load(self._h, str(path).encode(), C.byref(h)))
+        return RocBlob(self, h)
+
     # ------------------------------------------------------------- EF -----
+    def ef_import(self, list_offsets, universe, low, high, *, row_stride: int = 0) -> "EfBlob":
+        """idc_ef_blob_import: the inverse of EfBlob.export (bit vectors as numpy arrays or torch tensors, both on the
+        host or both on this context's device); samples and chunk directory are rebuilt on the device."""
+        off = _host_u64(list_offsets)
+        uni = np.ascontiguousarray(universe, dtype=np.uint64)
+        if not _is_torch(low):
+            low = np.ascontiguousarray(low, dtype=np.uint64)
+            high = np.ascontiguousarray(high, dtype=np.uint64)
+        pl, mem = _ptr(low)
+        ph, mem2 = _ptr(high)
+        assert mem == mem2, "low and high must live in the same memory"
+        h = C.c_void_p()
+        _check(self._l.idc_ef_blob_import(self._h, off.size - 1, off.ctypes.data, uni.ctypes.data, int(row_stride), pl, ph, mem, C.byref(h)))
+        return EfBlob(self, h)
+
+    def ef_load(self, path) -> "EfBlob":
+        h = C.c_void_p()
+        _check(self._l.idc_ef_blob_load(self._h, str(path).encode(), C.byref(h)))
+        return EfBlob(self, h)
+
     def ef_encode(self, offsets, ids, *, sorted_ids: bool = False) -> "EfBlob":
         offsets = _host_u64(offsets)
         ids, idb = _ids_array(ids)
@@ -187,6 +213,21 @@ class Context:
         return EfBlob(self, h)
 
     # ---------------------------------------------------- wavelet tree ----
+    def wt_import(self, exported: dict, *, wt_type: int = 0) -> "WtBlob":
+        """idc_wt_blob_import: the inverse of WtBlob.export (host arrays)."""
+        off = _host_u64(exported["list_offsets"])
+        arrs = [np.ascontiguousarray(exported[k], dtype=t) for k, t in (("bits", np.uint64), ("rank", np.uint32), ("sel1", np.uint32),
+                                                                         ("sel0", np.uint32), ("start", np.uint32))]
+        h = C.c_void_p()
+        _check(self._l.idc_wt_blob_import(self._h, off.size - 1, off.ctypes.data, int(wt_type), *(a.ctypes.data for a in arrs), MEM_HOST,
+                                          C.byref(h)))
+        return WtBlob(self, h)
+
+    def wt_load(self, path) -> "WtBlob":
+        h = C.c_void_p()
+        _check(self._l.idc_wt_blob_load(self._h, str(path).encode(), C.byref(h)))
+        return WtBlob(self, h)
+
     def wt_encode(self, offsets, ids, *, wt_type: int = 0) -> "WtBlob":
         offsets = _host_u64(offsets)
         ids, idb = _ids_array(ids)
@@ -266,6 +307,10 @@ class RocBlob:
     total_words = property(lambda s: int(s.info.total_words))
     ans_bytes = property(lambda s: int(s.info.ans_bytes))
     row_stride = property(lambda s: int(s.info.row_stride))
+
+    def save(self, path) -> None:
+        """idc_roc_blob_save: the blob's flat file form (csrc/idc_file.h); Context.roc_load reads it back."""
+        _check(self._l.idc_roc_blob_save(self._h, str(path).encode()))
 
     def export(self) -> dict:
         i = self.info
@@ -395,6 +440,10 @@ class EfBlob:
     bits_total = property(lambda s: int(s.info.bits_total))
     row_stride = property(lambda s: int(s.info.row_stride))
 
+    def save(self, path) -> None:
+        """idc_ef_blob_save: the blob's flat file form (csrc/idc_file.h); Context.ef_load reads it back."""
+        _check(self._l.idc_ef_blob_save(self._h, str(path).encode()))
+
     def export(self) -> dict:
         i = self.info
         d = dict(
@@ -490,6 +539,10 @@ class WtBlob:
     levels = property(lambda s: int(s.info.levels))
     bits_bytes = property(lambda s: int(s.info.bits_bytes))
     aux_bytes = property(lambda s: int(s.info.aux_bytes))
+
+    def save(self, path) -> None:
+        """idc_wt_blob_save: the blob's flat file form (csrc/idc_file.h); Context.wt_load reads it back."""
+        _check(self._l.idc_wt_blob_save(self._h, str(path).encode()))
 
     def export(self) -> dict:
         n, levels, nlist = self.total_ids, self.levels, self.nlist

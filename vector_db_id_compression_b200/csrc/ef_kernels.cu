@@ -15,6 +15,7 @@
 #include <numeric>
 
 #include "ef_core.cuh"
+#include "idc_file.h"
 #include "idc_host.h"
 #include "idc_prep.cuh"
 
@@ -910,6 +911,86 @@ __global__ void __launch_bounds__(kThreads) k_bits_unpack(const uint8_t* code, u
     out[k] = (T)v;
 }
 
+// ---- import: the derived arrays (chunk directory, select samples) from the bit vectors themselves.
+// One CTA per list walks the list's chunks 128 at a time: popcount of the chunk's words, block-wide exclusive scan ->
+// ids in front of every chunk; each thread then writes its chunk's descriptor and the samples (every 256-th one) that
+// fall into it.
+struct EfAuxArgs {
+    const uint64_t* list_off;
+    const uint8_t* l;
+    const uint64_t* low_off;
+    const uint64_t* high_off;
+    const uint64_t* samp_off;
+    const uint64_t* dir_off;
+    const uint64_t* high;
+    uint32_t* samples;
+    EfChunk* dir;
+    uint32_t nlist;
+    uint32_t* status;  // kStRange: a list's upper-bits vector does not hold as many ones as the list has ids
+};
+
+__global__ void __launch_bounds__(kThreads) k_ef_rebuild_aux(EfAuxArgs a) {
+    __shared__ uint32_t warp_tot[kThreads / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    for (uint32_t L = blockIdx.x; L < a.nlist; L += gridDim.x) {
+        const uint64_t o0 = a.list_off[L], m = a.list_off[L + 1] - o0;
+        if (m == 0) continue;  // the list's one descriptor stays zero: count 0
+        const uint64_t h0 = a.high_off[L], hw = a.high_off[L + 1] - h0;
+        const uint64_t nchunks = (hw + kDecChunkWords - 1) / kDecChunkWords;
+        const uint32_t l = a.l[L];
+        const uint64_t* hv = a.high + h0;
+        uint64_t running = 0;
+        for (uint64_t base = 0; base < nchunks; base += kThreads) {
+            const uint64_t C = base + tid, W = C * kDecChunkWords;
+            const uint32_t nw = C < nchunks ? (uint32_t)(hw - W < kDecChunkWords ? hw - W : kDecChunkWords) : 0u;
+            uint32_t pop = 0;
+            for (uint32_t w = 0; w < nw; w++) pop += (uint32_t)popc64(hv[W + w]);
+            uint32_t sc = pop;  // inclusive scan over the CTA
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, sc, o);
+                if ((int)lane >= o) sc += v;
+            }
+            __syncthreads();  // warp_tot of the previous round has been read
+            if (lane == 31u) warp_tot[wid] = sc;
+            __syncthreads();
+            uint32_t wbase = 0, total = 0;
+#pragma unroll
+            for (int j = 0; j < kThreads / 32; j++) {
+                const uint32_t t = warp_tot[j];
+                wbase += (uint32_t)j < wid ? t : 0u;
+                total += t;
+            }
+            const uint64_t before = running + wbase + sc - pop;
+            if (nw) {
+                EfChunk d;
+                d.a = (2 * (h0 + W)) | ((uint64_t)pop << 40) | ((uint64_t)l << 51) | ((uint64_t)(2u * nw) << 56);
+                d.low32 = 2 * a.low_off[L] + (before >> 5) * l;
+                d.out_base = o0;
+                d.b = before | ((W * 64 - before) << 32);
+                a.dir[a.dir_off[L] + C] = d;
+                if (pop) {
+                    for (uint64_t s = (before + kEfSample - 1) >> kEfSampleLog; (s << kEfSampleLog) < before + pop; s++) {
+                        uint32_t r = (uint32_t)((s << kEfSampleLog) - before);  // rank inside the chunk
+                        for (uint32_t w = 0; w < nw; w++) {
+                            const uint64_t word = hv[W + w];
+                            const uint32_t cw = (uint32_t)popc64(word);
+                            if (r < cw) {
+                                (a.samples + a.samp_off[L])[s] = (uint32_t)((W + w) * 64 + select64(word, r));
+                                break;
+                            }
+                            r -= cw;
+                        }
+                    }
+                }
+            }
+            running += total;
+        }
+        if (tid == 0 && running != m) atomicOr(a.status, kStRange);
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------ host
 
 int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint32_t flags,
@@ -1473,6 +1554,142 @@ int idc_bits_unpack(idc_ctx* c, uint64_t n, const uint8_t* code, uint64_t code_b
     if (out_mem == IDC_MEM_HOST) IDC_CUDA(cudaMemcpyAsync(out, d_out, n * val_bytes, cudaMemcpyDeviceToHost, c->stream));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
     return IDC_OK;
+}
+
+/* Build a blob from the exported form: the list CSR, every list's universe (max id) and the two bit vectors (HOST or
+ * DEVICE per `mem`); field widths and word offsets follow from (universe, list length) exactly as at encode time,
+ * the chunk directory and the select samples are rebuilt on the device. row_stride != 0: graph rows. */
+int idc_ef_blob_import(idc_ctx* c, uint64_t nlist, const uint64_t* list_offsets, const uint64_t* universe, uint32_t row_stride,
+                       const uint64_t* low, const uint64_t* high, int mem, idc_ef_blob** out) {
+    IDC_REQUIRE(c && out && list_offsets && (universe || nlist == 0), IDC_ERR_ARG, "idc_ef_blob_import: null argument");
+    IDC_REQUIRE(mem == IDC_MEM_HOST || mem == IDC_MEM_DEVICE, IDC_ERR_ARG, "mem must be IDC_MEM_HOST or IDC_MEM_DEVICE");
+    IDC_REQUIRE(nlist < (1ull << 32), IDC_ERR_ARG, "too many lists");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    std::unique_ptr<idc_ef_blob> b(new idc_ef_blob());
+    b->ctx = c;
+    b->ref.bind(c);
+    b->nlist = nlist;
+    b->row_stride = row_stride;
+    const uint64_t nl = nlist;
+    b->list_offsets.resize(nl + 1);
+    for (uint64_t i = 0; i <= nl; i++) {
+        IDC_REQUIRE(i == 0 || list_offsets[i] >= list_offsets[i - 1], IDC_ERR_ARG, "offsets must be non-decreasing");
+        b->list_offsets[i] = list_offsets[i] - list_offsets[0];
+    }
+    b->total_ids = b->list_offsets[nl];
+    b->l.resize(nl);
+    b->universe.assign(universe, universe + nl);
+    b->low_off.assign(nl + 1, 0);
+    b->high_off.assign(nl + 1, 0);
+    b->samp_off.assign(nl + 1, 0);
+    b->dir_off.assign(nl + 1, 0);
+    uint64_t bits_total = 0;
+    for (uint64_t i = 0; i < nl; i++) {
+        const uint64_t n = b->list_offsets[i + 1] - b->list_offsets[i];
+        IDC_REQUIRE(n < (1ull << 32) && universe[i] < (1ull << 32), IDC_ERR_DOMAIN, "list %llu: length or universe beyond 32 bits",
+                    (unsigned long long)i);
+        IDC_REQUIRE(!row_stride || n <= row_stride, IDC_ERR_ARG, "row %llu holds more than row_stride entries", (unsigned long long)i);
+        EfShape sh = ef_shape(universe[i], n);
+        IDC_REQUIRE(sh.high_bits < (1ull << 32), IDC_ERR_DOMAIN, "list %llu: upper-bits vector of %llu bits; the device path handles up to 2^32 - 1",
+                    (unsigned long long)i, (unsigned long long)sh.high_bits);
+        b->l[i] = (uint8_t)sh.l;
+        b->max_l = std::max<uint32_t>(b->max_l, sh.l);
+        b->low_off[i + 1] = b->low_off[i] + sh.low_words;
+        b->high_off[i + 1] = b->high_off[i] + sh.high_words;
+        b->samp_off[i + 1] = b->samp_off[i] + sh.samples;
+        b->dir_off[i + 1] = b->dir_off[i] + std::max<uint64_t>(1, (sh.high_words + kDecChunkWords - 1) / kDecChunkWords);
+        bits_total += sh.low_bits + sh.high_bits;
+    }
+    if (row_stride)
+        IDC_REQUIRE(row_stride <= kDecTile && 3ull * row_stride + 2 <= 64ull * kDecChunkWords, IDC_ERR_ARG, "row_stride %u out of range", row_stride);
+    b->low_words = b->low_off[nl];
+    b->high_words = b->high_off[nl];
+    b->nsamples = b->samp_off[nl];
+    b->ndir = b->dir_off[nl];
+    b->bits_total = bits_total;
+    IDC_REQUIRE((low || b->low_words == 0) && (high || b->high_words == 0), IDC_ERR_ARG, "idc_ef_blob_import: null bit vector");
+    uint64_t acct = 0;
+    IDC_TRY(dev_alloc(c, &b->d_list_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_l, nl, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_low_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_high_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_samp_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_dir_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_dir, b->ndir, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_low, b->low_words + 32, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_high, b->high_words + 2, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_samples, b->nsamples, &acct));
+    IDC_TRY(upload(c, b->d_list_off, b->list_offsets));
+    IDC_TRY(upload(c, b->d_l, b->l));
+    IDC_TRY(upload(c, b->d_low_off, b->low_off));
+    IDC_TRY(upload(c, b->d_high_off, b->high_off));
+    IDC_TRY(upload(c, b->d_samp_off, b->samp_off));
+    IDC_TRY(upload(c, b->d_dir_off, b->dir_off));
+    IDC_CUDA(cudaMemsetAsync(b->d_dir, 0, std::max<uint64_t>(b->ndir, 1) * sizeof(EfChunk), c->stream));
+    const cudaMemcpyKind kind = mem == IDC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (b->low_words) IDC_CUDA(cudaMemcpyAsync(b->d_low, low, b->low_words * 8, kind, c->stream));
+    if (b->high_words) IDC_CUDA(cudaMemcpyAsync(b->d_high, high, b->high_words * 8, kind, c->stream));
+    IDC_TRY(c->status.reserve(64));
+    uint32_t* d_status = c->status.as<uint32_t>();
+    IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    if (nl) {
+        EfAuxArgs a{b->d_list_off, b->d_l, b->d_low_off, b->d_high_off, b->d_samp_off, b->d_dir_off, b->d_high, b->d_samples, b->d_dir,
+                    (uint32_t)nl, d_status};
+        LaunchScope ls(c, "k_ef_rebuild_aux");
+        k_ef_rebuild_aux<<<(uint32_t)std::min<uint64_t>(nl, (uint64_t)c->sm_count * 16), kThreads, 0, c->stream>>>(a);
+    }
+    IDC_TRY(check_last_launch("k_ef_rebuild_aux"));
+    uint32_t st = 0;
+    IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    IDC_REQUIRE(st == 0, IDC_ERR_ARG, "idc_ef_blob_import: an upper-bits vector does not hold as many ones as its list has ids");
+    b->device_bytes = acct;
+    *out = b.release();
+    return IDC_OK;
+}
+
+// ---- flat file form (idc_file.h): header words, the list CSR, the universes and the two bit vectors
+int idc_ef_blob_save(const idc_ef_blob* b, const char* path) {
+    IDC_REQUIRE(b && path, IDC_ERR_ARG, "idc_ef_blob_save: null argument");
+    std::vector<uint64_t> low(b->low_words), high(b->high_words);
+    IDC_TRY(idc_ef_blob_export(b, nullptr, nullptr, nullptr, nullptr, nullptr, low.data(), high.data()));
+    std::vector<uint64_t> hdr{b->nlist, b->low_words, b->high_words, b->row_stride};
+    FileWriter w;
+    IDC_TRY(w.open(path, kFileEf, 5));
+    w.vec(hdr);
+    w.vec(b->list_offsets);
+    w.vec(b->universe);
+    w.vec(low);
+    w.vec(high);
+    return w.close(path);
+}
+
+int idc_ef_blob_load(idc_ctx* c, const char* path, idc_ef_blob** out) {
+    IDC_REQUIRE(c && path && out, IDC_ERR_ARG, "idc_ef_blob_load: null argument");
+    *out = nullptr;
+    FileReader r;
+    IDC_TRY(r.open(path, kFileEf));
+    std::vector<uint64_t> hdr, offs, uni, low, high;
+    IDC_TRY(r.vec(hdr));
+    IDC_TRY(r.vec(offs));
+    IDC_TRY(r.vec(uni));
+    IDC_TRY(r.vec(low));
+    IDC_TRY(r.vec(high));
+    IDC_REQUIRE(hdr.size() == 4 && offs.size() == hdr[0] + 1 && uni.size() == hdr[0] && low.size() == hdr[1] && high.size() == hdr[2],
+                IDC_ERR_ARG, "%s: section sizes do not match the header", path);
+    // the sizes the import derives from (universe, length) must be the stored ones: checked before any array is read
+    uint64_t lw = 0, hwords = 0;
+    for (uint64_t i = 0; i < hdr[0]; i++) {
+        IDC_REQUIRE(offs[i + 1] >= offs[i], IDC_ERR_ARG, "%s: list offsets decrease", path);
+        const EfShape sh = ef_shape(uni[i], offs[i + 1] - offs[i]);
+        lw += sh.low_words;
+        hwords += sh.high_words;
+    }
+    IDC_REQUIRE(lw == hdr[1] && hwords == hdr[2], IDC_ERR_ARG, "%s: bit-vector sizes do not follow from the list shapes", path);
+    return idc_ef_blob_import(c, hdr[0], offs.data(), uni.data(), (uint32_t)hdr[3], low.data(), high.data(), IDC_MEM_HOST, out);
 }
 
 }  // extern "C"

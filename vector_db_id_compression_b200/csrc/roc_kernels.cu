@@ -27,6 +27,7 @@
 #include <functional>
 #include <memory>
 
+#include "idc_file.h"
 #include "idc_host.h"
 #include "idc_prep.cuh"
 #include "roc_group.cuh"
@@ -1459,6 +1460,65 @@ int idc_roc_decode_rows(idc_ctx* c, const idc_roc_blob* b, const int32_t* row_no
             IDC_CUDA(cudaStreamSynchronize(c->stream));
         }
     }
+    return IDC_OK;
+}
+
+// ---- flat file form (idc_file.h): header words, the list CSR and the wire payload of idc_roc_blob_export_payload
+int idc_roc_blob_save(const idc_roc_blob* b, const char* path) {
+    IDC_REQUIRE(b && path, IDC_ERR_ARG, "idc_roc_blob_save: null argument");
+    const uint64_t nu = b->nunits;
+    std::vector<uint8_t> prec(nu);
+    std::vector<uint64_t> heads(nu);
+    std::vector<uint32_t> nw(nu), lo(nu), hi(nu), words(b->total_words);
+    IDC_TRY(idc_roc_blob_export_payload(b, IDC_MEM_HOST, prec.data(), heads.data(), nw.data(), lo.data(), hi.data(), words.data()));
+    std::vector<uint64_t> hdr{b->nlist, nu, b->total_words, b->max_unit, b->row_stride};
+    FileWriter w;
+    IDC_TRY(w.open(path, kFileRoc, 8));
+    w.vec(hdr);
+    w.vec(b->list_offsets);
+    w.vec(prec);
+    w.vec(heads);
+    w.vec(nw);
+    w.vec(lo);
+    w.vec(hi);
+    w.vec(words);
+    return w.close(path);
+}
+
+int idc_roc_blob_load(idc_ctx* c, const char* path, idc_roc_blob** out) {
+    IDC_REQUIRE(c && path && out, IDC_ERR_ARG, "idc_roc_blob_load: null argument");
+    *out = nullptr;
+    FileReader r;
+    IDC_TRY(r.open(path, kFileRoc));
+    std::vector<uint64_t> hdr, offs, heads;
+    std::vector<uint8_t> prec;
+    std::vector<uint32_t> nw, lo, hi, words;
+    IDC_TRY(r.vec(hdr));
+    IDC_TRY(r.vec(offs));
+    IDC_TRY(r.vec(prec));
+    IDC_TRY(r.vec(heads));
+    IDC_TRY(r.vec(nw));
+    IDC_TRY(r.vec(lo));
+    IDC_TRY(r.vec(hi));
+    IDC_TRY(r.vec(words));
+    IDC_REQUIRE(hdr.size() == 5 && offs.size() == hdr[0] + 1 && prec.size() == hdr[1] && heads.size() == hdr[1] && nw.size() == hdr[1] &&
+                    lo.size() == hdr[1] && hi.size() == hdr[1] && words.size() == hdr[2],
+                IDC_ERR_ARG, "%s: section sizes do not match the header", path);
+    // the units the list lengths imply (idc_roc_blob_assemble reads that many entries of the per-unit arrays)
+    const uint64_t mu = hdr[3] ? hdr[3] : IDC_MAX_UNIT_DEFAULT;
+    uint64_t implied = 0;
+    for (uint64_t l = 0; l < hdr[0]; l++) {
+        IDC_REQUIRE(offs[l + 1] >= offs[l], IDC_ERR_ARG, "%s: list offsets decrease", path);
+        const uint64_t n = offs[l + 1] - offs[l];
+        implied += n ? (n + mu - 1) / mu : 1;
+    }
+    IDC_REQUIRE(implied == hdr[1], IDC_ERR_ARG, "%s: %llu units stored, the list lengths imply %llu", path, (unsigned long long)hdr[1],
+                (unsigned long long)implied);
+    idc_roc_blob* b = nullptr;
+    IDC_TRY(idc_roc_blob_assemble(c, hdr[0], offs.data(), (uint32_t)hdr[3], IDC_MEM_HOST, prec.data(), heads.data(), nw.data(), lo.data(),
+                                  hi.data(), words.data(), words.size(), &b));
+    b->row_stride = (uint32_t)hdr[4];  // graph rows: one unit per row (empty rows own an empty unit), decoded by idc_roc_decode_rows
+    *out = b;
     return IDC_OK;
 }
 

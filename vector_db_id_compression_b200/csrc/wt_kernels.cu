@@ -21,6 +21,7 @@
 #include <memory>
 #include <vector>
 
+#include "idc_file.h"
 #include "idc_host.h"
 #include "wt_core.cuh"
 
@@ -832,6 +833,106 @@ int idc_wt_decode(idc_ctx* c, const idc_wt_blob* b, const uint64_t* list_nos, ui
         IDC_CUDA(cudaMemcpyAsync(ids_out, out_dev, total * id_bytes, cudaMemcpyDeviceToHost, c->stream));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
     return wt_status_to_error(st, "wt_decode");
+}
+
+/* Build a blob from the exported arrays (HOST or DEVICE per `mem`; shapes as idc_wt_blob_export documents them). */
+int idc_wt_blob_import(idc_ctx* c, uint64_t nlist, const uint64_t* list_offsets, int wt_type, const uint64_t* bits, const uint32_t* rank,
+                       const uint32_t* sel1, const uint32_t* sel0, const uint32_t* start, int mem, idc_wt_blob** out) {
+    IDC_REQUIRE(c && out && list_offsets, IDC_ERR_ARG, "idc_wt_blob_import: null argument");
+    IDC_REQUIRE(mem == IDC_MEM_HOST || mem == IDC_MEM_DEVICE, IDC_ERR_ARG, "mem must be IDC_MEM_HOST or IDC_MEM_DEVICE");
+    IDC_REQUIRE(wt_type == 0, IDC_ERR_ARG, "wt_type must be 0");
+    IDC_REQUIRE(nlist <= (1ull << 31), IDC_ERR_ARG, "too many lists");
+    *out = nullptr;
+    std::lock_guard<std::mutex> lock(c->mu);
+    IDC_CUDA(cudaSetDevice(c->device));
+    c->begin_call();
+    std::unique_ptr<idc_wt_blob> b(new idc_wt_blob());
+    b->ctx = c;
+    b->ref.bind(c);
+    b->nlist = nlist;
+    b->wt_type = wt_type;
+    b->list_offsets.resize(nlist + 1);
+    for (uint64_t l = 0; l <= nlist; l++) {
+        IDC_REQUIRE(l == 0 || list_offsets[l] >= list_offsets[l - 1], IDC_ERR_ARG, "offsets must be non-decreasing");
+        b->list_offsets[l] = list_offsets[l] - list_offsets[0];
+    }
+    const uint64_t n = b->list_offsets[nlist];
+    IDC_REQUIRE(n < (1ull << 32) - 4096, IDC_ERR_ARG, "ntotal must be below 2^32 - 4096 (32-bit positions)");
+    b->total_ids = n;
+    b->sh = wt_shape(nlist, n);
+    if (n == 0) {
+        b->sh.levels = 0;
+        *out = b.release();
+        return IDC_OK;
+    }
+    IDC_REQUIRE(bits && rank && sel1 && sel0 && start, IDC_ERR_ARG, "idc_wt_blob_import: null array");
+    const WtShape sh = b->sh;
+    IDC_TRY(dev_alloc(c, &b->d_list_off, nlist + 1, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_bits, sh.levels * sh.words, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_rank, sh.levels * sh.rank_stride, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_sel1, sh.levels * sh.samp_stride, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_sel0, sh.levels * sh.samp_stride, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_start, nlist, &b->device_bytes));
+    const cudaMemcpyKind kind = mem == IDC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    cudaStream_t s = c->stream;
+    IDC_CUDA(cudaMemcpyAsync(b->d_list_off, b->list_offsets.data(), (nlist + 1) * 8, cudaMemcpyHostToDevice, s));
+    IDC_CUDA(cudaMemcpyAsync(b->d_bits, bits, sh.levels * sh.words * 8, kind, s));
+    IDC_CUDA(cudaMemcpyAsync(b->d_rank, rank, sh.levels * sh.rank_stride * 4, kind, s));
+    IDC_CUDA(cudaMemcpyAsync(b->d_sel1, sel1, sh.levels * sh.samp_stride * 4, kind, s));
+    IDC_CUDA(cudaMemcpyAsync(b->d_sel0, sel0, sh.levels * sh.samp_stride * 4, kind, s));
+    IDC_CUDA(cudaMemcpyAsync(b->d_start, start, nlist * 4, kind, s));
+    IDC_CUDA(cudaStreamSynchronize(s));
+    *out = b.release();
+    return IDC_OK;
+}
+
+// ---- flat file form (idc_file.h): header words, the list CSR and the five arrays of idc_wt_blob_export
+int idc_wt_blob_save(const idc_wt_blob* b, const char* path) {
+    IDC_REQUIRE(b && path, IDC_ERR_ARG, "idc_wt_blob_save: null argument");
+    const WtShape& sh = b->sh;
+    const bool any = b->total_ids != 0;
+    std::vector<uint64_t> bits(any ? sh.levels * sh.words : 0);
+    std::vector<uint32_t> rank(any ? sh.levels * sh.rank_stride : 0), sel1(any ? sh.levels * sh.samp_stride : 0),
+        sel0(any ? sh.levels * sh.samp_stride : 0), start(any ? b->nlist : 0);
+    IDC_TRY(idc_wt_blob_export(b, nullptr, bits.data(), rank.data(), sel1.data(), sel0.data(), start.data()));
+    std::vector<uint64_t> hdr{b->nlist, (uint64_t)b->wt_type, b->total_ids};
+    FileWriter w;
+    IDC_TRY(w.open(path, kFileWt, 7));
+    w.vec(hdr);
+    w.vec(b->list_offsets);
+    w.vec(bits);
+    w.vec(rank);
+    w.vec(sel1);
+    w.vec(sel0);
+    w.vec(start);
+    return w.close(path);
+}
+
+int idc_wt_blob_load(idc_ctx* c, const char* path, idc_wt_blob** out) {
+    IDC_REQUIRE(c && path && out, IDC_ERR_ARG, "idc_wt_blob_load: null argument");
+    *out = nullptr;
+    FileReader r;
+    IDC_TRY(r.open(path, kFileWt));
+    std::vector<uint64_t> hdr, offs, bits;
+    std::vector<uint32_t> rank, sel1, sel0, start;
+    IDC_TRY(r.vec(hdr));
+    IDC_TRY(r.vec(offs));
+    IDC_TRY(r.vec(bits));
+    IDC_TRY(r.vec(rank));
+    IDC_TRY(r.vec(sel1));
+    IDC_TRY(r.vec(sel0));
+    IDC_TRY(r.vec(start));
+    IDC_REQUIRE(hdr.size() == 3 && offs.size() == hdr[0] + 1, IDC_ERR_ARG, "%s: section sizes do not match the header", path);
+    const uint64_t n = offs[hdr[0]] - offs[0];
+    IDC_REQUIRE(n == hdr[2], IDC_ERR_ARG, "%s: list offsets and the stored id count disagree", path);
+    if (n) {
+        const WtShape sh = wt_shape(hdr[0], n);
+        IDC_REQUIRE(bits.size() == sh.levels * sh.words && rank.size() == sh.levels * sh.rank_stride && sel1.size() == sh.levels * sh.samp_stride &&
+                        sel0.size() == sh.levels * sh.samp_stride && start.size() == hdr[0],
+                    IDC_ERR_ARG, "%s: array sizes do not follow from the index shape", path);
+    }
+    return idc_wt_blob_import(c, hdr[0], offs.data(), (int)hdr[1], bits.data(), rank.data(), sel1.data(), sel0.data(), start.data(),
+                              IDC_MEM_HOST, out);
 }
 
 }  // extern "C"
