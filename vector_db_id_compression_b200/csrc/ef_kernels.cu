@@ -47,9 +47,13 @@ struct idc_ef_blob {
     uint64_t nlist = 0, total_ids = 0, low_words = 0, high_words = 0, bits_total = 0, nsamples = 0;
     uint32_t row_stride = 0;
     uint32_t max_l = 0;
-    std::vector<uint64_t> list_offsets;  // nlist+1, ids per list (CSR)
-    std::vector<uint8_t> l;
-    std::vector<uint64_t> universe, low_off, high_off, samp_off, dir_off;  // nlist(+1)
+    // Host mirrors of the per-list tables. The tables are computed on the device (shapes + prefix sums); the mirrors
+    // are fetched on first use (export, save, decoding a subset of lists): see ef_host_tables.
+    mutable bool host_tables = false;
+    mutable std::vector<uint64_t> list_offsets;  // nlist+1, ids per list (CSR)
+    mutable std::vector<uint8_t> l;
+    mutable std::vector<uint64_t> universe, low_off, high_off, samp_off, dir_off;  // nlist(+1)
+    uint32_t* d_universe = nullptr;  // max id of each list
     uint64_t* d_list_off = nullptr;
     uint8_t* d_l = nullptr;
     uint64_t* d_low_off = nullptr;
@@ -70,6 +74,7 @@ struct idc_ef_blob {
     uint64_t ntiles = 0;
     ~idc_ef_blob() {
         if (ctx) ctx->pool_release(d_list_off);
+        if (ctx) ctx->pool_release(d_universe);
         if (ctx) ctx->pool_release(d_l);
         if (ctx) ctx->pool_release(d_low_off);
         if (ctx) ctx->pool_release(d_high_off);
@@ -186,7 +191,7 @@ struct EfTileDescArgs {
     const uint64_t* high_off;
     const uint64_t* samp_off;
     const uint64_t* dir_off;
-    const uint32_t* tile_base;
+    const uint64_t* tile_base;
     uint32_t nlist;
     EfTile* tiles;
 };
@@ -198,12 +203,12 @@ __global__ void __launch_bounds__(kThreads) k_ef_tile_desc(EfTileDescArgs a, uin
     uint32_t lo = 0, hi = a.nlist;  // tile_base[lo] <= g < tile_base[hi]
     while (hi - lo > 1u) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(a.tile_base + mid) <= g)
+        if (__ldg(reinterpret_cast<const unsigned long long*>(a.tile_base) + mid) <= g)
             lo = mid;
         else
             hi = mid;
     }
-    const uint32_t L = lo, t = g - a.tile_base[L], l = a.l[L];
+    const uint32_t L = lo, t = g - (uint32_t)a.tile_base[L], l = a.l[L];
     const uint64_t o0 = a.list_off[L], m = a.list_off[L + 1] - o0;
     const uint64_t h0 = a.high_off[L], hw = a.high_off[L + 1] - h0;
     const uint64_t i0 = (uint64_t)t * kEncTileIds;
@@ -991,20 +996,114 @@ __global__ void __launch_bounds__(kThreads) k_ef_rebuild_aux(EfAuxArgs a) {
     }
 }
 
+// ---- planning on the device: per-list shapes from (length, max id), then prefix sums (idc_prep.cuh: device_scan)
+struct EfShapeArgs {
+    const uint32_t* n;        // ids per list
+    const uint32_t* hi;       // max id per list
+    uint32_t nlist;
+    uint8_t* l;
+    uint64_t* sizes;          // [6][nlist]: lower-bits words, upper-bits words, samples, chunk descriptors, encoder tiles, ids
+    uint64_t* totals;         // [0] bits_total, [1] max l, [2] a list whose upper-bits vector has >= 2^32 bits (its number + 1)
+};
+
+__global__ void __launch_bounds__(kThreads) k_ef_shapes(EfShapeArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    uint64_t bits = 0;
+    uint32_t l = 0;
+    if (i < a.nlist) {
+        const uint32_t n = a.n[i];
+        const EfShape s = ef_shape(a.hi[i], n);
+        l = s.l;
+        a.l[i] = (uint8_t)s.l;
+        a.sizes[0ull * a.nlist + i] = s.low_words;
+        a.sizes[1ull * a.nlist + i] = s.high_words;
+        a.sizes[2ull * a.nlist + i] = s.samples;
+        const uint64_t nd = (s.high_words + kDecChunkWords - 1) / kDecChunkWords;
+        a.sizes[3ull * a.nlist + i] = nd ? nd : 1ull;  // an empty list still owns one (zero) descriptor
+        a.sizes[4ull * a.nlist + i] = ((uint64_t)n + kEncTileIds - 1) / kEncTileIds;
+        a.sizes[5ull * a.nlist + i] = n;
+        bits = s.low_bits + s.high_bits;
+        if (s.high_bits >= (1ull << 32)) atomicMax(reinterpret_cast<unsigned long long*>(a.totals + 2), (unsigned long long)i + 1ull);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        bits += __shfl_xor_sync(0xffffffffu, bits, o);
+        const uint32_t ol = __shfl_xor_sync(0xffffffffu, l, o);
+        l = ol > l ? ol : l;
+    }
+    if (lane == 0) {
+        if (bits) atomicAdd(reinterpret_cast<unsigned long long*>(a.totals), (unsigned long long)bits);
+        if (l) atomicMax(reinterpret_cast<unsigned long long*>(a.totals + 1), (unsigned long long)l);
+    }
+}
+
+// graph rows: row r starts at element r * K
+__global__ void __launch_bounds__(kThreads) k_ef_row_src(uint64_t* src, uint64_t nrows, uint32_t K) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nrows) src[r] = r * K;
+}
+
 // ------------------------------------------------------------------ host
 
-int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint32_t flags,
-             const std::vector<uint64_t>& list_src, uint64_t id_elems) {
+// Host mirrors of the per-list tables, fetched from the device on first use.
+int ef_host_tables(const idc_ef_blob* b) {
+    if (b->host_tables) return IDC_OK;
+    idc_ctx* c = b->ctx;
     const uint64_t nl = b->nlist;
+    cudaStream_t s = c->stream;
+    std::vector<uint32_t> uni32(nl);
+    b->list_offsets.resize(nl + 1);
+    b->l.resize(nl);
+    b->low_off.resize(nl + 1);
+    b->high_off.resize(nl + 1);
+    b->samp_off.resize(nl + 1);
+    b->dir_off.resize(nl + 1);
+    IDC_CUDA(cudaMemcpyAsync(b->list_offsets.data(), b->d_list_off, (nl + 1) * 8, cudaMemcpyDeviceToHost, s));
+    IDC_CUDA(cudaMemcpyAsync(b->low_off.data(), b->d_low_off, (nl + 1) * 8, cudaMemcpyDeviceToHost, s));
+    IDC_CUDA(cudaMemcpyAsync(b->high_off.data(), b->d_high_off, (nl + 1) * 8, cudaMemcpyDeviceToHost, s));
+    IDC_CUDA(cudaMemcpyAsync(b->samp_off.data(), b->d_samp_off, (nl + 1) * 8, cudaMemcpyDeviceToHost, s));
+    IDC_CUDA(cudaMemcpyAsync(b->dir_off.data(), b->d_dir_off, (nl + 1) * 8, cudaMemcpyDeviceToHost, s));
+    if (nl) IDC_CUDA(cudaMemcpyAsync(b->l.data(), b->d_l, nl, cudaMemcpyDeviceToHost, s));
+    if (nl) IDC_CUDA(cudaMemcpyAsync(uni32.data(), b->d_universe, nl * 4, cudaMemcpyDeviceToHost, s));
+    IDC_CUDA(cudaStreamSynchronize(s));
+    b->universe.assign(uni32.begin(), uni32.end());
+    b->host_tables = true;
+    return IDC_OK;
+}
+
+// What the caller of ef_build has put on the device (c->meta is carved by ef_build itself: the caller fills the two
+// arrays through the callbacks below once they exist).
+struct EfBuildIn {
+    const void* ids_dev;
+    int id_bytes;
+    uint32_t flags;
+    uint64_t id_elems;
+    const std::vector<uint64_t>* list_src;  // CSR mode: element offset of every list (host); null: graph rows
+    const std::vector<uint32_t>* n_host;    // CSR mode: ids per list (host)
+    uint32_t K;                             // graph rows: row r = elements [r K, r K + K), ids up to the first -1
+    const uint32_t* d_cnt;                  // graph rows: ids per row (device)
+};
+
+// Everything per list is computed on the device: universe (max id), field width and vector sizes (k_ef_shapes), the
+// offset tables (prefix sums); the host learns eight totals through one small copy. One million graph rows used to
+// cost 20 ms of host loops and table uploads per call.
+int ef_build(idc_ctx* c, idc_ef_blob* b, const EfBuildIn& in) {
+    const uint64_t nl = b->nlist;
+    const int id_bytes = in.id_bytes;
+    const void* ids_dev = in.ids_dev;
+    const bool rows = in.list_src == nullptr;
     HostTrace tr("ef_build");
-    // per-list metadata via the shared unit kernel (a list is one "unit" here)
-    std::vector<uint32_t> n32(nl);
-    for (uint64_t i = 0; i < nl; i++) {
-        uint64_t n = b->list_offsets[i + 1] - b->list_offsets[i];
-        IDC_REQUIRE(n < (1ull << 32), IDC_ERR_ARG, "list %llu too long", (unsigned long long)i);
-        n32[i] = (uint32_t)n;
-    }
-    IDC_TRY(c->meta.reserve(nl * (8 + 4 + 1 + 4 + 4) + 1024));
+    uint64_t acct = 0;
+    IDC_TRY(dev_alloc(c, &b->d_list_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_universe, nl, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_l, nl, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_low_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_high_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_samp_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_dir_off, nl + 1, &acct));
+    // per-call tables
+    const size_t scan_bytes = scan_scratch_bytes(nl, 6);
+    IDC_TRY(c->meta.reserve(nl * (8 + 4 + 4 + 1 + 6 * 8 + 8) + 8 + scan_bytes + 64 + 1024));
     uint8_t* mp = c->meta.as<uint8_t>();
     auto carve = [&](size_t bytes) {
         uint8_t* r = mp;
@@ -1012,16 +1111,29 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
         return r;
     };
     uint64_t* d_src = (uint64_t*)carve(nl * 8);
+    uint64_t* d_sizes = (uint64_t*)carve(nl * 6 * 8);
+    uint64_t* d_tile_base = (uint64_t*)carve((nl + 1) * 8);
+    uint64_t* d_scan = (uint64_t*)carve(scan_bytes);
+    uint64_t* d_totals = (uint64_t*)carve(64);
     uint32_t* d_n = (uint32_t*)carve(nl * 4);
     uint32_t* d_lo = (uint32_t*)carve(nl * 4);
-    uint32_t* d_hi = (uint32_t*)carve(nl * 4);
     uint8_t* d_prec = (uint8_t*)carve(nl);
+    uint32_t* d_hi = b->d_universe;
     IDC_TRY(c->status.reserve(64));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
-    IDC_TRY(upload(c, d_src, list_src));
-    IDC_TRY(upload(c, d_n, n32));
-    const bool sorted_in = (flags & IDC_F_SORTED) != 0;
+    IDC_CUDA(cudaMemsetAsync(d_totals, 0, 64, c->stream));
+    if (rows) {
+        if (nl) {
+            IDC_CUDA(cudaMemcpyAsync(d_n, in.d_cnt, nl * 4, cudaMemcpyDeviceToDevice, c->stream));
+            LaunchScope ls(c, "k_ef_row_src");
+            k_ef_row_src<<<grid_for(nl), kThreads, 0, c->stream>>>(d_src, nl, in.K);
+        }
+    } else {
+        IDC_TRY(upload(c, d_src, *in.list_src));
+        IDC_TRY(upload(c, d_n, *in.n_host));
+    }
+    const bool sorted_in = (in.flags & IDC_F_SORTED) != 0;
     if (sorted_in) {
         // the universe of an ascending list is its last id; order and width are verified by the encode kernel
         LaunchScope ls(c, "k_unit_meta");
@@ -1033,97 +1145,87 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
         }
     } else {
         MetaArgs m{ids_dev, d_src, d_n, (uint32_t)nl, 0u, 0u, d_prec, d_lo, d_hi, d_status, nullptr, nullptr, 0u};
-        IDC_TRY(run_unit_meta(c, m, n32, id_bytes));
+        if (rows)
+            IDC_TRY(run_unit_meta_small(c, m, nl, id_bytes));  // a row holds at most K <= 340 ids
+        else
+            IDC_TRY(run_unit_meta(c, m, *in.n_host, id_bytes));
     }
     IDC_TRY(check_last_launch("k_unit_meta"));
-    std::vector<uint32_t> hi(nl);
-    uint32_t st = 0;
-    if (nl) IDC_CUDA(cudaMemcpyAsync(hi.data(), d_hi, nl * 4, cudaMemcpyDeviceToHost, c->stream));
-    IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
-    IDC_CUDA(cudaStreamSynchronize(c->stream));
-    IDC_TRY(status_to_error(st, "ef_encode"));
-    tr.mark("unit metadata");
-
-    // shapes
-    b->l.resize(nl);
-    b->universe.resize(nl);
-    b->low_off.assign(nl + 1, 0);
-    b->high_off.assign(nl + 1, 0);
-    b->samp_off.assign(nl + 1, 0);
-    b->dir_off.assign(nl + 1, 0);
-    std::vector<uint32_t> tile_base(nl + 1, 0);  // first encoder tile of each list; the per-tile table is built on the device
-    uint64_t bits_total = 0;
-    for (uint64_t i = 0; i < nl; i++) {
-        EfShape s = ef_shape(hi[i], n32[i]);
-        IDC_REQUIRE(s.high_bits < (1ull << 32), IDC_ERR_DOMAIN,
-                    "list %llu: upper-bits vector of %llu bits; the device path handles up to 2^32 - 1",
-                    (unsigned long long)i, (unsigned long long)s.high_bits);
-        b->l[i] = (uint8_t)s.l;
-        b->max_l = std::max<uint32_t>(b->max_l, s.l);
-        b->universe[i] = hi[i];
-        b->low_off[i + 1] = b->low_off[i] + s.low_words;
-        b->high_off[i + 1] = b->high_off[i] + s.high_words;
-        b->samp_off[i + 1] = b->samp_off[i] + s.samples;
-        b->dir_off[i + 1] = b->dir_off[i] + std::max<uint64_t>(1, (s.high_words + kDecChunkWords - 1) / kDecChunkWords);
-        bits_total += s.low_bits + s.high_bits;
-        const uint64_t nt = tile_base[i] + ((uint64_t)n32[i] + kEncTileIds - 1) / kEncTileIds;
-        IDC_REQUIRE(nt < (1ull << 32), IDC_ERR_ARG, "too many encoder tiles");
-        tile_base[i + 1] = (uint32_t)nt;
+    // shapes + offset tables
+    if (nl) {
+        EfShapeArgs sa{d_n, d_hi, (uint32_t)nl, b->d_l, d_sizes, d_totals};
+        {
+            LaunchScope ls(c, "k_ef_shapes");
+            k_ef_shapes<<<grid_for(nl), kThreads, 0, c->stream>>>(sa);
+        }
+        IDC_TRY(check_last_launch("k_ef_shapes"));
     }
-    tr.mark("shapes + tile tables");
-    b->low_words = b->low_off[nl];
-    b->high_words = b->high_off[nl];
-    b->nsamples = b->samp_off[nl];
-    b->ndir = b->dir_off[nl];
-    b->bits_total = bits_total;
-    uint64_t acct = 0;
-    IDC_TRY(dev_alloc(c, &b->d_list_off, nl + 1, &acct));
-    IDC_TRY(dev_alloc(c, &b->d_l, nl, &acct));
-    IDC_TRY(dev_alloc(c, &b->d_low_off, nl + 1, &acct));
-    IDC_TRY(dev_alloc(c, &b->d_high_off, nl + 1, &acct));
-    IDC_TRY(dev_alloc(c, &b->d_samp_off, nl + 1, &acct));
-    IDC_TRY(dev_alloc(c, &b->d_dir_off, nl + 1, &acct));
+    {
+        const uint64_t* sin[6] = {d_sizes, d_sizes + nl, d_sizes + 2 * nl, d_sizes + 3 * nl, d_sizes + 4 * nl, d_sizes + 5 * nl};
+        uint64_t* sout[6] = {b->d_low_off, b->d_high_off, b->d_samp_off, b->d_dir_off, d_tile_base, b->d_list_off};
+        IDC_TRY(device_scan(c, 6, sin, sout, nl, d_scan));
+    }
+    uint64_t tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // low words, high words, samples, descriptors, tiles, ids, then d_totals[0..2)
+    uint64_t tot2[3] = {0, 0, 0};
+    uint32_t st = 0;
+    {
+        uint64_t* outs[6] = {b->d_low_off, b->d_high_off, b->d_samp_off, b->d_dir_off, d_tile_base, b->d_list_off};
+        for (int j = 0; j < 6; j++) IDC_CUDA(cudaMemcpyAsync(&tot[j], outs[j] + nl, 8, cudaMemcpyDeviceToHost, c->stream));
+        IDC_CUDA(cudaMemcpyAsync(tot2, d_totals, 24, cudaMemcpyDeviceToHost, c->stream));
+        IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+        IDC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    IDC_TRY(status_to_error(st, "ef_encode"));
+    IDC_REQUIRE(tot2[2] == 0, IDC_ERR_DOMAIN, "list %llu: its upper-bits vector has 2^32 bits or more; the device path handles up to 2^32 - 1",
+                (unsigned long long)(tot2[2] - 1));
+    tr.mark("metadata, shapes, offset tables");
+    b->low_words = tot[0];
+    b->high_words = tot[1];
+    b->nsamples = tot[2];
+    b->ndir = tot[3];
+    const uint64_t ntiles = tot[4];
+    b->total_ids = tot[5];
+    b->bits_total = tot2[0];
+    b->max_l = (uint32_t)tot2[1];
+    IDC_REQUIRE(ntiles < (1ull << 32), IDC_ERR_ARG, "too many encoder tiles");
     IDC_TRY(dev_alloc(c, &b->d_dir, b->ndir, &acct));
     IDC_TRY(dev_alloc(c, &b->d_low, b->low_words + 32, &acct));  // +256 B: the decoder's last group may read past the end
     IDC_TRY(dev_alloc(c, &b->d_high, b->high_words + 2, &acct));  // + 16 B: the decoder stages whole 16-byte pieces
     IDC_TRY(dev_alloc(c, &b->d_samples, b->nsamples, &acct));
-    IDC_TRY(upload(c, b->d_list_off, b->list_offsets));
-    IDC_TRY(upload(c, b->d_l, b->l));
-    IDC_TRY(upload(c, b->d_low_off, b->low_off));
-    IDC_TRY(upload(c, b->d_high_off, b->high_off));
-    IDC_TRY(upload(c, b->d_samp_off, b->samp_off));
-    IDC_TRY(upload(c, b->d_dir_off, b->dir_off));
     IDC_CUDA(cudaMemsetAsync(b->d_dir, 0, std::max<uint64_t>(b->ndir, 1) * sizeof(EfChunk), c->stream));  // empty lists: count 0
-
-    tr.mark("alloc + uploads");
+    tr.mark("alloc");
     // sort when needed (ids < 2^32 was checked by the metadata kernel)
     const void* enc_ids = ids_dev;
     int enc_id_bytes = id_bytes;
-    const uint64_t ntiles = tile_base[nl];
-    const size_t base_bytes = ((nl + 1) * 4 + 255) & ~size_t(255);
-    size_t tile_bytes = base_bytes + ((ntiles * sizeof(EfTile) + 255) & ~size_t(255));
+    size_t tile_bytes = (ntiles * sizeof(EfTile) + 255) & ~size_t(255);
     size_t ws_need = tile_bytes;
     size_t sorted_off = 0, sortidx_off = 0, big_off = 0, posbase_off = 0;
     uint32_t sort_grid = 0;
+    bool any_big = false;
     if (!sorted_in) {
         sort_grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nl, 1), (uint64_t)c->sm_count * 8);
         bool need_big = false;
-        for (uint64_t i = 0; i < nl; i++) {
-            IDC_REQUIRE(n32[i] <= kMaxUnit, IDC_ERR_DOMAIN,
-                        "unsorted list %llu has %u ids: the device sort handles lists of <= 65536 ids; "
-                        "pass ascending ids with IDC_F_SORTED", (unsigned long long)i, n32[i]);
-            need_big |= n32[i] > kSortSmem;
+        if (rows) {
+            need_big = in.K > kSortSmem;
+            any_big = in.K > kSortWarp;
+        } else {
+            for (uint64_t i = 0; i < nl; i++) {
+                const uint32_t n = (*in.n_host)[i];
+                IDC_REQUIRE(n <= kMaxUnit, IDC_ERR_DOMAIN,
+                            "unsorted list %llu has %u ids: the device sort handles lists of <= 65536 ids; "
+                            "pass ascending ids with IDC_F_SORTED", (unsigned long long)i, n);
+                need_big |= n > kSortSmem;
+                any_big |= n > kSortWarp;
+            }
         }
         sorted_off = (ws_need + 255) & ~size_t(255);
-        sortidx_off = sorted_off + ((id_elems * 4 + 255) & ~size_t(255));
-        posbase_off = sortidx_off + ((id_elems * 4 + 255) & ~size_t(255));
+        sortidx_off = sorted_off + ((in.id_elems * 4 + 255) & ~size_t(255));
+        posbase_off = sortidx_off + ((in.id_elems * 4 + 255) & ~size_t(255));
         big_off = posbase_off + ((nl * 4 + 255) & ~size_t(255));
         ws_need = big_off + (need_big ? (size_t)sort_grid * kMaxUnit * 8 : 0);
     }
     IDC_TRY(c->ws.reserve(ws_need + 256));
-    uint32_t* d_tile_base = c->ws.as<uint32_t>();
-    EfTile* d_tiles = reinterpret_cast<EfTile*>(c->ws.as<uint8_t>() + base_bytes);
-    IDC_TRY(upload(c, d_tile_base, tile_base));
+    EfTile* d_tiles = reinterpret_cast<EfTile*>(c->ws.as<uint8_t>());
     if (!sorted_in && nl) {
         uint32_t* d_sorted = (uint32_t*)(c->ws.as<uint8_t>() + sorted_off);
         uint32_t* d_sort_idx = (uint32_t*)(c->ws.as<uint8_t>() + sortidx_off);
@@ -1131,8 +1233,6 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const void* ids_dev, int id_bytes, uint
         IDC_CUDA(cudaMemsetAsync(d_posbase, 0, nl * 4, c->stream));
         SortArgs s{ids_dev, d_src, d_n, d_posbase, (uint32_t)nl, d_sorted, d_sort_idx,
                    (uint64_t*)(c->ws.as<uint8_t>() + big_off)};
-        bool any_big = false;
-        for (uint64_t i = 0; i < nl && !any_big; i++) any_big = n32[i] > kSortWarp;
         IDC_TRY(launch_sorts(c, s, id_bytes, sort_grid, any_big));
         enc_ids = d_sorted;
         enc_id_bytes = 4;
@@ -1238,10 +1338,16 @@ int idc_ef_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const voi
     b->nlist = nlist;
     b->list_offsets.resize(nlist + 1);
     std::vector<uint64_t> src(nlist);
+    std::vector<uint32_t> n32(nlist);
     for (uint64_t l = 0; l <= nlist; l++) {
         IDC_REQUIRE(l == 0 || offsets[l] >= offsets[l - 1], IDC_ERR_ARG, "offsets must be non-decreasing");
         b->list_offsets[l] = offsets[l] - offsets[0];
-        if (l < nlist) src[l] = offsets[l];
+        if (l < nlist) {
+            src[l] = offsets[l];
+            IDC_REQUIRE(offsets[l + 1] < offsets[l] || offsets[l + 1] - offsets[l] < (1ull << 32), IDC_ERR_ARG, "list %llu too long",
+                        (unsigned long long)l);
+            n32[l] = (uint32_t)(offsets[l + 1] - offsets[l]);
+        }
     }
     b->total_ids = b->list_offsets[nlist];
     uint64_t elems = offsets[nlist];
@@ -1252,7 +1358,8 @@ int idc_ef_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const voi
         IDC_CUDA(cudaMemcpyAsync(c->stage.p, ids, elems * id_bytes, cudaMemcpyHostToDevice, c->stream));
         ids_dev = c->stage.p;
     }
-    IDC_TRY(ef_build(c, b.get(), ids_dev, id_bytes, flags, src, elems));
+    EfBuildIn in{ids_dev, id_bytes, flags, elems, &src, &n32, 0u, nullptr};
+    IDC_TRY(ef_build(c, b.get(), in));
     *out = b.release();
     return IDC_OK;
 }
@@ -1280,29 +1387,18 @@ int idc_ef_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* da
         IDC_CUDA(cudaMemcpyAsync(c->stage.p, data, elems * 4, cudaMemcpyHostToDevice, c->stream));
         d_data = c->stage.as<int32_t>();
     }
-    std::vector<uint32_t> cnt(nrows);
+    // row lengths on the device; they stay there (shapes, offsets and the sort are planned on the device)
+    IDC_TRY(c->scratch.reserve(nrows * 4 + 256));
+    uint32_t* d_cnt = c->scratch.as<uint32_t>();
     if (nrows) {
-        IDC_TRY(c->meta.reserve(nrows * 4 + 256));
-        uint32_t* d_cnt = c->meta.as<uint32_t>();
         {
             LaunchScope ls(c, "k_row_counts");
             k_row_counts<<<grid_for(nrows * 32), kThreads, 0, c->stream>>>(d_data, nrows, K, d_cnt);
         }
         IDC_TRY(check_last_launch("k_row_counts"));
-        IDC_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, nrows * 4, cudaMemcpyDeviceToHost, c->stream));
-        IDC_CUDA(cudaStreamSynchronize(c->stream));
     }
-    b->list_offsets.resize(nrows + 1);
-    std::vector<uint64_t> src(nrows);
-    uint64_t total = 0;
-    for (uint64_t r = 0; r < nrows; r++) {
-        b->list_offsets[r] = total;
-        src[r] = r * K;
-        total += cnt[r];
-    }
-    b->list_offsets[nrows] = total;
-    b->total_ids = total;
-    IDC_TRY(ef_build(c, b.get(), d_data, 4, flags & ~IDC_F_SORTED, src, elems));
+    EfBuildIn in{d_data, 4, flags & ~IDC_F_SORTED, elems, nullptr, nullptr, K, d_cnt};
+    IDC_TRY(ef_build(c, b.get(), in));
     *out = b.release();
     return IDC_OK;
 }
@@ -1324,6 +1420,10 @@ int idc_ef_blob_export(const idc_ef_blob* b, uint64_t* list_offsets, uint8_t* l,
     IDC_REQUIRE(b, IDC_ERR_ARG, "null blob");
     IDC_CUDA(cudaSetDevice(b->ctx->device));
     cudaStream_t s = b->ctx->stream;
+    if (list_offsets || l || universe || low_offsets || high_offsets) {
+        std::lock_guard<std::mutex> lock(b->ctx->mu);
+        IDC_TRY(ef_host_tables(b));
+    }
     if (list_offsets) memcpy(list_offsets, b->list_offsets.data(), (b->nlist + 1) * 8);
     if (l && b->nlist) memcpy(l, b->l.data(), b->nlist);
     if (universe && b->nlist) memcpy(universe, b->universe.data(), b->nlist * 8);
@@ -1355,6 +1455,7 @@ int idc_ef_decode(idc_ctx* c, const idc_ef_blob* b, const uint64_t* list_nos, ui
     uint64_t total_out = 0, ntiles = 0;
     uint32_t* t_desc = nullptr;
     uint64_t* t_out = nullptr;
+    if (list_nos != nullptr || out_offsets != nullptr) IDC_TRY(ef_host_tables(b));
     {  // argument errors surface before anything is allocated
         uint64_t want = 0;
         if (list_nos == nullptr) want = b->total_ids;
@@ -1613,6 +1714,7 @@ int idc_ef_blob_import(idc_ctx* c, uint64_t nlist, const uint64_t* list_offsets,
     IDC_REQUIRE((low || b->low_words == 0) && (high || b->high_words == 0), IDC_ERR_ARG, "idc_ef_blob_import: null bit vector");
     uint64_t acct = 0;
     IDC_TRY(dev_alloc(c, &b->d_list_off, nl + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_universe, nl, &acct));
     IDC_TRY(dev_alloc(c, &b->d_l, nl, &acct));
     IDC_TRY(dev_alloc(c, &b->d_low_off, nl + 1, &acct));
     IDC_TRY(dev_alloc(c, &b->d_high_off, nl + 1, &acct));
@@ -1622,6 +1724,12 @@ int idc_ef_blob_import(idc_ctx* c, uint64_t nlist, const uint64_t* list_offsets,
     IDC_TRY(dev_alloc(c, &b->d_low, b->low_words + 32, &acct));
     IDC_TRY(dev_alloc(c, &b->d_high, b->high_words + 2, &acct));
     IDC_TRY(dev_alloc(c, &b->d_samples, b->nsamples, &acct));
+    b->host_tables = true;  // the mirrors were computed right here
+    {
+        std::vector<uint32_t> uni32(b->universe.begin(), b->universe.end());
+        IDC_TRY(upload(c, b->d_universe, uni32));
+        IDC_CUDA(cudaStreamSynchronize(c->stream));  // uni32 goes out of scope
+    }
     IDC_TRY(upload(c, b->d_list_off, b->list_offsets));
     IDC_TRY(upload(c, b->d_l, b->l));
     IDC_TRY(upload(c, b->d_low_off, b->low_off));
@@ -1654,8 +1762,8 @@ int idc_ef_blob_import(idc_ctx* c, uint64_t nlist, const uint64_t* list_offsets,
 // ---- flat file form (idc_file.h): header words, the list CSR, the universes and the two bit vectors
 int idc_ef_blob_save(const idc_ef_blob* b, const char* path) {
     IDC_REQUIRE(b && path, IDC_ERR_ARG, "idc_ef_blob_save: null argument");
-    std::vector<uint64_t> low(b->low_words), high(b->high_words);
-    IDC_TRY(idc_ef_blob_export(b, nullptr, nullptr, nullptr, nullptr, nullptr, low.data(), high.data()));
+    std::vector<uint64_t> low(b->low_words), high(b->high_words), offs(b->nlist + 1);
+    IDC_TRY(idc_ef_blob_export(b, offs.data(), nullptr, nullptr, nullptr, nullptr, low.data(), high.data()));  // (fetches the host tables)
     std::vector<uint64_t> hdr{b->nlist, b->low_words, b->high_words, b->row_stride};
     FileWriter w;
     IDC_TRY(w.open(path, kFileEf, 5));
