@@ -862,12 +862,14 @@ def sharded_section(args, ctx, offsets, ids, world, rank, dev, barrier):
                     one_ms.append(e0.elapsed_time(e1))
             a, b = whole.export_payload(device=dev), single.export_payload(device=dev)
             same = all(bool(torch.equal(a[k], b[k])) for k in a) and whole.ans_bytes == single.ans_bytes
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            d1, _ = single.decode(device=dev)
-            e1.record()
-            torch.cuda.synchronize()
-            one_dec = e0.elapsed_time(e1)
+            for it in range(2):  # the second pass is the measurement (the first allocates workspaces)
+                d1 = None
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                d1, _ = single.decode(device=dev)
+                e1.record()
+                torch.cuda.synchronize()
+                one_dec = e0.elapsed_time(e1)
             del d1, a, b
             t1 = float(np.mean(one_ms))
             out.update(byte_identical_to_one_gpu=bool(same), one_gpu_encode_ms=t1, one_gpu_decode_ms=one_dec,
