@@ -699,6 +699,48 @@ def e2e_buffers(ids):
     return host_in, host_out
 
 
+def pcie_ceiling(host_in, host_out, world, dev, barrier, chunk_bytes=1 << 30, reps=4):
+    """What the host link gives this rank while ALL ranks copy at the same time: pinned-host -> device alone, device ->
+    pinned-host alone, and both directions at once (two streams). The e2e step moves 8 B/id up and 8 B/id down, the
+    download after the upload, so its copy floor is bytes / h2d + bytes / d2h."""
+    import torch
+    import torch.distributed as dist
+
+    n = min(chunk_bytes // 8, int(host_in.numel()))
+    dbuf_a = torch.empty(n, dtype=torch.int64, device=dev)
+    dbuf_b = torch.empty(n, dtype=torch.int64, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    nchunk = max(1, min(reps, int(host_in.numel()) // n))
+
+    def run(up, down):
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(nchunk):
+            if up:
+                with torch.cuda.stream(s1):
+                    dbuf_a.copy_(host_in[k * n:(k + 1) * n], non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    host_out[k * n:(k + 1) * n].copy_(dbuf_b, non_blocking=True)
+        s1.synchronize()
+        s2.synchronize()
+        return 8.0 * n * nchunk / (time.perf_counter() - t0) / 1e9  # GB/s per direction
+
+    run(True, True)
+    vals = [run(True, False), run(False, True), run(True, True)]
+    out = {}
+    for name, v in zip(("h2d_GBs", "d2h_GBs", "duplex_GBs_per_direction"), vals):
+        allr = [v]
+        if world > 1:
+            g = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(g, torch.tensor([v], device=dev, dtype=torch.float64))
+            allr = [float(x.item()) for x in g]
+        out[name] = [round(x, 2) for x in allr]
+    del dbuf_a, dbuf_b
+    return out
+
+
 def e2e_section(args, ctx, offsets, ids, world, dev, barrier, host_bufs):
     import torch
     import torch.distributed as dist
@@ -744,10 +786,19 @@ def e2e_section(args, ctx, offsets, ids, world, dev, barrier, host_bufs):
         allr = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
         dist.all_gather(allr, torch.tensor([gbs], device=dev, dtype=torch.float64))
         rates = [float(x.item()) for x in allr]
-    return {"value": n_ids * world * steps / t, "unit": "ids/s", "h2d_bytes_per_step": 8 * n_ids,
-            "d2h_bytes_per_step": 8 * n_ids, "steps": steps, "ms_per_step": 1e3 * t / steps,
-            "roundtrip_all_lists_ok": ok, "pcie_GBs_per_rank": [round(r, 2) for r in rates],
-            "path": "idc_roc_encode(IDC_MEM_HOST, pinned) -> idc_roc_decode(IDC_MEM_HOST, pinned)"}
+    res = {"value": n_ids * world * steps / t, "unit": "ids/s", "h2d_bytes_per_step": 8 * n_ids,
+           "d2h_bytes_per_step": 8 * n_ids, "steps": steps, "ms_per_step": 1e3 * t / steps,
+           "roundtrip_all_lists_ok": ok, "pcie_GBs_per_rank": [round(r, 2) for r in rates],
+           "path": "idc_roc_encode(IDC_MEM_HOST, pinned) -> idc_roc_decode(IDC_MEM_HOST, pinned)"}
+    try:
+        ceil = pcie_ceiling(host_in, host_out, world, dev, barrier)
+        # copy floor of one step on the slowest rank: the download can only follow the upload
+        floor_ms = max(1e3 * (8.0 * n_ids / 1e9 / h + 8.0 * n_ids / 1e9 / d) for h, d in zip(ceil["h2d_GBs"], ceil["d2h_GBs"]))
+        res["pcie_ceiling"] = dict(ceil, what="pinned host <-> device copies of 1 GiB pieces, all ranks at the same time",
+                                   copy_floor_ms_per_step=round(floor_ms, 1), step_over_copy_floor=round(res["ms_per_step"] / floor_ms, 3))
+    except Exception as ex:  # the measurement must never take the e2e number down with it
+        res["pcie_ceiling"] = {"error": str(ex)[:200]}
+    return res
 
 
 # ------------------------------------------------------------------ sharded (rank 0 owns the index)
@@ -796,7 +847,10 @@ def sharded_section(args, ctx, offsets, ids, world, rank, dev, barrier):
         marks = []
 
         def tick(nm):
+            # every phase ends at a rendezvous of all ranks: a rank that finished its encode early would otherwise book
+            # the wait for the slowest rank under "gather"
             torch.cuda.synchronize()
+            barrier()
             marks.append((nm, time.perf_counter()))
 
         if whole is not None:
