@@ -494,15 +494,36 @@ __global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(const __grid_co
         if (fast) {
             uint32_t wide = 0;
             const IdT* rp = reinterpret_cast<const IdT*>(raw0 + (lane & 7u) * Smem::kSubStride) + (lane >> 3) * 32u;
+            if (sizeof(IdT) == 8) {
+                // 16-byte loads, two ids each: the eight lanes of a quarter-warp read different bank groups (the shared-
+                // memory pipe is this kernel's busiest unit; 8-byte loads cost twice the wavefronts). A run starts 0 or
+                // 8 bytes past a 16-byte boundary: in the second case 17 aligned loads cover it.
+                const uint4* q4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(rp) - skew);
+                if (skew == 0u) {
 #pragma unroll
-            for (int r = 0; r < 32; r++) {
-                if (sizeof(IdT) == 8) {
-                    const uint2 x = *reinterpret_cast<const uint2*>(rp + r);
-                    v[r] = x.x;
-                    wide |= x.y;
+                    for (int k = 0; k < 16; k++) {
+                        const uint4 x = q4[k];
+                        v[2 * k] = x.x;
+                        v[2 * k + 1] = x.z;
+                        wide |= x.y | x.w;
+                    }
                 } else {
-                    v[r] = (uint32_t)rp[r];
+#pragma unroll
+                    for (int k = 0; k <= 16; k++) {
+                        const uint4 x = q4[k];
+                        if (k > 0) {
+                            v[2 * k - 1] = x.x;
+                            wide |= x.y;
+                        }
+                        if (k < 16) {
+                            v[2 * k] = x.z;
+                            wide |= x.w;
+                        }
+                    }
                 }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 32; r++) v[r] = (uint32_t)rp[r];
             }
             hp_first = (v[0] >> l) + hb;
             const uint32_t hp_last = (v[31] >> l) + hb + 31u;
