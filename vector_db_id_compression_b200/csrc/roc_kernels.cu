@@ -43,11 +43,13 @@ struct idc_roc_blob {
     uint64_t nlist = 0, nunits = 0, total_ids = 0, total_words = 0, ans_bytes = 0;
     uint32_t max_unit = IDC_MAX_UNIT_DEFAULT, row_stride = 0;
     uint32_t max_n = 0;  // largest unit
-    // host metadata
-    std::vector<uint64_t> list_offsets;  // nlist+1 (CSR of ids; rows: l*K)
-    std::vector<uint64_t> unit_offsets;  // nlist+1
-    std::vector<uint32_t> unit_n;        // nunits
-    std::vector<uint64_t> unit_src;      // nunits: element offset of the unit in the id array
+    // host metadata (row blobs built by idc_roc_encode_rows are planned on the device: their host tables are fetched
+    // on first use, see roc_host_tables)
+    mutable bool host_tables = true;
+    mutable std::vector<uint64_t> list_offsets;  // nlist+1 (CSR of ids)
+    mutable std::vector<uint64_t> unit_offsets;  // nlist+1
+    mutable std::vector<uint32_t> unit_n;        // nunits
+    mutable std::vector<uint64_t> unit_src;      // nunits: element offset of the unit in the id array
     // device arrays
     uint32_t* d_unit_n = nullptr;
     uint8_t* d_unit_prec = nullptr;
@@ -687,6 +689,213 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
 }
 
 // list -> unit tables for CSR input
+// ---- graph rows, planned on the device -------------------------------------------------------------------
+// A million rows of <= K ids each: no host loop may touch them. Row r is unit r and launch slot r, it starts at
+// element r K, owns a fixed-size workspace and scratch slot (what a full row needs), and the packed word offsets come
+// from a prefix sum over the emitted word counts.
+struct RowTabArgs {
+    uint64_t* unit_src;
+    uint64_t* ws_off;
+    uint64_t* scratch_off;
+    uint32_t* posbase;
+    uint32_t* perm;
+    uint64_t nrows;
+    uint64_t K, slot_ws, slot_scratch;
+};
+
+__global__ void __launch_bounds__(kThreads) k_roc_row_tables(RowTabArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.nrows) return;
+    a.unit_src[r] = r * a.K;
+    a.ws_off[r] = r * a.slot_ws;
+    a.scratch_off[r] = r * a.slot_scratch;
+    a.posbase[r] = 0u;
+    a.perm[r] = (uint32_t)r;
+}
+
+// per row: stream words (0 for an empty row), "row is not empty", ids -- the inputs of the three prefix sums
+__global__ void __launch_bounds__(kThreads) k_roc_row_sizes(const uint32_t* unit_n, const uint32_t* nwords, uint64_t nrows, uint64_t* sizes) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const uint32_t n = unit_n[r];
+    sizes[r] = n ? nwords[r] : 0u;
+    sizes[nrows + r] = n ? 1u : 0u;
+    sizes[2 * nrows + r] = n;
+}
+
+// host tables of a row blob that was planned on the device
+int roc_host_tables(const idc_roc_blob* b) {
+    if (b->host_tables) return IDC_OK;
+    idc_ctx* c = b->ctx;
+    const uint64_t nr = b->nlist;
+    b->unit_n.resize(nr);
+    if (nr) IDC_CUDA(cudaMemcpyAsync(b->unit_n.data(), b->d_unit_n, nr * 4, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    b->list_offsets.resize(nr + 1);
+    b->unit_offsets.resize(nr + 1);
+    b->unit_src.resize(nr);
+    uint64_t total = 0;
+    for (uint64_t r = 0; r < nr; r++) {
+        b->list_offsets[r] = total;
+        b->unit_offsets[r] = r;
+        b->unit_src[r] = r * b->row_stride;
+        total += b->unit_n[r];
+    }
+    b->list_offsets[nr] = total;
+    b->unit_offsets[nr] = nr;
+    b->host_tables = true;
+    return IDC_OK;
+}
+
+int roc_encode_rows_device(idc_ctx* c, idc_roc_blob* b, const int32_t* d_data, uint32_t K, uint32_t flags) {
+    const uint64_t nr = b->nlist, elems = nr * K;
+    HostTrace tr("roc_encode_rows");
+    uint64_t acct = 0;
+    IDC_TRY(dev_alloc(c, &b->d_unit_n, nr, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_prec, nr, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_head, nr, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_word_off, nr + 1, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_lo, nr, &acct));
+    IDC_TRY(dev_alloc(c, &b->d_unit_hi, nr, &acct));
+    if (flags & IDC_F_WANT_ORDER) IDC_TRY(dev_alloc(c, &b->d_order, elems, &acct));
+    b->max_n = K;
+    b->host_tables = false;
+    const uint64_t slot_ws = enc_tree_bytes(K), slot_scratch = (uint64_t)K + 4u;
+    const size_t scan_bytes = scan_scratch_bytes(nr, 3);
+    IDC_TRY(c->meta.reserve(nr * (8 + 8 + 8 + 4 + 4 + 4 + 3 * 8 + 2 * 8) + scan_bytes + 1024));
+    uint8_t* mp = c->meta.as<uint8_t>();
+    auto carve = [&](size_t bytes) {
+        uint8_t* r = mp;
+        mp += (bytes + 15) & ~size_t(15);
+        return r;
+    };
+    uint64_t* d_unit_src = (uint64_t*)carve(nr * 8);
+    uint64_t* d_ws_off = (uint64_t*)carve(nr * 8);
+    uint64_t* d_scratch_off = (uint64_t*)carve(nr * 8);
+    uint64_t* d_sizes = (uint64_t*)carve(nr * 3 * 8);
+    uint64_t* d_sums = (uint64_t*)carve((nr + 1) * 2 * 8);  // prefix sums nobody keeps: "not empty", ids
+    uint64_t* d_scan = (uint64_t*)carve(scan_bytes);
+    uint32_t* d_posbase = (uint32_t*)carve(nr * 4);
+    uint32_t* d_perm = (uint32_t*)carve(nr * 4);
+    uint32_t* d_nwords = (uint32_t*)carve(nr * 4);
+    IDC_TRY(c->status.reserve(64));
+    uint32_t* d_status = c->status.as<uint32_t>();
+    IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    // workspaces: records, then the 32-bit sorted copy of the rows and the sort permutation
+    const bool need_big = K > kSortSmem, any_big = K > kSortWarp;
+    const uint32_t sort_grid = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nr, 1), (uint64_t)c->sm_count * 8);
+    const size_t sorted_off = (nr * slot_ws + 255) & ~size_t(255);
+    const size_t sortidx_off = sorted_off + ((elems * 4 + 255) & ~size_t(255));
+    const size_t big_off = sortidx_off + ((elems * 4 + 255) & ~size_t(255));
+    IDC_TRY(c->ws.reserve(big_off + (need_big ? (size_t)sort_grid * kMaxUnit * 8 : 0) + 256));
+    IDC_TRY(c->scratch.reserve(nr * slot_scratch * 4 + 256));
+    tr.mark("alloc");
+    if (nr) {
+        {
+            LaunchScope ls(c, "k_row_counts");
+            k_row_counts<<<grid_for(nr * 32), kThreads, 0, c->stream>>>(d_data, nr, K, b->d_unit_n);
+        }
+        IDC_TRY(check_last_launch("k_row_counts"));
+        {
+            LaunchScope ls(c, "k_roc_row_tables");
+            RowTabArgs t{d_unit_src, d_ws_off, d_scratch_off, d_posbase, d_perm, nr, K, slot_ws, slot_scratch};
+            k_roc_row_tables<<<grid_for(nr), kThreads, 0, c->stream>>>(t);
+        }
+        IDC_TRY(check_last_launch("k_roc_row_tables"));
+        MetaArgs m{d_data, d_unit_src, b->d_unit_n, (uint32_t)nr, 0u, (flags & IDC_F_PRECISION_SAFE) ? 1u : 0u, b->d_unit_prec,
+                   b->d_unit_lo, b->d_unit_hi, d_status, nullptr, nullptr, 0u, 0u, 0u, 0u};
+        IDC_TRY(run_unit_meta_small(c, m, nr, 4));
+        uint32_t* d_sorted = (uint32_t*)(c->ws.as<uint8_t>() + sorted_off);
+        uint32_t* d_sort_idx = (uint32_t*)(c->ws.as<uint8_t>() + sortidx_off);
+        SortArgs s{d_data, d_unit_src, b->d_unit_n, d_posbase, (uint32_t)nr, d_sorted, d_sort_idx, (uint64_t*)(c->ws.as<uint8_t>() + big_off)};
+        IDC_TRY(launch_sorts(c, s, 4, sort_grid, any_big));
+        IDC_TRY(check_last_launch("k_sort_units"));
+        EncArgs e{};
+        e.ids = d_sorted;
+        e.sort_idx = d_sort_idx;
+        e.unit_src = d_unit_src;
+        e.unit_n = b->d_unit_n;
+        e.unit_posbase = d_posbase;
+        e.unit_prec = b->d_unit_prec;
+        e.perm = d_perm;
+        e.ws_off = d_ws_off;
+        e.scratch_off = d_scratch_off;
+        e.ws = c->ws.as<uint8_t>();
+        e.scratch = c->scratch.as<uint32_t>();
+        e.unit_head = b->d_unit_head;
+        e.unit_nwords = d_nwords;
+        e.order = b->d_order;
+        e.status = d_status;
+        e.mt = c->d_mt;
+        e.rcp64 = c->d_rcp64;
+        e.q31 = c->d_q31;
+        e.nunits = (uint32_t)nr;
+        e.rec_base = 0;
+        e.rec_count = (uint32_t)nr;
+        {
+            LaunchScope ls(c, "k_enc_records");
+            k_enc_records<uint32_t><<<grid_for(nr * 32), kThreads, 0, c->stream>>>(e);
+        }
+        IDC_TRY(check_last_launch("k_enc_records"));
+        {
+            // one size class: every slot is sized for a full row
+            e.slot_base = 0;
+            e.slot_end = (uint32_t)nr;
+            e.sm_words = genc_sm_words(K);
+            const int G = group_lanes_for(K);
+            const uint32_t upw = 32u / (uint32_t)G;
+            const uint32_t warps = warps_for(e.sm_words, upw), threads = warps * 32;
+            const uint32_t nwarps = (uint32_t)((nr + upw - 1) / upw), grid = (nwarps + warps - 1) / warps;
+            const size_t smem = (size_t)e.sm_words * 4 * upw * warps;
+            LaunchScope ls(c, "k_roc_encode");
+            if (G == 8) {
+                IDC_TRY(set_max_smem(k_roc_encode<8, uint32_t>, smem));
+                k_roc_encode<8, uint32_t><<<grid, threads, smem, c->stream>>>(e);
+            } else if (G == 2) {
+                IDC_TRY(set_max_smem(k_roc_encode<2, uint32_t>, smem));
+                k_roc_encode<2, uint32_t><<<grid, threads, smem, c->stream>>>(e);
+            } else {
+                IDC_TRY(set_max_smem(k_roc_encode<4, uint32_t>, smem));
+                k_roc_encode<4, uint32_t><<<grid, threads, smem, c->stream>>>(e);
+            }
+        }
+        IDC_TRY(check_last_launch("k_roc_encode"));
+        {
+            LaunchScope ls(c, "k_roc_row_sizes");
+            k_roc_row_sizes<<<grid_for(nr), kThreads, 0, c->stream>>>(b->d_unit_n, d_nwords, nr, d_sizes);
+        }
+        IDC_TRY(check_last_launch("k_roc_row_sizes"));
+    }
+    {
+        const uint64_t* sin[3] = {d_sizes, d_sizes + nr, d_sizes + 2 * nr};
+        uint64_t* sout[3] = {b->d_word_off, d_sums, d_sums + nr + 1};
+        IDC_TRY(device_scan(c, 3, sin, sout, nr, d_scan));
+    }
+    uint64_t tot[3] = {0, 0, 0};
+    uint32_t st = 0;
+    IDC_CUDA(cudaMemcpyAsync(&tot[0], b->d_word_off + nr, 8, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaMemcpyAsync(&tot[1], d_sums + nr, 8, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaMemcpyAsync(&tot[2], d_sums + 2 * nr + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    IDC_TRY(status_to_error(st, "roc_encode_rows"));
+    tr.mark("kernels");
+    b->total_words = tot[0];
+    b->ans_bytes = 8 * tot[1] + 4 * tot[0];  // sum over non-empty rows of ANSState::size(), codec.h:42-44
+    b->total_ids = tot[2];
+    IDC_TRY(dev_alloc(c, &b->d_words, b->total_words, &acct));
+    if (nr) {
+        LaunchScope ls(c, "k_roc_compact");
+        k_roc_compact<<<grid_for(nr * 32), kThreads, 0, c->stream>>>(c->scratch.as<uint32_t>(), d_scratch_off, b->d_word_off, b->d_words,
+                                                                       (uint32_t)nr);
+    }
+    IDC_TRY(check_last_launch("k_roc_compact"));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    tr.mark("compaction");
+    b->device_bytes = acct;
+    return IDC_OK;
+}
+
 int plan_units_csr(idc_roc_blob* b, uint64_t nlist, const uint64_t* offsets, uint32_t max_unit,
                    std::vector<uint32_t>& posbase) {
     b->nlist = nlist;
@@ -915,35 +1124,8 @@ int idc_roc_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* d
         IDC_CUDA(cudaMemcpyAsync(c->stage.p, data, elems * 4, cudaMemcpyHostToDevice, c->stream));
         d_data = c->stage.as<int32_t>();
     }
-    // row lengths on the device, then back for planning
-    IDC_TRY(c->meta.reserve(nrows * 4 + 256));
-    b->unit_n.resize(nrows);
-    if (nrows) {
-        uint32_t* d_cnt = c->meta.as<uint32_t>();
-        {
-            LaunchScope ls(c, "k_row_counts");
-            k_row_counts<<<grid_for(nrows * 32), kThreads, 0, c->stream>>>(d_data, nrows, K, d_cnt);
-        }
-        IDC_TRY(check_last_launch("k_row_counts"));
-        IDC_CUDA(cudaMemcpyAsync(b->unit_n.data(), d_cnt, nrows * 4, cudaMemcpyDeviceToHost, c->stream));
-        IDC_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    b->list_offsets.resize(nrows + 1);
-    b->unit_offsets.resize(nrows + 1);
-    b->unit_src.resize(nrows);
-    std::vector<uint32_t> posbase(nrows, 0);
-    uint64_t total = 0;
-    for (uint64_t r = 0; r < nrows; r++) {
-        b->list_offsets[r] = total;
-        b->unit_offsets[r] = r;
-        b->unit_src[r] = r * K;
-        total += b->unit_n[r];
-    }
-    b->list_offsets[nrows] = total;
-    b->unit_offsets[nrows] = nrows;
-    b->total_ids = total;
-    tr.mark("row counts + tables");
-    IDC_TRY(roc_encode_units(c, b.get(), d_data, nullptr, 4, flags & ~IDC_F_SORTED, posbase, elems));
+    // lengths, tables, sort, coder and word offsets: all on the device (roc_encode_rows_device)
+    IDC_TRY(roc_encode_rows_device(c, b.get(), d_data, K, flags & ~IDC_F_SORTED));
     *out = b.release();
     return IDC_OK;
 }
@@ -966,6 +1148,10 @@ int idc_roc_blob_export(const idc_roc_blob* b, uint64_t* list_offsets, uint64_t*
     IDC_REQUIRE(b, IDC_ERR_ARG, "null blob");
     IDC_CUDA(cudaSetDevice(b->ctx->device));
     cudaStream_t s = b->ctx->stream;
+    if (!b->host_tables) {
+        std::lock_guard<std::mutex> lock(b->ctx->mu);
+        IDC_TRY(roc_host_tables(b));
+    }
     if (list_offsets) memcpy(list_offsets, b->list_offsets.data(), (b->nlist + 1) * 8);
     if (unit_offsets) memcpy(unit_offsets, b->unit_offsets.data(), (b->nlist + 1) * 8);
     if (unit_n && b->nunits) memcpy(unit_n, b->unit_n.data(), b->nunits * 4);
@@ -1466,6 +1652,10 @@ int idc_roc_decode_rows(idc_ctx* c, const idc_roc_blob* b, const int32_t* row_no
 // ---- flat file form (idc_file.h): header words, the list CSR and the wire payload of idc_roc_blob_export_payload
 int idc_roc_blob_save(const idc_roc_blob* b, const char* path) {
     IDC_REQUIRE(b && path, IDC_ERR_ARG, "idc_roc_blob_save: null argument");
+    if (!b->host_tables) {
+        std::lock_guard<std::mutex> lock(b->ctx->mu);
+        IDC_TRY(roc_host_tables(b));
+    }
     const uint64_t nu = b->nunits;
     std::vector<uint8_t> prec(nu);
     std::vector<uint64_t> heads(nu);
