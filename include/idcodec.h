@@ -384,10 +384,14 @@ int idc_ef_select(
  *
  * The lists must partition [0, ntotal), ntotal = offsets[nlist] - offsets[0],
  * each list strictly ascending -- the reference's asserts (:358-359) -- else
- * IDC_ERR_DOMAIN. wt_type 0 = sdsl::wt_int<> with plain bit vectors; wt_type 1
- * (rrr_vector<63>) is rejected with IDC_ERR_ARG: not implemented.
+ * IDC_ERR_DOMAIN. wt_type 0 = sdsl::wt_int<> with plain bit vectors; wt_type 1 =
+ * sdsl::wt_int<rrr_vector<63>> (custom_invlists_impl.h:105, .cpp:371-372): the same
+ * structure with every level stored as RRR(63) blocks -- class (ones among 63 bits)
+ * + offset in the combinatorial number system, eight blocks and 8 verbatim bits per
+ * 512-bit rank block (csrc/wt_core.cuh) -- selects decode one 63-bit block per level,
+ * whole-list decodes expand the levels once.
  * SDSL is a third-party dependency absent from the reference tree, so the word
- * layout and size_in_bytes() of its wt_int are not reproduced:
+ * layout and size_in_bytes() of its wt_int / rrr_vector are not reproduced:
  * select values are exact, the structure is a wavelet matrix of
  * bit_length(nlist - 1) levels x ntotal bits plus rank / select directories.
  */
@@ -406,7 +410,7 @@ int idc_wt_encode(
 typedef struct {
     uint64_t nlist;
     uint64_t total_ids;
-    uint64_t bits_bytes;       /* levels x ntotal bits, padded to 512-bit blocks */
+    uint64_t bits_bytes;       /* levels x ntotal bits, padded to 512-bit blocks; wt_type 1: classes + pointers + offset streams */
     uint64_t aux_bytes;        /* rank directory, select samples, list start table */
     uint64_t device_bytes;
     uint32_t levels;
@@ -443,6 +447,12 @@ int idc_wt_blob_import(
         const uint32_t* start,
         int mem,
         idc_wt_blob** out);
+/* wt_type = 1 only: the compressed arrays as they lie in HBM (HOST copies, any pointer may be NULL): cls[levels * nblk]
+ * (eight 6-bit classes + the block's 8 tail bits per 512-bit block, nblk = ceil(ntotal / 512)), ptr[levels * (nblk + 1)]
+ * (bit offset of the block's first offset field in its level's stream), off_base[levels + 1] (first 64-bit word of each
+ * level's stream; off_base[levels] = words in use), off[off_base[levels]]. idc_wt_blob_export returns the PLAIN levels
+ * for either type (that is what idc_wt_blob_import and the file form carry). */
+int idc_wt_blob_export_rrr(const idc_wt_blob* blob, uint64_t* cls, uint32_t* ptr, uint64_t* off_base, uint64_t* off);
 int idc_wt_blob_save(const idc_wt_blob* blob, const char* path);
 int idc_wt_blob_load(idc_ctx* ctx, const char* path, idc_wt_blob** out);
 

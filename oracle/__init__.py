@@ -457,6 +457,35 @@ class WtCodec:
         lib.oracle_wt_build.argtypes = [C.c_uint64, C.c_uint64, _u32p, _u64p, _u32p, _u32p, _u32p, _u32p]
         lib.oracle_wt_select.restype = C.c_int64
         lib.oracle_wt_select.argtypes = [C.c_uint64, C.c_uint64, _u64p, _u32p, _u32p, C.c_uint32, C.c_uint64]
+        lib.oracle_rrr_encode.restype = C.c_uint64
+        lib.oracle_rrr_encode.argtypes = [C.c_uint64, C.c_uint64, _u64p, _u64p, _u32p, _u64p, _u64p]
+        lib.oracle_rrr_decode.restype = None
+        lib.oracle_rrr_decode.argtypes = [C.c_uint64, C.c_uint64, _u64p, _u32p, _u64p, _u64p, _u64p]
+
+    def rrr_encode(self, bits) -> dict:
+        """wt_type = 1: the levels' plain bits [levels, nblk * 8] -> dict(cls[levels, nblk], ptr[levels, nblk + 1],
+        off_base[levels + 1], off[off_base[-1]]), the RRR(63) block form restated with plain loops."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        levels, words = bits.shape
+        nblk = words // 8
+        cls = np.zeros((levels, max(nblk, 1)), np.uint64)
+        ptr = np.zeros((levels, nblk + 1), np.uint32)
+        off_base = np.zeros(levels + 1, np.uint64)
+        off = np.zeros(levels * (nblk * 8 + 1) + 1, np.uint64)
+        used = int(self.lib.oracle_rrr_encode(levels, nblk, bits.reshape(-1) if bits.size else np.zeros(1, np.uint64),
+                                              cls.reshape(-1), ptr.reshape(-1), off_base, off))
+        return dict(cls=cls[:, :nblk], ptr=ptr, off_base=off_base, off=off[:used])
+
+    def rrr_decode(self, enc: dict) -> np.ndarray:
+        cls = np.ascontiguousarray(enc["cls"], dtype=np.uint64)
+        levels, nblk = cls.shape
+        bits = np.zeros((levels, max(nblk * 8, 1)), np.uint64)
+        self.lib.oracle_rrr_decode(levels, nblk, cls.reshape(-1) if cls.size else np.zeros(1, np.uint64),
+                                   np.ascontiguousarray(enc["ptr"], dtype=np.uint32).reshape(-1),
+                                   np.ascontiguousarray(enc["off_base"], dtype=np.uint64),
+                                   np.ascontiguousarray(enc["off"], dtype=np.uint64) if len(enc["off"]) else np.zeros(1, np.uint64),
+                                   bits.reshape(-1))
+        return bits[:, : nblk * 8]
 
     def levels(self, nlist: int) -> int:
         return int(self.lib.oracle_wt_levels(int(nlist)))

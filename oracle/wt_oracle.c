@@ -160,3 +160,90 @@ int64_t oracle_wt_select(uint64_t nlist, uint64_t n, const uint64_t* bits, const
     }
     return (int64_t)p;
 }
+
+/* ---- wt_type = 1: RRR(63) blocks (sdsl::rrr_vector<63> in the reference, custom_invlists_impl.h:105; SDSL absent:
+ * the framing below is this repository's, restated here with plain loops to pin the GPU arrays word for word).
+ * A 512-bit rank block = eight 63-bit blocks + 8 verbatim bits. A 63-bit block -> class k = number of ones and
+ * offset = sum over its ones (positions c_1 < c_2 < ...) of C(c_i, i) (combinatorial number system), stored in
+ * ceil(log2 C(63, k)) bits. Per level: cls[blk] = eight 6-bit classes | tail << 48; ptr[blk] = bit offset of the
+ * block's first offset field in the level's stream; streams lie one after the other, each padded to whole words + 1. */
+static uint64_t BIN[64][64];
+static uint32_t WID[64];
+static int rrr_ready = 0;
+static void rrr_init(void) {
+    if (rrr_ready) return;
+    for (int n = 0; n < 64; n++)
+        for (int k = 0; k < 64; k++) BIN[n][k] = k == 0 ? 1 : (n == 0 ? 0 : BIN[n - 1][k - 1] + BIN[n - 1][k]);
+    for (int k = 0; k < 64; k++) {
+        uint64_t m = BIN[63][k] - 1;
+        uint32_t w = 0;
+        while (m) { w++; m >>= 1; }
+        WID[k] = w;
+    }
+    rrr_ready = 1;
+}
+static int bit_of(const uint64_t* words, uint64_t i) { return (int)((words[i >> 6] >> (i & 63)) & 1u); }
+
+/* returns the number of 64-bit words of `off` in use (off_base[levels]); off must be zeroed and large enough
+ * (levels * (nblk * 8 + 1) words always suffice) */
+uint64_t oracle_rrr_encode(uint64_t levels, uint64_t nblk, const uint64_t* bits, uint64_t* cls, uint32_t* ptr,
+                           uint64_t* off_base, uint64_t* off) {
+    rrr_init();
+    uint64_t base = 0;
+    for (uint64_t lev = 0; lev < levels; lev++) {
+        const uint64_t* B = bits + lev * nblk * 8;
+        uint64_t p = 0;
+        off_base[lev] = base;
+        for (uint64_t blk = 0; blk < nblk; blk++) {
+            uint64_t cw = 0;
+            ptr[lev * (nblk + 1) + blk] = (uint32_t)p;
+            for (int j = 0; j < 8; j++) {
+                uint32_t k = 0;
+                uint64_t o = 0;
+                for (int c = 0; c < 63; c++)
+                    if (bit_of(B, blk * 512 + 63 * (uint64_t)j + c)) o += BIN[c][++k];
+                cw |= (uint64_t)k << (6 * j);
+                for (uint32_t t = 0; t < WID[k]; t++, p++)
+                    if ((o >> t) & 1u) off[base + (p >> 6)] |= 1ull << (p & 63);
+            }
+            for (int t = 0; t < 8; t++) cw |= (uint64_t)bit_of(B, blk * 512 + 504 + t) << (48 + t);
+            cls[lev * nblk + blk] = cw;
+        }
+        ptr[lev * (nblk + 1) + nblk] = (uint32_t)p;
+        base += (p + 63) / 64 + 1;
+    }
+    off_base[levels] = base;
+    return base;
+}
+
+/* the inverse: plain bits (levels * nblk * 8 words, zeroed by the caller) from the compressed arrays */
+void oracle_rrr_decode(uint64_t levels, uint64_t nblk, const uint64_t* cls, const uint32_t* ptr, const uint64_t* off_base,
+                       const uint64_t* off, uint64_t* bits) {
+    rrr_init();
+    for (uint64_t lev = 0; lev < levels; lev++) {
+        uint64_t* B = bits + lev * nblk * 8;
+        const uint64_t* S = off + off_base[lev];
+        for (uint64_t blk = 0; blk < nblk; blk++) {
+            const uint64_t cw = cls[lev * nblk + blk];
+            uint64_t p = ptr[lev * (nblk + 1) + blk];
+            for (int j = 0; j < 8; j++) {
+                const uint32_t k = (uint32_t)(cw >> (6 * j)) & 63u;
+                uint64_t o = 0;
+                for (uint32_t t = 0; t < WID[k]; t++, p++) o |= (uint64_t)bit_of(S, p) << t;
+                int c = 62;
+                for (uint32_t i = k; i >= 1; i--) {
+                    while (BIN[c][i] > o) c--;
+                    const uint64_t pos = blk * 512 + 63 * (uint64_t)j + (uint64_t)c;
+                    B[pos >> 6] |= 1ull << (pos & 63);
+                    o -= BIN[c][i];
+                    c--;
+                }
+            }
+            for (int t = 0; t < 8; t++)
+                if ((cw >> (48 + t)) & 1u) {
+                    const uint64_t pos = blk * 512 + 504 + (uint64_t)t;
+                    B[pos >> 6] |= 1ull << (pos & 63);
+                }
+        }
+    }
+}

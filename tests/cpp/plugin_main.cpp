@@ -144,13 +144,15 @@ int main(int argc, char** argv) {
         {
             CompressedIDInvertedListsWaveletTree wt(il, 0);
             check_invlists("CompressedIDInvertedListsWaveletTree", wt, il, true, true);
+            CompressedIDInvertedListsWaveletTree rrr(il, 1);  // rrr_vector<63> flavour (custom_invlists_impl.cpp:371-372)
+            check_invlists("CompressedIDInvertedListsWaveletTree(wt_type = 1)", rrr, il, true, true);
             bool threw = false;
             try {
-                CompressedIDInvertedListsWaveletTree rrr(il, 1);
+                CompressedIDInvertedListsWaveletTree bad(il, 2);
             } catch (const std::exception&) {
                 threw = true;
             }
-            CHECK(threw, "WaveletTree: wt_type 1 must be rejected (not implemented)");
+            CHECK(threw, "WaveletTree: wt_type must be 0 or 1 (custom_invlists_impl.cpp:349)");
         }
         if (all) {
             CompressedIDInvertedListsPackedBits pb(il);

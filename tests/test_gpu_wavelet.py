@@ -110,7 +110,7 @@ def test_wt_rejects_what_the_reference_asserts_and_level_counts(ctx, monkeypatch
         with pytest.raises(IdcError):
             ctx.wt_encode(offsets, bad)
     with pytest.raises(IdcError):
-        ctx.wt_encode([0, 2, 4], np.array([0, 3, 1, 2], dtype=np.int64), wt_type=1)  # rrr_vector<63>: not implemented
+        ctx.wt_encode([0, 2, 4], np.array([0, 3, 1, 2], dtype=np.int64), wt_type=2)  # custom_invlists_impl.cpp:349: 0 or 1
     many = ctx.wt_encode(np.arange(0, 200_001, 2), np.arange(200_000))  # 100 000 lists: 17 levels, 16-bit symbols after level 0
     wide = ctx.wt_encode(np.arange(0, 300_001, 2), np.arange(300_000))  # 150 000 lists: 18 levels, 32-bit symbols
     for bl, m in ((many, 200_000), (wide, 300_000)):
@@ -149,4 +149,73 @@ def test_plugin_wavelet_tree_like_reference_tests(ctx):
         assert int(out[q, j]) == want
     assert np.array_equal(ci.translate_labels(inv, labels, decode_1by1=True), out)
     with pytest.raises(Exception):
-        ci.CompressedIDInvertedListsWaveletTree(il, 1, ctx)
+        ci.CompressedIDInvertedListsWaveletTree(il, 2, ctx)  # custom_invlists_impl.cpp:349: wt_type is 0 or 1
+
+
+RRR_CASES = [(1, 700, 0), (7, 5000, 0), (256, 100_000, 0), (1000, 70_000, 1), (65, 20_481, 2), (5000, 1_300_001, 1)]
+
+
+@pytest.mark.parametrize("path", ["replay", "select"])
+@pytest.mark.parametrize("nlist,n,skew", RRR_CASES)
+def test_wt_type1_rrr_blocks_vs_oracle(ctx, monkeypatch, tmp_path, nlist, n, skew, path):
+    """wt_type = 1 (sdsl::wt_int<rrr_vector<63>>, custom_invlists_impl.cpp:371-372): the levels as RRR(63) blocks. The
+    compressed arrays word for word against oracle/wt_oracle.c (oracle_rrr_encode), every select / whole-list decode
+    against the input and against the plain flavour, the plain levels recovered exactly, the file form."""
+    monkeypatch.setenv("IDC_WT_DECODE", path)
+    rng = np.random.default_rng(3 * n + nlist)
+    if skew == 0:
+        offsets, ids, lab = make_lists(rng, nlist, n, empty=(2,) if nlist > 3 else ())
+    else:
+        offsets, ids, lab = skewed_lists(rng, nlist, n, skew == 2)
+    plain = ctx.wt_encode(offsets, ids, wt_type=0)
+    blob = ctx.wt_encode(offsets, ids, wt_type=1)
+    assert blob.info.wt_type == 1 and (blob.nlist, blob.total_ids, blob.levels) == (nlist, n, plain.levels)
+    ex0, ex1 = plain.export(), blob.export()
+    for key in ("list_offsets", "bits", "rank", "sel1", "sel0", "start"):  # export gives the plain levels back
+        assert np.array_equal(ex0[key], ex1[key]), key
+    want = oracle.wt.rrr_encode(ex0["bits"])
+    got = blob.export_rrr()
+    for key in ("cls", "ptr", "off_base", "off"):
+        assert np.array_equal(got[key], want[key]), key
+    assert np.array_equal(oracle.wt.rrr_decode(got), ex0["bits"])
+    nblk = (n + 511) // 512
+    assert blob.bits_bytes == blob.levels * nblk * 8 + blob.levels * (nblk + 1) * 4 + int(want["off_base"][-1]) * 8
+    if skew:  # skewed list sizes make skewed upper levels: that is where the block coder saves space
+        assert blob.bits_bytes < plain.bits_bytes
+    dec, off = blob.decode()
+    assert np.array_equal(off, offsets) and np.array_equal(dec, ids)
+    some = [l for l in (0, nlist // 2, nlist - 1) if l < nlist]
+    d2, o2 = blob.decode(some, id_bytes=4)
+    assert np.array_equal(d2.astype(np.int64), np.concatenate([ids[int(offsets[l]): int(offsets[l + 1])] for l in some]))
+    q = rng.integers(0, n, size=min(n, 3000))
+    ql = lab[ids[q]] if False else np.searchsorted(offsets, q, side="right") - 1  # position q of the CSR -> (list, offset)
+    qo = q - offsets[ql].astype(np.int64)
+    assert np.array_equal(blob.select(ql, qo), ids[q])
+    assert np.array_equal(blob.select(ql, qo), plain.select(ql, qo))
+    assert blob.select([nlist], [0]).tolist() == [-1]
+    path_f = tmp_path / "index_rrr.wt"
+    blob.save(path_f)
+    back = ctx.wt_load(path_f)
+    assert back.info.wt_type == 1 and back.bits_bytes == blob.bits_bytes
+    assert np.array_equal(back.select(ql, qo), ids[q])
+    for b in (back, blob, plain):
+        b.free()
+
+
+def test_wt_type1_plugin_class(ctx):
+    from vector_db_id_compression_b200 import custom_invlists as ci
+
+    rng = np.random.default_rng(17)
+    n, nlist = 3000, 8
+    lab = rng.integers(0, nlist, size=n)
+    il = ci.InvertedLists(nlist, 4)
+    for l in range(nlist):
+        sel = np.flatnonzero(lab == l)
+        il.add_entries(l, sel.astype(np.int64), rng.integers(0, 255, size=(sel.size, 4), dtype=np.uint8))
+    inv = ci.CompressedIDInvertedListsWaveletTree(il, 1, ctx)
+    assert inv.wt_type == 1
+    for l in range(nlist):
+        want = np.flatnonzero(lab == l)
+        assert np.array_equal(inv.get_ids(l), want)
+        for o in (0, want.size // 2, want.size - 1):
+            assert inv.get_single_id(l, o) == want[o]

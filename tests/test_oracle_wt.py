@@ -107,3 +107,24 @@ def test_property_random_partitions():
                 assert oracle.wt.select(wt, int(c), k) == int(order[a + k]) == oracle.wt.select_seq(S, int(c), k)
 
     check()
+
+
+def test_rrr_blocks_round_trip_and_sizes():
+    """wt_type = 1 restatement: plain levels -> RRR(63) blocks -> plain levels, every density; an all-zero or all-one
+    block has no offset bits, a balanced one at most 60 (ceil(log2 C(63, 31)))."""
+    rng = np.random.default_rng(5)
+    for dens in (0.0, 0.02, 0.3, 0.5, 0.9, 1.0):
+        bits = np.zeros((4, 5 * 8), np.uint64)
+        for l in range(4):
+            bits[l] = np.packbits(rng.random(5 * 512) < dens, bitorder="little").view(np.uint64)
+        enc = oracle.wt.rrr_encode(bits)
+        assert np.array_equal(oracle.wt.rrr_decode(enc), bits)
+        per_block = np.diff(enc["ptr"].astype(np.int64), axis=1)
+        assert per_block.min() >= 0 and per_block.max() <= 8 * 60
+        if dens in (0.0, 1.0):
+            assert per_block.max() == 0
+        cls = enc["cls"]
+        ones = sum(((cls >> np.uint64(6 * j)) & np.uint64(63)).astype(np.int64) for j in range(8))
+        tail = np.array([[bin(int(x) >> 48 & 0xFF).count("1") for x in row] for row in cls])
+        want = np.array([[bin(int(w)).count("1") for w in row] for row in bits]).reshape(4, 5, 8).sum(axis=2)
+        assert np.array_equal(ones + tail, want)

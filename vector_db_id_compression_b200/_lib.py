@@ -70,6 +70,7 @@ SYMBOLS = {
     "idc_wt_blob_info": (C.c_int, [vp, C.POINTER(WtInfo)]),
     "idc_wt_blob_export": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "idc_wt_blob_import": (C.c_int, [vp, u64, vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]),
+    "idc_wt_blob_export_rrr": (C.c_int, [vp, vp, vp, vp, vp]),
     "idc_wt_blob_save": (C.c_int, [vp, C.c_char_p]),
     "idc_wt_blob_load": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
     "idc_wt_blob_free": (C.c_int, [vp]),

@@ -578,6 +578,17 @@ class WtBlob:
         _check(self._l.idc_wt_decode(self.ctx._h, self._h, lp, nsel, p, id_bytes, mem, out_off.ctypes.data))
         return out[:total], out_off
 
+    def export_rrr(self) -> dict:
+        """wt_type = 1: the compressed arrays as they lie in HBM (idc_wt_blob_export_rrr)."""
+        levels, nblk = self.levels, (self.total_ids + 511) // 512
+        off_base = np.zeros(levels + 1, np.uint64)
+        _check(self._l.idc_wt_blob_export_rrr(self._h, None, None, off_base.ctypes.data, None))
+        cls = np.zeros((levels, max(nblk, 1)), np.uint64)
+        ptr = np.zeros((levels, nblk + 1), np.uint32)
+        off = np.zeros(max(int(off_base[-1]), 1), np.uint64)
+        _check(self._l.idc_wt_blob_export_rrr(self._h, cls.ctypes.data, ptr.ctypes.data, None, off.ctypes.data))
+        return dict(cls=cls[:, :nblk], ptr=ptr, off_base=off_base, off=off[: int(off_base[-1])])
+
     def select(self, list_nos, offsets_in_list, *, device=None):
         if device is not None:
             import torch

@@ -236,6 +236,7 @@ int idc_ctx_destroy(idc_ctx* c) {
     cudaFree(c->d_mt);
     cudaFree(c->d_rcp64);
     cudaFree(c->d_q31);
+    cudaFree(c->d_binom);
     c->pool_trim();
     for (auto& b : c->pool_live) cudaFree(b.first);
     c->pool_live.clear();

@@ -117,6 +117,8 @@ struct idc_ctx {
     uint32_t* d_mt = nullptr;     // first kMtWords outputs of std::mt19937(1234)
     uint64_t* d_rcp64 = nullptr;  // floor((2^64-1)/d), d = 0..65536
     uint32_t* d_q31 = nullptr;    // 2^31 / d
+    uint64_t* d_binom = nullptr;  // C(n, k), n, k < 64 (row-major 64 x 64), then 64 field widths: the RRR(63) block coder's
+                                  // tables, allocated by the first wt_type = 1 call (wt_kernels.cu)
     // grow-only scratch reused across calls
     idc::DevBuf ws;       // order-statistic workspaces
     idc::DevBuf scratch;  // encoder word scratch / staging

@@ -409,7 +409,7 @@ struct CompressedIDInvertedListsPackedBits : InvertedListsArrayCodes {
 };
 
 /// Wavelet-tree ids. custom_invlists_impl.h:100-124, .cpp:346-397: one structure over S[id] = list_no,
-/// get_single_id(list_no, offset) = wt.select(offset + 1, list_no). wt_type 1 (rrr_vector<63>) throws: not implemented.
+/// get_single_id(list_no, offset) = wt.select(offset + 1, list_no). wt_type 1 (rrr_vector<63>): the levels as RRR(63) blocks.
 struct CompressedIDInvertedListsWaveletTree : InvertedListsArrayCodes {
     idc_wt_blob* blob = nullptr;
     int wt_type = 0;

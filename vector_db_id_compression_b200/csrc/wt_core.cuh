@@ -79,15 +79,6 @@ IDC_HD uint64_t wt_partition_dest(uint64_t i, uint32_t bit, uint64_t zeros_of_le
     return bit ? zeros_of_level + ones_before : i - ones_before;
 }
 
-struct WtView {
-    const uint64_t* bits;
-    const uint32_t* rank;
-    const uint32_t* sel1;
-    const uint32_t* sel0;
-    const uint32_t* start;
-    WtShape sh;
-};
-
 IDC_HD uint32_t wt_ld32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
     return __ldg(p);
@@ -102,6 +93,84 @@ IDC_HD uint64_t wt_ld64(const uint64_t* p) {
 #else
     return *p;
 #endif
+}
+
+struct WtView {
+    const uint64_t* bits;
+    const uint32_t* rank;
+    const uint32_t* sel1;
+    const uint32_t* sel0;
+    const uint32_t* start;
+    WtShape sh;
+    // wt_type = 1: the bit vectors are block-compressed (bits == nullptr), see "RRR(63) blocks" below
+    const uint64_t* cls = nullptr;       // levels x nblk: eight 6-bit classes + the block's 8 tail bits
+    const uint32_t* ptr = nullptr;       // levels x (nblk + 1): bit offset of the block's first offset field in its level's stream
+    const uint64_t* off = nullptr;       // the offset streams of all levels
+    const uint64_t* off_base = nullptr;  // levels + 1: first word of each level's stream
+    const uint64_t* binom = nullptr;     // C(n, k), 64 x 64, followed by the 64 field widths
+};
+
+// ---- RRR(63) blocks (wt_type = 1; sdsl::rrr_vector<63> in the reference, custom_invlists_impl.h:105) -------------
+// A 63-bit block is stored as its class k (number of ones, 6 bits) and its offset among the C(63, k) blocks of that
+// class (ceil(log2 C(63, k)) bits, nothing for k = 0 and k = 63): the combinatorial number system -- with the ones at
+// positions c_1 < c_2 < ... < c_k the offset is sum C(c_i, i). A 512-bit rank block is eight such blocks plus its last
+// 8 bits verbatim, so the rank directory and the select samples of the plain layout stay what they are, and one
+// 64-bit word holds the eight classes and the tail. SDSL is absent from the reference tree: the framing is this
+// repository's, what is reproduced is the value of every select.
+constexpr uint32_t kRrrBits = 63;
+constexpr uint32_t kRrrPerBlock = 8;
+constexpr uint64_t kRrrMask = (1ull << kRrrBits) - 1ull;
+
+IDC_HD uint64_t rrr_binom(const uint64_t* tab, uint32_t n, uint32_t k) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const unsigned long long*>(tab) + n * 64u + k);
+#else
+    return tab[n * 64u + k];
+#endif
+}
+IDC_HD uint32_t rrr_width(const uint64_t* tab, uint32_t k) { return (uint32_t)rrr_binom(tab, 64u, k); }  // row 64 = the widths
+
+// offset of a 63-bit block among the blocks with as many ones
+IDC_HD uint64_t rrr_offset_of(const uint64_t* tab, uint64_t x) {
+    uint64_t off = 0;
+    uint32_t i = 0;
+    while (x) {
+        const uint32_t c = ctz64(x);
+        x &= x - 1;
+        off += rrr_binom(tab, c, ++i);
+    }
+    return off;
+}
+
+// the block of class k with that offset
+IDC_HD uint64_t rrr_block_of(const uint64_t* tab, uint32_t k, uint64_t off) {
+    uint64_t x = 0;
+    int32_t c = (int32_t)kRrrBits - 1;
+    for (uint32_t i = k; i >= 1; i--) {
+        while (rrr_binom(tab, (uint32_t)c, i) > off) c--;  // the largest position whose C(c, i) fits
+        x |= 1ull << c;
+        off -= rrr_binom(tab, (uint32_t)c, i);
+        c--;
+    }
+    return x;
+}
+
+// the 63 bits at bit 63 j of a 512-bit block held in eight words
+IDC_HD uint64_t rrr_piece(const uint64_t (&w)[8], uint32_t j) {
+    const uint32_t p = kRrrBits * j, a = p >> 6, s = p & 63u;
+    uint64_t x = w[a] >> s;
+    if (s > 1u) x |= w[a + 1] << (64u - s);  // s + 63 > 64; a + 1 <= 7 because 63 j + 63 <= 504
+    return x & kRrrMask;
+}
+
+// W bits (<= 60) at bit p of a stream
+IDC_HD uint64_t rrr_read(const uint64_t* stream, uint64_t p, uint32_t W) {
+    if (W == 0) return 0;
+    const uint64_t a = p >> 6;
+    const uint32_t s = (uint32_t)(p & 63u);
+    uint64_t x = wt_ld64(stream + a) >> s;
+    if (s + W > 64u) x |= wt_ld64(stream + a + 1) << (64u - s);
+    return x & ((1ull << W) - 1ull);
 }
 
 // position of the k-th (0-based) bit of value b in level lev; k < number of such bits. ~0 = corrupt directory.
@@ -125,6 +194,27 @@ IDC_HD uint64_t wt_level_select(const WtView& v, uint32_t lev, uint32_t b, uint6
     }
     uint64_t r0 = wt_ld32(rank + lo);
     uint32_t r = (uint32_t)(k - (b ? r0 : (lo << kWtBlockLog) - r0));
+    if (v.cls) {
+        // block-compressed level: walk the block's eight classes, decode the one 63-bit block that holds the target
+        const uint64_t cw = wt_ld64(v.cls + (uint64_t)lev * v.sh.nblk + lo);
+        uint64_t p = wt_ld32(v.ptr + (uint64_t)lev * (v.sh.nblk + 1) + lo);
+        const uint64_t* stream = v.off + wt_ld64(v.off_base + lev);
+        for (uint32_t j = 0; j < kRrrPerBlock; j++) {
+            const uint32_t kc = (uint32_t)(cw >> (6u * j)) & 63u, W = rrr_width(v.binom, kc);
+            const uint32_t c = b ? kc : kRrrBits - kc;
+            if (r < c) {
+                uint64_t x = rrr_block_of(v.binom, kc, rrr_read(stream, p, W));
+                if (!b) x = ~x & kRrrMask;
+                return (lo << kWtBlockLog) + kRrrBits * j + select64(x, r);
+            }
+            r -= c;
+            p += W;
+        }
+        uint64_t x = (cw >> 48) & 0xffull;
+        if (!b) x = ~x & 0xffull;
+        if (r < (uint32_t)popc64(x)) return (lo << kWtBlockLog) + kRrrBits * kRrrPerBlock + select64(x, r);
+        return ~0ull;
+    }
     const uint64_t* w = v.bits + (uint64_t)lev * v.sh.words + lo * kWtBlockWords;
     for (uint32_t i = 0; i < kWtBlockWords; i++) {
         uint64_t x = wt_ld64(w + i);

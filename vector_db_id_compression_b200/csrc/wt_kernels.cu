@@ -23,6 +23,7 @@
 
 #include "idc_file.h"
 #include "idc_host.h"
+#include "idc_scan.cuh"
 #include "wt_core.cuh"
 
 using namespace idc;
@@ -455,10 +456,28 @@ struct idc_wt_blob {
     uint32_t* d_sel1 = nullptr;
     uint32_t* d_sel0 = nullptr;
     uint32_t* d_start = nullptr;
+    // wt_type = 1: d_bits is null, the levels are stored as RRR(63) blocks (wt_core.cuh)
+    uint64_t* d_cls = nullptr;       // levels x nblk
+    uint32_t* d_ptr = nullptr;       // levels x (nblk + 1)
+    uint64_t* d_off = nullptr;       // offset streams, level after level
+    uint64_t* d_off_base = nullptr;  // levels + 1
+    std::vector<uint64_t> off_base;  // host copy; off_base[levels] = words of d_off in use
     uint64_t device_bytes = 0;
-    WtView view() const { return WtView{d_bits, d_rank, d_sel1, d_sel0, d_start, sh}; }
+    WtView view() const {
+        WtView v{d_bits, d_rank, d_sel1, d_sel0, d_start, sh};
+        v.cls = d_cls;
+        v.ptr = d_ptr;
+        v.off = d_off;
+        v.off_base = d_off_base;
+        v.binom = ctx ? ctx->d_binom : nullptr;
+        return v;
+    }
     ~idc_wt_blob() {
         if (!ctx) return;
+        ctx->pool_release(d_cls);
+        ctx->pool_release(d_ptr);
+        ctx->pool_release(d_off);
+        ctx->pool_release(d_off_base);
         ctx->pool_release(d_list_off);
         ctx->pool_release(d_bits);
         ctx->pool_release(d_rank);
@@ -469,6 +488,173 @@ struct idc_wt_blob {
 };
 
 namespace {
+
+// ---- wt_type = 1: RRR(63) block compression of the finished levels (layout: wt_core.cuh) -----------------------
+// One thread per 512-bit rank block. k_rrr_sizes: the eight classes + the tail byte (one word) and the number of
+// offset bits of the block; prefix sums over a level give every block its place in the level's stream; k_rrr_encode
+// writes the offsets there (atomicOr: neighbouring blocks share words); k_rrr_expand is the inverse.
+struct RrrArgs {
+    uint64_t* bits;         // levels x words (source of the encoder, destination of the expander)
+    uint64_t* cls;          // levels x nblk
+    uint32_t* ptr;          // levels x (nblk + 1)
+    uint64_t* off;
+    const uint64_t* off_base;
+    uint64_t* sizes;        // levels x nblk   (encoder scratch)
+    const uint64_t* ptr64;  // levels x (nblk + 1)   (encoder scratch: the prefix sums)
+    const uint64_t* binom;
+    uint64_t nblk, words;
+    uint32_t levels;
+};
+
+__global__ void __launch_bounds__(kThreads) k_rrr_sizes(RrrArgs a) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.nblk * a.levels) return;
+    const uint64_t lev = g / a.nblk, blk = g - lev * a.nblk;
+    uint64_t w[8];
+    const uint64_t* src = a.bits + lev * a.words + blk * kWtBlockWords;
+#pragma unroll
+    for (int j = 0; j < 8; j++) w[j] = src[j];
+    uint64_t cw = (w[7] >> 56) << 48, total = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < kRrrPerBlock; j++) {
+        const uint32_t k = (uint32_t)popc64(rrr_piece(w, j));
+        cw |= (uint64_t)k << (6u * j);
+        total += rrr_width(a.binom, k);
+    }
+    a.cls[g] = cw;
+    a.sizes[g] = total;
+}
+
+__global__ void __launch_bounds__(kThreads) k_rrr_encode(RrrArgs a) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.nblk * a.levels) return;
+    const uint64_t lev = g / a.nblk, blk = g - lev * a.nblk;
+    uint64_t w[8];
+    const uint64_t* src = a.bits + lev * a.words + blk * kWtBlockWords;
+#pragma unroll
+    for (int j = 0; j < 8; j++) w[j] = src[j];
+    uint64_t p = a.ptr64[lev * (a.nblk + 1) + blk];
+    a.ptr[lev * (a.nblk + 1) + blk] = (uint32_t)p;
+    if (blk + 1 == a.nblk) a.ptr[lev * (a.nblk + 1) + a.nblk] = (uint32_t)a.ptr64[lev * (a.nblk + 1) + a.nblk];
+    unsigned long long* stream = reinterpret_cast<unsigned long long*>(a.off + a.off_base[lev]);
+#pragma unroll 1
+    for (uint32_t j = 0; j < kRrrPerBlock; j++) {
+        const uint64_t x = rrr_piece(w, j);
+        const uint32_t W = rrr_width(a.binom, (uint32_t)popc64(x));
+        if (W) {
+            const uint64_t v = rrr_offset_of(a.binom, x);
+            const uint32_t s = (uint32_t)(p & 63u);
+            atomicOr(stream + (p >> 6), (unsigned long long)(v << s));
+            if (s + W > 64u) atomicOr(stream + (p >> 6) + 1, (unsigned long long)(v >> (64u - s)));
+            p += W;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_rrr_expand(RrrArgs a) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.nblk * a.levels) return;
+    const uint64_t lev = g / a.nblk, blk = g - lev * a.nblk;
+    const uint64_t cw = a.cls[g];
+    uint64_t p = a.ptr[lev * (a.nblk + 1) + blk];
+    const uint64_t* stream = a.off + a.off_base[lev];
+    uint64_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) w[j] = 0;
+#pragma unroll 1
+    for (uint32_t j = 0; j < kRrrPerBlock; j++) {
+        const uint32_t k = (uint32_t)(cw >> (6u * j)) & 63u, W = rrr_width(a.binom, k);
+        const uint64_t x = rrr_block_of(a.binom, k, rrr_read(stream, p, W));
+        p += W;
+        const uint32_t q = kRrrBits * j, i = q >> 6, s = q & 63u;
+        // (dynamic word index: the eight words live in local memory here; this kernel runs once per decode call)
+        w[i] |= x << s;
+        if (s > 1u) w[i + 1] |= x >> (64u - s);
+    }
+    w[7] |= ((cw >> 48) & 0xffull) << 56;
+    uint64_t* dst = a.bits + lev * a.words + blk * kWtBlockWords;
+#pragma unroll
+    for (int j = 0; j < 8; j++) dst[j] = w[j];
+}
+
+// C(n, k) for n, k < 64 and, as row 64, the offset widths ceil(log2 C(63, k))
+int wt_rrr_tables(idc_ctx* c) {
+    if (c->d_binom) return IDC_OK;
+    std::vector<uint64_t> t(65 * 64, 0);
+    for (uint32_t n = 0; n < 64; n++) {
+        t[n * 64] = 1;
+        for (uint32_t k = 1; k <= n; k++) t[n * 64 + k] = t[(n - 1) * 64 + k - 1] + (k <= n - 1 ? t[(n - 1) * 64 + k] : 0);
+    }
+    for (uint32_t k = 0; k < 64; k++) {
+        const uint64_t m = t[63 * 64 + k] - 1;  // offsets 0 .. C(63, k) - 1
+        t[64 * 64 + k] = m ? 64 - (uint64_t)__builtin_clzll(m) : 0;
+    }
+    IDC_CUDA(cudaMalloc(&c->d_binom, t.size() * 8));
+    IDC_CUDA(cudaMemcpy(c->d_binom, t.data(), t.size() * 8, cudaMemcpyHostToDevice));
+    return IDC_OK;
+}
+
+// plain levels (b->d_bits) -> RRR(63) blocks; the plain array goes back to the pool
+int wt_compress(idc_ctx* c, idc_wt_blob* b) {
+    const WtShape sh = b->sh;
+    const uint64_t nb = sh.nblk, L = sh.levels;
+    IDC_TRY(wt_rrr_tables(c));
+    IDC_TRY(dev_alloc(c, &b->d_cls, L * nb, &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_ptr, L * (nb + 1), &b->device_bytes));
+    IDC_TRY(dev_alloc(c, &b->d_off_base, L + 1, &b->device_bytes));
+    const size_t scan_bytes = scan_scratch_bytes(nb, 6);
+    IDC_TRY(c->ws.reserve(L * nb * 8 + L * (nb + 1) * 8 + scan_bytes + 1024));
+    uint64_t* d_sizes = c->ws.as<uint64_t>();
+    uint64_t* d_ptr64 = d_sizes + L * nb;
+    uint64_t* d_scan = d_ptr64 + L * (nb + 1);
+    RrrArgs a{b->d_bits, b->d_cls, b->d_ptr, nullptr, b->d_off_base, d_sizes, d_ptr64, c->d_binom, nb, sh.words, (uint32_t)L};
+    {
+        LaunchScope ls(c, "k_rrr_sizes");
+        k_rrr_sizes<<<grid_for(L * nb), kThreads, 0, c->stream>>>(a);
+    }
+    IDC_TRY(check_last_launch("k_rrr_sizes"));
+    for (uint64_t l0 = 0; l0 < L; l0 += 6) {
+        const int m = (int)std::min<uint64_t>(6, L - l0);
+        const uint64_t* sin[6];
+        uint64_t* sout[6];
+        for (int j = 0; j < m; j++) sin[j] = d_sizes + (l0 + j) * nb, sout[j] = d_ptr64 + (l0 + j) * (nb + 1);
+        IDC_TRY(device_scan(c, m, sin, sout, nb, d_scan));
+    }
+    std::vector<uint64_t> bits_of(L);
+    for (uint64_t l = 0; l < L; l++)
+        IDC_CUDA(cudaMemcpyAsync(&bits_of[l], d_ptr64 + l * (nb + 1) + nb, 8, cudaMemcpyDeviceToHost, c->stream));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    b->off_base.assign(L + 1, 0);
+    for (uint64_t l = 0; l < L; l++) {
+        IDC_REQUIRE(bits_of[l] < (1ull << 32), IDC_ERR_DOMAIN, "wavelet level %llu: offset stream of 2^32 bits or more", (unsigned long long)l);
+        b->off_base[l + 1] = b->off_base[l] + (bits_of[l] + 63) / 64 + 1;  // + 1: a field read may touch the next word
+    }
+    IDC_TRY(dev_alloc(c, &b->d_off, b->off_base[L], &b->device_bytes));
+    IDC_CUDA(cudaMemsetAsync(b->d_off, 0, std::max<uint64_t>(b->off_base[L], 1) * 8, c->stream));
+    IDC_CUDA(cudaMemcpyAsync(b->d_off_base, b->off_base.data(), (L + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    a.off = b->d_off;
+    {
+        LaunchScope ls(c, "k_rrr_encode");
+        k_rrr_encode<<<grid_for(L * nb), kThreads, 0, c->stream>>>(a);
+    }
+    IDC_TRY(check_last_launch("k_rrr_encode"));
+    IDC_CUDA(cudaStreamSynchronize(c->stream));
+    b->device_bytes -= L * sh.words * 8;
+    c->pool_release(b->d_bits);
+    b->d_bits = nullptr;
+    return IDC_OK;
+}
+
+// RRR(63) blocks -> plain levels at dst (levels x words)
+int wt_expand(idc_ctx* c, const idc_wt_blob* b, uint64_t* dst) {
+    const WtShape& sh = b->sh;
+    RrrArgs a{dst, b->d_cls, b->d_ptr, b->d_off, b->d_off_base, nullptr, nullptr, c->d_binom, sh.nblk, sh.words, sh.levels};
+    {
+        LaunchScope ls(c, "k_rrr_expand");
+        k_rrr_expand<<<grid_for((uint64_t)sh.levels * sh.nblk), kThreads, 0, c->stream>>>(a);
+    }
+    return check_last_launch("k_rrr_expand");
+}
 
 int wt_status_to_error(uint32_t st, const char* what) {
     if (st & kWtStRange) {
@@ -598,8 +784,6 @@ int idc_wt_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const voi
     IDC_REQUIRE(c && offsets && out, IDC_ERR_ARG, "idc_wt_encode: null argument");
     IDC_REQUIRE(id_bytes == 8 || id_bytes == 4, IDC_ERR_ARG, "id_bytes must be 4 or 8");
     IDC_REQUIRE(wt_type == 0 || wt_type == 1, IDC_ERR_ARG, "wt_type must be 0 or 1 (custom_invlists_impl.cpp:349)");
-    IDC_REQUIRE(wt_type == 0, IDC_ERR_ARG,
-                "wt_type 1 (sdsl rrr_vector<63> bit vectors) is not implemented: only the plain wt_int flavour is");
     IDC_REQUIRE(nlist <= (1ull << 31), IDC_ERR_ARG, "too many lists");
     *out = nullptr;
     std::lock_guard<std::mutex> lock(c->mu);
@@ -660,6 +844,7 @@ int idc_wt_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const voi
         IDC_TRY(wt_build<int64_t>(c, b.get(), static_cast<const int64_t*>(ids_dev)));
     else
         IDC_TRY(wt_build<uint32_t>(c, b.get(), static_cast<const uint32_t*>(ids_dev)));
+    if (wt_type == 1) IDC_TRY(wt_compress(c, b.get()));  // rrr_vector<63> flavour: the finished levels, block-compressed
     *out = b.release();
     return IDC_OK;
 }
@@ -669,6 +854,8 @@ int idc_wt_blob_info(const idc_wt_blob* b, idc_wt_info* info) {
     info->nlist = b->nlist;
     info->total_ids = b->total_ids;
     info->bits_bytes = (uint64_t)b->sh.levels * b->sh.words * 8;
+    if (b->wt_type == 1 && b->total_ids)  // classes + tails, block pointers, offset streams
+        info->bits_bytes = (uint64_t)b->sh.levels * b->sh.nblk * 8 + (uint64_t)b->sh.levels * (b->sh.nblk + 1) * 4 + b->off_base.back() * 8;
     info->aux_bytes = b->total_ids ? (uint64_t)b->sh.levels * (b->sh.rank_stride + 2 * b->sh.samp_stride) * 4 + b->nlist * 4 : 0;
     info->device_bytes = b->device_bytes;
     info->levels = b->sh.levels;
@@ -684,7 +871,16 @@ int idc_wt_blob_export(const idc_wt_blob* b, uint64_t* list_offsets, uint64_t* b
     if (list_offsets) memcpy(list_offsets, b->list_offsets.data(), (b->nlist + 1) * 8);
     if (b->total_ids) {
         const WtShape& sh = b->sh;
-        if (bits) IDC_CUDA(cudaMemcpyAsync(bits, b->d_bits, sh.levels * sh.words * 8, cudaMemcpyDeviceToHost, s));
+        if (bits) {
+            const uint64_t* src = b->d_bits;
+            if (b->wt_type == 1) {  // the plain form of the levels (what idc_wt_blob_import takes), expanded on the way out
+                std::lock_guard<std::mutex> lock(b->ctx->mu);
+                IDC_TRY(b->ctx->scratch.reserve(sh.levels * sh.words * 8));
+                IDC_TRY(wt_expand(b->ctx, b, b->ctx->scratch.as<uint64_t>()));
+                src = b->ctx->scratch.as<uint64_t>();
+            }
+            IDC_CUDA(cudaMemcpyAsync(bits, src, sh.levels * sh.words * 8, cudaMemcpyDeviceToHost, s));
+        }
         if (rank) IDC_CUDA(cudaMemcpyAsync(rank, b->d_rank, sh.levels * sh.rank_stride * 4, cudaMemcpyDeviceToHost, s));
         if (sel1) IDC_CUDA(cudaMemcpyAsync(sel1, b->d_sel1, sh.levels * sh.samp_stride * 4, cudaMemcpyDeviceToHost, s));
         if (sel0) IDC_CUDA(cudaMemcpyAsync(sel0, b->d_sel0, sh.levels * sh.samp_stride * 4, cudaMemcpyDeviceToHost, s));
@@ -800,9 +996,15 @@ int idc_wt_decode(idc_ctx* c, const idc_wt_blob* b, const uint64_t* list_nos, ui
         const uint32_t* in = nullptr;
         uint32_t* out = bufA;
         const uint32_t warp_grid = grid_for(sh.nblk * 32);
+        const uint64_t* all_bits = b->d_bits;
+        if (b->wt_type == 1) {  // block-compressed levels: expand them once, the passes stream over plain bits
+            IDC_TRY(c->scratch.reserve((uint64_t)sh.levels * sh.words * 8));
+            IDC_TRY(wt_expand(c, b, c->scratch.as<uint64_t>()));
+            all_bits = c->scratch.as<uint64_t>();
+        }
         for (uint32_t lev = 0; lev < sh.levels; lev++) {
             LaunchScope ls(c, "k_wt_replay");
-            const uint64_t* bits = b->d_bits + (uint64_t)lev * sh.words;
+            const uint64_t* bits = all_bits + (uint64_t)lev * sh.words;
             const uint32_t* rank = b->d_rank + (uint64_t)lev * sh.rank_stride;
             if (lev == 0)
                 k_wt_replay<true><<<warp_grid, kThreads, 0, c->stream>>>(nullptr, sh.n, sh.nblk, bits, rank, out);
@@ -840,7 +1042,7 @@ int idc_wt_blob_import(idc_ctx* c, uint64_t nlist, const uint64_t* list_offsets,
                        const uint32_t* sel1, const uint32_t* sel0, const uint32_t* start, int mem, idc_wt_blob** out) {
     IDC_REQUIRE(c && out && list_offsets, IDC_ERR_ARG, "idc_wt_blob_import: null argument");
     IDC_REQUIRE(mem == IDC_MEM_HOST || mem == IDC_MEM_DEVICE, IDC_ERR_ARG, "mem must be IDC_MEM_HOST or IDC_MEM_DEVICE");
-    IDC_REQUIRE(wt_type == 0, IDC_ERR_ARG, "wt_type must be 0");
+    IDC_REQUIRE(wt_type == 0 || wt_type == 1, IDC_ERR_ARG, "wt_type must be 0 or 1");
     IDC_REQUIRE(nlist <= (1ull << 31), IDC_ERR_ARG, "too many lists");
     *out = nullptr;
     std::lock_guard<std::mutex> lock(c->mu);
@@ -882,7 +1084,28 @@ int idc_wt_blob_import(idc_ctx* c, uint64_t nlist, const uint64_t* list_offsets,
     IDC_CUDA(cudaMemcpyAsync(b->d_sel0, sel0, sh.levels * sh.samp_stride * 4, kind, s));
     IDC_CUDA(cudaMemcpyAsync(b->d_start, start, nlist * 4, kind, s));
     IDC_CUDA(cudaStreamSynchronize(s));
+    if (wt_type == 1) IDC_TRY(wt_compress(c, b.get()));
     *out = b.release();
+    return IDC_OK;
+}
+
+/* wt_type = 1 only: the compressed arrays as they lie in HBM (HOST copies; any pointer may be NULL) -- cls[levels * nblk]
+ * (eight 6-bit classes + the block's 8 tail bits per 512-bit block), ptr[levels * (nblk + 1)] (bit offset of the
+ * block's first offset field in its level's stream), off_base[levels + 1] (first 64-bit word of each level's stream in
+ * off; off_base[levels] = words in use), off[off_base[levels]]. */
+int idc_wt_blob_export_rrr(const idc_wt_blob* b, uint64_t* cls, uint32_t* ptr, uint64_t* off_base, uint64_t* off) {
+    IDC_REQUIRE(b, IDC_ERR_ARG, "null blob");
+    IDC_REQUIRE(b->wt_type == 1, IDC_ERR_ARG, "not a wt_type = 1 blob");
+    IDC_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t s = b->ctx->stream;
+    if (b->total_ids) {
+        const WtShape& sh = b->sh;
+        if (cls) IDC_CUDA(cudaMemcpyAsync(cls, b->d_cls, sh.levels * sh.nblk * 8, cudaMemcpyDeviceToHost, s));
+        if (ptr) IDC_CUDA(cudaMemcpyAsync(ptr, b->d_ptr, sh.levels * (sh.nblk + 1) * 4, cudaMemcpyDeviceToHost, s));
+        if (off_base) memcpy(off_base, b->off_base.data(), (sh.levels + 1) * 8);
+        if (off && b->off_base.back()) IDC_CUDA(cudaMemcpyAsync(off, b->d_off, b->off_base.back() * 8, cudaMemcpyDeviceToHost, s));
+    }
+    IDC_CUDA(cudaStreamSynchronize(s));
     return IDC_OK;
 }
 

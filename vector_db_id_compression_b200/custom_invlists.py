@@ -219,7 +219,7 @@ class CompressedIDInvertedListsPackedBits(InvertedListsArrayCodes):
 class CompressedIDInvertedListsWaveletTree(InvertedListsArrayCodes):
     """Wavelet-tree ids (custom_invlists_impl.h:100-124, .cpp:346-397): ONE structure over S[id] = list_no;
     get_single_id(list_no, offset) = wt.select(offset + 1, list_no). wt_type 0 = sdsl::wt_int<> (plain bit
-    vectors); wt_type 1 (rrr_vector<63>) is not implemented and raises. Sizes are those of this repository's
+    vectors); wt_type 1 = rrr_vector<63>: the levels as RRR(63) blocks. Sizes are those of this repository's
     wavelet matrix (bits + rank / select directories), not sdsl::size_in_bytes (SDSL absent: unpinned)."""
 
     def __init__(self, il: InvertedLists, wt_type: int = 0, ctx: Optional[capi.Context] = None):
