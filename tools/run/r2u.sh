@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_roc_decode -s 8 -c 3 -o gpurun_out/r2u_dec -f python tools/probe.py --n 2e8 --zipf 1.0 --ef 0 --reps 2 > gpurun_out/r2u_ncu.log 2>&1
+tail -3 gpurun_out/r2u_ncu.log
+ls -la gpurun_out/r2u_dec.ncu-rep
