@@ -272,6 +272,9 @@ int idc_roc_decode_rows(
  * both LSB-first in 64-bit words (succinct bit_vector layout). A list whose
  * high-bits vector would reach 2^32 bits (more than ~1.4e9 ids) is rejected
  * with IDC_ERR_DOMAIN.
+ * Device id buffers are read in whole 16-byte pieces (bulk copies): up to 8 / 12 bytes past the last id of the
+ * array may be read (never used). Any cudaMalloc'd / framework-allocated buffer allows that (allocations are
+ * 256-byte granular); host buffers are staged by the library.
  */
 int idc_ef_encode(
         idc_ctx* ctx,

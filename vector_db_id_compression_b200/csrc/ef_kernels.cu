@@ -1375,7 +1375,7 @@ int idc_ef_encode(idc_ctx* c, uint64_t nlist, const uint64_t* offsets, const voi
     IDC_REQUIRE(ids != nullptr || elems == 0, IDC_ERR_ARG, "ids is NULL");
     const void* ids_dev = ids;
     if (ids_mem == IDC_MEM_HOST && elems) {
-        IDC_TRY(c->stage.reserve(elems * id_bytes));
+        IDC_TRY(c->stage.reserve(elems * id_bytes + 64));  // + 64: the encoder's bulk copies move whole 16-byte pieces
         IDC_CUDA(cudaMemcpyAsync(c->stage.p, ids, elems * id_bytes, cudaMemcpyHostToDevice, c->stream));
         ids_dev = c->stage.p;
     }
@@ -1404,7 +1404,7 @@ int idc_ef_encode_rows(idc_ctx* c, uint64_t nrows, uint32_t K, const int32_t* da
     const int32_t* d_data = data;
     uint64_t elems = nrows * K;
     if (data_mem == IDC_MEM_HOST && elems) {
-        IDC_TRY(c->stage.reserve(elems * 4));
+        IDC_TRY(c->stage.reserve(elems * 4 + 64));  // + 64: bulk copies move whole 16-byte pieces
         IDC_CUDA(cudaMemcpyAsync(c->stage.p, data, elems * 4, cudaMemcpyHostToDevice, c->stream));
         d_data = c->stage.as<int32_t>();
     }
