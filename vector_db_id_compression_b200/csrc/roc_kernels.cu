@@ -1525,8 +1525,14 @@ int idc_roc_translate(idc_ctx* c, const idc_roc_blob* b, const int64_t* labels, 
         IDC_CUDA(cudaStreamSynchronize(c->stream));
         lab = lab_h.data();
     }
-    std::vector<uint64_t> hit;  // distinct hit lists, ascending
-    hit.reserve(n);
+    // distinct hit lists, ascending, and where each of them starts in the decoded buffer. A flag per list when the batch
+    // is large against the index (one pass, no sort: a million labels cost 5 ms instead of 90), a sort of the hit list
+    // numbers when it is small.
+    const bool dense = b->nlist <= 4 * n + 1024;
+    std::vector<uint64_t> hit;
+    std::vector<uint8_t> flag;
+    if (dense) flag.assign(b->nlist, 0);
+    else hit.reserve(n);
     for (uint64_t i = 0; i < n; i++) {
         if (lab[i] < 0) continue;
         const uint64_t l = (uint64_t)lab[i] >> 32, o = (uint64_t)lab[i] & 0xffffffffull;
@@ -1535,16 +1541,25 @@ int idc_roc_translate(idc_ctx* c, const idc_roc_blob* b, const int64_t* labels, 
         IDC_REQUIRE(o < b->list_offsets[l + 1] - b->list_offsets[l], IDC_ERR_ARG,
                     "label %llu: offset %llu past the end of list %llu", (unsigned long long)i, (unsigned long long)o,
                     (unsigned long long)l);
-        hit.push_back(l);
+        if (dense) flag[l] = 1;
+        else hit.push_back(l);
     }
-    std::sort(hit.begin(), hit.end());
-    hit.erase(std::unique(hit.begin(), hit.end()), hit.end());
-    // decode plan for the hit lists; pos_of[list] = element offset of the list in the decoded buffer
+    if (dense) {
+        for (uint64_t l = 0; l < b->nlist; l++)
+            if (flag[l]) hit.push_back(l);
+    } else {
+        std::sort(hit.begin(), hit.end());
+        hit.erase(std::unique(hit.begin(), hit.end()), hit.end());
+    }
+    // decode plan for the hit lists; list_pos[h] = element offset of hit list h in the decoded buffer
     std::vector<uint32_t> units;
     std::vector<uint64_t> out_off, list_pos(hit.size());
+    std::vector<uint64_t> pos_of;  // dense: the same, indexed by list number
+    if (dense) pos_of.assign(b->nlist, 0);
     uint64_t pos = 0;
     for (size_t h = 0; h < hit.size(); h++) {
         list_pos[h] = pos;
+        if (dense) pos_of[hit[h]] = pos;
         for (uint64_t u = b->unit_offsets[hit[h]]; u < b->unit_offsets[hit[h] + 1]; u++) {
             units.push_back((uint32_t)u);
             out_off.push_back(pos);
@@ -1555,8 +1570,12 @@ int idc_roc_translate(idc_ctx* c, const idc_roc_blob* b, const int64_t* labels, 
     for (uint64_t i = 0; i < n; i++) {
         if (lab[i] < 0) continue;
         const uint64_t l = (uint64_t)lab[i] >> 32, o = (uint64_t)lab[i] & 0xffffffffull;
-        const size_t h = std::lower_bound(hit.begin(), hit.end(), l) - hit.begin();
-        src[i] = list_pos[h] + o;
+        if (dense) {
+            src[i] = pos_of[l] + o;
+        } else {
+            const size_t h = std::lower_bound(hit.begin(), hit.end(), l) - hit.begin();
+            src[i] = list_pos[h] + o;
+        }
     }
     // device buffers: decoded ids | src | labels (when they came from the host) | out (when it goes to the host)
     const size_t off_src = (pos * 8 + 255) & ~size_t(255), off_lab = off_src + ((n * 8 + 255) & ~size_t(255));
