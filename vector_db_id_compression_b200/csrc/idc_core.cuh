@@ -257,7 +257,7 @@ constexpr uint32_t kDecRingWait = 8;   // copies allowed in flight when a word i
 struct DecRing {
     uint32_t* base;       // this unit's ring in shared memory: word i at base[(i >> 2) * chunk_stride + (i & 3)]
     uint32_t chunk_stride;
-    IDC_HD uint32_t* at(uint32_t i) const { return base + (size_t)(i >> 2) * chunk_stride + (i & 3u); }
+    IDC_HD uint32_t* at(uint32_t i) const { return base + ((i >> 2) * chunk_stride + (i & 3u)); }  // 32-bit index math: a ring is a few KB
 };
 
 IDC_HD void ring_fetch_if(uint32_t* dst_smem, const uint32_t* src, bool cond) {

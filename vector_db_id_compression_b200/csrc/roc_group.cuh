@@ -53,7 +53,7 @@ struct Grp {
 struct SmView {
     uint32_t* base;
     uint32_t ng, q;
-    IDC_HD uint32_t* at(uint32_t w) const { return base + ((((size_t)(w >> 2) * ng) + q) << 2) + (w & 3u); }
+    IDC_HD uint32_t* at(uint32_t w) const { return base + (((((w >> 2) * ng) + q) << 2) + (w & 3u)); }  // 32-bit index math: a warp's region is < 64 KB
 };
 
 template <int N>
