@@ -911,7 +911,7 @@ def e2e_section(args, ctx, offsets, ids, world, dev, barrier, host_bufs):
     # stated variant: the same round trip with 4-byte ids on the wire (ids < 2^31 here; faiss::idx_t is 8 bytes, so this is
     # NOT the headline): half the PCIe bytes
     try:
-        if int(ids.max().item()) < (1 << 31):
+        if world == 1 and int(ids.max().item()) < (1 << 31):  # (N = 1 only: another 8 GB of pinned host memory per rank)
             h32 = torch.empty(n_ids, dtype=torch.int32, pin_memory=True)
             h32.copy_(ids.to(torch.int32))
             o32 = torch.empty(n_ids, dtype=torch.int32, pin_memory=True)
