@@ -251,7 +251,8 @@ struct EfEncSmem {
 // 32-bit words; every shift and word index is a constant (mask + shift-add per id, nothing data dependent). The words
 // are staged in shared memory (row stride L | 1: conflict-free) and leave as coalesced 128-byte stores.
 template <int L>
-__device__ __forceinline__ void ef_low_tile(const uint32_t (&v)[32], uint32_t* stage, uint32_t* low32, uint32_t run, uint32_t lane) {
+__device__ __forceinline__ void ef_low_tile(const uint32_t (&v)[32], uint32_t* stage, uint32_t* low32, uint32_t run, uint32_t lane,
+                                            uint32_t nlw) {  // nlw = 32-bit words the tile owns (a partial tile: fewer than 32 L)
     if constexpr (L > 0) {
         constexpr uint32_t kMask = (1u << L) - 1u, kRow = (uint32_t)L | 1u;
         uint32_t w[L];
@@ -274,11 +275,13 @@ __device__ __forceinline__ void ef_low_tile(const uint32_t (&v)[32], uint32_t* s
 #pragma unroll
         for (int k = 0; k < L; k++) {
             const uint32_t q = 32u * (uint32_t)k + lane;
-            if constexpr ((L & 1) != 0) {
-                low32[q] = stage[q];
-            } else {
-                const uint32_t rr = q / (uint32_t)L;
-                low32[q] = stage[q + rr];
+            if (q < nlw) {
+                if constexpr ((L & 1) != 0) {
+                    low32[q] = stage[q];
+                } else {
+                    const uint32_t rr = q / (uint32_t)L;
+                    low32[q] = stage[q + rr];
+                }
             }
         }
     }
@@ -488,11 +491,31 @@ __global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(const __grid_co
                                                              : (uint64_t)(uint32_t) * (reinterpret_cast<const IdT*>(raw0) - 1))
                                          : 0ull;
         uint32_t v[32];
-        uint32_t hpF = 0, hpL = 0, hp_first = 0, ann_c = 0, ann_before = 0xffffffffu;
+        uint32_t hpF = 0, hpL = 0, hpL_pad = 0, hp_first = 0, ann_c = 0, ann_before = 0xffffffffu;
         const uint32_t hb = i0w + 32u * run;  // fast path: hp(r) = (v[r] >> l) + hb + r
-        bool fast = cnt == kEncTileIds && l <= (uint32_t)kEncMaxFastL;
+        bool fast = l <= (uint32_t)kEncMaxFastL;
         if (fast) {
             uint32_t wide = 0;
+            // the tile's last id; a PARTIAL tile (always the last one of its list) is filled up with ids just past it
+            // whose lower bits are zero: they sort behind, pack to zero bits, and their ones land behind the tile's
+            // last one, where the write-out stops
+            uint64_t id_last;
+            {
+                const uint32_t e = cnt - 1u;
+                const IdT* lp = reinterpret_cast<const IdT*>(raw0 + (e >> 7) * Smem::kSubStride) + (e & (kEncSubIds - 1u));
+                id_last = sizeof(IdT) == 8 ? (uint64_t)*lp : (uint64_t)(uint32_t)*lp;
+            }
+            bool pad_overflow = false;
+            if (cnt < kEncTileIds) {
+                const uint64_t pad = ((id_last >> l) + 1ull) << l;
+                pad_overflow = (pad >> 32) != 0ull;  // (only a list that ends at the very top of the 32-bit range)
+                __syncwarp();  // every lane has read id_last
+                for (uint32_t e = cnt + lane; e < kEncTileIds; e += 32u) {
+                    IdT* pp = reinterpret_cast<IdT*>(const_cast<uint8_t*>(raw0) + (e >> 7) * Smem::kSubStride) + (e & (kEncSubIds - 1u));
+                    *pp = (IdT)pad;
+                }
+                __syncwarp();
+            }
             const IdT* rp = reinterpret_cast<const IdT*>(raw0 + (lane & 7u) * Smem::kSubStride) + (lane >> 3) * 32u;
             if (sizeof(IdT) == 8) {
                 // 16-byte loads, two ids each: the eight lanes of a quarter-warp read different bank groups (the shared-
@@ -528,10 +551,11 @@ __global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(const __grid_co
             hp_first = (v[0] >> l) + hb;
             const uint32_t hp_last = (v[31] >> l) + hb + 31u;
             hpF = __shfl_sync(0xffffffffu, hp_first, 0);
-            hpL = __shfl_sync(0xffffffffu, hp_last, 31);
+            hpL_pad = __shfl_sync(0xffffffffu, hp_last, 31);                 // last position the window pass touches
+            hpL = ((uint32_t)id_last >> l) + i0w + cnt - 1u;                 // the tile's last one
             const uint32_t next_first = __shfl_sync(0xffffffffu, v[0], lane_next);
             const uint32_t prev_last = __shfl_sync(0xffffffffu, hp_last, lane_prev);
-            bool no = wide != 0u;  // anything the slow path has to deal with (or refuse)
+            bool no = wide != 0u || pad_overflow;  // anything the slow path has to deal with (or refuse)
             if (a.check_input) {
                 // ascending? inside the run, across runs, across the tile's start
 #pragma unroll
@@ -546,7 +570,7 @@ __global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(const __grid_co
             const int64_t prev = run ? (int64_t)prev_last : (i0 ? (int64_t)((id_prev_tile >> l) + i0 - 1) : -1);
             const uint32_t c_lo = prev < 0 ? 0u : (uint32_t)(prev >> 10) + 1u, c_hi = hp_last >> 10;
             no |= c_hi > c_lo;                                  // two boundaries inside one run
-            no |= hpL - (hpF & ~31u) >= 32u * kEncWinWords;     // upper bits wider than the window
+            no |= hpL_pad - (hpF & ~31u) >= 32u * kEncWinWords; // upper bits wider than the window
             fast = !__any_sync(0xffffffffu, no);
             if (fast && c_hi == c_lo) {
                 // ids of the run before the boundary: hp(r) < 1024 C  <=>  (id(r) >> l) + r < T; the keys ascend and
@@ -559,7 +583,7 @@ __global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(const __grid_co
                     if (((uint32_t)rp[r] >> l) + r < T) before += step;
                 }
                 ann_c = c_lo;
-                ann_before = 32u * run + before;
+                if (32u * run + before < cnt) ann_before = 32u * run + before;  // (a boundary behind the tile's last id: the trailing loop's)
             }
         }
         uint32_t bad = 0;
@@ -578,6 +602,7 @@ __global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(const __grid_co
         // every lane is done with the raw buffer: the next tile (its descriptor has arrived) may land in it, and the
         // descriptor after that sets out
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (a partial tile's fill-up stores before the copy engine's writes)
         __syncwarp();
         if (tile + nwarps < a.ntiles) fetch(sm->desc[slot1]);
         fetch_desc(tile + 2u * nwarps, slot2);
@@ -585,9 +610,11 @@ __global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(const __grid_co
             uint32_t* low32 = reinterpret_cast<uint32_t*>(a.low) + tp->low32;
             uint32_t* high32 = reinterpret_cast<uint32_t*>(a.high + tp->high_off);
             // ---- upper bits: one window, based at the word of the tile's first one
-            const uint32_t wb = hpF & ~31u, nwin = ((hpL - wb) >> 5) + 1u;
-            for (uint32_t q = lane; q < nwin; q += 32) win[q] = 0u;
-            if ((run & 7u) == 0u) a.samples[tp->samp + (run >> 3)] = hp_first;
+            // (nwin words are written out: up to the tile's last one; the window pass of a filled-up partial tile
+            // touches nwin_pad words)
+            const uint32_t wb = hpF & ~31u, nwin = ((hpL - wb) >> 5) + 1u, nwin_pad = ((hpL_pad - wb) >> 5) + 1u;
+            for (uint32_t q = lane; q < nwin_pad; q += 32) win[q] = 0u;
+            if ((run & 7u) == 0u && 32u * run < cnt) a.samples[tp->samp + (run >> 3)] = hp_first;
             __syncwarp();
             {
                 const uint32_t hbw = hb - wb;
@@ -598,10 +625,11 @@ __global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(const __grid_co
                 }
             }
             // ---- lower bits (the staging area is the slow path's tile)
+            const uint32_t nlw = ((cnt * l + 63u) / 64u) * 2u;  // 32-bit words, a whole number of 64-bit words
             switch (l) {
 #define IDC_EF_LOW_CASE(LL)                       \
     case LL:                                      \
-        ef_low_tile<LL>(v, ts, low32, run, lane); \
+        ef_low_tile<LL>(v, ts, low32, run, lane, nlw); \
         break;
                 IDC_EF_LOW_CASE(1) IDC_EF_LOW_CASE(2) IDC_EF_LOW_CASE(3) IDC_EF_LOW_CASE(4) IDC_EF_LOW_CASE(5) IDC_EF_LOW_CASE(6)
                 IDC_EF_LOW_CASE(7) IDC_EF_LOW_CASE(8) IDC_EF_LOW_CASE(9) IDC_EF_LOW_CASE(10) IDC_EF_LOW_CASE(11) IDC_EF_LOW_CASE(12)
@@ -613,7 +641,8 @@ __global__ void __launch_bounds__(kEncWarps * 32, 4) k_ef_encode(const __grid_co
             }
             __syncwarp();
             for (uint32_t q = lane; q < nwin; q += 32) {
-                const uint32_t val = win[q];
+                uint32_t val = win[q];
+                if (q == nwin - 1u) val &= 0xffffffffu >> (31u - (hpL & 31u));  // nothing behind the tile's last one
                 if (q == 0u || q == nwin - 1u) {
                     if (val) atomicOr(high32 + (wb >> 5) + q, val);
                 } else {
