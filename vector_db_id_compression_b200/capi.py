@@ -361,8 +361,10 @@ class RocBlob:
         _check(self._l.idc_roc_blob_order(self._h, p, mem))
         return out[:n]
 
-    def decode(self, list_nos: Optional[Sequence[int]] = None, *, id_bytes: int = 8, device=None):
-        """-> (ids, out_offsets). device=None: numpy result; else a torch device."""
+    def decode(self, list_nos: Optional[Sequence[int]] = None, *, id_bytes: int = 8, device=None, out=None):
+        """-> (ids, out_offsets). device=None: numpy result; else a torch device. out: the caller's own buffer (numpy
+        array or torch tensor of int64 / int32, e.g. pinned host memory -- the large-output path then sends the
+        longest units' ids to the host while their chains are still running)."""
         if list_nos is None:
             nsel, lp = self.nlist, None
             total = self.total_ids
@@ -374,7 +376,13 @@ class RocBlob:
         if total is None:
             ex_off = self.export_list_offsets()
             total = int(sum(int(ex_off[int(l) + 1] - ex_off[int(l)]) for l in ln))
-        out = _alloc_like(None, total, np.int64 if id_bytes == 8 else np.int32, device)
+        if out is None:
+            out = _alloc_like(None, total, np.int64 if id_bytes == 8 else np.int32, device)
+        else:
+            isz = out.element_size() if _is_torch(out) else out.dtype.itemsize
+            cnt = int(out.numel() if _is_torch(out) else out.size)
+            if isz != id_bytes or cnt < total:
+                raise ValueError("out: wrong element size or too small")
         p, mem = _ptr(out)
         _check(self._l.idc_roc_decode(self.ctx._h, self._h, lp, nsel, p, id_bytes, mem, out_off.ctypes.data))
         return out[:total], out_off

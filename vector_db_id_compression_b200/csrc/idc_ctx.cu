@@ -102,9 +102,10 @@ void idc_ctx::pool_trim() {
     pool_free.clear();
 }
 
-int idc_ctx::copy_stream_get(cudaStream_t* s) {
-    if (!copy_stream) IDC_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    *s = copy_stream;
+int idc_ctx::copy_stream_get(cudaStream_t* s, int which) {
+    cudaStream_t& cs = which ? copy_stream2 : copy_stream;
+    if (!cs) IDC_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    *s = cs;
     return IDC_OK;
 }
 
@@ -233,6 +234,7 @@ int idc_ctx_destroy(idc_ctx* c) {
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     for (auto e : c->sync_events) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->copy_stream2) cudaStreamDestroy(c->copy_stream2);
     cudaFree(c->d_mt);
     cudaFree(c->d_rcp64);
     cudaFree(c->d_q31);

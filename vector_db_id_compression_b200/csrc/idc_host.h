@@ -137,10 +137,10 @@ struct idc_ctx {
     std::vector<cudaEvent_t> aux_done;
     cudaEvent_t fork_ev = nullptr;
     // copy engine stream + reusable ordering events (host<->device copies overlapped with the kernels)
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr;
     std::vector<cudaEvent_t> sync_events;
     size_t sync_used = 0;
-    int copy_stream_get(cudaStream_t* s);
+    int copy_stream_get(cudaStream_t* s, int which = 0);
     int sync_event(cudaEvent_t* e);  // an event for ordering only; recycled at the next begin_call()
     int fork(int n);              // make aux[0..n) wait for everything queued on `stream`
     int join(int n);              // make `stream` wait for aux[0..n)

@@ -20,6 +20,9 @@
 //   k_roc_decode    the decoder (also the row mode: slot-derived tables for NSG rows)
 //   k_translate_gather   ids of (list_no << 32 | offset) labels from the decoded hit lists
 // Host buffers (IDC_MEM_HOST) are uploaded / downloaded in chunks on a copy stream, overlapped with the kernels.
+#include <dlfcn.h>
+#include <cuda.h>  // types of the driver entry point cuStreamWaitValue32 only (looked up at run time, not linked)
+
 #include <algorithm>
 #include <cstring>
 #include <numeric>
@@ -251,6 +254,13 @@ struct DecArgs {
     uint64_t slot_ws;
     uint32_t nrows;
     uint32_t row_base;          // rows == nullptr: slot s decodes row row_base + s
+    // progress milestones (the longest size class of a decode into host memory): every warp adds 1 to progress[m]
+    // once all its units have finished (m + 1) * ms_seg steps -- their outputs out[n - (m + 1) * ms_seg, n) are then
+    // final and visible device-wide, and the copy stream, which waits for the counter to reach the warp count, can
+    // send them to the host while the chains go on
+    uint32_t* progress;
+    uint32_t ms_seg;
+    uint32_t ms_count;
 };
 
 template <int G, typename OutT>
@@ -299,6 +309,7 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
     uint32_t ib = 0;                          // block covers i = ib .. ib+31
     uint32_t q31_blk = tab_q31(0), q31_nxt = tab_q31(32);
     uint32_t q31_next = __shfl_sync(0xffffffffu, q31_blk, 0);  // one step ahead, see k_roc_encode
+    uint32_t ms_next = a.progress ? a.ms_seg : 0xffffffffu, ms_done = 0;
     for (uint32_t i = 0; i < tmax; ++i) {
         const uint32_t q31 = q31_next;
         {
@@ -311,6 +322,21 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
             q31_next = __shfl_sync(0xffffffffu, q31_blk, in - ib);
         }
         gdec_step<G>(g, U, i, q31, a.mt, i < n);
+        if (i + 1u == ms_next) {  // warp-uniform
+            if (ms_done < a.ms_count) {
+                __threadfence();
+                __syncwarp();
+                if (lane_id == 0) atomicAdd(a.progress + ms_done, 1u);
+            }
+            ms_done++;
+            ms_next += a.ms_seg;
+        }
+    }
+    if (a.progress) {  // a warp of shorter units reports the milestones it never reached: nothing of it is awaited
+        __threadfence();
+        __syncwarp();
+        if (lane_id == 0)
+            for (uint32_t m = ms_done; m < a.ms_count; m++) atomicAdd(a.progress + m, 1u);
     }
     if (valid) {
         if (a.row_stride)
@@ -963,7 +989,45 @@ int build_decode_plan(idc_ctx* c, const idc_roc_blob* b, const std::vector<uint3
 struct DecodeOverlap {
     std::vector<cudaEvent_t> class_done;
     std::vector<uint32_t> class_min_n;
+    std::vector<uint64_t> class_est;  // estimated completion in steps: the classes before it on its stream + its own longest unit
+    // milestones of the longest class (see DecArgs::progress); ms_count == 0: none
+    bool want_ms = false;
+    uint32_t ms_seg = 0, ms_count = 0, ms_expect = 0;
+    uint32_t* d_progress = nullptr;
+    cudaEvent_t ms_armed = nullptr;  // the counters are zero once this event has passed
 };
+
+// cuStreamWaitValue32 through the runtime's driver entry point lookup (the library does not link libcuda)
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValue32Fn stream_wait_value32() {
+    static StreamWaitValue32Fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<StreamWaitValue32Fn>(p);
+    }();
+    return fn;
+}
+
+// cudaMemcpyBatchAsync (CUDA 12.8): many copies in one call -- looked up at run time, an older runtime simply goes
+// without the milestones
+typedef cudaError_t (*MemcpyBatchFn)(void**, void**, size_t*, size_t, cudaMemcpyAttributes*, size_t*, size_t, size_t*, cudaStream_t);
+MemcpyBatchFn memcpy_batch() {
+    static MemcpyBatchFn fn = reinterpret_cast<MemcpyBatchFn>(dlsym(RTLD_DEFAULT, "cudaMemcpyBatchAsync"));
+    return fn;
+}
+
+inline uint32_t ms_parts() {
+    if (const char* e = getenv("IDC_MS_PARTS")) {  // experiments
+        int v = atoi(e);
+        if (v >= 2 && v <= 8) return (uint32_t)v;
+    }
+    return 8;  // the longest class's output leaves in this many pieces per unit
+}
+constexpr uint32_t kMsMinUnit = 16384;    // ... when its units are at least this long
+constexpr uint32_t kMsWordOffset = 8;     // the counters live behind the status word (words 8 .. 15 of the status buffer)
 
 int finish_decode(idc_ctx* c) {
     uint32_t st = 0;
@@ -987,7 +1051,11 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     IDC_TRY(c->ws.reserve(ws_bytes + 256));
     IDC_TRY(c->status.reserve(64));
     uint32_t* d_status = c->status.as<uint32_t>();
-    IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    IDC_CUDA(cudaMemsetAsync(d_status, 0, 64, c->stream));
+    if (ov && ov->want_ms) {
+        IDC_TRY(c->sync_event(&ov->ms_armed));
+        IDC_CUDA(cudaEventRecord(ov->ms_armed, c->stream));
+    }
     {
         LaunchScope ls(c, "memset_ws");  // empty bucket slots must read as 0xffffffff (dec_tree_insert_rank)
         IDC_CUDA(cudaMemsetAsync(c->ws.p, 0xff, ws_bytes, c->stream));
@@ -1021,7 +1089,20 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
         LaunchScope ls(c, "k_roc_decode");
         const std::vector<int> cstream = class_streams(cls);
         IDC_TRY(c->fork(class_stream_count()));
-        for (size_t k = 0; k < cls.size(); k++) {
+        uint64_t stream_load[kMaxClassStreams] = {0};
+        // Launch order. Kernel alone: descending length (the LPT order the streams were balanced for). With the
+        // output leaving for the host as it is produced (ov): the longest class first, then the SHORTEST classes --
+        // inside a stream the order does not change when the stream is done, but the short lists' ids are final
+        // within the first milliseconds and keep the copy engine busy until the long chains deliver.
+        std::vector<size_t> korder(cls.size());
+        std::iota(korder.begin(), korder.end(), (size_t)0);
+        if (ov && cls.size() > 2) std::reverse(korder.begin() + 1, korder.end());
+        if (ov) {
+            ov->class_done.assign(cls.size(), nullptr);
+            ov->class_min_n.assign(cls.size(), 0u);
+            ov->class_est.assign(cls.size(), 0ull);
+        }
+        for (size_t k : korder) {
             DecArgs ak = a;
             ak.slot_base = cls[k].slot_base;
             ak.slot_end = cls[k].slot_end;
@@ -1032,6 +1113,16 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
             const uint32_t slots = ak.slot_end - ak.slot_base, nwarps = (slots + upw - 1) / upw;
             const uint32_t grid = (nwarps + warps - 1) / warps;
             const size_t smem = (size_t)ak.sm_words * 4 * upw * warps;
+            const bool ms = ov && ov->want_ms && k == 0 && cls[k].max_n >= kMsMinUnit;
+            if (ms) {
+                ov->ms_seg = (cls[k].max_n + ms_parts() - 1) / ms_parts();
+                ov->ms_count = ms_parts() - 1;
+                ov->ms_expect = grid * warps;
+                ov->d_progress = d_status + kMsWordOffset;
+                ak.progress = ov->d_progress;
+                ak.ms_seg = ov->ms_seg;
+                ak.ms_count = ov->ms_count;
+            }
 #define IDC_LAUNCH_DEC(GG, TT)                                                       \
     do {                                                                             \
         IDC_TRY(set_max_smem(k_roc_decode<GG, TT>, smem));                            \
@@ -1046,12 +1137,16 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
             }
 #undef IDC_LAUNCH_DEC
             c->launches++;
+            stream_load[cstream[k]] += cls[k].max_n ? cls[k].max_n : 1u;
             if (ov) {
                 cudaEvent_t ev;
                 IDC_TRY(c->sync_event(&ev));
                 IDC_CUDA(cudaEventRecord(ev, c->aux[cstream[k]]));
-                ov->class_done.push_back(ev);
-                ov->class_min_n.push_back(n_of_slot(cls[k].slot_end - 1));
+                ov->class_done[k] = ev;
+                ov->class_min_n[k] = n_of_slot(cls[k].slot_end - 1);
+                ov->class_est[k] = stream_load[cstream[k]];
+                // insurance: whatever happened inside the kernel, a wait on its counters ends with it
+                if (ms) IDC_CUDA(cudaMemsetAsync(ov->d_progress, 0x40, 4 * ov->ms_count, c->aux[cstream[k]]));
             }
         }
         c->launches--;
@@ -1439,10 +1534,25 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
             // stream, each as soon as the size classes of its units are done (Zipf-length lists in CSR order: the
             // short lists at the end of the array are finished, and on their way, long before the longest class).
             DecodeOverlap ov;
+            HostTrace tr("roc_decode(host)");
+            // milestone copies need the caller's buffer pinned / registered (copies into pageable memory are staged
+            // by the driver and hold the host)
+            void* host_dev = nullptr;
+            {
+                cudaPointerAttributes pa0{}, pa1{};
+                if (cudaPointerGetAttributes(&pa0, ids_out) == cudaSuccess &&
+                    cudaPointerGetAttributes(&pa1, (const uint8_t*)ids_out + total_out * id_bytes - 1) == cudaSuccess &&
+                    pa0.type == cudaMemoryTypeHost && pa1.type == cudaMemoryTypeHost && pa0.devicePointer && pa1.devicePointer &&
+                    (const uint8_t*)pa1.devicePointer - (const uint8_t*)pa0.devicePointer == (ptrdiff_t)(total_out * id_bytes - 1))
+                    host_dev = pa0.devicePointer;
+                (void)cudaGetLastError();
+            }
+            ov.want_ms = host_dev != nullptr && stream_wait_value32() != nullptr && memcpy_batch() != nullptr && getenv("IDC_NO_MILESTONES") == nullptr;
             rc = run_decode(c, b, d_unit, d_out, d_ws, ws_bytes, nunits_sel, out_dev, id_bytes, nullptr, 0,
                             ns.empty() ? 0u : ns[0], [&](uint64_t slot) { return ns[slot]; }, &ov);
-            cudaStream_t copy_s = nullptr;
+            cudaStream_t copy_s = nullptr, copy_ms = nullptr;
             if (rc == IDC_OK) rc = c->copy_stream_get(&copy_s);
+            if (rc == IDC_OK) rc = c->copy_stream_get(&copy_ms, 1);
             if (rc == IDC_OK) {
                 auto class_of = [&](uint32_t n) {
                     size_t k = 0;
@@ -1450,42 +1560,127 @@ int idc_roc_decode(idc_ctx* c, const idc_roc_blob* b, const uint64_t* list_nos, 
                     return k;
                 };
                 const uint64_t first = b->list_offsets[0], target = (total_out + 15) / 16;
-                struct Chunk {
-                    uint64_t e0, e1;
+                // A copy job is a range of whole units that waits for the size classes of its units (mask). The
+                // units of the longest class, whose chains bound the kernel, do not wait for its end: the ids their
+                // last ms_seg steps produced leave as ONE batch of copies (cudaMemcpyBatchAsync, a piece per unit)
+                // per milestone counter of k_roc_decode -- the bulk of the output is on its way while the chains
+                // are still running. Measured and dropped: a cudaMemcpy2DAsync per run of full-length units (10 456
+                // calls at 17 us of host time each -- more than the kernels take), and a kernel that writes the
+                // pieces into the pinned buffer itself (its PCIe stores back up into the SMs' memory pipes and slow
+                // the chains next to them: decode 109 -> 165 ms).
+                struct Job {
+                    uint64_t e0, e1;   // elements [e0, e1) of the output; e1 == e0: milestone `part` of the longest class
                     uint32_t mask;
+                    uint32_t part;
+                    uint64_t est;      // estimated step at which it can go (the copy stream is in order)
                 };
-                std::vector<Chunk> chunks;
+                std::vector<Job> jobs;
+                const bool ms = ov.ms_count != 0;
+                const uint32_t parts = ov.ms_count + 1u;
+                auto est_of_mask = [&](uint32_t m) {
+                    uint64_t e = 0;
+                    for (size_t k = 0; k < ov.class_est.size(); k++)
+                        if (m >> k & 1u) e = std::max(e, ov.class_est[k]);
+                    return e;
+                };
+                auto by_milestone = [&](uint64_t u) { return ms && b->unit_n[u] && class_of(b->unit_n[u]) == 0; };
                 for (uint64_t u0 = 0; u0 < b->nunits;) {
                     uint64_t u1 = u0;
-                    Chunk ch{b->unit_src[u0] - first, b->unit_src[u0] - first, 0u};
-                    while (u1 < b->nunits && ch.e1 - ch.e0 < target) {
-                        if (b->unit_n[u1]) ch.mask |= 1u << class_of(b->unit_n[u1]);
-                        ch.e1 = b->unit_src[u1] - first + b->unit_n[u1];
+                    if (by_milestone(u0)) {
+                        u0++;
+                        continue;
+                    }
+                    Job j{b->unit_src[u0] - first, b->unit_src[u0] - first, 0u, 0u, 0};
+                    while (u1 < b->nunits && j.e1 - j.e0 < target && !by_milestone(u1)) {
+                        if (b->unit_n[u1]) {
+                            // a range of some size is not held back by (nor holds back) units that are ready at another time
+                            const uint32_t k = (uint32_t)class_of(b->unit_n[u1]);
+                            if (j.mask && !(j.mask >> k & 1u) && j.e1 - j.e0 >= (1ull << 20) && ov.class_est[k] != est_of_mask(j.mask)) break;
+                            j.mask |= 1u << k;
+                        }
+                        j.e1 = b->unit_src[u1] - first + b->unit_n[u1];
                         u1++;
                     }
-                    if (ch.e1 > ch.e0) chunks.push_back(ch);
+                    j.est = est_of_mask(j.mask);
+                    if (j.e1 > j.e0) jobs.push_back(j);
                     u0 = u1;
                 }
-                // the copy stream is in order: chunks that only need the short classes (done early) go first
-                auto longest_class = [](uint32_t m) { return m ? (uint32_t)__builtin_ctz(m) : 32u; };
-                std::stable_sort(chunks.begin(), chunks.end(),
-                                 [&](const Chunk& x, const Chunk& y) { return longest_class(x.mask) > longest_class(y.mask); });
+                std::vector<uint64_t> ms_units;
+                std::vector<void*> bd, bs;
+                std::vector<size_t> bn;
+                if (ms)
+                    for (uint64_t u = 0; u < b->nunits; u++)
+                        if (by_milestone(u)) ms_units.push_back(u);
+                if (ms)
+                    for (uint32_t q = 0; q < parts; q++)
+                        jobs.push_back(Job{0, 0, 1u, q, q + 1 < parts ? (uint64_t)(q + 1) * ov.ms_seg : ov.class_est[0]});
+                // Two in-order copy streams: the ranges (queued first -- a batch call holds the host until the device
+                // has taken its copies) and the milestone batches; each in the order its jobs become ready.
+                std::stable_sort(jobs.begin(), jobs.end(), [](const Job& x, const Job& y) {
+                    const bool mx = x.e1 == x.e0, my = y.e1 == y.e0;
+                    return mx != my ? my : x.est < y.est;
+                });
+                tr.mark("launches + copy plan");
                 cudaError_t e = cudaSuccess;
-                for (const Chunk& ch : chunks) {
-                    for (size_t k = 0; k < ov.class_done.size() && e == cudaSuccess; k++)
-                        if (ch.mask >> k & 1u) e = cudaStreamWaitEvent(copy_s, ov.class_done[k], 0);
-                    if (e == cudaSuccess)
-                        e = cudaMemcpyAsync((uint8_t*)ids_out + ch.e0 * id_bytes, (const uint8_t*)out_dev + ch.e0 * id_bytes,
-                                            (ch.e1 - ch.e0) * id_bytes, cudaMemcpyDeviceToHost, copy_s);
+                if (ms) e = cudaStreamWaitEvent(copy_ms, ov.ms_armed, 0);
+                uint32_t waited_mask = 0;  // classes the (in-order) copy stream is already behind
+                const auto t_jobs = std::chrono::steady_clock::now();
+                size_t job_no = 0;
+                for (const Job& j : jobs) {
                     if (e != cudaSuccess) break;
+                    if (tr.on && (j.e1 == j.e0 || job_no % 128 == 0 || (j.e1 - j.e0) * id_bytes > (32u << 20)))
+                        fprintf(stderr, "[idc host]   job %zu (%s, est %llu, %.1f MB) issued at %.2f ms\n", job_no, j.e1 == j.e0 ? "milestone" : "range",
+                                (unsigned long long)j.est, (j.e1 - j.e0) * id_bytes / 1e6,
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_jobs).count());
+                    job_no++;
+                    const bool by_counter = j.e1 == j.e0 && j.part + 1 < parts;
+                    if (by_counter) {
+                        if (stream_wait_value32()((CUstream)copy_ms, (CUdeviceptr)(uintptr_t)(ov.d_progress + j.part), ov.ms_expect,
+                                                  CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                            e = cudaErrorUnknown;
+                    } else if (j.e1 == j.e0) {
+                        e = cudaStreamWaitEvent(copy_ms, ov.class_done[0], 0);
+                    } else {
+                        for (size_t k = 0; k < ov.class_done.size() && e == cudaSuccess; k++)
+                            if ((j.mask & ~waited_mask) >> k & 1u) e = cudaStreamWaitEvent(copy_s, ov.class_done[k], 0);
+                        waited_mask |= j.mask;
+                    }
+                    if (e != cudaSuccess) break;
+                    if (j.e1 == j.e0) {
+                        // a unit of n ids writes out[n - 1 - i] at step i: steps [part * seg, (part + 1) * seg)
+                        const uint64_t s0 = (uint64_t)j.part * ov.ms_seg, s1 = s0 + ov.ms_seg;
+                        bd.clear(), bs.clear(), bn.clear();
+                        for (uint64_t u : ms_units) {
+                            const uint64_t n = b->unit_n[u], base = b->unit_src[u] - first;
+                            const uint64_t hi = n - std::min(n, s0), lo = n - std::min(n, s1);
+                            if (hi == lo) continue;
+                            bd.push_back((uint8_t*)ids_out + (base + lo) * id_bytes);
+                            bs.push_back((uint8_t*)out_dev + (base + lo) * id_bytes);
+                            bn.push_back((hi - lo) * id_bytes);
+                        }
+                        if (!bd.empty()) {
+                            cudaMemcpyAttributes at{};
+                            at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+                            at.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+                            size_t at_idx = 0, fail = 0;
+                            e = memcpy_batch()(bd.data(), bs.data(), bn.data(), bd.size(), &at, &at_idx, 1, &fail, copy_ms);
+                        }
+                    } else {
+                        e = cudaMemcpyAsync((uint8_t*)ids_out + j.e0 * id_bytes, (const uint8_t*)out_dev + j.e0 * id_bytes,
+                                            (j.e1 - j.e0) * id_bytes, cudaMemcpyDeviceToHost, copy_s);
+                    }
                 }
                 if (e != cudaSuccess) {
                     set_error("D2H copy failed: %s", cudaGetErrorString(e));
                     rc = IDC_ERR_CUDA;
                 }
             }
+            tr.mark("copies queued");
             int rc2 = finish_decode(c);
+            tr.mark("kernels done");
             if (copy_s) cudaStreamSynchronize(copy_s);
+            if (copy_ms) cudaStreamSynchronize(copy_ms);
+            tr.mark("copies done");
             if (rc == IDC_OK) rc = rc2;
         } else {
             if (rc == IDC_OK)
