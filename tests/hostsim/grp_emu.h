@@ -46,6 +46,7 @@ struct HostGrp {
     }
     uint32_t shfl_xor(uint32_t v, uint32_t m) const { return shfl(v, sub ^ m); }
     void sync() const { barrier(); }
+    bool warp_any(bool p) const { return ballot(p) != 0u; }  // the emulated warp holds one group
     void host_sync() const { barrier(); }
 };
 

@@ -72,12 +72,14 @@ static void group_decode(uint64_t head, const uint32_t* words, uint32_t nwords, 
         if (force_degenerate) U.tree.ovf_cap = force_degenerate - 1;
         dec_state_init(U.st, head, words, nwords, DecRing{ring.data(), 4u}, g.sub == 0);
         g.sync();
-        dec_ring_prime(U.st);
+        dec_ring_prime(U.st, mt);
         U.out = out;
         U.n = n;
         U.prec = prec;
+        gdec_unit_start(U);
         for (uint32_t i = 0; i < n; i++)
             gdec_step<G>(g, U, i, (uint32_t)((1ull << 31) / (i + 1)), mt, true);
+        gdec_finish(g, U);
         if (g.sub == 0) *status_out = U.st.status;
     });
 }

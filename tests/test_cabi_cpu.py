@@ -71,3 +71,21 @@ def test_plugin_header_compiles(tmp_path):
     cc = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
     subprocess.run([cc, "-std=c++17", "-fsyntax-only", "-Wall", f"-I{ROOT / 'tests'}", f"-I{ROOT / 'include'}",
                     f"-I{ROOT / 'vector_db_id_compression_b200' / 'csrc' / 'plugin'}", str(src)], check=True)
+
+
+def test_mt19937_constants_of_the_device_decoder(tmp_path):
+    """idc_core.cuh's mt_word() holds the first outputs of std::mt19937(1234) (ANSState::stack_slice's fallback source,
+    codec.h:32-40) as immediates on the device; they must be what the standard generator yields."""
+    import re
+    import subprocess
+
+    src = (Path(__file__).resolve().parents[1] / "vector_db_id_compression_b200" / "csrc" / "idc_core.cuh").read_text()
+    m = re.search(r"constexpr uint32_t w\[kMtWords\] = \{([^}]*)\}", src)
+    assert m, "mt_word constants not found"
+    have = [int(x.strip().rstrip("u")) for x in m.group(1).split(",") if x.strip()]
+    prog = tmp_path / "mt.cpp"
+    prog.write_text('#include <random>\n#include <cstdio>\nint main(){std::mt19937 g(1234);for(int i=0;i<8;i++)printf("%u\\n",(unsigned)g());}\n')
+    exe = tmp_path / "mt"
+    subprocess.run(["g++", "-O1", "-o", str(exe), str(prog)], check=True)
+    want = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert have == want

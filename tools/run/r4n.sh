@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+bash tools/ab.sh "IDC_X=0" 2>&1 | tail -1
+bash tools/ab.sh "IDC_DEC_NO_DEFER=1" 2>&1 | tail -1
+bash tools/ab.sh "IDC_X=0" --zipf-s 0 2>&1 | tail -1
+bash tools/ab.sh "IDC_DEC_NO_DEFER=1" --zipf-s 0 2>&1 | tail -1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_roc_decode -s 8 -c 1 -o gpurun_out/r4n_dec -f python tools/probe.py --n 2e8 --zipf 1.0 --ef 0 --reps 2 > gpurun_out/r4n_ncu.log 2>&1
+tail -2 gpurun_out/r4n_ncu.log

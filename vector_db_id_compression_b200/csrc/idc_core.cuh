@@ -247,12 +247,20 @@ IDC_HD void enc_push_id32(EncState& st, uint32_t id, int precision) {
 // the codec's valid domain -- violations are flagged, not assumed away).
 
 // The blob's words are consumed top-down through a ring of kDecRing words in SHARED memory that is kept full by
-// asynchronous copies (cp.async: global -> shared without a destination register). Why not registers: a warp's
-// scoreboard is per register, not per lane -- with 8 units per warp some group re-loads its look-ahead register at
-// almost every pop, and every other group's next read of "its" copy of that register then waits for that load
-// (measured: 570 of the decoder's 3 100 cycles per step, with one and with two words of look-ahead).
-constexpr uint32_t kDecRing = 16;      // words of look-ahead
-constexpr uint32_t kDecRingWait = 8;   // copies allowed in flight when a word is read (it was issued 16 pops ago)
+// asynchronous copies (cp.async: global -> shared without a destination register). Why not global loads into
+// look-ahead registers: a warp's scoreboard is per register, not per lane -- with 8 units per warp some group
+// re-loads its look-ahead register at almost every pop, and every other group's next read of "its" copy of that
+// register then waits for that load (measured: 570 of the decoder's 3 100 cycles per step).
+//
+// The next THREE words sit in registers (pk0..pk2), loaded from the ring once per step by dec_ring_advance(), which
+// the step runs in the shadow of its bucket request together with the refill of the slots that were freed. A
+// renormalisation on the serial chain -- `if (h < 2^31) h = (h << 32) | pop()` -- is then a compare, a select among
+// the three registers and a shift: no memory operation, no pointer update, no branch. Between two calls of
+// dec_ring_advance() a stream of this codec takes at most three words (one by the push -- which leaves the head
+// >= 2^31 -- and one by each of the two 16-bit pops of the next id); a fourth is flagged like a second overlay word.
+constexpr uint32_t kDecRing = 16;      // words of look-ahead in shared memory
+constexpr uint32_t kDecRingWait = 2;   // copy groups (one per step) allowed in flight at a step's rendezvous
+constexpr uint32_t kDecPeek = 3;       // words of look-ahead in registers
 
 struct DecRing {
     uint32_t* base;       // this unit's ring in shared memory: word i at base[(i >> 2) * chunk_stride + (i & 3)]
@@ -287,19 +295,20 @@ struct DecState {
     const uint32_t* words;  // the unit's words (read directly only by the host emulation, see dec_ring_word)
     const uint32_t* fp;  // next word to FETCH into the ring is fp[-1]
     uint32_t fleft;      // words of the blob's stack not fetched yet
-    uint32_t sp;         // words of the blob's stack not popped yet
-    uint32_t rpos;       // ring slot of the next word to pop
-    uint32_t peek;       // that word, read from the ring right after the previous pop (off the critical path)
+    uint32_t sp;         // words of the blob's stack not consumed yet, as of the last dec_ring_advance()
+    uint32_t rpos;       // ring slot of pk0
+    uint32_t pk0, pk1, pk2;  // the next three words pop() returns: the blob's, then the mt19937(1234) fallback of codec.h:32-40
+    uint32_t used;       // how many of them have been taken since the last dec_ring_advance()
     DecRing ring;
     uint32_t fetcher;    // this lane issues the copies (lane 0 of the group that owns the unit)
     uint32_t ov;         // overlay: the one word the decoder may hold above the blob's stack
     uint32_t has_ov;
-    uint32_t draws;
+    uint32_t draws;      // fallback words consumed, as of the last dec_ring_advance()
     uint32_t status;
 };
 
 // every lane of the group calls this; afterwards the caller synchronises the group (the fetching lane has waited
-// for the copies, the other lanes see them after the rendezvous)
+// for the copies, the other lanes see them after the rendezvous) and calls dec_ring_prime()
 IDC_HD void dec_state_init(DecState& st, uint64_t head, const uint32_t* words, uint32_t nwords, DecRing ring, bool fetcher) {
     st.head = head;
     st.words = words;
@@ -317,62 +326,95 @@ IDC_HD void dec_state_init(DecState& st, uint64_t head, const uint32_t* words, u
     st.has_ov = 0;
     st.draws = 0;
     st.status = 0;
-    st.peek = 0;  // set by dec_ring_prime() once the group has met
+    st.pk0 = st.pk1 = st.pk2 = 0;  // set by dec_ring_prime() once the group has met
+    st.used = 0;
 }
 
-// after dec_state_init and a rendezvous of the group
-IDC_HD void dec_ring_prime(DecState& st);
-
-// The word the next pop returns. Device: the ring slot st.rpos (every lane of the warp reads it in the same
-// instruction, long after the copy that filled it has landed). The host emulation's lanes are free-running
-// threads, so there the fetching lane's refill of a slot could overtake a slower lane's read: it reads the blob
-// itself.
-IDC_HD uint32_t dec_ring_word(const DecState& st) {
+// The k-th word below the consumed part of the blob's stack. Device: the ring slot (every lane of the group reads it
+// long after the copy that filled it has landed and a rendezvous has made it visible). The host emulation's lanes
+// are free-running threads, so there the fetching lane's refill of a slot could overtake a slower lane's read: it
+// reads the blob itself.
+IDC_HD uint32_t dec_ring_word(const DecState& st, uint32_t k) {
 #if defined(__CUDA_ARCH__)
-    return *st.ring.at(st.rpos);
+    return *st.ring.at((st.rpos + k) & (kDecRing - 1u));
 #else
-    return st.sp ? st.words[st.sp - 1u] : 0u;
+    return st.words[st.sp - 1u - k];
 #endif
 }
 
-// Once per step, before the first pop: all but the kDecRingWait most recent copy groups have landed. A word is
-// popped kDecRing pops after its copy was issued, at most three pops (= groups) happen per step, and every step ends
-// with a rendezvous of the group, so the word every lane reads is complete and visible.
+// Once per step, before the step's rendezvous: all but the kDecRingWait most recent copy groups (one per step) have
+// landed. A slot is refilled when its word is consumed and read again 14 words -- at three words per step at most,
+// five steps -- later: its copy is waited for at the start of the third step after it and visible after that
+// step's rendezvous.
 IDC_HD void dec_ring_sync() { ring_wait<kDecRingWait>(); }
 
-// `if (h < 2^31) h = (h << 32) | pop()` of codec.cpp:83-87 / :56-60 as straight-line code. pop() = the overlay if
-// there is one, else the blob's next word (from the ring; its slot is refilled at once with the word kDecRing
-// below), else the mt19937(1234) fallback of codec.h:32-40 (only at the very bottom of a stream: the one cold
-// branch).
+// d-th output of std::mt19937(1234). Device: a select chain over immediates, NOT a load from the table -- ptxas puts
+// every global load of a kernel on one scoreboard, so a register that any LDG may write (even on a path never taken)
+// is guarded by a wait for ALL global loads in flight, the step's bucket request included (measured: 1 050 cycles
+// per step in the shadow of that request). tests/test_cabi_cpu.py checks the constants against std::mt19937.
+IDC_HD uint32_t mt_word(uint32_t d, const uint32_t* mt) {
+#if defined(__CUDA_ARCH__)
+    (void)mt;
+    constexpr uint32_t w[kMtWords] = {822569775u, 2137449171u, 2671936806u, 3512589365u,
+                                      1880026316u, 2629000564u, 3373089432u, 3312965625u};
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < (uint32_t)kMtWords; k++) r = d == k ? w[k] : r;
+    return r;
+#else
+    return d < (uint32_t)kMtWords ? mt[d] : 0u;
+#endif
+}
+
+// Account for the `used` words taken since the last call: free their ring slots and refill them with the words
+// kDecRing further down (fetching lane), count fallback draws, reload the look-ahead registers. Off the serial chain:
+// nothing here depends on the step's rank.
+IDC_HD void dec_ring_advance(DecState& st, const uint32_t* mt) {
+    const uint32_t u = st.used;
+    const uint32_t fromblob = u < st.sp ? u : st.sp;
+#pragma unroll
+    for (uint32_t k = 0; k < kDecPeek; k++) {
+        const bool more = (k < fromblob) & (st.fleft != 0u);
+        ring_fetch_if(st.ring.at((st.rpos + k) & (kDecRing - 1u)), st.fp - 1, more & (st.fetcher != 0u));
+        st.fp -= more ? 1 : 0;
+        st.fleft -= more ? 1u : 0u;
+    }
+    ring_commit();
+    st.sp -= fromblob;
+    st.rpos = (st.rpos + fromblob) & (kDecRing - 1u);
+    st.draws += u - fromblob;
+    if (st.draws > (uint32_t)kMtWords) st.status |= kStMtDraws;
+    uint32_t pk[kDecPeek];
+#pragma unroll
+    for (uint32_t k = 0; k < kDecPeek; k++) {
+        if (k < st.sp) {
+            pk[k] = dec_ring_word(st, k);
+        } else {  // below the blob's bottom: the fallback words (cold: the last steps of a stream at most)
+            const uint32_t d = st.draws + (k - st.sp);
+            pk[k] = mt_word(d, mt);
+        }
+    }
+    st.pk0 = pk[0], st.pk1 = pk[1], st.pk2 = pk[2];
+    st.used = 0;
+}
+
+// after dec_state_init and a rendezvous of the group
+IDC_HD void dec_ring_prime(DecState& st, const uint32_t* mt) { dec_ring_advance(st, mt); }
+
+// `if (h < 2^31) h = (h << 32) | pop()` of codec.cpp:83-87 / :56-60 as straight-line register code. pop() = the
+// overlay if there is one, else the next look-ahead word.
 IDC_HD uint64_t dec_renorm(DecState& st, uint64_t h, const uint32_t* mt) {
     const bool rf = h < kRansL;
     const bool o = st.has_ov != 0u;
-    const bool blob = rf & !o;
-    uint32_t* slot = st.ring.at(st.rpos);
-    uint32_t w = o ? st.ov : st.peek;
-    if (blob & (st.sp == 0u)) {
-        uint32_t d = st.draws++;
-        w = 0;
-        if (d >= (uint32_t)kMtWords)
-            st.status |= kStMtDraws;
-        else
-            w = mt[d];
-    } else {
-        const uint32_t dec = blob ? 1u : 0u;
-        const bool more = blob & (st.fleft != 0u);
-        ring_fetch_if(slot, st.fp - 1, more & (st.fetcher != 0u));
-        st.sp -= dec;
-        st.rpos = (st.rpos + dec) & (kDecRing - 1u);
-        st.fp -= more ? 1 : 0;
-        st.fleft -= more ? 1u : 0u;
-        st.peek = dec_ring_word(st);  // (same slot again when nothing was popped)
-    }
-    ring_commit();
+    const bool take = rf & !o;
+    (void)mt;
+    st.status |= (take & (st.used >= kDecPeek)) ? kStOverlay : 0u;  // a fourth word inside one step: not a stream of this codec
+    const uint32_t pk = st.used == 0u ? st.pk0 : (st.used == 1u ? st.pk1 : st.pk2);
+    const uint32_t w = o ? st.ov : pk;
+    st.used += take ? 1u : 0u;
     st.has_ov = rf ? 0u : st.has_ov;
     return rf ? ((h << 32) | (uint64_t)w) : h;
 }
-
-IDC_HD void dec_ring_prime(DecState& st) { st.peek = dec_ring_word(st); }
 
 // codec.cpp:78-90; p in 0..16
 IDC_HD uint32_t dec_pop_bits(DecState& st, uint32_t p, const uint32_t* mt) {

@@ -43,6 +43,7 @@ struct Grp {
     }
     __device__ __forceinline__ uint32_t shfl_xor(uint32_t v, uint32_t m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ bool warp_any(bool p) const { return __any_sync(0xffffffffu, p); }  // all groups of the warp
     __device__ __forceinline__ void host_sync() const { __syncwarp(); }  // off the critical path where it is used
 };
 #endif
@@ -462,34 +463,102 @@ struct GDecHit {
     bool normal;    // bucket path taken (unit has work and is not degenerate)
 };
 
-// rank of v among the ids decoded so far. The only collective (the final sum) is reached by every lane of the
-// warp; `act` false: no memory is touched.
-template <int G, class GR, typename OutT>
-IDC_HD uint32_t gdec_rank(const GR& g, const GDecTree& t, uint32_t v, const OutT* out_prev, uint32_t decoded, bool act,
-                          GDecHit& hit) {
+template <class GR>
+IDC_HD void gdec_insert(const GR& g, GDecTree& t, uint32_t v, const GDecHit& hit);
+
+template <typename OutT>
+struct GDecUnit {
+    DecState st;
+    GDecTree tree;
+    OutT* out;  // the unit's n output slots
+    uint32_t n;
+    int prec;
+    // The insert of the previous step, not applied yet: the bucket store, the three counters and the output store of
+    // step i do not feed step i + 1's bucket REQUEST (only its count word, checked below), so they are issued in the
+    // shadow of that request instead of in front of it -- a warp is one instruction stream, and whatever stands
+    // between "rank known" and "next line requested" is on the unit's serial chain whether it depends on it or not.
+    GDecHit pend_hit;
+    uint32_t pend_id, pend_pos, pend_has;
+    uint32_t no_defer;  // experiments (IDC_DEC_NO_DEFER=1): every insert is applied ahead of the next request
+};
+
+template <typename OutT>
+IDC_HD void gdec_unit_start(GDecUnit<OutT>& U) {
+    U.pend_has = 0, U.pend_id = 0, U.pend_pos = 0, U.no_defer = 0;
+    U.pend_hit.normal = false, U.pend_hit.b = 0, U.pend_hit.cnt = 0, U.pend_hit.w0 = 0, U.pend_hit.p0 = nullptr;
+}
+
+// apply the pending insert (lane 0 stores); the caller synchronises the group before anything reads it back
+template <class GR, typename OutT>
+IDC_HD void gdec_flush(const GR& g, GDecUnit<OutT>& U) {
+    if (!U.pend_has) return;
+    gdec_insert(g, U.tree, U.pend_id, U.pend_hit);
+    if (g.sub == 0) U.out[U.pend_pos] = (OutT)U.pend_id;
+    if (U.tree.degenerate) U.st.status |= kStDegenerate;
+    U.pend_has = 0;
+}
+
+// rank of v among the ids decoded so far, the previous step's insert applied on the way. The collectives (the
+// warp-wide vote, the rendezvous after the flush, the final sum) are reached by every lane of the warp; `act`
+// false: no memory is touched. `shadow()` is work of the caller that nothing here depends on (table look-ahead);
+// it runs while the bucket request is in flight.
+template <int G, class GR, typename OutT, class Shadow>
+IDC_HD uint32_t gdec_rank(const GR& g, GDecUnit<OutT>& U, uint32_t v, uint32_t decoded, bool act, GDecHit& hit,
+                          const uint32_t* mt, Shadow&& shadow) {
     constexpr int SL = 32 / G;  // bucket slots per lane and line
+    GDecTree& t = U.tree;
     uint32_t part = 0;
-    hit.normal = act && !t.degenerate;
     hit.b = 0, hit.cnt = 0, hit.w0 = 0, hit.p0 = nullptr;
-    if (act && t.degenerate) {
-        for (uint32_t i = g.sub; i < decoded; i += (uint32_t)G) part += ((uint32_t)out_prev[i] < v) ? 1u : 0u;
-    } else if (act) {
-        const uint32_t b = gdec_bucket(t, v);
-        const uint32_t grp = b >> 4, sct = grp >> 4;
+    bool normal = act && !t.degenerate;
+    uint32_t b = 0;
+    uint32_t* p0 = nullptr;
+    if (normal) {
+        b = gdec_bucket(t, v);
+        p0 = t.sm.at(t.sm_l0 + (b >> 2));
+    }
+    // The pending insert must be in place BEFORE the request when this step reads what it writes ahead of the
+    // request -- the bucket's count word (4 buckets per word), hence also the bucket itself -- or when it may change
+    // the unit's mode (an overflowing bucket can fill the spill list: brute-force ranks from then on), or when this
+    // step does not take the bucket path at all. Rare (a few steps in a thousand); decided for the whole warp.
+    const bool hazard = U.pend_has && (U.no_defer || !normal || !U.pend_hit.normal || U.pend_hit.cnt >= kBkSlots || (b >> 2) == (U.pend_hit.b >> 2));
+    const bool early = g.warp_any(hazard);
+    if (early) {
+        dec_ring_advance(U.st, mt);
+        gdec_flush(g, U);
+        g.sync();
+        normal = act && !t.degenerate;
+    }
+    hit.normal = normal;
+    uint32_t s0[SL], s1[SL];
+    bool need0 = false, need1 = false;
+    uint32_t cnt = 0;
+    if (normal) {
         // this bucket's count (same word in every lane) decides which slices of the bucket are fetched: DRAM
         // traffic and latency follow the number of 32-byte sectors asked for (fetching all four sectors of the
         // first line unconditionally, before the count is known, was measured 10 % slower)
-        uint32_t* p0 = t.sm.at(t.sm_l0 + (b >> 2));
         const uint32_t w0 = *p0;
-        const uint32_t cnt = (w0 >> (8u * (b & 3u))) & 0xffu;
+        cnt = (w0 >> (8u * (b & 3u))) & 0xffu;
         hit.b = b, hit.cnt = cnt, hit.w0 = w0, hit.p0 = p0;
         const uint32_t sv = cnt < kBkSlots ? cnt : kBkSlots;
         const uint32_t* bk = t.rec + (size_t)b * kBkSlots;
-        uint32_t s0[SL], s1[SL];
-        const bool need0 = sv > g.sub * SL, need1 = sv > 32u + g.sub * SL;
+        need0 = sv > g.sub * SL, need1 = sv > 32u + g.sub * SL;
         if (need0) ld_line_slice<SL>(bk, g.sub, s0);
         if (need1) ld_line_slice<SL>(bk + 32u, g.sub, s1);
-        issue_fence();  // the bucket fetch is in flight before the count levels are read
+    }
+    issue_fence();  // the bucket fetch is in flight before anything below is issued
+    if (!early) {
+        dec_ring_advance(U.st, mt);
+        gdec_flush(g, U);
+        shadow();
+        g.sync();  // the insert (and the stream words that have landed) are visible to every lane of the group
+    } else {
+        shadow();
+    }
+    if (act && !normal) {
+        const OutT* out_prev = U.out + (U.n - decoded);
+        for (uint32_t i = g.sub; i < decoded; i += (uint32_t)G) part += ((uint32_t)out_prev[i] < v) ? 1u : 0u;
+    } else if (normal) {
+        const uint32_t grp = b >> 4, sct = grp >> 4;
         // ---- counts below the bucket, one slice per lane
 #pragma unroll
         for (uint32_t j0 = 0; j0 < 4u; j0 += (uint32_t)G) {
@@ -535,8 +604,7 @@ IDC_HD uint32_t gdec_rank(const GR& g, const GDecTree& t, uint32_t v, const OutT
     return group_sum(g, part, G);
 }
 
-// record v in its bucket and bump the three count levels (after the coder state has moved on: nothing of the
-// next step's critical path waits for these stores)
+// record v in its bucket and bump the three count levels
 template <class GR>
 IDC_HD void gdec_insert(const GR& g, GDecTree& t, uint32_t v, const GDecHit& hit) {
     if (!hit.normal) return;
@@ -558,30 +626,37 @@ IDC_HD void gdec_insert(const GR& g, GDecTree& t, uint32_t v, const GDecHit& hit
     }
 }
 
-template <typename OutT>
-struct GDecUnit {
-    DecState st;
-    GDecTree tree;
-    OutT* out;  // the unit's n output slots
-    uint32_t n;
-    int prec;
+struct NoShadow {
+    IDC_HD void operator()() const {}
 };
 
-// i = 0-based step; q31 = 2^31 / (i + 1)
-template <int G, class GR, typename OutT>
-IDC_HD void gdec_step(const GR& g, GDecUnit<OutT>& U, uint32_t i, uint32_t q31, const uint32_t* mt, bool act) {
+// i = 0-based step; q31 = 2^31 / (i + 1). The step's insert and output store stay pending until the next step (or
+// gdec_finish) applies them.
+template <int G, class GR, typename OutT, class Shadow = NoShadow>
+IDC_HD void gdec_step(const GR& g, GDecUnit<OutT>& U, uint32_t i, uint32_t q31, const uint32_t* mt, bool act,
+                      Shadow&& shadow = Shadow()) {
     uint32_t id = 0;
+    // the fetching lane's copies of three and more steps ago have landed; the rendezvous in gdec_rank() makes them
+    // visible to the group. (Not in the shadow of the bucket request: the wait is a DEPBAR on the scoreboard the
+    // compiler also gives the bucket loads, and with a threshold this low it would wait for them -- measured.)
     dec_ring_sync();
     if (act) id = dec_pop_id32(U.st, U.prec, mt);
     GDecHit hit;
-    const uint32_t rank = gdec_rank<G>(g, U.tree, id, U.out + (U.n - i), i, act, hit);
+    const uint32_t rank = gdec_rank<G>(g, U, id, i, act, hit, mt, shadow);
     if (act) {
         dec_push_uniform(U.st, rank, i + 1u, q31, mt);
-        gdec_insert(g, U.tree, id, hit);
-        if (g.sub == 0) U.out[U.n - 1u - i] = (OutT)id;
-        if (U.tree.degenerate) U.st.status |= kStDegenerate;
+        U.pend_hit = hit;
+        U.pend_id = id;
+        U.pend_pos = U.n - 1u - i;
+        U.pend_has = 1u;
     }
-    g.sync();  // the bucket / count / output stores of this step are ordered before the next step's loads
+}
+
+// after the last step: the last insert's output store (every lane of the warp calls this)
+template <class GR, typename OutT>
+IDC_HD void gdec_finish(const GR& g, GDecUnit<OutT>& U) {
+    gdec_flush(g, U);
+    g.sync();
 }
 
 }  // namespace idc

@@ -261,6 +261,7 @@ struct DecArgs {
     uint32_t* progress;
     uint32_t ms_seg;
     uint32_t ms_count;
+    uint32_t no_defer;          // experiments: IDC_DEC_NO_DEFER=1
 };
 
 template <int G, typename OutT>
@@ -302,16 +303,22 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
     U.tree = gdec_tree_at(a.ws + (row_mode ? (uint64_t)slot * a.slot_ws : (valid ? a.sel_ws[slot] : 0ull)), sm, n ? n : 1u,
                           valid ? a.unit_lo[u] : 0u, valid ? a.unit_hi[u] : 0u);
     __syncwarp();
-    dec_ring_prime(U.st);
+    dec_ring_prime(U.st, a.mt);
     const uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
     // 2^31 / (i + 1) from the table, 32 entries per coalesced load and one block ahead (see k_roc_encode)
     auto tab_q31 = [&](uint32_t ib) { uint32_t e = ib + lane_id + 1u; return __ldg(a.q31 + (e <= kMaxUnit ? e : kMaxUnit)); };
     uint32_t ib = 0;                          // block covers i = ib .. ib+31
     uint32_t q31_blk = tab_q31(0), q31_nxt = tab_q31(32);
     uint32_t q31_next = __shfl_sync(0xffffffffu, q31_blk, 0);  // one step ahead, see k_roc_encode
+    gdec_unit_start(U);
+    U.no_defer = a.no_defer;
+    // milestone m is reported once step (m + 1) * ms_seg has RUN: it applied the pending output store of the step before
     uint32_t ms_next = a.progress ? a.ms_seg : 0xffffffffu, ms_done = 0;
     for (uint32_t i = 0; i < tmax; ++i) {
         const uint32_t q31 = q31_next;
+        // The table look-ahead for step i + 1: the block refresh (a global load every 32 steps) stays in front of the
+        // pops -- behind the bucket request it would wait for it (one scoreboard for all global loads) -- the
+        // shuffle runs in the shadow of the request.
         {
             const uint32_t in = i + 1u;
             if (in - ib == 32u) {
@@ -319,10 +326,10 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
                 q31_blk = q31_nxt;
                 q31_nxt = tab_q31(ib + 32u);
             }
-            q31_next = __shfl_sync(0xffffffffu, q31_blk, in - ib);
         }
-        gdec_step<G>(g, U, i, q31, a.mt, i < n);
-        if (i + 1u == ms_next) {  // warp-uniform
+        auto look_ahead = [&]() { q31_next = __shfl_sync(0xffffffffu, q31_blk, i + 1u - ib); };
+        gdec_step<G>(g, U, i, q31, a.mt, i < n, look_ahead);
+        if (i == ms_next) {  // warp-uniform
             if (ms_done < a.ms_count) {
                 __threadfence();
                 __syncwarp();
@@ -332,6 +339,7 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
             ms_next += a.ms_seg;
         }
     }
+    gdec_finish(g, U);
     if (a.progress) {  // a warp of shorter units reports the milestones it never reached: nothing of it is awaited
         __threadfence();
         __syncwarp();
@@ -1083,6 +1091,7 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     a.slot_ws = slot_ws;
     a.nrows = (uint32_t)b->nlist;
     a.row_base = (uint32_t)row_base;
+    a.no_defer = getenv("IDC_DEC_NO_DEFER") ? 1u : 0u;
     {
         auto cls = size_classes(nsel, n_of_slot);
         (void)max_n;
