@@ -73,6 +73,7 @@ static void group_decode(uint64_t head, const uint32_t* words, uint32_t nwords, 
         dec_state_init(U.st, head, words, nwords, DecRing{ring.data(), 4u}, g.sub == 0);
         g.sync();
         dec_ring_prime(U.st, mt);
+        dec_pop_start(U.st, mt);
         U.out = out;
         U.n = n;
         U.prec = prec;

@@ -424,11 +424,19 @@ IDC_HD uint32_t dec_pop_bits(DecState& st, uint32_t p, const uint32_t* mt) {
     return sym;
 }
 
-// codec.cpp:107-121 for precision <= 32: the slices at lower = 48 and 32 have precision 0 -- they pop nothing
-// but still renormalise (codec.cpp:83-87); never needed after a push_with_finer_precision, kept for exactness.
+// codec.cpp:107-121 for precision <= 32: the slices at lower = 48 and 32 have precision 0 -- they pop nothing but
+// still renormalise (codec.cpp:83-87). The encoder leaves every head >= 2^31 (its initial state is 2^31, a
+// vrans_push never ends below it), and what the decoder pops from is the head a push_with_finer_precision left --
+// the encoder's head before the matching pop -- so inside a stream of this codec those two renormalisations do
+// nothing. dec_pop_start() runs them once, for whatever head a blob was imported with; the per-id pop flags a head
+// below 2^31 (not a stream of this codec) instead of branching on it.
+IDC_HD void dec_pop_start(DecState& st, const uint32_t* mt) {
+    if (st.head < kRansL) st.head = dec_renorm(st, st.head, mt);
+    if (st.head < kRansL) st.head = dec_renorm(st, st.head, mt);
+}
+
 IDC_HD uint32_t dec_pop_id32(DecState& st, int precision, const uint32_t* mt) {
-    if (st.head < kRansL) st.head = dec_renorm(st, st.head, mt);
-    if (st.head < kRansL) st.head = dec_renorm(st, st.head, mt);
+    st.status |= st.head < kRansL ? kStOverlay : 0u;
     const uint32_t p0 = precision < 16 ? (uint32_t)precision : 16u;
     const uint32_t p1 = (uint32_t)precision - p0;
     const uint32_t hi = dec_pop_bits(st, p1, mt);

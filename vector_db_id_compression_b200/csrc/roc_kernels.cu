@@ -261,7 +261,6 @@ struct DecArgs {
     uint32_t* progress;
     uint32_t ms_seg;
     uint32_t ms_count;
-    uint32_t no_defer;          // experiments: IDC_DEC_NO_DEFER=1
 };
 
 template <int G, typename OutT>
@@ -304,6 +303,7 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
                           valid ? a.unit_lo[u] : 0u, valid ? a.unit_hi[u] : 0u);
     __syncwarp();
     dec_ring_prime(U.st, a.mt);
+    dec_pop_start(U.st, a.mt);
     const uint32_t tmax = __reduce_max_sync(0xffffffffu, n);
     // 2^31 / (i + 1) from the table, 32 entries per coalesced load and one block ahead (see k_roc_encode)
     auto tab_q31 = [&](uint32_t ib) { uint32_t e = ib + lane_id + 1u; return __ldg(a.q31 + (e <= kMaxUnit ? e : kMaxUnit)); };
@@ -311,7 +311,6 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
     uint32_t q31_blk = tab_q31(0), q31_nxt = tab_q31(32);
     uint32_t q31_next = __shfl_sync(0xffffffffu, q31_blk, 0);  // one step ahead, see k_roc_encode
     gdec_unit_start(U);
-    U.no_defer = a.no_defer;
     // milestone m is reported once step (m + 1) * ms_seg has RUN: it applied the pending output store of the step before
     uint32_t ms_next = a.progress ? a.ms_seg : 0xffffffffu, ms_done = 0;
     for (uint32_t i = 0; i < tmax; ++i) {
@@ -1091,7 +1090,6 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     a.slot_ws = slot_ws;
     a.nrows = (uint32_t)b->nlist;
     a.row_base = (uint32_t)row_base;
-    a.no_defer = getenv("IDC_DEC_NO_DEFER") ? 1u : 0u;
     {
         auto cls = size_classes(nsel, n_of_slot);
         (void)max_n;
