@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3",
     "--expt-relaxed-constexpr",
+    *os.environ.get("IDC_NVCC_EXTRA", "").split(),
 ]
 
 

@@ -180,8 +180,13 @@ IDC_HD uint32_t genc_sm_init_word(uint32_t n, const EncTreeLayout& L, uint32_t w
 // 66.7 -> 61.3 ms), the 4-lane classes lose 5 % (Zipf: 103.9 -> 108.7 ms) -- so it follows the lane count.
 template <int G>
 struct EncSearch {
-    static constexpr bool kLocal = G == 2;
-    static constexpr int kEa = kLocal ? 16 : 16 / G;  // level-A entries held by a lane
+    static constexpr bool kLocal = G == 2;            // levels A and B by every lane on its own
+#if defined(IDC_ENC_LOCAL_A)
+    static constexpr bool kLocalA = true;             // experiment: level A alone (registers only) local for every width
+#else
+    static constexpr bool kLocalA = kLocal;
+#endif
+    static constexpr int kEa = kLocalA ? 16 : 16 / G;  // level-A entries held by a lane
 };
 
 template <int G>
@@ -199,8 +204,7 @@ IDC_HD void genc_tree_init(const GR& g, GEncTree<G>& t, uint32_t n) {
     t.sm_l0 = 8u * L.supers;
     const uint32_t total = t.sm_l0 + L.l0_words;
     for (uint32_t w = g.sub; w < total; w += (uint32_t)G) *t.sm.at(w) = genc_sm_init_word(n, L, w);
-    constexpr bool kEncLocalSearch = EncSearch<G>::kLocal;
-    if (kEncLocalSearch) {
+    if (EncSearch<G>::kLocalA) {
 #pragma unroll
         for (int j = 0; j < 16; j++) t.ea[j % EncSearch<G>::kEa] = enc_full_before(n, (uint32_t)j * kRecPerSuper);
     } else {
@@ -268,13 +272,23 @@ IDC_HD uint32_t genc_select_remove(const GR& g, GEncTree<G>& t, uint32_t k, uint
     uint32_t base, sb, p;
     uint32_t wb[kEncLocalSearch ? 8 : WB];
     uint32_t* pb;
-    if (kEncLocalSearch) {
+    constexpr bool kLocalA = EncSearch<G>::kLocalA;
+    if (kLocalA) {
         // ---- level A (registers, every lane all 16 entries)
         uint32_t ea16[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) ea16[j] = t.ea[j % EncSearch<G>::kEa];
         sb = local_cum_find(ea16, k, base);
         k -= base;
+    } else {
+        // ---- level A (registers, 16/G entries per lane)
+        uint32_t eal[EA];
+#pragma unroll
+        for (int j = 0; j < EA; j++) eal[j] = t.ea[j % EncSearch<G>::kEa];
+        sb = group_cum_find<EA>(g, eal, k, base);
+        k -= base;
+    }
+    if (kEncLocalSearch) {
         // ---- level B (every lane loads the superblock's 8 words)
 #pragma unroll
         for (int j = 0; j < 8; j++) wb[j % (kEncLocalSearch ? 8 : WB)] = 0u;
@@ -295,12 +309,6 @@ IDC_HD uint32_t genc_select_remove(const GR& g, GEncTree<G>& t, uint32_t k, uint
         p = local_cum_find(eb16, k, base);
         k -= base;
     } else {
-        // ---- level A (registers, 16/G entries per lane)
-        uint32_t eal[EA];
-#pragma unroll
-        for (int j = 0; j < EA; j++) eal[j] = t.ea[j];
-        sb = group_cum_find<EA>(g, eal, k, base);
-        k -= base;
         // ---- level B
         uint32_t eb[2 * WB];
 #pragma unroll
@@ -343,9 +351,14 @@ IDC_HD uint32_t genc_select_remove(const GR& g, GEncTree<G>& t, uint32_t k, uint
     // ---- the count updates ride in the shadow of the line fetch; every lane updates its own entries only
     g.host_sync();  // all lanes have read the C words before lane 0 rewrites one (racecheck: warp-level WAR)
     if (act) {
-        if (kEncLocalSearch) {
+        if (kLocalA) {
 #pragma unroll
             for (int j = 1; j < 16; j++) t.ea[j % EncSearch<G>::kEa] -= ((uint32_t)j > sb) ? 1u : 0u;
+        } else {
+#pragma unroll
+            for (int j = 0; j < EA; j++) t.ea[j % EncSearch<G>::kEa] -= (g.sub * EA + (uint32_t)j > sb) ? 1u : 0u;
+        }
+        if (kEncLocalSearch) {
             if (g.sub == 0) {  // one lane rewrites the superblock's 8 words
                 uint32_t h0[4], h1[4];
 #pragma unroll
@@ -358,8 +371,6 @@ IDC_HD uint32_t genc_select_remove(const GR& g, GEncTree<G>& t, uint32_t k, uint
                 sm_store<4>(t.sm.at(8u * sb + 4u), h1);
             }
         } else {
-#pragma unroll
-            for (int j = 0; j < EA; j++) t.ea[j] -= (g.sub * EA + (uint32_t)j > sb) ? 1u : 0u;
             uint32_t wl[WB];
 #pragma unroll
             for (int j = 0; j < WB; j++) {
