@@ -220,7 +220,10 @@ int idc_roc_blob_load(idc_ctx* ctx, const char* path, idc_roc_blob** out);
  * in bulk. list_nos (HOST, may be NULL = all lists in order) selects nsel lists;
  * ids_out receives them concatenated, each list in the reference's decode
  * order (for multi-unit lists: unit after unit). out_offsets (HOST, nsel+1,
- * may be NULL) receives the CSR offsets of the output. */
+ * may be NULL) receives the CSR offsets of the output.
+ * Whole-index decodes into HOST memory (list_nos == NULL, >= 2^22 ids) overlap the download with the kernels; when
+ * ids_out is pinned or registered host memory (cudaHostAlloc / cudaHostRegister) the ids of the longest units leave
+ * while their chains are still running. Pageable memory works, without that overlap. */
 int idc_roc_decode(
         idc_ctx* ctx,
         const idc_roc_blob* blob,

@@ -1029,12 +1029,12 @@ MemcpyBatchFn memcpy_batch() {
 inline uint32_t ms_parts() {
     if (const char* e = getenv("IDC_MS_PARTS")) {  // experiments
         int v = atoi(e);
-        if (v >= 2 && v <= 8) return (uint32_t)v;
+        if (v >= 2 && v <= 16) return (uint32_t)v;
     }
     return 8;  // the longest class's output leaves in this many pieces per unit
 }
 constexpr uint32_t kMsMinUnit = 16384;    // ... when its units are at least this long
-constexpr uint32_t kMsWordOffset = 8;     // the counters live behind the status word (words 8 .. 15 of the status buffer)
+constexpr uint32_t kMsWordOffset = 8;     // the counters live behind the status word (words 8 .. 23 of the status buffer)
 
 int finish_decode(idc_ctx* c) {
     uint32_t st = 0;
@@ -1056,9 +1056,9 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
         return IDC_OK;
     }
     IDC_TRY(c->ws.reserve(ws_bytes + 256));
-    IDC_TRY(c->status.reserve(64));
+    IDC_TRY(c->status.reserve(128));
     uint32_t* d_status = c->status.as<uint32_t>();
-    IDC_CUDA(cudaMemsetAsync(d_status, 0, 64, c->stream));
+    IDC_CUDA(cudaMemsetAsync(d_status, 0, 128, c->stream));
     if (ov && ov->want_ms) {
         IDC_TRY(c->sync_event(&ov->ms_armed));
         IDC_CUDA(cudaEventRecord(ov->ms_armed, c->stream));
