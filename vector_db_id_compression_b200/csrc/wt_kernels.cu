@@ -430,14 +430,27 @@ __global__ void __launch_bounds__(kThreads) k_wt_emit(WtEmitArgs a) {
     if (base >= a.total) return;
     uint32_t own[16];
     tile_owners(a.out_off, a.nsel, base, a.total - 1, lane, own);
+    // lists are long compared to a tile: the two table entries of an element's list are re-read only when the list changes
+    uint32_t cur = 0xffffffffu;
+    int64_t delta = 0;  // payload position minus output position inside the current list
+    uint32_t v[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) {
         uint64_t e = base + (uint64_t)t * 32 + lane;
+        v[t] = 0;
         if (e < a.total) {
-            uint64_t L = a.sel ? __ldg(a.sel + own[t]) : own[t];
-            uint64_t src = (uint64_t)__ldg(a.start + L) + (e - __ldg(a.out_off + own[t]));
-            reinterpret_cast<OutT*>(a.out)[e] = (OutT)__ldg(a.payload + src);
+            if (own[t] != cur) {
+                cur = own[t];
+                uint64_t L = a.sel ? __ldg(a.sel + cur) : cur;
+                delta = (int64_t)__ldg(a.start + L) - (int64_t)__ldg(a.out_off + cur);
+            }
+            v[t] = __ldg(a.payload + (uint64_t)((int64_t)e + delta));
         }
+    }
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        uint64_t e = base + (uint64_t)t * 32 + lane;
+        if (e < a.total) reinterpret_cast<OutT*>(a.out)[e] = (OutT)v[t];
     }
 }
 
