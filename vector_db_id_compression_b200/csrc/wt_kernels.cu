@@ -412,6 +412,74 @@ __global__ void __launch_bounds__(kThreads) k_wt_replay(const uint32_t* __restri
     }
 }
 
+// Two levels per pass. The elements of a tile with bit 0 at level v sit next to each other at level v + 1 (stable
+// partition: positions [base - r1, base - r1 + zeros of the tile)), those with bit 1 likewise ([z + r1, ...)): each
+// run is at most 512 positions long, hence inside a window of two rank blocks of level v + 1 -- 32 words, one per
+// lane, with a warp prefix sum of their popcounts on top of the window's directory entry. An element then finds its
+// bit and the ones before it at level v + 1 with two shuffles per side, and moves straight to its place at level
+// v + 2: the payload crosses HBM once for two levels.
+template <bool kIota>
+__global__ void __launch_bounds__(kThreads, 12) k_wt_replay2(const uint32_t* __restrict__ in, uint32_t n, uint32_t nblk,
+                                                         const uint64_t* __restrict__ bits0, const uint32_t* __restrict__ rank0,
+                                                         const uint64_t* __restrict__ bits1, const uint32_t* __restrict__ rank1,
+                                                         uint32_t* __restrict__ out) {
+    // per warp: [0, 32) window words of the zero side, [32, 64) of the one side, [64, 128) their exclusive prefixes
+    __shared__ uint32_t s_win[kThreads / 32][128];
+    const uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // all positions fit 32 bits (ntotal < 2^32 - 4096)
+    const uint32_t lane = threadIdx.x & 31u;
+    if (blk >= nblk) return;
+    uint32_t* win = s_win[threadIdx.x >> 5];
+    const uint32_t base = blk << kWtBlockLog;
+    const uint32_t z0 = n - __ldg(rank0 + nblk), z1 = n - __ldg(rank1 + nblk);
+    const uint32_t r1 = __ldg(rank0 + blk);
+    const uint32_t word = lane < 16 ? __ldg(reinterpret_cast<const uint32_t*>(bits0) + (size_t)blk * 16 + lane) : 0u;
+    uint32_t v[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        const uint32_t i = base + (uint32_t)t * 32 + lane;
+        v[t] = kIota ? i : (i < n ? __ldg(in + i) : 0u);
+    }
+    // the two windows of level v + 1
+    const uint32_t zs = base - r1, os = z0 + r1;  // where the tile's zeros / ones start at level v + 1
+    const uint32_t zb = zs >> kWtBlockLog, ob = os >> kWtBlockLog;
+    const uint32_t nwords = nblk * 16;
+    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(bits1);
+    const uint32_t zi = zb * 16 + lane, oi = ob * 16 + lane;
+    const uint32_t wz = zi < nwords ? __ldg(w1 + zi) : 0u, wo = oi < nwords ? __ldg(w1 + oi) : 0u;
+    const uint32_t cz = (uint32_t)__popc(wz), co = (uint32_t)__popc(wo);
+    uint32_t pz = cz, po = co;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(kFull, pz, d), b = __shfl_up_sync(kFull, po, d);
+        if (lane >= (uint32_t)d) pz += a, po += b;
+    }
+    // exclusive prefix = ones of level v + 1 before the lane's window word
+    win[lane] = wz;
+    win[32 + lane] = wo;
+    win[64 + lane] = pz - cz + __ldg(rank1 + (zb <= nblk ? zb : nblk));
+    win[96 + lane] = po - co + __ldg(rank1 + (ob <= nblk ? ob : nblk));
+    __syncwarp();
+    const uint32_t zwin = zb << kWtBlockLog, owin = ob << kWtBlockLog;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t ones = r1;  // ones of level v before the current round
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        const uint32_t i = base + (uint32_t)t * 32 + lane;
+        const uint32_t m = __shfl_sync(kFull, word, t);  // bits past n are zero: they were built from zero symbols
+        const uint32_t b0 = (m >> lane) & 1u;
+        const uint32_t ones_before = ones + (uint32_t)__popc(m & lt);
+        const uint32_t p = b0 ? z0 + ones_before : i - ones_before;  // position at level v + 1
+        const uint32_t rel = p - (b0 ? owin : zwin);                 // < 1024 for every valid element
+        const uint32_t src = ((rel >> 5) & 31u) + (b0 << 5);
+        const uint32_t x = win[src], y = win[64 + src];
+        const uint32_t sh = rel & 31u;
+        const uint32_t b1 = (x >> sh) & 1u;
+        const uint32_t ones_before1 = y + (uint32_t)__popc(x & ((1u << sh) - 1u));
+        if (i < n) out[b1 ? z1 + ones_before1 : p - ones_before1] = v[t];
+        ones += (uint32_t)__popc(m);
+    }
+}
+
 struct WtEmitArgs {
     const uint32_t* payload;
     const uint32_t* start;
@@ -1015,14 +1083,26 @@ int idc_wt_decode(idc_ctx* c, const idc_wt_blob* b, const uint64_t* list_nos, ui
             IDC_TRY(wt_expand(c, b, c->scratch.as<uint64_t>()));
             all_bits = c->scratch.as<uint64_t>();
         }
-        for (uint32_t lev = 0; lev < sh.levels; lev++) {
+        const bool two = getenv("IDC_WT_REPLAY1") == nullptr;  // (experiments: one level per pass)
+        for (uint32_t lev = 0; lev < sh.levels;) {
             LaunchScope ls(c, "k_wt_replay");
             const uint64_t* bits = all_bits + (uint64_t)lev * sh.words;
             const uint32_t* rank = b->d_rank + (uint64_t)lev * sh.rank_stride;
-            if (lev == 0)
-                k_wt_replay<true><<<warp_grid, kThreads, 0, c->stream>>>(nullptr, sh.n, sh.nblk, bits, rank, out);
-            else
-                k_wt_replay<false><<<warp_grid, kThreads, 0, c->stream>>>(in, sh.n, sh.nblk, bits, rank, out);
+            if (two && lev + 1 < sh.levels) {  // two levels per pass
+                const uint64_t* bits1 = bits + sh.words;
+                const uint32_t* rank1 = rank + sh.rank_stride;
+                if (lev == 0)
+                    k_wt_replay2<true><<<warp_grid, kThreads, 0, c->stream>>>(nullptr, (uint32_t)sh.n, (uint32_t)sh.nblk, bits, rank, bits1, rank1, out);
+                else
+                    k_wt_replay2<false><<<warp_grid, kThreads, 0, c->stream>>>(in, (uint32_t)sh.n, (uint32_t)sh.nblk, bits, rank, bits1, rank1, out);
+                lev += 2;
+            } else {
+                if (lev == 0)
+                    k_wt_replay<true><<<warp_grid, kThreads, 0, c->stream>>>(nullptr, sh.n, sh.nblk, bits, rank, out);
+                else
+                    k_wt_replay<false><<<warp_grid, kThreads, 0, c->stream>>>(in, sh.n, sh.nblk, bits, rank, out);
+                lev += 1;
+            }
             in = out;
             out = out == bufA ? bufB : bufA;
         }
