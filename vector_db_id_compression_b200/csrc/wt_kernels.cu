@@ -313,31 +313,34 @@ __global__ void __launch_bounds__(kThreads) k_wt_directory(const uint32_t* __res
     if (d.has0) sel0[d.m0] = (uint32_t)j;
 }
 
-// stable partition of a level by its bit: zeros keep their order in [0, z), ones theirs in [z, n)
+// stable partition of a level by its bit: zeros keep their order in [0, z), ones theirs in [z, n). All positions in
+// 32 bits (ntotal < 2^32 - 4096 is a precondition of the structure): the 64-bit version of this pass was issue-bound.
 template <typename InT, typename OutT>
-__global__ void __launch_bounds__(kThreads) k_wt_level_scatter(const InT* __restrict__ seq, uint64_t n, uint64_t nblk,
+__global__ void __launch_bounds__(kThreads) k_wt_level_scatter(const InT* __restrict__ seq, uint64_t n64, uint64_t nblk64,
                                                                uint32_t shift, const uint32_t* __restrict__ rank,
                                                                OutT* __restrict__ next) {
-    const uint64_t blk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n = (uint32_t)n64, nblk = (uint32_t)nblk64;
+    const uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     if (blk >= nblk) return;
-    const uint64_t base = blk << kWtBlockLog;
-    const uint64_t z = n - __ldg(rank + nblk);
-    uint64_t r1 = __ldg(rank + blk);
+    const uint32_t base = blk << kWtBlockLog;
+    const uint32_t z = n - __ldg(rank + nblk);
+    uint32_t r1 = __ldg(rank + blk);
+    const uint32_t lt = (1u << lane) - 1u;
     uint32_t v[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        uint64_t i = base + (uint64_t)t * 32 + lane;
+        const uint32_t i = base + (uint32_t)t * 32 + lane;
         v[t] = i < n ? (uint32_t)__ldg(seq + i) : 0u;
     }
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        uint64_t i = base + (uint64_t)t * 32 + lane;
-        bool valid = i < n;
-        uint32_t b = (v[t] >> shift) & 1u;
-        uint32_t m = __ballot_sync(kFull, valid && b);
-        uint64_t ones_before = r1 + (uint32_t)__popc(m & ((1u << lane) - 1u));
-        if (valid) next[wt_partition_dest(i, b, z, ones_before)] = (OutT)v[t];
+        const uint32_t i = base + (uint32_t)t * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t b = (v[t] >> shift) & 1u;
+        const uint32_t m = __ballot_sync(kFull, valid && b);
+        const uint32_t ones_before = r1 + (uint32_t)__popc(m & lt);
+        if (valid) next[b ? z + ones_before : i - ones_before] = (OutT)v[t];
         r1 += (uint32_t)__popc(m);
     }
 }
