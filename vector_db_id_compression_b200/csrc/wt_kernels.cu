@@ -202,34 +202,35 @@ __global__ void __launch_bounds__(kThreads) k_wt_apply(const uint64_t* __restric
     seq[p >> 32] = (uint32_t)p;
 }
 
-// ---- one level: bits of every rank block + its popcount
+// ---- one level: bits of every rank block + its popcount (32-bit positions, see k_wt_level_scatter)
 template <typename SymT>
-__global__ void __launch_bounds__(kThreads) k_wt_level_bits(const SymT* __restrict__ seq, uint64_t n, uint64_t nblk,
+__global__ void __launch_bounds__(kThreads) k_wt_level_bits(const SymT* __restrict__ seq, uint64_t n64, uint64_t nblk64,
                                                             uint32_t shift, uint32_t check_holes,
                                                             uint64_t* __restrict__ bits, uint32_t* __restrict__ ones,
                                                             uint32_t* status) {
-    const uint64_t blk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp-uniform
+    const uint32_t n = (uint32_t)n64, nblk = (uint32_t)nblk64;
+    const uint32_t blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp-uniform
     const uint32_t lane = threadIdx.x & 31u;
     if (blk >= nblk) return;
-    const uint64_t base = blk << kWtBlockLog;
+    const uint32_t base = blk << kWtBlockLog;
     uint32_t v[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        uint64_t i = base + (uint64_t)t * 32 + lane;
+        const uint32_t i = base + (uint32_t)t * 32 + lane;
         v[t] = i < n ? (uint32_t)__ldg(seq + i) : 0u;
     }
     uint32_t mine = 0, cnt = 0;
     bool hole = false;
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        uint64_t i = base + (uint64_t)t * 32 + lane;
+        const uint32_t i = base + (uint32_t)t * 32 + lane;
         hole |= sizeof(SymT) == 4 && check_holes && i < n && v[t] == kWtHole;
-        uint32_t m = __ballot_sync(kFull, (v[t] >> shift) & 1u);
+        const uint32_t m = __ballot_sync(kFull, (v[t] >> shift) & 1u);
         if (lane == (uint32_t)t) mine = m;
         cnt += (uint32_t)__popc(m);
     }
     // 16 32-bit words = the block's 8 little-endian 64-bit words
-    if (lane < 16) reinterpret_cast<uint32_t*>(bits)[blk * 16 + lane] = mine;
+    if (lane < 16) reinterpret_cast<uint32_t*>(bits)[(size_t)blk * 16 + lane] = mine;
     if (lane == 0) ones[blk] = cnt;
     if (hole) atomicOr(status, kWtStHole);
 }
