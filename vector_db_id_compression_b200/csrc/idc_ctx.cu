@@ -127,7 +127,8 @@ int idc_ctx::fork(int n) {
         // aux[0] carries the longest units, whose serial chains bound the kernel: highest priority first
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
-        int prio = std::min(least, greatest + (int)aux.size());
+        // (streams past the third carry pieces of the longest class: highest priority again)
+        int prio = aux.size() >= 3 ? greatest : std::min(least, greatest + (int)aux.size());
         IDC_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio));
         IDC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         aux.push_back(s);

@@ -592,7 +592,11 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
     // the class streams wait for what has been queued so far (tables, memsets), not for the chunks
     auto cls = size_classes(nu, [&](uint64_t slot) { return b->unit_n[perm[slot]]; });
     const std::vector<int> cstream = class_streams(cls);
-    IDC_TRY(c->fork(class_stream_count()));
+    // Host input arriving in chunks: the longest class, whose chains bound the call, is launched in up to four pieces
+    // that start as their own units arrive (below); the extra pieces get streams of their own.
+    constexpr int kEncPieces = 4;
+    const int nstreams = class_stream_count() + (pipelined ? kEncPieces - 1 : 0);
+    IDC_TRY(c->fork(nstreams));
 
     // 1. per chunk: upload, unit metadata, [sort], records
     MetaArgs m{ids_dev, d_unit_src, b->d_unit_n, (uint32_t)nu, sorted_in ? 1u : 0u,
@@ -651,13 +655,52 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
     }
 
     tr.mark("chunks: meta, sort, records");
-    // 3. encode: a class starts when the chunk with its last unit is ready
+    // (IDC_TRACE_HOST: device-side time line of the size classes, relative to the first thing queued behind the tables)
+    std::vector<cudaEvent_t> tl_ev;
+    size_t tl_n = 0;
+    if (tr.on) {
+        tl_ev.resize(1 + 2 * (cls.size() + kEncPieces));
+        for (auto& ev : tl_ev) cudaEventCreate(&ev);
+        cudaEventRecord(tl_ev[0], c->aux[cstream.empty() ? 0 : cstream[0]]);  // (the class streams were forked before the chunks were queued)
+    }
+    // 3. encode: a class starts when the chunk with its last unit is ready. The longest class does not wait for ITS
+    // last unit as a whole: its slots (descending length) are cut where the latest chunk needed so far changes, the
+    // last three such values get a launch of their own -- with Zipf-length lists in CSR order the full-length units
+    // (66 % of the upload) start 10 ms before the last unit of the class (72 %) has arrived, and their 65 536-step
+    // chains are what the call waits for.
+    struct Piece {
+        uint32_t slot_base, slot_end, cls;
+        int stream;
+        size_t chunk;
+    };
+    std::vector<Piece> pieces;
+    for (size_t k = 0; k < cls.size(); k++) {
+        std::vector<size_t> need(cls[k].slot_end - cls[k].slot_base);  // running maximum of the chunk a slot's unit is in
+        size_t run = 0;
+        for (uint32_t sl = cls[k].slot_base; sl < cls[k].slot_end; sl++) {
+            run = std::max(run, nchunk ? chunk_of_unit(perm[sl]) : (size_t)0);
+            need[sl - cls[k].slot_base] = run;
+        }
+        std::vector<uint32_t> cuts{cls[k].slot_base};
+        if (pipelined && k == 0 && nchunk > 1) {
+            std::vector<uint32_t> steps;  // slots where the running maximum grows
+            for (uint32_t i = 1; i < need.size(); i++)
+                if (need[i] != need[i - 1]) steps.push_back(cls[k].slot_base + i);
+            const size_t keep = std::min<size_t>(steps.size(), (size_t)kEncPieces - 1);
+            cuts.insert(cuts.end(), steps.end() - keep, steps.end());
+        }
+        cuts.push_back(cls[k].slot_end);
+        for (size_t i = 0; i + 1 < cuts.size(); i++)
+            pieces.push_back(Piece{cuts[i], cuts[i + 1], (uint32_t)k, i == 0 ? cstream[k] : class_stream_count() + (int)i - 1,
+                                   need[cuts[i + 1] - 1 - cls[k].slot_base]});
+    }
     {
         LaunchScope ls(c, "k_roc_encode");
-        for (size_t k = 0; k < cls.size(); k++) {
+        for (const Piece& pc : pieces) {
+            const size_t k = pc.cls;
             EncArgs ek = e;
-            ek.slot_base = cls[k].slot_base;
-            ek.slot_end = cls[k].slot_end;
+            ek.slot_base = pc.slot_base;
+            ek.slot_end = pc.slot_end;
             ek.sm_words = genc_sm_words(cls[k].max_n ? cls[k].max_n : 1u);
             const int G = group_lanes_for(cls[k].max_n);
             const uint32_t upw = 32u / (uint32_t)G;  // units per warp
@@ -665,13 +708,13 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
             const uint32_t slots = ek.slot_end - ek.slot_base, nwarps = (slots + upw - 1) / upw;
             const uint32_t grid = (nwarps + warps - 1) / warps;
             const size_t smem = (size_t)ek.sm_words * 4 * upw * warps;
-            uint32_t last_unit = 0;
-            for (uint32_t sl = ek.slot_base; sl < ek.slot_end; sl++) last_unit = std::max(last_unit, perm[sl]);
-            IDC_CUDA(cudaStreamWaitEvent(c->aux[cstream[k]], ev_ready[nchunk ? chunk_of_unit(last_unit) : 0], 0));
+            cudaStream_t ps = c->aux[pc.stream];
+            IDC_CUDA(cudaStreamWaitEvent(ps, ev_ready[nchunk ? pc.chunk : 0], 0));
+            if (tr.on) cudaEventRecord(tl_ev[1 + 2 * tl_n], ps);
 #define IDC_LAUNCH_ENC(GG, TT)                                                       \
     do {                                                                             \
         IDC_TRY(set_max_smem(k_roc_encode<GG, TT>, smem));                            \
-        k_roc_encode<GG, TT><<<grid, threads, smem, c->aux[cstream[k]]>>>(ek);       \
+        k_roc_encode<GG, TT><<<grid, threads, smem, ps>>>(ek);                        \
     } while (0)
             if (G == 8) {
                 if (enc_id_bytes == 8) IDC_LAUNCH_ENC(8, int64_t); else IDC_LAUNCH_ENC(8, uint32_t);
@@ -681,10 +724,11 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
                 if (enc_id_bytes == 8) IDC_LAUNCH_ENC(4, int64_t); else IDC_LAUNCH_ENC(4, uint32_t);
             }
 #undef IDC_LAUNCH_ENC
+            if (tr.on) cudaEventRecord(tl_ev[2 + 2 * tl_n], ps), tl_n++;
             c->launches++;
         }
         c->launches--;  // LaunchScope counted one already
-        IDC_TRY(c->join(class_stream_count()));
+        IDC_TRY(c->join(nstreams));
     }
     IDC_TRY(check_last_launch("k_roc_encode"));
 
@@ -697,6 +741,17 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
     IDC_CUDA(cudaStreamSynchronize(c->stream));
     IDC_TRY(status_to_error(st, "roc_encode"));
     tr.mark("wait for the kernels");
+    if (tr.on) {
+        for (size_t k = 0; k < tl_n; k++) {
+            float a = 0, z = 0;
+            cudaEventElapsedTime(&a, tl_ev[0], tl_ev[1 + 2 * k]);
+            cudaEventElapsedTime(&z, tl_ev[0], tl_ev[2 + 2 * k]);
+            fprintf(stderr, "[idc host]   launch %zu (class %u, slots %u..%u, longest unit %u, stream %d, chunk %zu): starts %.1f ms, ends %.1f ms\n", k,
+                    pieces[k].cls, pieces[k].slot_base, pieces[k].slot_end, b->unit_n[perm[pieces[k].slot_base]], pieces[k].stream,
+                    pieces[k].chunk, a, z);
+        }
+        for (auto& ev : tl_ev) cudaEventDestroy(ev);
+    }
     std::vector<uint64_t> word_off(nu + 1);
     word_off[0] = 0;
     uint64_t ans_bytes = 0;
