@@ -1169,7 +1169,7 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const EfBuildIn& in) {
     uint32_t* d_lo = (uint32_t*)carve(nl * 4);
     uint8_t* d_prec = (uint8_t*)carve(nl);
     uint32_t* d_hi = b->d_universe;
-    IDC_TRY(c->status.reserve(64));
+    IDC_TRY(c->status.reserve(128));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
     IDC_CUDA(cudaMemsetAsync(d_totals, 0, 64, c->stream));
@@ -1344,7 +1344,7 @@ int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_sel_desc, 
     uint32_t stage_words = std::min<uint32_t>(33u * b->max_l + 1u, kDecStageCap);
     if (const char* ev = getenv("IDC_EF_DEC_STAGE")) stage_words = std::min<uint32_t>(33u * b->max_l + 1u, (uint32_t)atoi(ev));  // experiments
     stage_words = (stage_words + 3u) & ~3u;
-    IDC_TRY(c->status.reserve(64));
+    IDC_TRY(c->status.reserve(128));
     uint32_t* d_status = c->status.as<uint32_t>();
     if (row_stride) IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
     EfDecArgs a{b->d_dir, b->d_low, b->d_high, d_sel_desc, d_sel_out, d_row_nos, out_dev, counts_dev, ntiles, row_stride,
@@ -1790,7 +1790,7 @@ int idc_ef_blob_import(idc_ctx* c, uint64_t nlist, const uint64_t* list_offsets,
     const cudaMemcpyKind kind = mem == IDC_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     if (b->low_words) IDC_CUDA(cudaMemcpyAsync(b->d_low, low, b->low_words * 8, kind, c->stream));
     if (b->high_words) IDC_CUDA(cudaMemcpyAsync(b->d_high, high, b->high_words * 8, kind, c->stream));
-    IDC_TRY(c->status.reserve(64));
+    IDC_TRY(c->status.reserve(128));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
     if (nl) {

@@ -514,7 +514,7 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
     uint32_t* d_nwords = (uint32_t*)carve(nu * 4);
     uint32_t* d_tile_unit = (uint32_t*)carve(ntile * 4);
     uint32_t* d_tile_idx = (uint32_t*)carve(ntile * 4);
-    IDC_TRY(c->status.reserve(64));
+    IDC_TRY(c->status.reserve(128));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
     IDC_TRY(upload(c, d_unit_src, b->unit_src));
@@ -866,7 +866,7 @@ int roc_encode_rows_device(idc_ctx* c, idc_roc_blob* b, const int32_t* d_data, u
     uint32_t* d_posbase = (uint32_t*)carve(nr * 4);
     uint32_t* d_perm = (uint32_t*)carve(nr * 4);
     uint32_t* d_nwords = (uint32_t*)carve(nr * 4);
-    IDC_TRY(c->status.reserve(64));
+    IDC_TRY(c->status.reserve(128));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
     // workspaces: records, then the 32-bit sorted copy of the rows and the sort permutation
@@ -1105,7 +1105,7 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
                const int32_t* rows_dev = nullptr, uint64_t slot_ws = 0, uint64_t row_base = 0) {
     if (nsel == 0) {
         if (ov) {
-            IDC_TRY(c->status.reserve(64));
+            IDC_TRY(c->status.reserve(128));
             IDC_CUDA(cudaMemsetAsync(c->status.p, 0, 4, c->stream));
         }
         return IDC_OK;

@@ -788,7 +788,7 @@ int wt_build(idc_ctx* c, idc_wt_blob* b, const IdT* ids_dev) {
     uint32_t* part = local + Epad;
     unsigned long long* cursor = reinterpret_cast<unsigned long long*>(local + dir_words);
     uint64_t* pairs = reinterpret_cast<uint64_t*>(cursor + nb_pad);
-    IDC_TRY(c->status.reserve(64));
+    IDC_TRY(c->status.reserve(128));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, s));
     IDC_CUDA(cudaMemsetAsync(seq, 0xff, n * sizeof(uint32_t), s));
@@ -1065,7 +1065,7 @@ int idc_wt_decode(idc_ctx* c, const idc_wt_blob* b, const uint64_t* list_nos, ui
         IDC_TRY(c->stage.reserve(total * id_bytes));
         out_dev = c->stage.p;
     }
-    IDC_TRY(c->status.reserve(64));
+    IDC_TRY(c->status.reserve(128));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
     // A large share of the index: replay the partitions on the ids themselves (streaming passes, cost independent
