@@ -289,6 +289,77 @@ void sim_wt_replay_all(uint64_t nlist, uint64_t n, const uint64_t* bits, const u
     for (uint64_t l = 0; l < nlist; l++)
         for (uint64_t k = 0; k < list_off[l + 1] - list_off[l]; k++) out[list_off[l] + k] = in[start[l] + k];
 }
+// k_wt_replay2 + k_wt_emit lane by lane: two levels per pass through the per-tile windows of level v + 1 (32 words per
+// side, exclusive popcount prefix on top of the window's directory entry), 32-bit positions -- the kernel's index
+// arithmetic restated with plain loops; an odd last level takes the single-level pass
+void sim_wt_replay2_all(uint64_t nlist, uint64_t n64, const uint64_t* bits, const uint32_t* rank, const uint32_t* start,
+                        const uint64_t* list_off, int64_t* out) {
+    WtShape sh = wt_shape(nlist, n64);
+    const uint32_t n = (uint32_t)n64, nblk = (uint32_t)sh.nblk;
+    std::vector<uint32_t> in(n), nxt(n);
+    for (uint32_t i = 0; i < n; i++) in[i] = i;
+    for (uint32_t lev = 0; lev < sh.levels;) {
+        const uint32_t* B0 = reinterpret_cast<const uint32_t*>(bits + (uint64_t)lev * sh.words);
+        const uint32_t* R0 = rank + (uint64_t)lev * sh.rank_stride;
+        const uint32_t z0 = n - R0[nblk];
+        if (lev + 1 < sh.levels) {
+            const uint32_t* B1 = reinterpret_cast<const uint32_t*>(bits + (uint64_t)(lev + 1) * sh.words);
+            const uint32_t* R1 = rank + (uint64_t)(lev + 1) * sh.rank_stride;
+            const uint32_t z1 = n - R1[nblk], nwords = nblk * 16;
+            for (uint32_t blk = 0; blk < nblk; blk++) {
+                const uint32_t base = blk << kWtBlockLog, r1 = R0[blk];
+                const uint32_t zs = base - r1, os = z0 + r1, zb = zs >> kWtBlockLog, ob = os >> kWtBlockLog;
+                uint32_t win[128];
+                uint32_t pz = R1[zb <= nblk ? zb : nblk], po = R1[ob <= nblk ? ob : nblk];
+                for (uint32_t lane = 0; lane < 32; lane++) {
+                    const uint32_t zi = zb * 16 + lane, oi = ob * 16 + lane;
+                    win[lane] = zi < nwords ? B1[zi] : 0u;
+                    win[32 + lane] = oi < nwords ? B1[oi] : 0u;
+                    win[64 + lane] = pz;
+                    win[96 + lane] = po;
+                    pz += (uint32_t)__builtin_popcount(win[lane]);
+                    po += (uint32_t)__builtin_popcount(win[32 + lane]);
+                }
+                const uint32_t zwin = zb << kWtBlockLog, owin = ob << kWtBlockLog;
+                uint32_t ones = r1;
+                for (int t = 0; t < 16; t++) {
+                    const uint32_t m = B0[blk * 16 + t];
+                    for (uint32_t lane = 0; lane < 32; lane++) {
+                        const uint32_t i = base + (uint32_t)t * 32 + lane;
+                        const uint32_t b0 = (m >> lane) & 1u;
+                        const uint32_t before = ones + (uint32_t)__builtin_popcount(m & ((1u << lane) - 1u));
+                        const uint32_t p = b0 ? z0 + before : i - before;
+                        const uint32_t rel = p - (b0 ? owin : zwin);
+                        const uint32_t src = ((rel >> 5) & 31u) + (b0 << 5);
+                        const uint32_t x = win[src], y = win[64 + src], shf = rel & 31u;
+                        const uint32_t b1 = (x >> shf) & 1u;
+                        const uint32_t before1 = y + (uint32_t)__builtin_popcount(x & ((1u << shf) - 1u));
+                        if (i < n) nxt[b1 ? z1 + before1 : p - before1] = in[i];
+                    }
+                    ones += (uint32_t)__builtin_popcount(m);
+                }
+            }
+            lev += 2;
+        } else {
+            for (uint32_t blk = 0; blk < nblk; blk++) {
+                uint32_t r1 = R0[blk];
+                for (int t = 0; t < 16; t++) {
+                    const uint32_t m = B0[blk * 16 + t];
+                    for (uint32_t lane = 0; lane < 32; lane++) {
+                        const uint32_t i = (blk << kWtBlockLog) + (uint32_t)t * 32 + lane;
+                        const uint32_t before = r1 + (uint32_t)__builtin_popcount(m & ((1u << lane) - 1u));
+                        if (i < n) nxt[((m >> lane) & 1u) ? z0 + before : i - before] = in[i];
+                    }
+                    r1 += (uint32_t)__builtin_popcount(m);
+                }
+            }
+            lev += 1;
+        }
+        in.swap(nxt);
+    }
+    for (uint64_t l = 0; l < nlist; l++)
+        for (uint64_t k = 0; k < list_off[l + 1] - list_off[l]; k++) out[list_off[l] + k] = in[start[l] + k];
+}
 // every id of every list in one call (list_off = CSR of the list sizes)
 void sim_wt_decode_all(uint64_t nlist, uint64_t n, const uint64_t* bits, const uint32_t* rank, const uint32_t* sel1,
                        const uint32_t* sel0, const uint32_t* start, const uint64_t* list_off, int64_t* out) {

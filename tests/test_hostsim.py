@@ -47,6 +47,8 @@ def sim():
     lib.sim_wt_fill_bucketed.argtypes = [C.c_uint64, C.c_uint64, i64p, u64p, C.c_uint32, u32p]
     lib.sim_wt_replay_all.restype = None
     lib.sim_wt_replay_all.argtypes = [C.c_uint64, C.c_uint64, u64p, u32p, u32p, u64p, i64p]
+    lib.sim_wt_replay2_all.restype = None
+    lib.sim_wt_replay2_all.argtypes = [C.c_uint64, C.c_uint64, u64p, u32p, u32p, u64p, i64p]
     lib.sim_wt_decode_all.restype = None
     lib.sim_wt_decode_all.argtypes = wt_arrays + [u64p, i64p]
     return lib
@@ -199,6 +201,9 @@ def test_wavelet_matrix_build_and_select(sim, nlist, n, skew):
     out2 = np.zeros(n, np.int64)
     sim.sim_wt_replay_all(nlist, n, bits, rank, start, offsets, out2)
     assert np.array_equal(out2, ids)
+    out3 = np.zeros(n, np.int64)  # two levels per pass, the index arithmetic of k_wt_replay2
+    sim.sim_wt_replay2_all(nlist, n, bits, rank, start, offsets, out3)
+    assert np.array_equal(out3, ids)
     for i in rng.integers(0, n, size=300):
         assert sim.sim_wt_access(nlist, n, bits, rank, sel1, sel0, start, int(i)) == int(S[i])
     for c, k in [(0, 0), (nlist - 1, 0)]:
