@@ -330,17 +330,12 @@ IDC_HD void dec_state_init(DecState& st, uint64_t head, const uint32_t* words, u
     st.used = 0;
 }
 
-// The k-th word below the consumed part of the blob's stack. Device: the ring slot (every lane of the group reads it
-// long after the copy that filled it has landed and a rendezvous has made it visible). The host emulation's lanes
-// are free-running threads, so there the fetching lane's refill of a slot could overtake a slower lane's read: it
-// reads the blob itself.
-IDC_HD uint32_t dec_ring_word(const DecState& st, uint32_t k) {
-#if defined(__CUDA_ARCH__)
-    return *st.ring.at((st.rpos + k) & (kDecRing - 1u));
-#else
-    return st.words[st.sp - 1u - k];
-#endif
-}
+// The k-th word below the consumed part of the blob's stack: ring slot rpos + k. Every lane of the group reads it long
+// after the copy that filled it has landed and a rendezvous has made it visible; the slots dec_ring_advance() reads
+// (rpos .. rpos + 2 after the advance) are never the ones the fetching lane refills in the same or in the next call
+// before the step's rendezvous, so the protocol holds for lanes that are a whole step phase apart -- the host
+// emulation (free-running threads, copies that land at once) runs it as is.
+IDC_HD uint32_t dec_ring_word(const DecState& st, uint32_t k) { return *st.ring.at((st.rpos + k) & (kDecRing - 1u)); }
 
 // Once per step, before the step's rendezvous: all but the kDecRingWait most recent copy groups (one per step) have
 // landed. A slot is refilled when its word is consumed and read again 14 words -- at three words per step at most,
