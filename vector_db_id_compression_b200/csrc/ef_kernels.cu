@@ -1335,9 +1335,25 @@ int ef_build(idc_ctx* c, idc_ef_blob* b, const EfBuildIn& in) {
     return IDC_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the function on a device, shared by every context of the
+// process: raised when a launch needs more, never lowered (two driver calls less per single-row call).
+int ef_dec_smem_limit(int device, size_t smem) {
+    static std::mutex mu;
+    static size_t have[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& h = have[(unsigned)device & 63u];
+    if (smem <= h) return IDC_OK;
+    IDC_CUDA(cudaFuncSetAttribute(k_ef_decode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IDC_CUDA(cudaFuncSetAttribute(k_ef_decode<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h = smem;
+    return IDC_OK;
+}
+
+// rows_checked: the row numbers were range-checked by the caller (host rows), the kernel cannot raise kStRange and the
+// status word is neither cleared nor fetched. Returns with the stream synchronised.
 int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_sel_desc, const uint64_t* d_sel_out,
                   const int32_t* d_row_nos, uint64_t ntiles, void* out_dev, int id_bytes, uint32_t* counts_dev,
-                  uint32_t row_stride) {
+                  uint32_t row_stride, bool rows_checked = false) {
     if (ntiles == 0) return IDC_OK;
     // stage up to 33 groups of max_l words per warp, capped so that 6 CTAs of 8 warps still fit an SM (chunks that need
     // more -- short lists with wide fields -- read their lower bits straight from global memory)
@@ -1346,14 +1362,14 @@ int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_sel_desc, 
     stage_words = (stage_words + 3u) & ~3u;
     IDC_TRY(c->status.reserve(128));
     uint32_t* d_status = c->status.as<uint32_t>();
-    if (row_stride) IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    const bool want_status = row_stride && !rows_checked;
+    if (want_status) IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
     EfDecArgs a{b->d_dir, b->d_low, b->d_high, d_sel_desc, d_sel_out, d_row_nos, out_dev, counts_dev, ntiles, row_stride,
                 stage_words, b->nlist, d_status};
     const uint32_t wpb = kDecThreads / 32;
     const uint32_t grid = (uint32_t)((ntiles + wpb - 1) / wpb);
     const size_t smem = (size_t)wpb * ef_dec_warp_bytes(stage_words, 1) + 512u;  // + 512: the output pass reads (and ignores) up to 3 groups past a chunk's words
-    IDC_CUDA(cudaFuncSetAttribute(k_ef_decode<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IDC_CUDA(cudaFuncSetAttribute(k_ef_decode<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IDC_TRY(ef_dec_smem_limit(c->device, smem));
     {
         LaunchScope ls(c, "k_ef_decode");
         if (id_bytes == 8)
@@ -1363,7 +1379,7 @@ int ef_run_decode(idc_ctx* c, const idc_ef_blob* b, const uint32_t* d_sel_desc, 
     }
     IDC_TRY(check_last_launch("k_ef_decode"));
     uint32_t st = 0;
-    if (row_stride) IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (want_status) IDC_CUDA(cudaMemcpyAsync(&st, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
     IDC_REQUIRE((st & kStRange) == 0, IDC_ERR_ARG, "ef_decode_rows: a row number is out of range (such rows were set to -1)");
     return IDC_OK;
@@ -1584,9 +1600,27 @@ int idc_ef_decode_rows(idc_ctx* c, const idc_ef_blob* b, const int32_t* row_nos,
     IDC_REQUIRE(3ull * K + 2 <= 64ull * kDecChunkWords, IDC_ERR_ARG, "row stride %u too large: a row must fit one 2048-bit chunk", K);
     // rows are addressed directly by the kernel (list = row number, chunk 0): no tile tables
     const int32_t* d_rows = row_nos;
-    if (row_nos && rows_mem == IDC_MEM_HOST) {
+    const bool host_rows = row_nos && rows_mem == IDC_MEM_HOST;
+    if (host_rows)
         for (uint64_t i = 0; i < nsel; i++)
             IDC_REQUIRE(row_nos[i] >= 0 && (uint64_t)row_nos[i] < b->nlist, IDC_ERR_ARG, "row %d out of range", row_nos[i]);
+    if (host_rows && out_mem == IDC_MEM_HOST && nsel <= 4096) {
+        // a few rows, everything on the host (what NSG search does per visited node, altid_impl.cpp:92-101): through the
+        // context's mailbox -- [row numbers | counts | rows], read and written by the kernel in place
+        const size_t o_cnt = (nsel * 4 + 15) & ~size_t(15), o_out = 2 * o_cnt;
+        void *mh = nullptr, *md = nullptr;
+        IDC_TRY(c->mailbox_get(o_out + nsel * K * 4, &mh, &md));
+        if (mh) {
+            std::memcpy(mh, row_nos, nsel * 4);
+            uint8_t *h8 = static_cast<uint8_t*>(mh), *d8 = static_cast<uint8_t*>(md);
+            IDC_TRY(ef_run_decode(c, b, nullptr, nullptr, reinterpret_cast<const int32_t*>(d8), nsel, d8 + o_out, 4,
+                                  reinterpret_cast<uint32_t*>(d8 + o_cnt), K, true));  // synchronises the stream
+            std::memcpy(out, h8 + o_out, nsel * K * 4);
+            if (counts) std::memcpy(counts, h8 + o_cnt, nsel * 4);
+            return IDC_OK;
+        }
+    }
+    if (host_rows) {
         IDC_TRY(c->meta.reserve(nsel * 4 + 256));
         IDC_CUDA(cudaMemcpyAsync(c->meta.p, row_nos, nsel * 4, cudaMemcpyHostToDevice, c->stream));
         d_rows = c->meta.as<int32_t>();
@@ -1598,7 +1632,7 @@ int idc_ef_decode_rows(idc_ctx* c, const idc_ef_blob* b, const int32_t* row_nos,
         out_dev = c->stage.as<int32_t>();
         cnt_dev = reinterpret_cast<uint32_t*>(c->stage.as<uint8_t>() + nsel * K * 4);
     }
-    IDC_TRY(ef_run_decode(c, b, nullptr, nullptr, d_rows, nsel, out_dev, 4, cnt_dev, K));
+    IDC_TRY(ef_run_decode(c, b, nullptr, nullptr, d_rows, nsel, out_dev, 4, cnt_dev, K, host_rows));
     if (out_mem == IDC_MEM_HOST) {
         IDC_CUDA(cudaMemcpyAsync(out, out_dev, nsel * K * 4, cudaMemcpyDeviceToHost, c->stream));
         if (counts) IDC_CUDA(cudaMemcpyAsync(counts, cnt_dev, nsel * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1615,6 +1649,27 @@ int idc_ef_select(idc_ctx* c, const idc_ef_blob* b, const uint64_t* list_nos, co
     IDC_CUDA(cudaSetDevice(c->device));
     c->begin_call();
     if (nq == 0) return IDC_OK;
+    if (query_mem == IDC_MEM_HOST && out_mem == IDC_MEM_HOST && nq <= 2048) {
+        // a few queries from the host (get_single_id, custom_invlists_impl.cpp:314-318): through the context's mailbox
+        // -- [list numbers | offsets | ids], read and written by the kernel in place: one launch, one synchronisation
+        void *mh = nullptr, *md = nullptr;
+        IDC_TRY(c->mailbox_get(nq * 24, &mh, &md));
+        if (mh) {
+            uint64_t *h = static_cast<uint64_t*>(mh), *d = static_cast<uint64_t*>(md);
+            std::memcpy(h, list_nos, nq * 8);
+            std::memcpy(h + nq, offsets_in_list, nq * 8);
+            EfSelArgs a{b->d_list_off, b->d_l, b->d_low_off, b->d_high_off, b->d_samp_off, b->d_low, b->d_high, b->d_samples,
+                        d, d + nq, reinterpret_cast<int64_t*>(d + 2 * nq), nq, b->nlist};
+            {
+                LaunchScope ls(c, "k_ef_select");
+                k_ef_select<<<grid_for(nq), kThreads, 0, c->stream>>>(a);
+            }
+            IDC_TRY(check_last_launch("k_ef_select"));
+            IDC_CUDA(cudaStreamSynchronize(c->stream));
+            std::memcpy(ids_out, h + 2 * nq, nq * 8);
+            return IDC_OK;
+        }
+    }
     const uint64_t *d_ql = list_nos, *d_qo = offsets_in_list;
     size_t need = (query_mem == IDC_MEM_HOST ? nq * 16 : 0) + (out_mem == IDC_MEM_HOST ? nq * 8 : 0);
     IDC_TRY(c->stage.reserve(need + 256));

@@ -109,6 +109,28 @@ int idc_ctx::copy_stream_get(cudaStream_t* s, int which) {
     return IDC_OK;
 }
 
+int idc_ctx::mailbox_get(size_t bytes, void** host, void** dev) {
+    *host = *dev = nullptr;
+    if (mailbox_off || bytes > kMailboxBytes) return IDC_OK;
+    if (!mailbox) {
+        void* h = nullptr;
+        void* d = nullptr;
+        if (cudaHostAlloc(&h, kMailboxBytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+            cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) {
+            // no mapped host memory on this platform: the copy path does the same job
+            if (h) cudaFreeHost(h);
+            cudaGetLastError();
+            mailbox_off = true;
+            return IDC_OK;
+        }
+        mailbox = h;
+        mailbox_dev = d;
+    }
+    *host = mailbox;
+    *dev = mailbox_dev;
+    return IDC_OK;
+}
+
 int idc_ctx::sync_event(cudaEvent_t* e) {
     if (sync_used == sync_events.size()) {
         cudaEvent_t ev;
@@ -177,6 +199,7 @@ int idc_ctx_create_on_stream(int device, void* cuda_stream, idc_ctx** out) {
     cudaDeviceProp prop;
     IDC_CUDA(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->mailbox_off = getenv("IDC_NO_MAILBOX") != nullptr || !prop.canMapHostMemory;
     // The ROC kernels read isolated 32-byte sectors (tree nodes, bucket records) scattered over GBs: L2 can be asked
     // not to promote such misses to 64/128-byte DRAM fetches (measured 3 sectors fetched per sector used otherwise).
     // That limit is DEVICE-GLOBAL -- it changes the behaviour of every other kernel of the process (Faiss, torch) --
@@ -240,6 +263,7 @@ int idc_ctx_destroy(idc_ctx* c) {
     cudaFree(c->d_rcp64);
     cudaFree(c->d_q31);
     cudaFree(c->d_binom);
+    if (c->mailbox) cudaFreeHost(c->mailbox);
     c->pool_trim();
     for (auto& b : c->pool_live) cudaFree(b.first);
     c->pool_live.clear();

@@ -141,6 +141,14 @@ struct idc_ctx {
     std::vector<cudaEvent_t> sync_events;
     size_t sync_used = 0;
     int copy_stream_get(cudaStream_t* s, int which = 0);
+    // Mailbox of the small synchronous calls (one graph row, a handful of rows): pinned host memory the device addresses
+    // directly. The kernel reads the row numbers from it and stores its output into it, so such a call is one launch and
+    // one stream synchronisation -- no copy calls (each costs as much as the decode of a row). IDC_NO_MAILBOX=1: off.
+    static constexpr size_t kMailboxBytes = 64u << 10;
+    void* mailbox = nullptr;      // host address
+    void* mailbox_dev = nullptr;  // the same bytes as the device sees them
+    bool mailbox_off = false;
+    int mailbox_get(size_t bytes, void** host, void** dev);  // *host == nullptr: not available for this size
     int sync_event(cudaEvent_t* e);  // an event for ordering only; recycled at the next begin_call()
     int fork(int n);              // make aux[0..n) wait for everything queued on `stream`
     int join(int n);              // make `stream` wait for aux[0..n)

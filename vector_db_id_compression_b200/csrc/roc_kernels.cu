@@ -1897,6 +1897,23 @@ int idc_roc_decode_rows(idc_ctx* c, const idc_roc_blob* b, const int32_t* row_no
     // numbers stay where they are when they live on the device
     const uint64_t slot_ws = dec_tree_bytes(K);
     const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(nsel, (4ull << 30) / slot_ws));
+    if (row_nos && rows_mem == IDC_MEM_HOST && out_mem == IDC_MEM_HOST && nsel <= 4096 && nsel <= chunk) {
+        // a few rows, everything on the host (what NSG search does per visited node, altid_impl.cpp:153-165): through the
+        // context's mailbox -- [row numbers | counts | rows], read and written by the kernel in place: no copy calls
+        const size_t o_cnt = (nsel * 4 + 15) & ~size_t(15), o_out = 2 * o_cnt;
+        void *mh = nullptr, *md = nullptr;
+        IDC_TRY(c->mailbox_get(o_out + nsel * K * 4, &mh, &md));
+        if (mh) {
+            std::memcpy(mh, row_nos, nsel * 4);
+            uint8_t *h8 = static_cast<uint8_t*>(mh), *d8 = static_cast<uint8_t*>(md);
+            // (run_decode synchronises the stream and turns an out-of-range row into IDC_ERR_ARG)
+            IDC_TRY(run_decode(c, b, nullptr, nullptr, nullptr, nsel * slot_ws, nsel, d8 + o_out, 4, reinterpret_cast<uint32_t*>(d8 + o_cnt),
+                               K, K, [&](uint64_t) { return K; }, nullptr, reinterpret_cast<const int32_t*>(d8), slot_ws, 0));
+            std::memcpy(out, h8 + o_out, nsel * K * 4);
+            if (counts) std::memcpy(counts, h8 + o_cnt, nsel * 4);
+            return IDC_OK;
+        }
+    }
     int32_t* out_dev = out;
     uint32_t* cnt_dev = counts;
     if (out_mem == IDC_MEM_HOST) {

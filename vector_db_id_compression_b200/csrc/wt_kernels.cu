@@ -1001,26 +1001,41 @@ int idc_wt_select(idc_ctx* c, const idc_wt_blob* b, const uint64_t* list_nos, co
         return IDC_OK;
     }
     const uint64_t *d_ql = list_nos, *d_qo = offsets_in_list;
-    size_t need = (query_mem == IDC_MEM_HOST ? nq * 16 : 0) + (out_mem == IDC_MEM_HOST ? nq * 8 : 0);
-    IDC_TRY(c->stage.reserve(need + 256));
-    uint8_t* sp = c->stage.as<uint8_t>();
-    if (query_mem == IDC_MEM_HOST) {
-        IDC_CUDA(cudaMemcpyAsync(sp, list_nos, nq * 8, cudaMemcpyHostToDevice, c->stream));
-        IDC_CUDA(cudaMemcpyAsync(sp + nq * 8, offsets_in_list, nq * 8, cudaMemcpyHostToDevice, c->stream));
-        d_ql = reinterpret_cast<uint64_t*>(sp);
-        d_qo = reinterpret_cast<uint64_t*>(sp + nq * 8);
-        sp += nq * 16;
+    // a few queries from the host (get_single_id, custom_invlists_impl.cpp:380-384): through the context's mailbox --
+    // [list numbers | offsets | ids], read and written by the kernel in place: one launch, one synchronisation
+    void *mh = nullptr, *md = nullptr;
+    if (query_mem == IDC_MEM_HOST && out_mem == IDC_MEM_HOST && nq <= 2048) IDC_TRY(c->mailbox_get(nq * 24, &mh, &md));
+    int64_t* out_dev = ids_out;
+    if (mh) {
+        uint64_t *h = static_cast<uint64_t*>(mh), *d = static_cast<uint64_t*>(md);
+        std::memcpy(h, list_nos, nq * 8);
+        std::memcpy(h + nq, offsets_in_list, nq * 8);
+        d_ql = d;
+        d_qo = d + nq;
+        out_dev = reinterpret_cast<int64_t*>(d + 2 * nq);
+    } else {
+        size_t need = (query_mem == IDC_MEM_HOST ? nq * 16 : 0) + (out_mem == IDC_MEM_HOST ? nq * 8 : 0);
+        IDC_TRY(c->stage.reserve(need + 256));
+        uint8_t* sp = c->stage.as<uint8_t>();
+        if (query_mem == IDC_MEM_HOST) {
+            IDC_CUDA(cudaMemcpyAsync(sp, list_nos, nq * 8, cudaMemcpyHostToDevice, c->stream));
+            IDC_CUDA(cudaMemcpyAsync(sp + nq * 8, offsets_in_list, nq * 8, cudaMemcpyHostToDevice, c->stream));
+            d_ql = reinterpret_cast<uint64_t*>(sp);
+            d_qo = reinterpret_cast<uint64_t*>(sp + nq * 8);
+            sp += nq * 16;
+        }
+        if (out_mem == IDC_MEM_HOST) out_dev = reinterpret_cast<int64_t*>(sp);
     }
-    int64_t* out_dev = out_mem == IDC_MEM_HOST ? reinterpret_cast<int64_t*>(sp) : ids_out;
     WtSelArgs a{b->view(), b->d_list_off, b->nlist, d_ql, d_qo, out_dev, nq};
     {
         LaunchScope ls(c, "k_wt_select");
         k_wt_select<<<grid_for(nq), kThreads, 0, c->stream>>>(a);
     }
     IDC_TRY(check_last_launch("k_wt_select"));
-    if (out_mem == IDC_MEM_HOST)
+    if (out_mem == IDC_MEM_HOST && !mh)
         IDC_CUDA(cudaMemcpyAsync(ids_out, out_dev, nq * 8, cudaMemcpyDeviceToHost, c->stream));
     IDC_CUDA(cudaStreamSynchronize(c->stream));
+    if (mh) std::memcpy(ids_out, static_cast<uint64_t*>(mh) + 2 * nq, nq * 8);
     return IDC_OK;
 }
 
