@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../vector_db_id_compression_b200/csrc/roc_group.cuh"
+#include "../../vector_db_id_compression_b200/csrc/roc_small.cuh"
 #include "grp_emu.h"
 #include "../../vector_db_id_compression_b200/csrc/ef_core.cuh"
 #include "../../vector_db_id_compression_b200/csrc/wt_core.cuh"
@@ -86,6 +87,19 @@ static void group_decode(uint64_t head, const uint32_t* words, uint32_t nwords, 
 }
 
 extern "C" {
+
+// roc_small.cuh: one unit per thread (graph rows); out[n - 1 - i] = i-th decoded id like the kernel's write-out
+void sim_small_decode(uint64_t head, const uint32_t* words, uint32_t nwords, uint32_t n, int prec, int64_t* out,
+                      uint32_t* status_out) {
+    uint32_t mt[kMtWords];
+    tables(mt);
+    std::vector<uint32_t> seen(n + 1, 0);
+    SmallDec s;
+    small_dec_init(s, head, words, nwords);
+    small_dec_unit(s, n, prec, [&](uint32_t j) -> uint32_t& { return seen[j]; }, mt);
+    for (uint32_t i = 0; i < n; i++) out[n - 1 - i] = (int64_t)seen[i];
+    *status_out = s.status;
+}
 
 int64_t sim_group_encode(int G, uint32_t n, const uint64_t* ids, int prec, uint64_t* head_out, uint32_t* words_out,
                          uint32_t cap, uint32_t* order_out, uint32_t* status_out) {

@@ -30,6 +30,8 @@ def sim():
     lib.sim_group_encode.argtypes = [C.c_int] + enc_args
     lib.sim_group_decode.restype = None
     lib.sim_group_decode.argtypes = [C.c_int] + dec_args
+    lib.sim_small_decode.restype = None
+    lib.sim_small_decode.argtypes = [C.c_uint64, u32p, C.c_uint32, C.c_uint32, C.c_int, i64p, C.POINTER(C.c_uint32)]
     lib.sim_ef_shape.argtypes = [C.c_uint64, C.c_uint64, u64p]
     lib.sim_ef_encode.argtypes = [i64p, C.c_uint64, C.c_uint64, u64p, u64p, u32p]
     lib.sim_ef_select.restype = C.c_uint64
@@ -106,6 +108,39 @@ def test_group_codec_random_sets(sim, G):
             d2, st = grp_dec(sim, G, h, w, n, p, lo=int(srt[0]), hi=int(srt[-1]), force=1 + int(rng.integers(0, 3)))
         assert np.array_equal(d2.astype(np.uint64), d), (trial, n, p, mode)
         assert st & ~32 == 0
+
+
+def small_dec(lib, h, w, n, p):
+    out = np.zeros(max(n, 1), np.int64)
+    st = C.c_uint32()
+    lib.sim_small_decode(h, w if w.size else np.zeros(1, np.uint32), w.size, n, p, out, C.byref(st))
+    return out[:n], st.value
+
+
+def test_thread_per_unit_decoder(sim, roc_golden):
+    """csrc/roc_small.cuh (one short unit per thread: the graph rows' decoder) against the oracle: random sets of
+    1..64 ids (and a few longer ones -- the functions do not depend on the limit) at every precision, sets that fill
+    their universe, streams that run into the mt19937 fallback, the golden vectors."""
+    rng = np.random.default_rng(64)
+    for trial in range(3000):
+        p = int(rng.integers(1, 33))
+        n = min(int(rng.integers(1, 65 if trial % 10 else 400)), 1 << p)
+        if rng.random() < 0.3:
+            p = max(1, int(np.ceil(np.log2(n + 1))))
+        ids = rand_set(rng, n, p)
+        n = ids.size
+        h, w = oracle.port.encode(ids, p)
+        d2, st = small_dec(sim, h, w, n, p)
+        assert np.array_equal(d2.astype(np.uint64), oracle.port.decode(h, w, n, p)) and st == 0, (trial, n, p)
+    for c in roc_golden:
+        if c["p"] > 32 or c["ids"].size > 5000:
+            continue
+        d2, st = small_dec(sim, c["head"], c["words"], c["ids"].size, c["p"])
+        assert np.array_equal(d2.astype(np.uint64), c["dec"]) and st == 0, c["tag"]
+    # precision 0 (max_id = 1: the one id 0) and the reference's power-of-two rule (ids >= 2^p are coded unmasked)
+    h, w = oracle.port.encode(np.array([0], np.uint64), 0)
+    d2, st = small_dec(sim, h, w, 1, 0)
+    assert d2.tolist() == [0] and st == 0
 
 
 @pytest.mark.parametrize("G,n,p", [(4, 15259, 30), (4, 65536, 17), (8, 65536, 31), (4, 65000, 20), (8, 4097, 13), (4, 2233, 12), (2, 65536, 30), (2, 15259, 20)])

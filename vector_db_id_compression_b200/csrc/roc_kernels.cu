@@ -34,6 +34,7 @@
 #include "idc_host.h"
 #include "idc_prep.cuh"
 #include "roc_group.cuh"
+#include "roc_small.cuh"
 
 using namespace idc;
 
@@ -353,6 +354,68 @@ __global__ void __launch_bounds__(kThreads) k_roc_decode(DecArgs a) {
             uint32_t st = U.st.status & ~kStDegenerate;
             if (st) atomicOr(a.status, st);
         }
+    }
+}
+
+// ---- short units (graph rows, K <= kSmallUnit): one unit per THREAD (roc_small.cuh). The ids decoded so far are a
+// column of shared memory (seen[j][thread], pitch + 1: the scan of a step and the transposed write-out are both free of
+// bank conflicts); a warp writes its 32 rows out as full coalesced stores, in the reference's order (codec.cpp:150).
+struct SmallDecArgs {
+    const uint32_t* unit_n;
+    const uint8_t* unit_prec;
+    const uint64_t* unit_head;
+    const uint64_t* word_off;
+    const uint32_t* words;
+    const int32_t* rows;   // row numbers (device-addressable; null: slot s decodes row row_base + s)
+    uint32_t nrows;
+    uint32_t row_base;
+    uint32_t nsel;
+    uint32_t row_stride;
+    void* out;
+    uint32_t* counts;
+    uint32_t* status;
+    const uint32_t* mt;
+};
+
+constexpr uint32_t kSmallThreads = 128;
+
+template <typename OutT>
+__global__ void __launch_bounds__(kSmallThreads) k_roc_decode_small(SmallDecArgs a) {
+    extern __shared__ __align__(16) uint32_t s_seen[];
+    constexpr uint32_t kPitch = kSmallThreads + 1u;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wbase = tid & ~31u;
+    const uint32_t slot = blockIdx.x * kSmallThreads + tid;
+    uint32_t n = 0;
+    if (slot < a.nsel) {
+        const int64_t r = a.rows ? (int64_t)a.rows[slot] : (int64_t)a.row_base + slot;
+        if (r < 0 || r >= (int64_t)a.nrows) {
+            atomicOr(a.status, kStRange);  // the row is written as empty (-1 everywhere, count 0)
+        } else {
+            const uint32_t u = (uint32_t)r;
+            n = a.unit_n[u];
+            if (n > a.row_stride) {  // not a row of this blob's shape
+                atomicOr(a.status, kStRange);
+                n = 0;
+            }
+            if (n) {
+                const uint64_t w0 = a.word_off[u], w1 = a.word_off[u + 1];
+                SmallDec st;
+                small_dec_init(st, a.unit_head[u], a.words + w0, (uint32_t)(w1 - w0));
+                small_dec_unit(st, n, (int)a.unit_prec[u], [&](uint32_t j) -> uint32_t& { return s_seen[j * kPitch + tid]; }, a.mt);
+                if (st.status) atomicOr(a.status, st.status);
+            }
+        }
+        if (a.counts) a.counts[slot] = n;
+    }
+    __syncwarp();
+    OutT* out = reinterpret_cast<OutT*>(a.out);
+    for (uint32_t r = 0; r < 32u; r++) {
+        const uint32_t slot_r = blockIdx.x * kSmallThreads + wbase + r;
+        if (slot_r >= a.nsel) break;  // warp-uniform
+        const uint32_t n_r = __shfl_sync(0xffffffffu, n, r);
+        OutT* o = out + (uint64_t)slot_r * a.row_stride;
+        for (uint32_t t = lane; t < a.row_stride; t += 32u)
+            o[t] = t < n_r ? (OutT)s_seen[(n_r - 1u - t) * kPitch + wbase + r] : (OutT)-1;
     }
 }
 
@@ -1219,6 +1282,29 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     return finish_decode(c);
 }
 
+// rows of at most kSmallUnit ids: the thread-per-row decoder (no workspace, one launch). IDC_ROC_ROWS_GROUP=1 keeps the
+// lane-group kernel for them (experiments, tests of both paths).
+bool small_rows(uint32_t K) {
+    return K <= kSmallUnit && getenv("IDC_ROC_ROWS_GROUP") == nullptr;
+}
+
+int run_decode_small(idc_ctx* c, const idc_roc_blob* b, const int32_t* rows_dev, uint64_t row_base, uint64_t nsel, int32_t* out_dev,
+                     uint32_t* counts_dev, uint32_t K) {
+    if (nsel == 0) return IDC_OK;
+    IDC_TRY(c->status.reserve(128));
+    uint32_t* d_status = c->status.as<uint32_t>();
+    IDC_CUDA(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    SmallDecArgs a{b->d_unit_n, b->d_unit_prec, b->d_unit_head, b->d_word_off, b->d_words, rows_dev, (uint32_t)b->nlist,
+                   (uint32_t)row_base, (uint32_t)nsel, K, out_dev, counts_dev, d_status, c->d_mt};
+    const size_t smem = (size_t)K * (kSmallThreads + 1u) * 4u;  // <= 33 KB
+    {
+        LaunchScope ls(c, "k_roc_decode_small");
+        k_roc_decode_small<int32_t><<<(uint32_t)((nsel + kSmallThreads - 1) / kSmallThreads), kSmallThreads, smem, c->stream>>>(a);
+    }
+    IDC_TRY(check_last_launch("k_roc_decode_small"));
+    return finish_decode(c);
+}
+
 }  // namespace
 
 // --------------------------------------------------------------------------
@@ -1907,8 +1993,12 @@ int idc_roc_decode_rows(idc_ctx* c, const idc_roc_blob* b, const int32_t* row_no
             std::memcpy(mh, row_nos, nsel * 4);
             uint8_t *h8 = static_cast<uint8_t*>(mh), *d8 = static_cast<uint8_t*>(md);
             // (run_decode synchronises the stream and turns an out-of-range row into IDC_ERR_ARG)
-            IDC_TRY(run_decode(c, b, nullptr, nullptr, nullptr, nsel * slot_ws, nsel, d8 + o_out, 4, reinterpret_cast<uint32_t*>(d8 + o_cnt),
-                               K, K, [&](uint64_t) { return K; }, nullptr, reinterpret_cast<const int32_t*>(d8), slot_ws, 0));
+            if (small_rows(K))
+                IDC_TRY(run_decode_small(c, b, reinterpret_cast<const int32_t*>(d8), 0, nsel, reinterpret_cast<int32_t*>(d8 + o_out),
+                                         reinterpret_cast<uint32_t*>(d8 + o_cnt), K));
+            else
+                IDC_TRY(run_decode(c, b, nullptr, nullptr, nullptr, nsel * slot_ws, nsel, d8 + o_out, 4, reinterpret_cast<uint32_t*>(d8 + o_cnt),
+                                   K, K, [&](uint64_t) { return K; }, nullptr, reinterpret_cast<const int32_t*>(d8), slot_ws, 0));
             std::memcpy(out, h8 + o_out, nsel * K * 4);
             if (counts) std::memcpy(counts, h8 + o_cnt, nsel * 4);
             return IDC_OK;
@@ -1931,8 +2021,11 @@ int idc_roc_decode_rows(idc_ctx* c, const idc_roc_blob* b, const int32_t* row_no
         const uint64_t m = std::min(chunk, nsel - s);
         int32_t* od = out_mem == IDC_MEM_HOST ? out_dev : out_dev + s * K;
         uint32_t* cd = cnt_dev ? (out_mem == IDC_MEM_HOST ? cnt_dev : cnt_dev + s) : nullptr;
-        IDC_TRY(run_decode(c, b, nullptr, nullptr, nullptr, m * slot_ws, m, od, 4, cd, K, K, [&](uint64_t) { return K; },
-                           nullptr, rows_dev ? rows_dev + s : nullptr, slot_ws, s));
+        if (small_rows(K))
+            IDC_TRY(run_decode_small(c, b, rows_dev ? rows_dev + s : nullptr, s, m, od, cd, K));
+        else
+            IDC_TRY(run_decode(c, b, nullptr, nullptr, nullptr, m * slot_ws, m, od, 4, cd, K, K, [&](uint64_t) { return K; },
+                               nullptr, rows_dev ? rows_dev + s : nullptr, slot_ws, s));
         if (out_mem == IDC_MEM_HOST) {
             IDC_CUDA(cudaMemcpyAsync(out + s * K, out_dev, m * K * 4, cudaMemcpyDeviceToHost, c->stream));
             if (counts) IDC_CUDA(cudaMemcpyAsync(counts + s, cnt_dev, m * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -1,0 +1,118 @@
+// roc_small.cuh -- ROC decode of SHORT units (graph rows, K <= 64 ids), one unit per THREAD.
+//
+// The lane-group decoder of roc_group.cuh is built for chains of up to 65 536 steps: a bucket structure in HBM, count
+// levels in shared memory, a stream ring, one rendezvous per step -- about 560 warp instructions per step for the 8
+// units of a warp. A graph row has at most 64 ids (altid_impl.h:53-67): "insert, then rank" (fenwick_tree.h:42-94) is a
+// count over the ids decoded so far, which sit in shared memory, and the stream is ~30 words. One thread runs the
+// reference's loop (codec.cpp:140-152) as it stands; a warp decodes 32 rows at ~10 warp instructions per row step.
+//
+// IDC_HD like idc_core.cuh: tests/hostsim runs these functions against the oracle on the CPU.
+#pragma once
+
+#include "idc_core.cuh"
+
+namespace idc {
+
+constexpr uint32_t kSmallUnit = 64;  // longest unit this decoder takes (shared memory: 4 bytes per id and thread)
+
+struct SmallDec {
+    uint64_t head;
+    const uint32_t* words;  // the unit's stack in the blob, bottom first
+    uint32_t sp;            // words of it not consumed yet
+    uint32_t nxt;           // words[sp - 1], loaded when its predecessor was consumed (off the chain)
+    uint32_t ov;            // the one word the decoder may hold above the blob's stack (see dec_push_uniform)
+    uint32_t has_ov;
+    uint32_t draws;         // words taken from the mt19937(1234) fallback (codec.h:32-40)
+    uint32_t status;
+};
+
+IDC_HD uint32_t small_ld(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+IDC_HD void small_dec_init(SmallDec& s, uint64_t head, const uint32_t* words, uint32_t nwords) {
+    s.head = head;
+    s.words = words;
+    s.sp = nwords;
+    s.nxt = nwords ? small_ld(words + nwords - 1u) : 0u;
+    s.ov = 0;
+    s.has_ov = 0;
+    s.draws = 0;
+    s.status = 0;
+}
+
+// ANSState::stack_slice (codec.h:32-40): the top of the stack -- the overlay word, else the blob's next word, else the
+// next output of std::mt19937(1234)
+IDC_HD uint32_t small_refill(SmallDec& s, const uint32_t* mt) {
+    if (s.has_ov) {
+        s.has_ov = 0;
+        return s.ov;
+    }
+    if (s.sp) {
+        const uint32_t w = s.nxt;
+        s.sp--;
+        if (s.sp) s.nxt = small_ld(s.words + s.sp - 1u);
+        return w;
+    }
+    const uint32_t d = s.draws++;
+    if (d >= (uint32_t)kMtWords) {
+        s.status |= kStMtDraws;
+        return 0u;
+    }
+    return small_ld(mt + d);
+}
+
+// vrans_pop (codec.cpp:78-90), p in 0..16; p == 0 still runs the refill test
+IDC_HD uint32_t small_pop_bits(SmallDec& s, uint32_t p, const uint32_t* mt) {
+    uint64_t h = s.head;
+    const uint32_t sym = (uint32_t)h & ((1u << p) - 1u);
+    h >>= p;
+    if (h < kRansL) h = (h << 32) | (uint64_t)small_refill(s, mt);
+    s.head = h;
+    return sym;
+}
+
+// codec_pop (codec.cpp:107-121) for precision <= 32: slices at lower = 48, 32 (precision 0: refill test only), 16, 0
+IDC_HD uint32_t small_pop_id(SmallDec& s, int precision, const uint32_t* mt) {
+    const uint32_t p0 = precision < 16 ? (uint32_t)precision : 16u;
+    const uint32_t p1 = (uint32_t)precision - p0;
+    (void)small_pop_bits(s, 0u, mt);
+    (void)small_pop_bits(s, 0u, mt);
+    const uint32_t hi = small_pop_bits(s, p1, mt);
+    const uint32_t lo = small_pop_bits(s, p0, mt);
+    return (hi << 16) | lo;
+}
+
+// push_with_finer_precision (codec.cpp:44-63); q31 = 2^31 / nmax
+IDC_HD void small_push_uniform(SmallDec& s, uint32_t sym, uint32_t nmax, uint32_t q31, const uint32_t* mt) {
+    uint64_t h = s.head;
+    const uint32_t hi = (uint32_t)(h >> 32);
+    if (hi >= q31) {  // h >= (2^31 / nmax) << 32: the low word goes on the stack
+        if (s.has_ov) s.status |= kStOverlay;  // a second word above the blob's stack: not a stream of this codec
+        s.ov = (uint32_t)h;
+        s.has_ov = 1;
+        h = (uint64_t)hi;
+    }
+    h = h * nmax + sym;
+    if (h < kRansL) h = (uint64_t)small_refill(s, mt) | (h << 32);
+    s.head = h;
+}
+
+// One unit, start to end (decompress, codec.cpp:140-152). seen(j) is a reference to the j-th id decoded (the caller's
+// storage: a shared-memory column on the device); the output order is the reference's: data[n - 1 - i] = i-th decoded.
+template <class Seen>
+IDC_HD void small_dec_unit(SmallDec& s, uint32_t n, int precision, Seen&& seen, const uint32_t* mt) {
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t id = small_pop_id(s, precision, mt);
+        uint32_t rank = 0;  // insert_then_forward_lookup(...).start: the ids below it (fenwick_tree.h:42-94)
+        for (uint32_t j = 0; j < i; j++) rank += seen(j) < id ? 1u : 0u;
+        seen(i) = id;
+        small_push_uniform(s, rank, i + 1u, (uint32_t)(kRansL / (i + 1u)), mt);
+    }
+}
+
+}  // namespace idc
