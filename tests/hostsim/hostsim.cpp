@@ -101,6 +101,23 @@ void sim_small_decode(uint64_t head, const uint32_t* words, uint32_t nwords, uin
     *status_out = s.status;
 }
 
+// encoder twin: ids ascending, n <= 64; returns the word count (-1: scratch overflow)
+int64_t sim_small_encode(uint32_t n, const uint64_t* ids, int prec, uint64_t* head_out, uint32_t* words_out, uint32_t cap,
+                         uint32_t* order_out, uint32_t* status_out) {
+    uint32_t mt[kMtWords];
+    tables(mt);
+    EncState st{kRansL, words_out, 0, cap, 0, 0, 1u};
+    uint64_t mask = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+    for (uint32_t t = n; t >= 1; --t) {
+        const uint32_t pos = small_enc_step(st, mask, t, prec, ~0ull / t, (uint32_t)((1ull << 31) / t),
+                                            [&](uint32_t p) { return (uint32_t)ids[p]; }, mt);
+        order_out[n - t] = pos;
+    }
+    *head_out = st.head;
+    *status_out = st.status;
+    return st.status & kStScratch ? -1 : (int64_t)st.sp;
+}
+
 int64_t sim_group_encode(int G, uint32_t n, const uint64_t* ids, int prec, uint64_t* head_out, uint32_t* words_out,
                          uint32_t cap, uint32_t* order_out, uint32_t* status_out) {
     return G == 8   ? group_encode<8>(n, ids, prec, head_out, words_out, cap, order_out, status_out)

@@ -30,6 +30,8 @@ def sim():
     lib.sim_group_encode.argtypes = [C.c_int] + enc_args
     lib.sim_group_decode.restype = None
     lib.sim_group_decode.argtypes = [C.c_int] + dec_args
+    lib.sim_small_encode.restype = C.c_int64
+    lib.sim_small_encode.argtypes = enc_args
     lib.sim_small_decode.restype = None
     lib.sim_small_decode.argtypes = [C.c_uint64, u32p, C.c_uint32, C.c_uint32, C.c_int, i64p, C.POINTER(C.c_uint32)]
     lib.sim_ef_shape.argtypes = [C.c_uint64, C.c_uint64, u64p]
@@ -132,6 +134,14 @@ def test_thread_per_unit_decoder(sim, roc_golden):
         h, w = oracle.port.encode(ids, p)
         d2, st = small_dec(sim, h, w, n, p)
         assert np.array_equal(d2.astype(np.uint64), oracle.port.decode(h, w, n, p)) and st == 0, (trial, n, p)
+        if n <= 64:  # the encoder twin (a 64-bit presence mask): stream and sample order
+            srt = np.sort(ids.astype(np.uint64))
+            w2 = np.zeros(n + 4, np.uint32)
+            o2 = np.zeros(n, np.uint32)
+            h2, st2 = C.c_uint64(), C.c_uint32()
+            r = sim.sim_small_encode(n, srt, p, C.byref(h2), w2, n + 4, o2, C.byref(st2))
+            assert r == w.size and h2.value == h and np.array_equal(w2[:r], w) and st2.value == 0, (trial, n, p)
+            assert np.array_equal(srt[o2], oracle.port.decode(h, w, n, p)), (trial, n, p)
     for c in roc_golden:
         if c["p"] > 32 or c["ids"].size > 5000:
             continue

@@ -419,6 +419,104 @@ __global__ void __launch_bounds__(kSmallThreads) k_roc_decode_small(SmallDecArgs
     }
 }
 
+// rows of at most kSmallUnit ids: the thread-per-row coders (no workspace, one launch). IDC_ROC_ROWS_GROUP=1 keeps the
+// lane-group kernels for them (experiments, tests of both paths).
+bool small_rows(uint32_t K) {
+    return K <= kSmallUnit && getenv("IDC_ROC_ROWS_GROUP") == nullptr;
+}
+
+// The encoder twin (roc_small.cuh): one row per thread. The warp first lays its 32 ascending rows into shared-memory
+// columns (coalesced reads); a step is pop-uniform, a select on the row's 64-bit presence mask, the push of that id.
+// Stream words go to the row's scratch slot like k_roc_encode's (compacted afterwards by the same kernels).
+__global__ void __launch_bounds__(kSmallThreads) k_roc_encode_small(EncArgs a) {
+    extern __shared__ __align__(16) uint32_t s_ids[];
+    constexpr uint32_t kPitch = kSmallThreads + 1u;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wbase = tid & ~31u;
+    const uint32_t slot = a.slot_base + blockIdx.x * kSmallThreads + tid;
+    const uint32_t* ids = reinterpret_cast<const uint32_t*>(a.ids);
+    for (uint32_t r = 0; r < 32u; r++) {
+        const uint32_t slot_r = a.slot_base + blockIdx.x * kSmallThreads + wbase + r;
+        if (slot_r >= a.slot_end) break;  // warp-uniform
+        const uint32_t u_r = a.perm[slot_r];
+        const uint32_t n_r = min(a.unit_n[u_r], kSmallUnit);
+        const uint32_t* src = ids + a.unit_src[u_r];
+        for (uint32_t t = lane; t < n_r; t += 32u) s_ids[t * kPitch + wbase + r] = src[t];
+    }
+    __syncwarp();
+    if (slot >= a.slot_end) return;
+    const uint32_t u = a.perm[slot];
+    const uint32_t n = a.unit_n[u];
+    EncState st{kRansL, a.scratch + a.scratch_off[u], 0u, n + 4u, 0u, 0u, 1u};
+    if (n > kSmallUnit) {  // not a unit for this kernel (the host never sends one)
+        atomicOr(a.status, kStScratch);
+    } else if (n) {
+        const int prec = (int)a.unit_prec[u];
+        const uint64_t src_off = a.unit_src[u];
+        const uint32_t* sidx = a.sort_idx ? a.sort_idx + src_off : nullptr;
+        uint32_t* order = a.order ? a.order + src_off : nullptr;
+        const uint32_t pos_base = a.unit_posbase[u];
+        uint64_t mask = n >= 64u ? ~0ull : ((1ull << n) - 1ull);
+        uint64_t rcp = __ldg(a.rcp64 + n);
+        uint32_t q31 = __ldg(a.q31 + n);
+        for (uint32_t t = n; t >= 1u; --t) {
+            // the next step's table entries are requested before this step's chain starts
+            const uint64_t rcp_n = __ldg(a.rcp64 + (t - 1u));
+            const uint32_t q31_n = __ldg(a.q31 + (t - 1u));
+            const uint32_t pos = small_enc_step(st, mask, t, prec, rcp, q31, [&](uint32_t p) { return s_ids[p * kPitch + tid]; }, a.mt);
+            if (order) order[n - t] = sidx ? sidx[pos] : pos_base + pos;
+            rcp = rcp_n;
+            q31 = q31_n;
+        }
+    }
+    a.unit_head[u] = st.head;
+    a.unit_nwords[u] = st.sp;
+    if (st.status) atomicOr(a.status, st.status);
+}
+
+// The latency flavour of the same decoder for a handful of rows (one get_neighbors call, a row and its neighbours'
+// rows): one WARP per row. Every lane runs the coder (same inputs, same arithmetic, nothing to exchange); lane j keeps
+// the j-th and (j + 32)-th decoded id in two registers, a rank is two ballots. ~10x the issue slots of the
+// thread-per-row kernel per row, a third of its latency: used when the rows would not fill the chip anyway.
+template <typename OutT>
+__global__ void __launch_bounds__(kSmallThreads) k_roc_decode_small_warp(SmallDecArgs a) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t slot = blockIdx.x * (kSmallThreads / 32u) + (threadIdx.x >> 5);
+    if (slot >= a.nsel) return;  // warp-uniform
+    uint32_t n = 0, s0 = 0, s1 = 0;
+    const int64_t r = a.rows ? (int64_t)a.rows[slot] : (int64_t)a.row_base + slot;
+    if (r < 0 || r >= (int64_t)a.nrows) {
+        if (lane == 0) atomicOr(a.status, kStRange);
+    } else {
+        const uint32_t u = (uint32_t)r;
+        n = a.unit_n[u];
+        if (n > a.row_stride || n > kSmallUnit) {
+            if (lane == 0) atomicOr(a.status, kStRange);
+            n = 0;
+        }
+        if (n) {
+            const uint64_t w0 = a.word_off[u], w1 = a.word_off[u + 1];
+            const int prec = (int)a.unit_prec[u];
+            SmallDec st;
+            small_dec_init(st, a.unit_head[u], a.words + w0, (uint32_t)(w1 - w0));
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t id = small_pop_id(st, prec, a.mt);
+                const uint32_t below0 = __ballot_sync(0xffffffffu, lane < i && s0 < id);
+                const uint32_t below1 = __ballot_sync(0xffffffffu, lane + 32u < i && s1 < id);
+                if (lane == (i & 31u)) {
+                    if (i < 32u) s0 = id; else s1 = id;
+                }
+                small_push_uniform(st, (uint32_t)(__popc(below0) + __popc(below1)), i + 1u, (uint32_t)(kRansL / (i + 1u)), a.mt);
+            }
+            if (st.status && lane == 0) atomicOr(a.status, st.status);
+        }
+    }
+    if (a.counts && lane == 0) a.counts[slot] = n;
+    OutT* o = reinterpret_cast<OutT*>(a.out) + (uint64_t)slot * a.row_stride;
+    if (lane < n) o[n - 1u - lane] = (OutT)s0;  // data[n - 1 - i] = i-th decoded id (codec.cpp:150)
+    if (lane + 32u < n) o[n - 33u - lane] = (OutT)s1;
+    for (uint32_t t = n + lane; t < a.row_stride; t += 32u) o[t] = (OutT)-1;
+}
+
 // --------------------------------------------------------------- host side
 
 // launch order: units by descending n (counting sort; n <= 65536)
@@ -983,12 +1081,19 @@ int roc_encode_rows_device(idc_ctx* c, idc_roc_blob* b, const int32_t* d_data, u
         e.nunits = (uint32_t)nr;
         e.rec_base = 0;
         e.rec_count = (uint32_t)nr;
-        {
-            LaunchScope ls(c, "k_enc_records");
-            k_enc_records<uint32_t><<<grid_for(nr * 32), kThreads, 0, c->stream>>>(e);
-        }
-        IDC_TRY(check_last_launch("k_enc_records"));
-        {
+        if (small_rows(K)) {
+            // rows of at most 64 ids: one row per thread, no record workspace (roc_small.cuh)
+            e.slot_base = 0;
+            e.slot_end = (uint32_t)nr;
+            LaunchScope ls(c, "k_roc_encode_small");
+            k_roc_encode_small<<<(uint32_t)((nr + kSmallThreads - 1) / kSmallThreads), kSmallThreads,
+                                 (size_t)K * (kSmallThreads + 1u) * 4u, c->stream>>>(e);
+        } else {
+            {
+                LaunchScope ls(c, "k_enc_records");
+                k_enc_records<uint32_t><<<grid_for(nr * 32), kThreads, 0, c->stream>>>(e);
+            }
+            IDC_TRY(check_last_launch("k_enc_records"));
             // one size class: every slot is sized for a full row
             e.slot_base = 0;
             e.slot_end = (uint32_t)nr;
@@ -1282,12 +1387,6 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     return finish_decode(c);
 }
 
-// rows of at most kSmallUnit ids: the thread-per-row decoder (no workspace, one launch). IDC_ROC_ROWS_GROUP=1 keeps the
-// lane-group kernel for them (experiments, tests of both paths).
-bool small_rows(uint32_t K) {
-    return K <= kSmallUnit && getenv("IDC_ROC_ROWS_GROUP") == nullptr;
-}
-
 int run_decode_small(idc_ctx* c, const idc_roc_blob* b, const int32_t* rows_dev, uint64_t row_base, uint64_t nsel, int32_t* out_dev,
                      uint32_t* counts_dev, uint32_t K) {
     if (nsel == 0) return IDC_OK;
@@ -1297,7 +1396,13 @@ int run_decode_small(idc_ctx* c, const idc_roc_blob* b, const int32_t* rows_dev,
     SmallDecArgs a{b->d_unit_n, b->d_unit_prec, b->d_unit_head, b->d_word_off, b->d_words, rows_dev, (uint32_t)b->nlist,
                    (uint32_t)row_base, (uint32_t)nsel, K, out_dev, counts_dev, d_status, c->d_mt};
     const size_t smem = (size_t)K * (kSmallThreads + 1u) * 4u;  // <= 33 KB
-    {
+    // up to a warp per scheduler of the chip the rows' chains run side by side whichever way: take the shorter chain
+    static const uint64_t warp_rows = getenv("IDC_ROC_ROWS_WARP") ? (uint64_t)atoll(getenv("IDC_ROC_ROWS_WARP")) : 1024u;
+    if (nsel <= warp_rows) {
+        LaunchScope ls(c, "k_roc_decode_small_warp");
+        const uint32_t wpb = kSmallThreads / 32u;
+        k_roc_decode_small_warp<int32_t><<<(uint32_t)((nsel + wpb - 1) / wpb), kSmallThreads, 0, c->stream>>>(a);
+    } else {
         LaunchScope ls(c, "k_roc_decode_small");
         k_roc_decode_small<int32_t><<<(uint32_t)((nsel + kSmallThreads - 1) / kSmallThreads), kSmallThreads, smem, c->stream>>>(a);
     }

@@ -1,4 +1,4 @@
-// roc_small.cuh -- ROC decode of SHORT units (graph rows, K <= 64 ids), one unit per THREAD.
+// roc_small.cuh -- ROC decode and encode of SHORT units (graph rows, K <= 64 ids), one unit per THREAD.
 //
 // The lane-group decoder of roc_group.cuh is built for chains of up to 65 536 steps: a bucket structure in HBM, count
 // levels in shared memory, a stream ring, one rendezvous per step -- about 560 warp instructions per step for the 8
@@ -113,6 +113,27 @@ IDC_HD void small_dec_unit(SmallDec& s, uint32_t n, int precision, Seen&& seen, 
         seen(i) = id;
         small_push_uniform(s, rank, i + 1u, (uint32_t)(kRansL / (i + 1u)), mt);
     }
+}
+
+// ---- encode (compress, codec.cpp:123-138): the ids still in the set are a 64-bit mask over the ascending row --
+// "select the k-th remaining id, remove it" (fenwick_tree.h:96-140) is a select on the mask.
+
+// position of the r-th (0-based) set bit of a 64-bit mask with more than r ones
+IDC_HD uint32_t small_select64(uint64_t m, uint32_t r) {
+    const uint32_t lo = (uint32_t)m, c = (uint32_t)popc32(lo);
+    return r < c ? select32(lo, r) : 32u + select32((uint32_t)(m >> 32), r - c);
+}
+
+// One encoder step: nmax ids are left (the caller walks nmax from n down to 1). ids(pos) is the pos-th id of the
+// ascending row; returns pos (the caller records the sample order with it).
+template <class Ids>
+IDC_HD uint32_t small_enc_step(EncState& st, uint64_t& mask, uint32_t nmax, int precision, uint64_t rcp, uint32_t q31,
+                               Ids&& ids, const uint32_t* mt) {
+    const uint32_t k = enc_pop_uniform(st, nmax, rcp, q31, mt);
+    const uint32_t pos = small_select64(mask, k);
+    mask &= ~(1ull << pos);
+    enc_push_id32(st, ids(pos), precision);
+    return pos;
 }
 
 }  // namespace idc
