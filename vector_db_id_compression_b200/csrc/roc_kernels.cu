@@ -517,6 +517,135 @@ __global__ void __launch_bounds__(kSmallThreads) k_roc_decode_small_warp(SmallDe
     for (uint32_t t = n + lane; t < a.row_stride; t += 32u) o[t] = (OutT)-1;
 }
 
+// ---- calls of at most kWarpCallUnits units whose LONGEST unit has at most kWarpUnit ids (IVF indexes with few, short
+// lists: IVF256 over 10^5 ids, IVF1024 over 10^6): one unit per WARP, everything on chip. Such a call cannot fill the
+// chip with lane-group chains, so the step's latency is what counts: every lane runs the coder (roc_small.cuh: same inputs,
+// same arithmetic), the order statistic is cooperative --
+//   decode: the ids decoded so far sit in shared memory, a rank is a strided count + one warp reduction;
+//   encode: the ascending ids sit in shared memory, lane j keeps the presence mask of words j and j + 32 and the
+//           number of ids still present in front of them in registers; select-k-th is two ballots, a shuffle, a
+//           select on one mask word -- no memory on the chain but the id itself.
+// ~450 cycles per step instead of ~2 300. Calls with longer units keep the lane-group kernels for all their classes.
+constexpr uint32_t kWarpUnit = 2048;
+constexpr uint32_t kWarpKThreads = 256;
+
+constexpr uint64_t kWarpCallUnits = 4096;  // a warp per unit repeats the coder in 32 lanes: beyond a few units per
+                                           // scheduler of the chip the lane-group kernels' shared instruction stream wins
+                                           // (IVF65536 over 10^7 ids: 65 536 units of ~150 ids are issue-bound either way)
+
+bool warp_units(uint32_t max_n, uint64_t units) {
+    return max_n <= kWarpUnit && units <= kWarpCallUnits && getenv("IDC_ROC_NO_WARP_UNITS") == nullptr;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kWarpKThreads) k_roc_decode_warp(DecArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
+    const uint32_t slot = a.slot_base + blockIdx.x * (kWarpKThreads / 32u) + wic;
+    if (slot >= a.slot_end) return;  // warp-uniform
+    const bool row_mode = a.sel_out == nullptr;
+    uint32_t u = 0, n = 0;
+    bool valid = true;
+    if (!row_mode) {
+        u = a.sel_unit[slot];
+    } else {
+        const int64_t r = a.rows ? (int64_t)a.rows[slot] : (int64_t)a.row_base + slot;
+        if (r < 0 || r >= (int64_t)a.nrows) {
+            if (lane == 0) atomicOr(a.status, kStRange);
+            valid = false;
+        } else {
+            u = (uint32_t)r;
+        }
+    }
+    if (valid) n = a.unit_n[u];
+    if (n > a.sm_words) {  // longer than the class was sized for (the host never sends one)
+        if (lane == 0) atomicOr(a.status, kStScratch);
+        n = 0;
+    }
+    OutT* out = reinterpret_cast<OutT*>(a.out) + (row_mode ? (uint64_t)slot * a.row_stride : a.sel_out[slot]);
+    uint32_t* seen = smem + (size_t)wic * a.sm_words;
+    if (n) {
+        const uint64_t w0 = a.word_off[u], w1 = a.word_off[u + 1];
+        const int prec = (int)a.unit_prec[u];
+        SmallDec st;
+        small_dec_init(st, a.unit_head[u], a.words + w0, (uint32_t)(w1 - w0));
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t q31 = __ldg(a.q31 + i + 1u);  // requested before the step's chain starts
+            const uint32_t id = small_pop_id(st, prec, a.mt);
+            uint32_t cnt = 0;
+            for (uint32_t j = lane; j < i; j += 32u) cnt += seen[j] < id ? 1u : 0u;
+            const uint32_t rank = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) seen[i] = id;
+            __syncwarp();
+            small_push_uniform(st, rank, i + 1u, q31, a.mt);
+        }
+        if (st.status && lane == 0) atomicOr(a.status, st.status);
+        for (uint32_t t = lane; t < n; t += 32u) out[t] = (OutT)seen[n - 1u - t];  // codec.cpp:150
+    }
+    for (uint32_t t = n + lane; t < a.row_stride; t += 32u) out[t] = (OutT)-1;
+    if (a.counts && lane == 0) a.counts[slot] = n;
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(kWarpKThreads) k_roc_encode_warp(EncArgs a) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, wic = threadIdx.x >> 5;
+    const uint32_t slot = a.slot_base + blockIdx.x * (kWarpKThreads / 32u) + wic;
+    if (slot >= a.slot_end) return;  // warp-uniform
+    const uint32_t u = a.perm[slot];
+    uint32_t n = a.unit_n[u];
+    EncState st{kRansL, a.scratch + a.scratch_off[u], 0u, n + 4u, 0u, 0u, lane == 0 ? 1u : 0u};
+    if (n > a.sm_words) {  // longer than the class was sized for (the host never sends one)
+        st.status |= kStScratch;
+        n = 0;
+    }
+    if (n) {
+        uint32_t* sid = smem + (size_t)wic * a.sm_words;
+        const uint64_t src_off = a.unit_src[u];
+        const IdT* src = reinterpret_cast<const IdT*>(a.ids) + src_off;
+        for (uint32_t t = lane; t < n; t += 32u) sid[t] = (uint32_t)load_id(src + t);
+        const uint32_t W = (n + 31u) >> 5;  // mask words in use (<= 64)
+        auto word_mask = [&](uint32_t w) { return w * 32u + 32u <= n ? 0xffffffffu : (w * 32u < n ? (1u << (n - w * 32u)) - 1u : 0u); };
+        uint32_t m0 = word_mask(lane), m1 = word_mask(lane + 32u);
+        // ids still present in front of word j / j + 32; a lane without a word never qualifies
+        uint32_t e0 = lane < W ? lane * 32u : 0xffffffffu, e1 = lane + 32u < W ? (lane + 32u) * 32u : 0xffffffffu;
+        __syncwarp();
+        const int prec = (int)a.unit_prec[u];
+        const uint32_t* sidx = a.sort_idx ? a.sort_idx + src_off : nullptr;
+        uint32_t* order = a.order ? a.order + src_off : nullptr;
+        const uint32_t pos_base = a.unit_posbase[u];
+        uint64_t rcp = __ldg(a.rcp64 + n);
+        uint32_t q31 = __ldg(a.q31 + n);
+        for (uint32_t t = n; t >= 1u; --t) {
+            const uint64_t rcp_n = __ldg(a.rcp64 + (t - 1u));
+            const uint32_t q31_n = __ldg(a.q31 + (t - 1u));
+            const uint32_t k = enc_pop_uniform(st, t, rcp, q31, a.mt);
+            // the words whose front count is <= k are a prefix of the row of words; the last of them holds the k-th id
+            const uint32_t word = (uint32_t)(__popc(__ballot_sync(0xffffffffu, e0 <= k)) + __popc(__ballot_sync(0xffffffffu, e1 <= k))) - 1u;
+            const bool hi = word >= 32u;
+            const uint32_t ew = __shfl_sync(0xffffffffu, hi ? e1 : e0, word & 31u);
+            const uint32_t mw = __shfl_sync(0xffffffffu, hi ? m1 : m0, word & 31u);
+            const uint32_t bit = select32(mw, k - ew);
+            const uint32_t pos = word * 32u + bit;
+            if (lane == (word & 31u)) {
+                if (hi) m1 &= ~(1u << bit); else m0 &= ~(1u << bit);
+            }
+            e0 -= (lane > word && lane < W) ? 1u : 0u;
+            e1 -= (lane + 32u > word && lane + 32u < W) ? 1u : 0u;
+            enc_push_id32(st, sid[pos], prec);
+            if (order && lane == 0) order[n - t] = sidx ? sidx[pos] : pos_base + pos;
+            __syncwarp();  // the stream words lane 0 stored are ordered before a later step's refill (enc_refill)
+            rcp = rcp_n;
+            q31 = q31_n;
+        }
+    }
+    if (lane == 0) {
+        a.unit_head[u] = st.head;
+        a.unit_nwords[u] = st.sp;
+        if (st.status) atomicOr(a.status, st.status);
+    }
+}
+
 // --------------------------------------------------------------- host side
 
 // launch order: units by descending n (counting sort; n <= 65536)
@@ -872,6 +1001,22 @@ int roc_encode_units(idc_ctx* c, idc_roc_blob* b, const void* ids_dev, const voi
             cudaStream_t ps = c->aux[pc.stream];
             IDC_CUDA(cudaStreamWaitEvent(ps, ev_ready[nchunk ? pc.chunk : 0], 0));
             if (tr.on) cudaEventRecord(tl_ev[1 + 2 * tl_n], ps);
+            if (warp_units(max_n, nu)) {
+                // every unit of the call short: one unit per warp, on chip (k_roc_encode_warp)
+                ek.sm_words = ((cls[k].max_n ? cls[k].max_n : 1u) + 31u) & ~31u;
+                const uint32_t wpb = kWarpKThreads / 32u, wgrid = (slots + wpb - 1) / wpb;
+                const size_t wsmem = (size_t)ek.sm_words * 4 * wpb;
+                if (enc_id_bytes == 8) {
+                    IDC_TRY(set_max_smem(k_roc_encode_warp<int64_t>, wsmem));
+                    k_roc_encode_warp<int64_t><<<wgrid, kWarpKThreads, wsmem, ps>>>(ek);
+                } else {
+                    IDC_TRY(set_max_smem(k_roc_encode_warp<uint32_t>, wsmem));
+                    k_roc_encode_warp<uint32_t><<<wgrid, kWarpKThreads, wsmem, ps>>>(ek);
+                }
+                if (tr.on) cudaEventRecord(tl_ev[2 + 2 * tl_n], ps), tl_n++;
+                c->launches++;
+                continue;
+            }
 #define IDC_LAUNCH_ENC(GG, TT)                                                       \
     do {                                                                             \
         IDC_TRY(set_max_smem(k_roc_encode<GG, TT>, smem));                            \
@@ -1278,7 +1423,10 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
         }
         return IDC_OK;
     }
-    IDC_TRY(c->ws.reserve(ws_bytes + 256));
+    auto cls = size_classes(nsel, n_of_slot);
+    // every unit of the call short: one unit per warp, on chip (k_roc_decode_warp) -- no bucket workspace
+    const bool warp_mode = warp_units(cls.empty() ? 0u : cls[0].max_n, nsel);
+    if (!warp_mode) IDC_TRY(c->ws.reserve(ws_bytes + 256));
     IDC_TRY(c->status.reserve(128));
     uint32_t* d_status = c->status.as<uint32_t>();
     IDC_CUDA(cudaMemsetAsync(d_status, 0, 128, c->stream));
@@ -1286,7 +1434,7 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
         IDC_TRY(c->sync_event(&ov->ms_armed));
         IDC_CUDA(cudaEventRecord(ov->ms_armed, c->stream));
     }
-    {
+    if (!warp_mode) {
         LaunchScope ls(c, "memset_ws");  // empty bucket slots must read as 0xffffffff (dec_tree_insert_rank)
         IDC_CUDA(cudaMemsetAsync(c->ws.p, 0xff, ws_bytes, c->stream));
     }
@@ -1314,9 +1462,8 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
     a.nrows = (uint32_t)b->nlist;
     a.row_base = (uint32_t)row_base;
     {
-        auto cls = size_classes(nsel, n_of_slot);
         (void)max_n;
-        LaunchScope ls(c, "k_roc_decode");
+        LaunchScope ls(c, "k_roc_decode");  // (the logical kernel: k_roc_decode_warp in warp mode)
         const std::vector<int> cstream = class_streams(cls);
         IDC_TRY(c->fork(class_stream_count()));
         uint64_t stream_load[kMaxClassStreams] = {0};
@@ -1344,6 +1491,19 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
             const uint32_t grid = (nwarps + warps - 1) / warps;
             const size_t smem = (size_t)ak.sm_words * 4 * upw * warps;
             const bool ms = ov && ov->want_ms && k == 0 && cls[k].max_n >= kMsMinUnit;
+            if (warp_mode) {
+                ak.sm_words = ((cls[k].max_n ? cls[k].max_n : 1u) + 31u) & ~31u;
+                const uint32_t wpb = kWarpKThreads / 32u, wslots = ak.slot_end - ak.slot_base;
+                const uint32_t wgrid = (wslots + wpb - 1) / wpb;
+                const size_t wsmem = (size_t)ak.sm_words * 4 * wpb;
+                if (id_bytes == 8) {
+                    IDC_TRY(set_max_smem(k_roc_decode_warp<int64_t>, wsmem));
+                    k_roc_decode_warp<int64_t><<<wgrid, kWarpKThreads, wsmem, c->aux[cstream[k]]>>>(ak);
+                } else {
+                    IDC_TRY(set_max_smem(k_roc_decode_warp<int32_t>, wsmem));
+                    k_roc_decode_warp<int32_t><<<wgrid, kWarpKThreads, wsmem, c->aux[cstream[k]]>>>(ak);
+                }
+            } else {
             if (ms) {
                 ov->ms_seg = (cls[k].max_n + ms_parts() - 1) / ms_parts();
                 ov->ms_count = ms_parts() - 1;
@@ -1366,6 +1526,7 @@ int run_decode(idc_ctx* c, const idc_roc_blob* b, const uint32_t* d_unit, const 
                 if (id_bytes == 8) IDC_LAUNCH_DEC(4, int64_t); else IDC_LAUNCH_DEC(4, int32_t);
             }
 #undef IDC_LAUNCH_DEC
+            }
             c->launches++;
             stream_load[cstream[k]] += cls[k].max_n ? cls[k].max_n : 1u;
             if (ov) {
