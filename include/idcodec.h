@@ -255,7 +255,11 @@ int idc_roc_translate(
  * out is nsel x K int32; entries past the row's length are set to -1;
  * counts (may be NULL) receives the true neighbour count per row (the
  * reference returns K). row_nos HOST or DEVICE per rows_mem;
- * NULL = all rows in order. */
+ * NULL = all rows in order. A call with host row numbers and a host output of
+ * at most 64 KB (one row, a row and its neighbours' rows) goes through the
+ * context's pinned mailbox: one launch and one stream synchronisation, no
+ * copies. The same holds for idc_ef_decode_rows, idc_ef_select and
+ * idc_wt_select. */
 int idc_roc_decode_rows(
         idc_ctx* ctx,
         const idc_roc_blob* blob,
