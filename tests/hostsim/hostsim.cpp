@@ -101,6 +101,55 @@ void sim_small_decode(uint64_t head, const uint32_t* words, uint32_t nwords, uin
     *status_out = s.status;
 }
 
+// one unit per warp (warp_dec_unit / warp_dec_row / warp_enc_unit): 32 host threads play the lanes
+void sim_warp_decode(uint64_t head, const uint32_t* words, uint32_t nwords, uint32_t n, int prec, int row, int64_t* out,
+                     uint32_t* status_out) {
+    uint32_t mt[kMtWords];
+    tables(mt);
+    std::vector<uint32_t> seen(n + 64, 0), q31(n + 2, 0);
+    for (uint32_t d = 1; d < n + 2; d++) q31[d] = (uint32_t)((1ull << 31) / d);
+    run_group(32, [&](const HostGrp& g) {
+        SmallDec st;
+        small_dec_init(st, head, words, nwords);
+        if (row) {  // n <= 64: the decoded ids stay in two "registers" per lane
+            uint32_t s0 = 0, s1 = 0;
+            warp_dec_row(g, st, n, prec, s0, s1, mt);
+            if (g.sub < n) seen[g.sub] = s0;
+            if (g.sub + 32u < n) seen[g.sub + 32u] = s1;
+        } else {
+            warp_dec_unit(g, st, n, prec, seen.data(), q31.data(), mt);
+        }
+        g.sync();
+        if (g.sub == 0) *status_out = st.status;
+    });
+    for (uint32_t i = 0; i < n; i++) out[n - 1 - i] = (int64_t)seen[i];
+}
+
+int64_t sim_warp_encode(uint32_t n, const uint64_t* ids, int prec, uint64_t* head_out, uint32_t* words_out, uint32_t cap,
+                        uint32_t* order_out, uint32_t* status_out) {
+    uint32_t mt[kMtWords];
+    tables(mt);
+    std::vector<uint32_t> sid(n + 1), q31(n + 2, 0);
+    std::vector<uint64_t> rcp(n + 2, 0);
+    for (uint32_t i = 0; i < n; i++) sid[i] = (uint32_t)ids[i];
+    for (uint32_t d = 1; d < n + 2; d++) q31[d] = (uint32_t)((1ull << 31) / d), rcp[d] = ~0ull / d;
+    int64_t result = 0;
+    run_group(32, [&](const HostGrp& g) {
+        EncState st{kRansL, words_out, 0, cap, 0, 0, g.sub == 0 ? 1u : 0u};
+        warp_enc_unit(g, st, n, prec, sid.data(), rcp.data(), q31.data(),
+                      [&](uint32_t step, uint32_t pos) {
+                          if (g.sub == 0) order_out[step] = pos;
+                      },
+                      mt);
+        if (g.sub == 0) {
+            *head_out = st.head;
+            *status_out = st.status;
+            result = st.status & kStScratch ? -1 : (int64_t)st.sp;
+        }
+    });
+    return result;
+}
+
 // encoder twin: ids ascending, n <= 64; returns the word count (-1: scratch overflow)
 int64_t sim_small_encode(uint32_t n, const uint64_t* ids, int prec, uint64_t* head_out, uint32_t* words_out, uint32_t cap,
                          uint32_t* order_out, uint32_t* status_out) {

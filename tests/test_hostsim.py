@@ -30,6 +30,10 @@ def sim():
     lib.sim_group_encode.argtypes = [C.c_int] + enc_args
     lib.sim_group_decode.restype = None
     lib.sim_group_decode.argtypes = [C.c_int] + dec_args
+    lib.sim_warp_encode.restype = C.c_int64
+    lib.sim_warp_encode.argtypes = enc_args
+    lib.sim_warp_decode.restype = None
+    lib.sim_warp_decode.argtypes = [C.c_uint64, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, i64p, C.POINTER(C.c_uint32)]
     lib.sim_small_encode.restype = C.c_int64
     lib.sim_small_encode.argtypes = enc_args
     lib.sim_small_decode.restype = None
@@ -151,6 +155,34 @@ def test_thread_per_unit_decoder(sim, roc_golden):
     h, w = oracle.port.encode(np.array([0], np.uint64), 0)
     d2, st = small_dec(sim, h, w, 1, 0)
     assert d2.tolist() == [0] and st == 0
+
+
+def test_warp_per_unit_coders(sim):
+    """The warp-per-unit kernels' bodies (csrc/roc_small.cuh: warp_enc_unit, warp_dec_unit, warp_dec_row; 32 host threads
+    play the lanes, the collectives are rendezvous) against the oracle: stream, sample order, decode order; unit lengths
+    around the 32-id word and 1024-id half boundaries of the encoder's presence masks, up to the 2 048-id limit."""
+    rng = np.random.default_rng(2048)
+    sizes = [1, 2, 31, 32, 33, 63, 64, 65, 100, 500, 1023, 1024, 1025, 1500, 2047, 2048] + [int(x) for x in rng.integers(1, 700, size=14)]
+    for trial, n in enumerate(sizes):
+        p = int(rng.integers(max(1, int(np.ceil(np.log2(n + 1)))), 33))
+        ids = rand_set(rng, n, p)
+        if ids.size < n:  # (a 64-bit draw may repeat)
+            ids = np.unique(np.concatenate([ids, rand_set(rng, n, p)]))[:n]
+        n = ids.size
+        srt = np.sort(ids.astype(np.uint64))
+        h, w = oracle.port.encode(ids, p)
+        d = oracle.port.decode(h, w, n, p)
+        w2 = np.zeros(n + 4, np.uint32)
+        o2 = np.zeros(n, np.uint32)
+        h2, st2 = C.c_uint64(), C.c_uint32()
+        r = sim.sim_warp_encode(n, srt, p, C.byref(h2), w2, n + 4, o2, C.byref(st2))
+        assert r == w.size and h2.value == h and np.array_equal(w2[:r], w) and st2.value == 0, (trial, n, p)
+        assert np.array_equal(srt[o2], d), (trial, n, p)
+        for row in ((0, 1) if n <= 64 else (0,)):
+            out = np.zeros(n, np.int64)
+            st = C.c_uint32()
+            sim.sim_warp_decode(h, w if w.size else np.zeros(1, np.uint32), w.size, n, p, row, out, C.byref(st))
+            assert np.array_equal(out.astype(np.uint64), d) and st.value == 0, (trial, n, p, row)
 
 
 @pytest.mark.parametrize("G,n,p", [(4, 15259, 30), (4, 65536, 17), (8, 65536, 31), (4, 65000, 20), (8, 4097, 13), (4, 2233, 12), (2, 65536, 30), (2, 15259, 20)])

@@ -1,7 +1,8 @@
 """CPU: the lane-group protocol of the ROC step code (csrc/roc_group.cuh, idc_core.cuh: stream ring serviced once per step,
 insert deferred into the next step, shared-memory counters) under ThreadSanitizer. The host emulation runs every lane as
 a free-running thread -- lanes drift apart between two rendezvous exactly as the lanes of a group do on the device -- so a
-read that is not ordered against another lane's write by a rendezvous shows up as a data race here."""
+read that is not ordered against another lane's write by a rendezvous shows up as a data race here. The warp-per-unit
+coders of csrc/roc_small.cuh (32 lanes) run in the same build."""
 import shutil
 import subprocess
 from pathlib import Path
@@ -24,4 +25,6 @@ def test_group_protocol_is_race_free_under_tsan(tmp_path):
     out = run.stdout + run.stderr
     lines = [l for l in run.stdout.splitlines() if l.startswith("G=")]
     assert len(lines) == 12 and all(l.endswith("roundtrip=ok") for l in lines), out[-2000:]
+    wl = [l for l in run.stdout.splitlines() if l.startswith("W=32")]  # the warp-per-unit coders of roc_small.cuh
+    assert len(wl) == 3 and all(l.endswith("roundtrip=ok") for l in wl), out[-2000:]
     assert "ThreadSanitizer" not in out, out[-4000:]

@@ -498,15 +498,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_roc_decode_small_warp(SmallDe
             const int prec = (int)a.unit_prec[u];
             SmallDec st;
             small_dec_init(st, a.unit_head[u], a.words + w0, (uint32_t)(w1 - w0));
-            for (uint32_t i = 0; i < n; i++) {
-                const uint32_t id = small_pop_id(st, prec, a.mt);
-                const uint32_t below0 = __ballot_sync(0xffffffffu, lane < i && s0 < id);
-                const uint32_t below1 = __ballot_sync(0xffffffffu, lane + 32u < i && s1 < id);
-                if (lane == (i & 31u)) {
-                    if (i < 32u) s0 = id; else s1 = id;
-                }
-                small_push_uniform(st, (uint32_t)(__popc(below0) + __popc(below1)), i + 1u, (uint32_t)(kRansL / (i + 1u)), a.mt);
-            }
+            warp_dec_row(Grp<32>(), st, n, prec, s0, s1, a.mt);
             if (st.status && lane == 0) atomicOr(a.status, st.status);
         }
     }
@@ -569,16 +561,7 @@ __global__ void __launch_bounds__(kWarpKThreads) k_roc_decode_warp(DecArgs a) {
         const int prec = (int)a.unit_prec[u];
         SmallDec st;
         small_dec_init(st, a.unit_head[u], a.words + w0, (uint32_t)(w1 - w0));
-        for (uint32_t i = 0; i < n; i++) {
-            const uint32_t q31 = __ldg(a.q31 + i + 1u);  // requested before the step's chain starts
-            const uint32_t id = small_pop_id(st, prec, a.mt);
-            uint32_t cnt = 0;
-            for (uint32_t j = lane; j < i; j += 32u) cnt += seen[j] < id ? 1u : 0u;
-            const uint32_t rank = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0) seen[i] = id;
-            __syncwarp();
-            small_push_uniform(st, rank, i + 1u, q31, a.mt);
-        }
+        warp_dec_unit(Grp<32>(), st, n, prec, seen, a.q31, a.mt);
         if (st.status && lane == 0) atomicOr(a.status, st.status);
         for (uint32_t t = lane; t < n; t += 32u) out[t] = (OutT)seen[n - 1u - t];  // codec.cpp:150
     }
@@ -604,40 +587,16 @@ __global__ void __launch_bounds__(kWarpKThreads) k_roc_encode_warp(EncArgs a) {
         const uint64_t src_off = a.unit_src[u];
         const IdT* src = reinterpret_cast<const IdT*>(a.ids) + src_off;
         for (uint32_t t = lane; t < n; t += 32u) sid[t] = (uint32_t)load_id(src + t);
-        const uint32_t W = (n + 31u) >> 5;  // mask words in use (<= 64)
-        auto word_mask = [&](uint32_t w) { return w * 32u + 32u <= n ? 0xffffffffu : (w * 32u < n ? (1u << (n - w * 32u)) - 1u : 0u); };
-        uint32_t m0 = word_mask(lane), m1 = word_mask(lane + 32u);
-        // ids still present in front of word j / j + 32; a lane without a word never qualifies
-        uint32_t e0 = lane < W ? lane * 32u : 0xffffffffu, e1 = lane + 32u < W ? (lane + 32u) * 32u : 0xffffffffu;
         __syncwarp();
         const int prec = (int)a.unit_prec[u];
         const uint32_t* sidx = a.sort_idx ? a.sort_idx + src_off : nullptr;
         uint32_t* order = a.order ? a.order + src_off : nullptr;
         const uint32_t pos_base = a.unit_posbase[u];
-        uint64_t rcp = __ldg(a.rcp64 + n);
-        uint32_t q31 = __ldg(a.q31 + n);
-        for (uint32_t t = n; t >= 1u; --t) {
-            const uint64_t rcp_n = __ldg(a.rcp64 + (t - 1u));
-            const uint32_t q31_n = __ldg(a.q31 + (t - 1u));
-            const uint32_t k = enc_pop_uniform(st, t, rcp, q31, a.mt);
-            // the words whose front count is <= k are a prefix of the row of words; the last of them holds the k-th id
-            const uint32_t word = (uint32_t)(__popc(__ballot_sync(0xffffffffu, e0 <= k)) + __popc(__ballot_sync(0xffffffffu, e1 <= k))) - 1u;
-            const bool hi = word >= 32u;
-            const uint32_t ew = __shfl_sync(0xffffffffu, hi ? e1 : e0, word & 31u);
-            const uint32_t mw = __shfl_sync(0xffffffffu, hi ? m1 : m0, word & 31u);
-            const uint32_t bit = select32(mw, k - ew);
-            const uint32_t pos = word * 32u + bit;
-            if (lane == (word & 31u)) {
-                if (hi) m1 &= ~(1u << bit); else m0 &= ~(1u << bit);
-            }
-            e0 -= (lane > word && lane < W) ? 1u : 0u;
-            e1 -= (lane + 32u > word && lane + 32u < W) ? 1u : 0u;
-            enc_push_id32(st, sid[pos], prec);
-            if (order && lane == 0) order[n - t] = sidx ? sidx[pos] : pos_base + pos;
-            __syncwarp();  // the stream words lane 0 stored are ordered before a later step's refill (enc_refill)
-            rcp = rcp_n;
-            q31 = q31_n;
-        }
+        warp_enc_unit(Grp<32>(), st, n, prec, sid, a.rcp64, a.q31,
+                      [&](uint32_t step, uint32_t pos) {
+                          if (order && lane == 0) order[step] = sidx ? sidx[pos] : pos_base + pos;
+                      },
+                      a.mt);
     }
     if (lane == 0) {
         a.unit_head[u] = st.head;

@@ -136,4 +136,98 @@ IDC_HD uint32_t small_enc_step(EncState& st, uint64_t& mask, uint32_t nmax, int 
     return pos;
 }
 
+// ---- one unit per WARP: the coder runs in every lane (same inputs, same arithmetic), the order statistic is cooperative.
+// GR is the warp as a lane group -- Grp<32> on the device (roc_group.cuh), 32 host threads in tests/hostsim: `sub` is the
+// lane, ballot / shfl / sync are the warp collectives.
+
+IDC_HD uint64_t small_ld64(const uint64_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+template <class GR>
+IDC_HD uint32_t warp_sum(const GR& g, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    (void)g;
+    return __reduce_add_sync(0xffffffffu, v);
+#else
+    for (uint32_t m = 16; m; m >>= 1) v += g.shfl_xor(v, m);
+    return v;
+#endif
+}
+
+// Decode of a unit of up to 2 048 ids (decompress, codec.cpp:140-152). seen[0 .. n): the warp's shared memory, the i-th
+// decoded id at seen[i]; a rank is a strided count over it plus one warp reduction. q31[d] = 2^31 / d.
+template <class GR>
+IDC_HD void warp_dec_unit(const GR& g, SmallDec& st, uint32_t n, int prec, uint32_t* seen, const uint32_t* q31, const uint32_t* mt) {
+    const uint32_t lane = g.sub;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t q = small_ld(q31 + i + 1u);  // requested before the step's chain starts
+        const uint32_t id = small_pop_id(st, prec, mt);
+        uint32_t cnt = 0;
+        for (uint32_t j = lane; j < i; j += 32u) cnt += seen[j] < id ? 1u : 0u;
+        const uint32_t rank = warp_sum(g, cnt);
+        if (lane == 0) seen[i] = id;
+        g.sync();
+        small_push_uniform(st, rank, i + 1u, q, mt);
+    }
+}
+
+// Decode of a graph row of up to 64 ids: lane j keeps the j-th and (j + 32)-th decoded id (s0, s1), a rank is two ballots.
+template <class GR>
+IDC_HD void warp_dec_row(const GR& g, SmallDec& st, uint32_t n, int prec, uint32_t& s0, uint32_t& s1, const uint32_t* mt) {
+    const uint32_t lane = g.sub;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t id = small_pop_id(st, prec, mt);
+        const uint32_t below0 = g.ballot(lane < i && s0 < id);
+        const uint32_t below1 = g.ballot(lane + 32u < i && s1 < id);
+        if (lane == (i & 31u)) {
+            if (i < 32u) s0 = id; else s1 = id;
+        }
+        small_push_uniform(st, (uint32_t)(popc32(below0) + popc32(below1)), i + 1u, (uint32_t)(kRansL / (i + 1u)), mt);
+    }
+}
+
+// Encode of a unit of up to 2 048 ascending ids sid[0 .. n) (compress, codec.cpp:123-138). Lane j keeps the presence
+// masks of words j and j + 32 of the unit (m0, m1) and the number of ids still present in FRONT of those words (e0, e1) in
+// registers. The front counts are non-decreasing over the words, so the words with front count <= k are a prefix and the
+// last of them holds the k-th remaining id: two ballots, a shuffle of its count and mask, select32. A removal decrements
+// the front counts of the words behind it. order(step, pos) records the sample order (pos = position in the ascending unit).
+template <class GR, class Order>
+IDC_HD void warp_enc_unit(const GR& g, EncState& st, uint32_t n, int prec, const uint32_t* sid, const uint64_t* rcp64,
+                          const uint32_t* q31tab, Order&& order, const uint32_t* mt) {
+    const uint32_t lane = g.sub;
+    const uint32_t W = (n + 31u) >> 5;  // mask words in use (<= 64)
+    auto word_mask = [&](uint32_t w) { return w * 32u + 32u <= n ? 0xffffffffu : (w * 32u < n ? (1u << (n - w * 32u)) - 1u : 0u); };
+    uint32_t m0 = word_mask(lane), m1 = word_mask(lane + 32u);
+    // a lane without a word never qualifies
+    uint32_t e0 = lane < W ? lane * 32u : 0xffffffffu, e1 = lane + 32u < W ? (lane + 32u) * 32u : 0xffffffffu;
+    uint64_t rcp = small_ld64(rcp64 + n);
+    uint32_t q31 = small_ld(q31tab + n);
+    for (uint32_t t = n; t >= 1u; --t) {
+        const uint64_t rcp_n = small_ld64(rcp64 + (t - 1u));  // the next step's table entries, ahead of this step's chain
+        const uint32_t q31_n = small_ld(q31tab + (t - 1u));
+        const uint32_t k = enc_pop_uniform(st, t, rcp, q31, mt);
+        const uint32_t word = (uint32_t)(popc32(g.ballot(e0 <= k)) + popc32(g.ballot(e1 <= k))) - 1u;
+        const bool hi = word >= 32u;
+        const uint32_t ew = g.shfl(hi ? e1 : e0, word & 31u);
+        const uint32_t mw = g.shfl(hi ? m1 : m0, word & 31u);
+        const uint32_t bit = select32(mw, k - ew);
+        const uint32_t pos = word * 32u + bit;
+        if (lane == (word & 31u)) {
+            if (hi) m1 &= ~(1u << bit); else m0 &= ~(1u << bit);
+        }
+        e0 -= (lane > word && lane < W) ? 1u : 0u;
+        e1 -= (lane + 32u > word && lane + 32u < W) ? 1u : 0u;
+        enc_push_id32(st, sid[pos], prec);
+        order(n - t, pos);
+        g.sync();  // the stream words lane 0 stored are ordered before a later step's refill (enc_refill)
+        rcp = rcp_n;
+        q31 = q31_n;
+    }
+}
+
 }  // namespace idc
